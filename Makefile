@@ -1,0 +1,48 @@
+# Top-level build: the CUDA engine (C ABI), the host CLI and the checkers under oracle/.
+#   make            -> pangenomesim_b200/lib/libpgs.so, pangenomesim_b200/bin/pangenomesim-b200, oracle
+#   make lib|cli|oracle|clean
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CXX      ?= g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-ffp-contract=off -Xptxas -v
+CSRC     := pangenomesim_b200/csrc
+HOST     := pangenomesim_b200/host
+LIBDIR   := pangenomesim_b200/lib
+BINDIR   := pangenomesim_b200/bin
+OBJDIR   := build/obj
+
+LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/kernels.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp
+LIB_HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/pgs.h
+LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/kernels.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o
+
+all: lib cli oracle
+
+lib: $(LIBDIR)/libpgs.so
+cli: $(BINDIR)/pangenomesim-b200
+oracle:
+	$(MAKE) -C oracle
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(LIB_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+	@grep -E "error|warning|spill|registers" $(OBJDIR)/$*.ptxas.log | grep -v "0 bytes spill" | head -40 || true
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(LIB_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off -c $< -o $@
+
+$(LIBDIR)/libpgs.so: $(LIB_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart shared -Xlinker -rpath,/usr/local/cuda/lib64
+
+HOST_SRCS := $(wildcard $(HOST)/*.cpp)
+$(BINDIR)/pangenomesim-b200: $(HOST_SRCS) $(wildcard $(HOST)/*.h) include/pgs.h $(LIBDIR)/libpgs.so
+	@mkdir -p $(BINDIR)
+	@if [ -n "$(HOST_SRCS)" ]; then \
+	  $(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude $(HOST_SRCS) -o $@ -L$(LIBDIR) -lpgs -Wl,-rpath,'$$ORIGIN/../lib' -lpthread ; \
+	else echo "host CLI sources not present yet"; fi
+
+clean:
+	rm -rf build $(LIBDIR) $(BINDIR)
+	$(MAKE) -C oracle clean
+.PHONY: all lib cli oracle clean

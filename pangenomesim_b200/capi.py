@@ -1,0 +1,239 @@
+"""ctypes binding of include/pgs.h (one class, no logic of its own).
+
+Every method maps 1:1 onto a C entry point; arrays are numpy and are passed as plain pointers.
+There is deliberately no fallback: if ``libpgs.so`` cannot be loaded, or no CUDA device is
+usable, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+PGS_ALL_GENOMES = -1
+PGS_FLAG_NO_GRAPH = 1
+OUT_REF, OUT_CORE, OUT_ACCESSORY, OUT_GENOMES, OUT_MAF, OUT_ALL = 1, 2, 4, 8, 16, 31
+
+
+class PgsError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"pgs error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class _Config(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("gene_length", C.c_int64), ("device", C.c_int32), ("flags", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "n_nodes", "n_genomes", "n_genes", "n_dense_genes", "blocks_per_gene", "rows_total",
+        "rows_written", "rows_read", "rows_origin", "leaf_nucleotides", "site_edges", "levels",
+        "kernel_launches", "device_bytes")] + [(k, C.c_double) for k in (
+        "sweep_ms", "rootgen_ms", "mismatch_ms", "format_ms")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64)
+
+
+class OutputSpec(C.Structure):
+    _fields_ = [("out_dir", C.c_char_p), ("what", C.c_uint32), ("n_ref_core", C.c_int64),
+                ("ref_core", C.POINTER(C.c_int64)), ("n_ref_acc", C.c_int64), ("ref_acc", C.POINTER(C.c_int64)),
+                ("sink", SINK_FN), ("sink_user", C.c_void_p)]
+
+
+class OutputReport(C.Structure):
+    _fields_ = [("files", C.c_int64), ("bytes", C.c_int64), ("records", C.c_int64),
+                ("device_ms", C.c_double), ("wall_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("PGS_LIBRARY", _HERE / "lib" / "libpgs.so"))
+
+
+def load_library():
+    """Load libpgs.so (built in-tree by ``make lib`` / ``__graft_entry__.build()``)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not path.exists():
+        raise PgsError(-6, f"{path} is missing: build it with `make lib`; there is no CPU fallback")
+    lib = C.CDLL(str(path))
+    P = C.POINTER
+    lib.pgs_abi_version.restype = C.c_int
+    lib.pgs_last_error.restype = C.c_char_p
+    lib.pgs_last_error.argtypes = [C.c_void_p]
+    lib.pgs_create.argtypes = [P(_Config), P(C.c_void_p)]
+    lib.pgs_destroy.argtypes = [C.c_void_p]
+    lib.pgs_destroy.restype = None
+    lib.pgs_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pgs_sync.argtypes = [C.c_void_p]
+    lib.pgs_set_tree.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pgs_set_genes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pgs_sweep.argtypes = [C.c_void_p]
+    lib.pgs_get_stats.argtypes = [C.c_void_p, P(Stats)]
+    lib.pgs_mismatch.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
+    lib.pgs_mismatch_device.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
+    lib.pgs_write_outputs.argtypes = [C.c_void_p, P(OutputSpec), P(OutputReport)]
+    lib.pgs_genome_name.argtypes = [C.c_int64, C.c_char_p, C.c_size_t]
+    lib.pgs_copy_packed.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+    lib.pgs_copy_dense.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.pgs_row_index.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
+    lib.pgs_row_index.restype = C.c_int64
+    lib.pgs_get_edge_table.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, P(C.c_int32)]
+    _LIB = lib
+    return lib
+
+
+def genome_name(index: int) -> str:
+    buf = C.create_string_buffer(64)
+    load_library().pgs_genome_name(index, buf, 64)
+    return buf.value.decode()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    """One engine = one CUDA device.  Mirrors the call order of include/pgs.h."""
+
+    def __init__(self, seed: int, gene_length: int, device: int = -1, flags: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        cfg = _Config(seed, gene_length, device, flags)
+        rc = self._lib.pgs_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise PgsError(rc, self._lib.pgs_last_error(None).decode())
+        self.gene_length = gene_length
+        self.n_nodes = 0
+        self.n_genomes = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc < 0:
+            raise PgsError(rc, self._lib.pgs_last_error(self._h).decode())
+        return rc
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.pgs_set_stream(self._h, cuda_stream_ptr))
+
+    def sync(self):
+        self._check(self._lib.pgs_sync(self._h))
+
+    def set_tree(self, parent, rate, leaf_genome):
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        rate = np.ascontiguousarray(rate, dtype=np.float64)
+        leaf_genome = np.ascontiguousarray(leaf_genome, dtype=np.int32)
+        assert parent.shape == rate.shape == leaf_genome.shape
+        self._check(self._lib.pgs_set_tree(self._h, len(parent), _ptr(parent), _ptr(rate), _ptr(leaf_genome)))
+        self.n_nodes = len(parent)
+        self.n_genomes = int((leaf_genome >= 0).sum())
+
+    def set_genes(self, gene_id, origin, carrier_off, carrier_genome, all_order=None):
+        gene_id = np.ascontiguousarray(gene_id, dtype=np.int64)
+        origin = np.ascontiguousarray(origin, dtype=np.int32)
+        carrier_off = np.ascontiguousarray(carrier_off, dtype=np.int64)
+        carrier_genome = np.ascontiguousarray(carrier_genome, dtype=np.int32)
+        if all_order is not None:
+            all_order = np.ascontiguousarray(all_order, dtype=np.int32)
+        assert len(origin) == len(gene_id) and len(carrier_off) == len(gene_id) + 1
+        self._check(self._lib.pgs_set_genes(self._h, len(gene_id), _ptr(gene_id), _ptr(origin),
+                                            _ptr(carrier_off), _ptr(carrier_genome), _ptr(all_order)))
+        self.n_genes = len(gene_id)
+
+    def set_core_genes(self, n_genes: int, root: int, first_id: int = 0):
+        """Convenience: n_genes genes with ids first_id.., origin = root, carried by every genome."""
+        ids = np.arange(first_id, first_id + n_genes, dtype=np.int64)
+        self.set_genes(ids, np.full(n_genes, root, np.int32), np.arange(n_genes + 1, dtype=np.int64),
+                       np.full(n_genes, PGS_ALL_GENOMES, np.int32))
+
+    def sweep(self):
+        self._check(self._lib.pgs_sweep(self._h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.pgs_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def mismatch(self):
+        out = np.zeros((self.n_genomes, self.n_genomes), dtype=np.uint32)
+        sites = C.c_int64()
+        self._check(self._lib.pgs_mismatch(self._h, _ptr(out), C.byref(sites)))
+        return out, sites.value
+
+    def mismatch_device(self, device_ptr: int) -> int:
+        sites = C.c_int64()
+        self._check(self._lib.pgs_mismatch_device(self._h, device_ptr, C.byref(sites)))
+        return sites.value
+
+    def blocks_per_gene(self) -> int:
+        return (self.gene_length + 63) // 64
+
+    def copy_packed(self, node: int, gene_index: int):
+        """Packed row as uint32 words, or None when the gene is absent at the node."""
+        dst = np.zeros(self.blocks_per_gene() * 4, dtype=np.uint32)
+        rc = self._check(self._lib.pgs_copy_packed(self._h, node, gene_index, _ptr(dst)))
+        return None if rc == 1 else dst
+
+    def copy_dense(self, node: int, n_dense: int):
+        dst = np.zeros((n_dense, self.blocks_per_gene() * 4), dtype=np.uint32)
+        self._check(self._lib.pgs_copy_dense(self._h, node, _ptr(dst)))
+        return dst
+
+    def row_index(self, node: int, gene_index: int) -> int:
+        return self._lib.pgs_row_index(self._h, node, gene_index)
+
+    def edge_table(self, node: int):
+        H = np.zeros(65, dtype=np.uint64)
+        k = C.c_int32()
+        self._check(self._lib.pgs_get_edge_table(self._h, node, _ptr(H), C.byref(k)))
+        return H, k.value
+
+    def write_outputs(self, out_dir=None, what=OUT_ALL, ref_core=(), ref_acc=(), sink=None):
+        rc_arr = np.ascontiguousarray(ref_core, dtype=np.int64)
+        ra_arr = np.ascontiguousarray(ref_acc, dtype=np.int64)
+        spec = OutputSpec()
+        spec.out_dir = str(out_dir).encode() if out_dir is not None else None
+        spec.what = what
+        spec.n_ref_core = len(rc_arr)
+        spec.ref_core = rc_arr.ctypes.data_as(C.POINTER(C.c_int64))
+        spec.n_ref_acc = len(ra_arr)
+        spec.ref_acc = ra_arr.ctypes.data_as(C.POINTER(C.c_int64))
+        cb = None
+        if sink is not None:
+            def _cb(user, name, offset, data, length):
+                try:
+                    return int(sink(name.decode(), offset, data, length) or 0)
+                except Exception:  # never unwind through C
+                    return 1
+            cb = SINK_FN(_cb)
+            spec.sink = cb
+        rep = OutputReport()
+        self._check(self._lib.pgs_write_outputs(self._h, C.byref(spec), C.byref(rep)))
+        return rep.as_dict()

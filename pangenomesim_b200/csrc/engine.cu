@@ -1,0 +1,702 @@
+// engine.cu -- C ABI (include/pgs.h): planning of the row layout and of the level sweep, device
+// tables, launches.  There is no CPU path: every compute entry point ends in a CUDA kernel of
+// kernels.cu / format.cu and fails with PGS_ERR_NO_DEVICE / PGS_ERR_CUDA otherwise.
+#include "engine.h"
+#include "edge_table.h"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <new>
+
+namespace pgs {
+
+static thread_local std::string g_create_error;
+
+void DevBuf::release()
+{
+	if (p) cudaFree(p);
+	p = nullptr;
+	bytes = 0;
+}
+
+Engine::~Engine()
+{
+	drop_graph();
+	for (auto &x : ev)
+		if (x) cudaEventDestroy(x);
+	if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+int Engine::fail(int code, const std::string &msg)
+{
+	err = msg;
+	return code;
+}
+
+int Engine::cuda_fail(cudaError_t e, const char *what)
+{
+	err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+	return e == cudaErrorMemoryAllocation ? PGS_ERR_NOMEM : PGS_ERR_CUDA;
+}
+
+int Engine::alloc(DevBuf &b, size_t bytes, const char *what)
+{
+	b.release();
+	if (bytes == 0) bytes = 16;
+	cudaError_t e = cudaMalloc(&b.p, bytes);
+	if (e != cudaSuccess) {
+		b.p = nullptr;
+		cudaGetLastError();
+		return cuda_fail(e, what);
+	}
+	b.bytes = bytes;
+	return PGS_OK;
+}
+
+int Engine::upload(DevBuf &b, const void *src, size_t bytes, const char *what)
+{
+	int rc = alloc(b, bytes, what);
+	if (rc) return rc;
+	if (bytes) {
+		cudaError_t e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+		if (e != cudaSuccess) return cuda_fail(e, what);
+	}
+	return PGS_OK;
+}
+
+int64_t Engine::device_bytes() const
+{
+	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
+						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch};
+	int64_t s = 0;
+	for (auto b : all) s += (int64_t)b->bytes;
+	return s;
+}
+
+void Engine::drop_graph()
+{
+	if (graph_exec) cudaGraphExecDestroy(graph_exec);
+	if (graph) cudaGraphDestroy(graph);
+	graph_exec = nullptr;
+	graph = nullptr;
+}
+
+int64_t Engine::row_index(int32_t node, int64_t g) const
+{
+	if (!have_genes || node < 0 || node >= n_nodes || g < 0 || g >= n_genes) return -1;
+	if (dense_slot[g] >= 0) return row_base[node] + dense_slot[g];
+	const int64_t *b = sp_gene.data() + sp_off[node], *e = sp_gene.data() + sp_off[node + 1];
+	const int64_t *it = std::lower_bound(b, e, g);
+	if (it == e || *it != g) return -1;
+	return row_base[node] + (int64_t)dense_gid.size() + (it - b);
+}
+
+// K1 for every level below the root: dense region, then sparse region.  Levels are separated by
+// stream order (each launch reads rows written by the previous level's launches).
+void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
+{
+	const DenseTask *dt = d_dense_tasks.as<DenseTask>();
+	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
+	for (int32_t lvl = 1; lvl <= max_level; lvl++) {
+		const int64_t nd = dense_level_off[lvl + 1] - dense_level_off[lvl];
+		if (nd > 0 && tables.n_dense > 0) {
+			launch_sweep_dense(tables, dt + dense_level_off[lvl], (int32_t)nd, s);
+			(*launches)++;
+		}
+		const int64_t ns = sparse_level_off[lvl + 1] - sparse_level_off[lvl];
+		if (ns > 0) {
+			launch_sweep_sparse(tables, st + sparse_level_off[lvl], ns, s);
+			(*launches)++;
+		}
+	}
+}
+
+} // namespace pgs
+
+using pgs::Engine;
+
+#define ENGINE_OR_RETURN(h)                \
+	if (!(h)) return PGS_ERR_ARG;          \
+	Engine &e = (h)->e;                    \
+	{                                      \
+		cudaError_t ce_ = cudaSetDevice(e.device); \
+		if (ce_ != cudaSuccess) return e.cuda_fail(ce_, "cudaSetDevice"); \
+	}
+
+extern "C" {
+
+int pgs_abi_version(void)
+{
+	return PGS_ABI_VERSION;
+}
+
+const char *pgs_last_error(const pgs_engine *h)
+{
+	return h ? h->e.err.c_str() : pgs::g_create_error.c_str();
+}
+
+int pgs_create(const pgs_config *cfg, pgs_engine **out)
+{
+	if (!cfg || !out) {
+		pgs::g_create_error = "pgs_create: null argument";
+		return PGS_ERR_ARG;
+	}
+	*out = nullptr;
+	if (cfg->gene_length < 1 || cfg->gene_length > (int64_t)1 << 36) {
+		pgs::g_create_error = "pgs_create: gene_length out of range";
+		return PGS_ERR_ARG;
+	}
+	int count = 0;
+	cudaError_t ce = cudaGetDeviceCount(&count);
+	if (ce != cudaSuccess || count == 0) {
+		cudaGetLastError();
+		pgs::g_create_error = std::string("pgs_create: no usable CUDA device (") +
+							  (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") +
+							  "); this engine has no CPU path";
+		return PGS_ERR_NO_DEVICE;
+	}
+	int dev = cfg->device;
+	if (dev < 0) {
+		ce = cudaGetDevice(&dev);
+		if (ce != cudaSuccess) dev = 0;
+	}
+	if (dev >= count) {
+		pgs::g_create_error = "pgs_create: device ordinal out of range";
+		return PGS_ERR_ARG;
+	}
+	pgs_engine *h = new (std::nothrow) pgs_engine();
+	if (!h) {
+		pgs::g_create_error = "pgs_create: out of host memory";
+		return PGS_ERR_NOMEM;
+	}
+	Engine &e = h->e;
+	e.cfg = *cfg;
+	e.device = dev;
+	ce = cudaSetDevice(dev);
+	if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 6 && ce == cudaSuccess; i++) ce = cudaEventCreate(&e.ev[i]);
+	if (ce != cudaSuccess) {
+		pgs::g_create_error = std::string("pgs_create: ") + cudaGetErrorString(ce);
+		delete h;
+		return PGS_ERR_CUDA;
+	}
+	e.stream = e.own_stream;
+	e.blocks = (cfg->gene_length + 63) / 64;
+	e.last_valid = (int32_t)(cfg->gene_length - (e.blocks - 1) * 64);
+	*out = h;
+	return PGS_OK;
+}
+
+void pgs_destroy(pgs_engine *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->e.device);
+	cudaStreamSynchronize(h->e.stream);
+	delete h;
+}
+
+int pgs_set_stream(pgs_engine *h, void *cuda_stream)
+{
+	ENGINE_OR_RETURN(h);
+	cudaStreamSynchronize(e.stream);
+	e.stream = cuda_stream ? (cudaStream_t)cuda_stream : e.own_stream;
+	return PGS_OK;
+}
+
+int pgs_sync(pgs_engine *h)
+{
+	ENGINE_OR_RETURN(h);
+	cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_sync");
+	return PGS_OK;
+}
+
+int pgs_set_tree(pgs_engine *h, int32_t n_nodes, const int32_t *parent, const double *rate,
+				 const int32_t *leaf_genome)
+{
+	ENGINE_OR_RETURN(h);
+	if (n_nodes < 1 || !parent || !rate || !leaf_genome) return e.fail(PGS_ERR_ARG, "pgs_set_tree: null or empty");
+	e.have_tree = e.have_genes = e.swept = false;
+	e.drop_graph();
+
+	int32_t root = -1;
+	std::vector<int32_t> deg(n_nodes + 1, 0);
+	for (int32_t v = 0; v < n_nodes; v++) {
+		const int32_t p = parent[v];
+		if (p == -1) {
+			if (root != -1) return e.fail(PGS_ERR_ARG, "pgs_set_tree: more than one root");
+			root = v;
+		} else if (p < 0 || p >= n_nodes || p == v) {
+			return e.fail(PGS_ERR_ARG, "pgs_set_tree: parent index out of range");
+		} else {
+			deg[p]++;
+		}
+		if (p != -1 && !(rate[v] >= 0.0)) return e.fail(PGS_ERR_ARG, "pgs_set_tree: negative or NaN rate");
+	}
+	if (root == -1) return e.fail(PGS_ERR_ARG, "pgs_set_tree: no root");
+
+	e.child_off.assign(n_nodes + 1, 0);
+	for (int32_t v = 0; v < n_nodes; v++) e.child_off[v + 1] = e.child_off[v] + deg[v];
+	e.child.assign(e.child_off[n_nodes], 0);
+	{
+		std::vector<int32_t> fill(e.child_off.begin(), e.child_off.end() - 1);
+		for (int32_t v = 0; v < n_nodes; v++)
+			if (parent[v] >= 0) e.child[fill[parent[v]]++] = v;
+	}
+	// levels by breadth-first walk from the root; unreachable nodes mean a cycle
+	e.level.assign(n_nodes, -1);
+	std::vector<int32_t> queue;
+	queue.reserve(n_nodes);
+	queue.push_back(root);
+	e.level[root] = 0;
+	int32_t max_level = 0;
+	for (size_t qi = 0; qi < queue.size(); qi++) {
+		const int32_t v = queue[qi];
+		for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++) {
+			const int32_t u = e.child[c];
+			e.level[u] = e.level[v] + 1;
+			max_level = std::max(max_level, e.level[u]);
+			queue.push_back(u);
+		}
+	}
+	if ((int32_t)queue.size() != n_nodes) return e.fail(PGS_ERR_ARG, "pgs_set_tree: cycle or disconnected node");
+
+	int32_t n_genomes = 0;
+	for (int32_t v = 0; v < n_nodes; v++) {
+		const int32_t g = leaf_genome[v];
+		if (g < -1) return e.fail(PGS_ERR_ARG, "pgs_set_tree: leaf_genome < -1");
+		if (g >= 0) {
+			if (deg[v] != 0) return e.fail(PGS_ERR_ARG, "pgs_set_tree: genome assigned to an internal node");
+			n_genomes = std::max(n_genomes, g + 1);
+		}
+	}
+	e.genome_leaf.assign(n_genomes, -1);
+	for (int32_t v = 0; v < n_nodes; v++) {
+		const int32_t g = leaf_genome[v];
+		if (g >= 0) {
+			if (e.genome_leaf[g] != -1) return e.fail(PGS_ERR_ARG, "pgs_set_tree: duplicate genome index");
+			e.genome_leaf[g] = v;
+		}
+	}
+	for (int32_t g = 0; g < n_genomes; g++)
+		if (e.genome_leaf[g] < 0) return e.fail(PGS_ERR_ARG, "pgs_set_tree: genome indices are not 0..n-1");
+
+	e.n_nodes = n_nodes;
+	e.n_genomes = n_genomes;
+	e.root = root;
+	e.max_level = max_level;
+	e.parent.assign(parent, parent + n_nodes);
+	e.rate.assign(rate, rate + n_nodes);
+	e.leaf_genome.assign(leaf_genome, leaf_genome + n_nodes);
+	e.have_tree = true;
+	return PGS_OK;
+}
+
+int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const int32_t *origin_node,
+				  const int64_t *carrier_off, const int32_t *carrier_genome, const int32_t *all_order)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.have_tree) return e.fail(PGS_ERR_STATE, "pgs_set_genes: call pgs_set_tree first");
+	if (n_genes < 0 || (n_genes > 0 && (!gene_id || !origin_node || !carrier_off || !carrier_genome)))
+		return e.fail(PGS_ERR_ARG, "pgs_set_genes: null table");
+	e.have_genes = e.swept = false;
+	e.drop_graph();
+	const int32_t N = e.n_nodes, n = e.n_genomes;
+
+	// ---- copy and validate the gene table
+	e.n_genes = n_genes;
+	e.gene_id.assign(gene_id, gene_id + n_genes);
+	e.origin.assign(origin_node, origin_node + n_genes);
+	e.all_order.resize(n);
+	if (all_order) {
+		std::vector<char> seen(n, 0);
+		for (int32_t i = 0; i < n; i++) {
+			const int32_t g = all_order[i];
+			if (g < 0 || g >= n || seen[g]) return e.fail(PGS_ERR_ARG, "pgs_set_genes: all_order is not a permutation");
+			seen[g] = 1;
+			e.all_order[i] = g;
+		}
+	} else {
+		for (int32_t i = 0; i < n; i++) e.all_order[i] = i;
+	}
+	e.dense_slot.assign(n_genes, -1);
+	std::vector<std::pair<uint32_t, int64_t>> dense; // (gene_id, table index)
+	for (int64_t g = 0; g < n_genes; g++) {
+		if (gene_id[g] < 0 || gene_id[g] >= (int64_t)0xFFFFFFFFll)
+			return e.fail(PGS_ERR_ARG, "pgs_set_genes: gene_id outside [0, 2^32-1)");
+		if (origin_node[g] < 0 || origin_node[g] >= N) return e.fail(PGS_ERR_ARG, "pgs_set_genes: origin out of range");
+		const int64_t b = carrier_off[g], c = carrier_off[g + 1];
+		if (b < 0 || c < b) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier_off not monotone");
+		if (c - b == 1 && carrier_genome[b] == PGS_ALL_GENOMES && origin_node[g] == e.root)
+			dense.emplace_back((uint32_t)gene_id[g], g);
+	}
+	std::sort(dense.begin(), dense.end());
+	const int64_t D = (int64_t)dense.size();
+	e.dense_gid.resize(D);
+	e.dense_gene.resize(D);
+	for (int64_t s = 0; s < D; s++) {
+		e.dense_gid[s] = dense[s].first;
+		e.dense_gene[s] = dense[s].second;
+		e.dense_slot[dense[s].second] = (int32_t)s;
+	}
+
+	// ---- sparse genes: expand carriers, mark the nodes on the paths carrier -> origin
+	e.carrier_off.assign(n_genes + 1, 0);
+	e.carrier_genome.clear();
+	std::vector<std::vector<int64_t>> at_node(N);
+	std::vector<int64_t> stamp(N, -1);
+	e.genome_gene_count.assign(n, D);
+	for (int64_t g = 0; g < n_genes; g++) {
+		e.carrier_off[g] = (int64_t)e.carrier_genome.size();
+		if (e.dense_slot[g] >= 0) continue;
+		const int64_t b = carrier_off[g], c = carrier_off[g + 1];
+		const int32_t org = origin_node[g];
+		if (c - b == 1 && carrier_genome[b] == PGS_ALL_GENOMES) {
+			// every genome below a non-root origin, in all_order
+			for (int32_t i = 0; i < n; i++) {
+				int32_t v = e.genome_leaf[e.all_order[i]];
+				while (v != -1 && v != org) v = e.parent[v];
+				if (v == org) e.carrier_genome.push_back(e.all_order[i]);
+			}
+		} else {
+			for (int64_t k = b; k < c; k++) {
+				const int32_t cg = carrier_genome[k];
+				if (cg < 0 || cg >= n) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier genome out of range");
+				e.carrier_genome.push_back(cg);
+			}
+		}
+		for (int64_t k = e.carrier_off[g]; k < (int64_t)e.carrier_genome.size(); k++) {
+			int32_t v = e.genome_leaf[e.carrier_genome[k]];
+			if (stamp[v] == g) return e.fail(PGS_ERR_ARG, "pgs_set_genes: genome listed twice for a gene");
+			e.genome_gene_count[e.carrier_genome[k]]++;
+			while (stamp[v] != g) {
+				stamp[v] = g;
+				at_node[v].push_back(g);
+				if (v == org) break;
+				v = e.parent[v];
+				if (v < 0) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier is not below the gene's origin");
+			}
+		}
+	}
+	e.carrier_off[n_genes] = (int64_t)e.carrier_genome.size();
+	{ // gene ids must be unique across the whole table
+		std::vector<int64_t> ids(e.gene_id);
+		std::sort(ids.begin(), ids.end());
+		if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
+			return e.fail(PGS_ERR_ARG, "pgs_set_genes: duplicate gene_id");
+	}
+
+	e.sp_off.assign(N + 1, 0);
+	for (int32_t v = 0; v < N; v++) e.sp_off[v + 1] = e.sp_off[v] + (int64_t)at_node[v].size();
+	e.sp_gene.resize(e.sp_off[N]);
+	for (int32_t v = 0; v < N; v++) std::copy(at_node[v].begin(), at_node[v].end(), e.sp_gene.begin() + e.sp_off[v]);
+	at_node.clear();
+	at_node.shrink_to_fit();
+
+	// ---- row layout: node-major, dense region first
+	e.row_base.assign(N, 0);
+	int64_t rows = 0;
+	for (int32_t v = 0; v < N; v++) {
+		e.row_base[v] = rows;
+		rows += D + (e.sp_off[v + 1] - e.sp_off[v]);
+	}
+	if (rows >= (int64_t)pgs::kNoRow) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32-2 rows on one engine; shard the genes");
+	if (D * e.blocks >= (int64_t)1 << 31) return e.fail(PGS_ERR_ARG, "pgs_set_genes: dense region of a node exceeds 2^31 blocks; shard the genes");
+	e.rows_total = rows;
+
+	// ---- tasks, grouped by the level of the children
+	const int32_t ML = e.max_level;
+	std::vector<std::vector<pgs::DenseTask>> dl(ML + 2);
+	std::vector<std::vector<pgs::SparseTask>> sl(ML + 2);
+	e.rows_written = e.rows_read = 0;
+	for (int32_t p = 0; p < N; p++) {
+		const int32_t nc = e.child_off[p + 1] - e.child_off[p];
+		if (nc == 0) continue;
+		const int32_t lvl = e.level[p] + 1;
+		const int64_t *pg = e.sp_gene.data() + e.sp_off[p];
+		const int64_t np = e.sp_off[p + 1] - e.sp_off[p];
+		for (int32_t ci = 0; ci < nc; ci += 2) {
+			const int32_t l = e.child[e.child_off[p] + ci];
+			const int32_t r = (ci + 1 < nc) ? e.child[e.child_off[p] + ci + 1] : -1;
+			if (D > 0) {
+				dl[lvl].push_back(pgs::DenseTask{p, l, r});
+				e.rows_read += D;
+				e.rows_written += D * (r >= 0 ? 2 : 1);
+			}
+			// merge the parent's sparse list with the children's (all ascending)
+			const int64_t *lg = e.sp_gene.data() + e.sp_off[l];
+			const int64_t nl = e.sp_off[l + 1] - e.sp_off[l];
+			const int64_t *rg = r >= 0 ? e.sp_gene.data() + e.sp_off[r] : nullptr;
+			const int64_t nr = r >= 0 ? e.sp_off[r + 1] - e.sp_off[r] : 0;
+			int64_t il = 0, ir = 0;
+			for (int64_t ip = 0; ip < np; ip++) {
+				const int64_t g = pg[ip];
+				while (il < nl && lg[il] < g) il++;
+				while (ir < nr && rg[ir] < g) ir++;
+				const bool hl = il < nl && lg[il] == g, hr = ir < nr && rg[ir] == g;
+				if (!hl && !hr) continue;
+				pgs::SparseTask t;
+				t.src = (uint32_t)(e.row_base[p] + D + ip);
+				t.dst_left = hl ? (uint32_t)(e.row_base[l] + D + il) : pgs::kNoRow;
+				t.dst_right = hr ? (uint32_t)(e.row_base[r] + D + ir) : pgs::kNoRow;
+				t.gid = (uint32_t)e.gene_id[g];
+				t.edge_left = l;
+				t.edge_right = r;
+				sl[lvl].push_back(t);
+				e.rows_read += 1;
+				e.rows_written += (hl ? 1 : 0) + (hr ? 1 : 0);
+			}
+		}
+	}
+	std::vector<pgs::DenseTask> dense_tasks;
+	std::vector<pgs::SparseTask> sparse_tasks;
+	e.dense_level_off.assign(ML + 2, 0);
+	e.sparse_level_off.assign(ML + 2, 0);
+	for (int32_t lvl = 0; lvl <= ML; lvl++) {
+		e.dense_level_off[lvl] = (int64_t)dense_tasks.size();
+		e.sparse_level_off[lvl] = (int64_t)sparse_tasks.size();
+		dense_tasks.insert(dense_tasks.end(), dl[lvl].begin(), dl[lvl].end());
+		sparse_tasks.insert(sparse_tasks.end(), sl[lvl].begin(), sl[lvl].end());
+	}
+	e.dense_level_off[ML + 1] = (int64_t)dense_tasks.size();
+	e.sparse_level_off[ML + 1] = (int64_t)sparse_tasks.size();
+	e.n_dense_tasks = (int64_t)dense_tasks.size();
+	e.n_sparse_tasks = (int64_t)sparse_tasks.size();
+
+	std::vector<pgs::RootTask> root_tasks;
+	root_tasks.reserve(n_genes);
+	for (int64_t s = 0; s < D; s++) root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[e.root] + s), e.dense_gid[s]});
+	for (int64_t g = 0; g < n_genes; g++) {
+		if (e.dense_slot[g] >= 0) continue;
+		const int32_t v = e.origin[g];
+		const int64_t *b = e.sp_gene.data() + e.sp_off[v], *en = e.sp_gene.data() + e.sp_off[v + 1];
+		const int64_t *it = std::lower_bound(b, en, g);
+		if (it == en || *it != g) continue; // gene carried by no genome: no rows at all
+		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + D + (it - b)), (uint32_t)e.gene_id[g]});
+	}
+	e.n_root_tasks = (int64_t)root_tasks.size();
+	e.rows_origin = e.n_root_tasks;
+
+	// ---- per-branch decision tables
+	e.h1_host.assign(N, 0);
+	e.tab_off_host.assign(N, 0);
+	e.kmax_host.assign(N, 0);
+	e.tab_host.clear();
+	for (int32_t v = 0; v < N; v++) {
+		uint64_t H[65];
+		const int km = (v == e.root) ? 0 : pgs::build_edge_table(e.rate[v], H);
+		e.tab_off_host[v] = (int32_t)e.tab_host.size();
+		e.kmax_host[v] = km;
+		e.h1_host[v] = km > 0 ? H[1] : 0;
+		for (int k = 1; k <= km; k++) e.tab_host.push_back(H[k]);
+	}
+
+	// ---- device
+	int rc;
+	const size_t row_bytes = (size_t)e.blocks * 16;
+	if ((rc = e.alloc(e.d_rows, (size_t)rows * row_bytes, "rows (HBM sequence store)"))) return rc;
+	if ((rc = e.upload(e.d_row_base, e.row_base.data(), sizeof(int64_t) * N, "row_base"))) return rc;
+	if ((rc = e.upload(e.d_h1, e.h1_host.data(), sizeof(uint64_t) * N, "h1"))) return rc;
+	if ((rc = e.upload(e.d_tab, e.tab_host.data(), sizeof(uint64_t) * e.tab_host.size(), "tab"))) return rc;
+	if ((rc = e.upload(e.d_tab_off, e.tab_off_host.data(), sizeof(int32_t) * N, "tab_off"))) return rc;
+	if ((rc = e.upload(e.d_kmax, e.kmax_host.data(), sizeof(int32_t) * N, "kmax"))) return rc;
+	if ((rc = e.upload(e.d_dense_gid, e.dense_gid.data(), sizeof(uint32_t) * D, "dense_gid"))) return rc;
+	if ((rc = e.upload(e.d_dense_tasks, dense_tasks.data(), sizeof(pgs::DenseTask) * dense_tasks.size(), "dense tasks"))) return rc;
+	if ((rc = e.upload(e.d_sparse_tasks, sparse_tasks.data(), sizeof(pgs::SparseTask) * sparse_tasks.size(), "sparse tasks"))) return rc;
+	if ((rc = e.upload(e.d_root_tasks, root_tasks.data(), sizeof(pgs::RootTask) * root_tasks.size(), "root tasks"))) return rc;
+	std::vector<int64_t> leaf_words(n);
+	for (int32_t g = 0; g < n; g++) leaf_words[g] = e.row_base[e.genome_leaf[g]] * e.blocks * 4;
+	if ((rc = e.upload(e.d_leaf_base_words, leaf_words.data(), sizeof(int64_t) * n, "leaf bases"))) return rc;
+	e.d_mismatch.release();
+
+	pgs::DeviceTables &t = e.tables;
+	t.rows = e.d_rows.as<uint4>();
+	t.row_base = e.d_row_base.as<int64_t>();
+	t.h1 = e.d_h1.as<uint64_t>();
+	t.tab = e.d_tab.as<uint64_t>();
+	t.tab_off = e.d_tab_off.as<int32_t>();
+	t.kmax = e.d_kmax.as<int32_t>();
+	t.dense_gid = e.d_dense_gid.as<uint32_t>();
+	t.n_dense = (uint32_t)D;
+	t.blocks = (uint32_t)e.blocks;
+	t.last_valid = e.last_valid;
+	t.div_blocks = pgs::make_fastdiv((uint32_t)e.blocks);
+	t.keys = pgs::make_philox_keys(e.cfg.seed);
+	e.have_genes = true;
+	return PGS_OK;
+}
+
+int pgs_sweep(pgs_engine *h)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.have_genes) return e.fail(PGS_ERR_STATE, "pgs_sweep: call pgs_set_tree and pgs_set_genes first");
+	cudaError_t ce;
+	int64_t launches = 0;
+	cudaEventRecord(e.ev[0], e.stream);
+	pgs::launch_rootgen(e.tables, e.d_root_tasks.as<pgs::RootTask>(), e.n_root_tasks, e.stream);
+	if (e.n_root_tasks) launches++;
+	cudaEventRecord(e.ev[1], e.stream);
+	if (e.cfg.flags & PGS_FLAG_NO_GRAPH) {
+		e.enqueue_levels(e.stream, &launches);
+	} else {
+		if (!e.graph_exec) {
+			// capture the level launches once; replays cost one graph launch per sweep
+			int64_t captured = 0;
+			ce = cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal);
+			if (ce != cudaSuccess) return e.cuda_fail(ce, "cudaStreamBeginCapture");
+			e.enqueue_levels(e.stream, &captured);
+			ce = cudaStreamEndCapture(e.stream, &e.graph);
+			if (ce != cudaSuccess) return e.cuda_fail(ce, "cudaStreamEndCapture");
+			ce = cudaGraphInstantiate(&e.graph_exec, e.graph, 0);
+			if (ce != cudaSuccess) return e.cuda_fail(ce, "cudaGraphInstantiate");
+			e.launches_last_sweep = captured;
+		}
+		launches += e.launches_last_sweep;
+		ce = cudaGraphLaunch(e.graph_exec, e.stream);
+		if (ce != cudaSuccess) return e.cuda_fail(ce, "cudaGraphLaunch");
+	}
+	cudaEventRecord(e.ev[2], e.stream);
+	ce = cudaGetLastError();
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_sweep launch");
+	if (e.cfg.flags & PGS_FLAG_NO_GRAPH) e.launches_last_sweep = launches - (e.n_root_tasks ? 1 : 0);
+	(void)launches;
+	e.swept = true;
+	return PGS_OK;
+}
+
+int pgs_get_stats(pgs_engine *h, pgs_stats *out)
+{
+	ENGINE_OR_RETURN(h);
+	if (!out) return e.fail(PGS_ERR_ARG, "pgs_get_stats: null");
+	std::memset(out, 0, sizeof(*out));
+	out->n_nodes = e.n_nodes;
+	out->n_genomes = e.n_genomes;
+	out->blocks_per_gene = e.blocks;
+	if (e.have_genes) {
+		out->n_genes = e.n_genes;
+		out->n_dense_genes = (int64_t)e.dense_gid.size();
+		out->rows_total = e.rows_total;
+		out->rows_written = e.rows_written;
+		out->rows_read = e.rows_read;
+		out->rows_origin = e.rows_origin;
+		int64_t leaf_genes = 0;
+		for (auto c : e.genome_gene_count) leaf_genes += c;
+		out->leaf_nucleotides = leaf_genes * e.cfg.gene_length;
+		out->site_edges = e.rows_written * e.cfg.gene_length;
+		out->levels = e.max_level;
+		out->kernel_launches = e.launches_last_sweep + (e.n_root_tasks ? 1 : 0);
+		out->device_bytes = e.device_bytes();
+	}
+	if (e.swept) {
+		cudaError_t ce = cudaStreamSynchronize(e.stream);
+		if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_get_stats sync");
+		float a = 0, b = 0;
+		if (cudaEventElapsedTime(&a, e.ev[0], e.ev[1]) == cudaSuccess) out->rootgen_ms = a;
+		if (cudaEventElapsedTime(&b, e.ev[1], e.ev[2]) == cudaSuccess) out->sweep_ms = b;
+		cudaGetLastError();
+	}
+	out->mismatch_ms = e.mismatch_ms;
+	out->format_ms = e.format_ms;
+	return PGS_OK;
+}
+
+int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_mismatch: call pgs_sweep first");
+	if (!out_device_u32) return e.fail(PGS_ERR_ARG, "pgs_mismatch: null output");
+	const int64_t D = (int64_t)e.dense_gid.size();
+	cudaEvent_t t0 = e.ev[3], t1 = e.ev[4];
+	cudaEventRecord(t0, e.stream);
+	pgs::launch_mismatch(e.tables.rows, e.d_leaf_base_words.as<int64_t>(), e.n_genomes, D * e.blocks * 4,
+						 static_cast<uint32_t *>(out_device_u32), e.stream);
+	cudaEventRecord(t1, e.stream);
+	cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce == cudaSuccess) ce = cudaGetLastError();
+	float ms = 0;
+	if (ce == cudaSuccess) cudaEventElapsedTime(&ms, t0, t1);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch");
+	e.mismatch_ms = ms;
+	if (sites_out) *sites_out = D * e.cfg.gene_length;
+	return PGS_OK;
+}
+
+int pgs_mismatch(pgs_engine *h, uint32_t *out_host, int64_t *sites_out)
+{
+	ENGINE_OR_RETURN(h);
+	if (!out_host) return e.fail(PGS_ERR_ARG, "pgs_mismatch: null output");
+	const size_t bytes = sizeof(uint32_t) * (size_t)e.n_genomes * (size_t)e.n_genomes;
+	if (e.d_mismatch.bytes < bytes) {
+		int rc = e.alloc(e.d_mismatch, bytes, "mismatch matrix");
+		if (rc) return rc;
+	}
+	int rc = pgs_mismatch_device(h, e.d_mismatch.p, sites_out);
+	if (rc) return rc;
+	cudaError_t ce = cudaMemcpy(out_host, e.d_mismatch.p, bytes, cudaMemcpyDeviceToHost);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch copy");
+	return PGS_OK;
+}
+
+int pgs_write_outputs(pgs_engine *h, const pgs_output_spec *spec, pgs_output_report *report)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_write_outputs: call pgs_sweep first");
+	if (!spec) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: null spec");
+	return pgs::write_outputs(e, spec, report);
+}
+
+int pgs_genome_name(int64_t genome_index, char *dst, size_t cap)
+{
+	return pgs::format_genome_name(genome_index, dst, cap);
+}
+
+int64_t pgs_row_index(pgs_engine *h, int32_t node, int64_t gene_index)
+{
+	if (!h) return -1;
+	return h->e.row_index(node, gene_index);
+}
+
+int pgs_copy_packed(pgs_engine *h, int32_t node, int64_t gene_index, void *dst)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_copy_packed: call pgs_sweep first");
+	if (!dst) return e.fail(PGS_ERR_ARG, "pgs_copy_packed: null dst");
+	if (node < 0 || node >= e.n_nodes || gene_index < 0 || gene_index >= e.n_genes)
+		return e.fail(PGS_ERR_ARG, "pgs_copy_packed: index out of range");
+	const int64_t row = e.row_index(node, gene_index);
+	if (row < 0) return 1;
+	cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce == cudaSuccess)
+		ce = cudaMemcpy(dst, e.tables.rows + row * e.blocks, (size_t)e.blocks * 16, cudaMemcpyDeviceToHost);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_copy_packed");
+	return PGS_OK;
+}
+
+int pgs_copy_dense(pgs_engine *h, int32_t node, void *dst)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_copy_dense: call pgs_sweep first");
+	if (!dst || node < 0 || node >= e.n_nodes) return e.fail(PGS_ERR_ARG, "pgs_copy_dense: bad argument");
+	cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce == cudaSuccess)
+		ce = cudaMemcpy(dst, e.tables.rows + e.row_base[node] * e.blocks,
+						(size_t)e.dense_gid.size() * (size_t)e.blocks * 16, cudaMemcpyDeviceToHost);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_copy_dense");
+	return PGS_OK;
+}
+
+int pgs_get_edge_table(pgs_engine *h, int32_t node, uint64_t H[65], int32_t *kmax)
+{
+	if (!h) return PGS_ERR_ARG;
+	Engine &e = h->e;
+	if (!e.have_genes) return e.fail(PGS_ERR_STATE, "pgs_get_edge_table: call pgs_set_genes first");
+	if (node < 0 || node >= e.n_nodes || !H) return e.fail(PGS_ERR_ARG, "pgs_get_edge_table: bad argument");
+	H[0] = std::numeric_limits<uint64_t>::max();
+	for (int k = 1; k <= 64; k++) H[k] = k <= e.kmax_host[node] ? e.tab_host[e.tab_off_host[node] + k - 1] : 0;
+	if (kmax) *kmax = e.kmax_host[node];
+	return PGS_OK;
+}
+
+} // extern "C"

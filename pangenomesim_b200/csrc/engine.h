@@ -1,0 +1,93 @@
+// engine.h -- host-side state of one engine (one CUDA device): tree, gene table, row plan,
+// device tables.  Internal; the public surface is include/pgs.h.
+#pragma once
+#include "../../include/pgs.h"
+#include "kernels.cuh"
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pgs {
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t bytes = 0;
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	~DevBuf() { release(); }
+	void release();
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Engine {
+	pgs_config cfg{};
+	int device = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // 0-2 sweep, 3-4 mismatch, 5 format
+	std::string err;
+
+	// ---- tree (pgs_set_tree)
+	int32_t n_nodes = 0, n_genomes = 0, root = -1, max_level = 0;
+	std::vector<int32_t> parent, leaf_genome, genome_leaf, level;
+	std::vector<double> rate;
+	std::vector<int32_t> child_off, child; // CSR children, ascending node index
+	bool have_tree = false;
+
+	// ---- genes (pgs_set_genes)
+	int64_t n_genes = 0;
+	std::vector<int64_t> gene_id;
+	std::vector<int32_t> origin;
+	std::vector<int64_t> carrier_off;  // CSR over carrier_genome, sparse genes only expanded
+	std::vector<int32_t> carrier_genome;
+	std::vector<int32_t> all_order;    // MAF order of genomes for dense genes
+	std::vector<int32_t> dense_slot;   // per gene: slot in the dense region or -1
+	std::vector<uint32_t> dense_gid;   // per dense slot: gene_id (ascending)
+	std::vector<int64_t> dense_gene;   // per dense slot: gene table index
+	std::vector<int64_t> sp_off;       // [N+1] CSR: sparse genes present at node (ascending index)
+	std::vector<int64_t> sp_gene;
+	std::vector<int64_t> row_base;     // [N]
+	std::vector<int64_t> genome_gene_count; // [n_genomes] genes carried
+	bool have_genes = false, swept = false;
+
+	// ---- plan
+	int64_t blocks = 0;       // 64-site blocks per gene
+	int32_t last_valid = 64;  // real sites in the last block
+	int64_t rows_total = 0, rows_written = 0, rows_read = 0, rows_origin = 0;
+	std::vector<int64_t> dense_level_off;  // [max_level+2] into dense tasks (index = child level)
+	std::vector<int64_t> sparse_level_off; // [max_level+2]
+	int64_t n_dense_tasks = 0, n_sparse_tasks = 0, n_root_tasks = 0;
+	std::vector<uint64_t> tab_host; // concatenated H[1..kmax]
+	std::vector<int32_t> tab_off_host, kmax_host;
+	std::vector<uint64_t> h1_host;
+
+	// ---- device
+	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
+	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch;
+	DeviceTables tables{};
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t graph_exec = nullptr;
+	int64_t launches_last_sweep = 0;
+	double mismatch_ms = 0.0, format_ms = 0.0;
+
+	~Engine();
+	int fail(int code, const std::string &msg);
+	int cuda_fail(cudaError_t e, const char *what);
+	int alloc(DevBuf &b, size_t bytes, const char *what);
+	int upload(DevBuf &b, const void *src, size_t bytes, const char *what);
+	int64_t device_bytes() const;
+	int64_t row_index(int32_t node, int64_t gene_index) const;
+	void drop_graph();
+	void enqueue_levels(cudaStream_t s, int64_t *launches);
+};
+
+// format.cu
+int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report);
+int format_genome_name(int64_t genome_index, char *dst, size_t cap);
+
+} // namespace pgs
+
+struct pgs_engine {
+	pgs::Engine e;
+};

@@ -1,0 +1,75 @@
+// kernels.cuh -- device tables and launchers of the sm_100a kernels (K0 root rows, K1 level
+// sweep, K2 pairwise mismatch, K3 text formatter).  See DESIGN.md §4 for the roofline of each.
+#pragma once
+#include "philox.cuh"
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pgs {
+
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+
+// One K1 work unit of the dense region: parent node and up to two children (right = -1: none).
+struct DenseTask {
+	int32_t parent, left, right;
+};
+// One K1 work unit of the sparse region: one parent row and the rows it produces.
+struct SparseTask {
+	uint32_t src, dst_left, dst_right; // row indices, kNoRow = child does not carry the gene
+	uint32_t gid;                      // gene_id (Philox counter word 1)
+	int32_t edge_left, edge_right;     // child node indices
+};
+struct RootTask {
+	uint32_t row, gid;
+};
+
+// Unsigned division by a launch constant: q = umulhi(x, mul) >> shift (x < 2^31).
+struct FastDiv {
+	uint32_t mul, shift, div;
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+	FastDiv f;
+	f.div = d;
+	if (d == 1) {
+		f.mul = 0;
+		f.shift = 0;
+		return f;
+	}
+	uint32_t s = 0;
+	while ((1ull << s) < d) s++;
+	// ceil(2^(32+s) / d) - 2^32 would need 33 bits; use the 2^(31+s) variant valid for x < 2^31
+	f.shift = s - 1;
+	f.mul = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
+	return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, const FastDiv &f)
+{
+	return f.div == 1 ? x : (__umulhi(x, f.mul) >> f.shift);
+}
+
+struct DeviceTables {
+	uint4 *rows;              // all (node, gene) rows, blocks_per_gene uint4 each
+	const int64_t *row_base;  // [N] first row of node
+	const uint64_t *h1;       // [N] floor(2^64 P(K>=1)) of the branch above node
+	const uint64_t *tab;      // concatenated H[1..kmax] per node
+	const int32_t *tab_off;   // [N] offset into tab
+	const int32_t *kmax;      // [N]
+	const uint32_t *dense_gid; // [D] gene_id of dense slot (ascending)
+	uint32_t n_dense;         // D
+	uint32_t blocks;          // blocks per gene (Bg)
+	int32_t last_valid;       // real sites in the last block of a gene (1..64)
+	FastDiv div_blocks;
+	PhiloxKeys keys;
+};
+
+void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_tasks, cudaStream_t s);
+void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
+void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);
+
+// K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
+// i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).
+void launch_mismatch(const uint4 *rows, const int64_t *leaf_base, int32_t n, int64_t words_per_leaf,
+					 uint32_t *out, cudaStream_t s);
+
+} // namespace pgs

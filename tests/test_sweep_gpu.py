@@ -1,0 +1,219 @@
+"""GPU parity of K0/K1 (origin rows + level sweep) against the host Philox replay in oracle/,
+through the C ABI.  Bit-exact: this is integer/byte work."""
+import numpy as np
+import pytest
+
+import treegen
+from pangenomesim_b200 import Engine, PgsError
+from pangenomesim_b200.capi import PGS_FLAG_NO_GRAPH
+
+pytestmark = pytest.mark.gpu
+
+
+def build(seed, L, parent, rate, leaf_genome, genes, flags=0):
+    e = Engine(seed, L, flags=flags)
+    e.set_tree(parent, rate, leaf_genome)
+    e.set_genes(*genes)
+    e.sweep()
+    e.sync()
+    return e
+
+
+def core_table(n_core, root, first=0):
+    ids = np.arange(first, first + n_core, dtype=np.int64)
+    return ids, np.full(n_core, root, np.int32), np.arange(n_core + 1, dtype=np.int64), np.full(n_core, -1, np.int32)
+
+
+def check_all_nodes(e, oracle, seed, parent, rate, gene_id, origin, L, gene_indices):
+    for gi in gene_indices:
+        want = oracle.gene_all_nodes(seed, parent, rate, int(origin[gi]), int(gene_id[gi]), L)
+        for v in range(len(parent)):
+            got = e.copy_packed(v, int(gi))
+            if got is None:
+                continue
+            assert np.array_equal(got, want[v]), f"gene index {gi} node {v}"
+
+
+@pytest.mark.parametrize("L", [1, 63, 64, 65, 100, 130, 1000, 1500])
+def test_core_genes_every_node(oracle, L):
+    n, seed = 9, 7 + L
+    parent, rate, leaf = treegen.coalescent(n, seed=3, mut_rate=0.3)
+    genes = core_table(5, len(parent) - 1)
+    with build(seed, L, parent, rate, leaf, genes) as e:
+        s = e.stats()
+        assert s["n_dense_genes"] == 5 and s["rows_total"] == 5 * len(parent)
+        assert s["rows_written"] == 5 * (len(parent) - 1) and s["rows_read"] == 5 * (n - 1)
+        check_all_nodes(e, oracle, seed, parent, rate, genes[0], genes[1], L, range(5))
+
+
+@pytest.mark.parametrize("mut_rate", [1e-6, 0.01, 2.0, 50.0])
+def test_rate_regimes(oracle, mut_rate):
+    """ultra-sparse (copy), default, dense (K ~ 30 per block) and saturated (p = 3/4) branches"""
+    n, L, seed = 12, 200, 99
+    parent, rate, leaf = treegen.coalescent(n, seed=5, mut_rate=mut_rate)
+    genes = core_table(7, len(parent) - 1, first=1000)
+    with build(seed, L, parent, rate, leaf, genes) as e:
+        check_all_nodes(e, oracle, seed, parent, rate, genes[0], genes[1], L, range(7))
+
+
+def test_edge_tables_match_oracle(oracle):
+    parent, rate, leaf = treegen.coalescent(40, seed=11, mut_rate=0.05)
+    rate[3] = 0.0
+    rate[4] = 1e-12
+    rate[5] = 30.0
+    with build(1, 64, parent, rate, leaf, core_table(1, len(parent) - 1)) as e:
+        for v in range(len(parent) - 1):
+            H, k = e.edge_table(v)
+            Ho, ko = oracle.edge_table(rate[v])
+            assert k == ko and np.array_equal(H, Ho), f"edge {v} rate {rate[v]}"
+
+
+def test_accessory_presence_and_rows(oracle):
+    n, L, seed = 30, 150, 2024
+    parent, rate, leaf = treegen.coalescent(n, seed=8, mut_rate=0.2)
+    gene_id, origin, off, car = treegen.gene_table(parent, leaf, n_core=6, n_acc=40, seed=4)
+    with build(seed, L, parent, rate, leaf, (gene_id, origin, off, car)) as e:
+        genome_leaf = {int(g): v for v, g in enumerate(leaf) if g >= 0}
+        for gi in range(len(gene_id)):
+            c = car[off[gi]:off[gi + 1]]
+            if len(c) == 1 and c[0] == -1:
+                needed = set(range(len(parent)))
+            else:
+                needed = set()
+                for g in c:
+                    v = genome_leaf[int(g)]
+                    while True:
+                        needed.add(v)
+                        if v == origin[gi]:
+                            break
+                        v = int(parent[v])
+            want = oracle.gene_all_nodes(seed, parent, rate, int(origin[gi]), int(gene_id[gi]), L)
+            for v in range(len(parent)):
+                got = e.copy_packed(v, gi)
+                assert (got is not None) == (v in needed), f"presence gene {gene_id[gi]} node {v}"
+                if got is not None:
+                    assert np.array_equal(got, want[v]), f"gene {gene_id[gi]} node {v}"
+        s = e.stats()
+        assert s["n_dense_genes"] == 6
+
+
+def test_graph_and_plain_launches_agree_and_repeat(oracle):
+    n, L, seed = 50, 1000, 5
+    parent, rate, leaf = treegen.coalescent(n, seed=2, mut_rate=0.05)
+    genes = treegen.gene_table(parent, leaf, n_core=20, n_acc=15, seed=1)
+    with build(seed, L, parent, rate, leaf, genes) as a, \
+            build(seed, L, parent, rate, leaf, genes, flags=PGS_FLAG_NO_GRAPH) as b:
+        a.sweep()  # a second sweep overwrites every row with the same values
+        a.sync()
+        for v in (0, n - 1, n, len(parent) - 1):
+            assert np.array_equal(a.copy_dense(v, 20), b.copy_dense(v, 20))
+        for gi in range(len(genes[0])):
+            for v in range(0, len(parent), 7):
+                ra, rb = a.copy_packed(v, gi), b.copy_packed(v, gi)
+                assert (ra is None) == (rb is None)
+                if ra is not None:
+                    assert np.array_equal(ra, rb)
+
+
+def test_sharding_does_not_change_rows(oracle):
+    """genes are independent: an engine holding half of the table produces the same rows"""
+    n, L, seed = 20, 300, 31
+    parent, rate, leaf = treegen.coalescent(n, seed=6, mut_rate=0.1)
+    root = len(parent) - 1
+    full = core_table(10, root)
+    with build(seed, L, parent, rate, leaf, full) as e, \
+            build(seed, L, parent, rate, leaf, core_table(5, root, first=5)) as half:
+        for v in range(len(parent)):
+            assert np.array_equal(e.copy_dense(v, 10)[5:], half.copy_dense(v, 5))
+
+
+def test_config2_sample(oracle):
+    """BASELINE config 2: num-genomes=100, core-size=1000, gene-length=1000."""
+    n, L, seed = 100, 1000, 1
+    parent, rate, leaf = treegen.coalescent(n, seed=1, mut_rate=0.01)
+    root = len(parent) - 1
+    with build(seed, L, parent, rate, leaf, core_table(1000, root)) as e:
+        s = e.stats()
+        assert s["leaf_nucleotides"] == 100 * 1000 * 1000
+        assert s["site_edges"] == 198 * 1000 * 1000
+        rng = np.random.default_rng(0)
+        sample = sorted(rng.choice(1000, size=25, replace=False))
+        dense = {v: e.copy_dense(v, 1000) for v in range(len(parent))}
+        for g in sample:
+            want = oracle.gene_all_nodes(seed, parent, rate, root, int(g), L)
+            for v in range(len(parent)):
+                assert np.array_equal(dense[v][g], want[v]), f"gene {g} node {v}"
+        # every substitution is a real change and padding stays zero
+        pad_sites = 16 * 64 - 1000
+        for v in (0, 50, root):
+            codes = oracle.unpack_codes(dense[v], 1024)
+            assert not codes[:, 1000:].any() and pad_sites == 24
+
+
+def test_base_composition_and_jc_distance(oracle):
+    """statistical parity: uniform base composition at the root and observed
+    pairwise p-distance within the 99% band of the JC expectation, Bonferroni over all pairs."""
+    from scipy.stats import norm
+    n, L, G, seed = 16, 1000, 400, 12345
+    parent, rate, leaf = treegen.coalescent(n, seed=21, mut_rate=0.05)
+    root = len(parent) - 1
+    with build(seed, L, parent, rate, leaf, core_table(G, root)) as e:
+        S = G * L
+        rootc = oracle.unpack_codes(e.copy_dense(root, G), L)
+        freq = np.bincount(rootc.ravel(), minlength=4) / S
+        assert np.all(np.abs(freq - 0.25) < 4.5 * np.sqrt(0.25 * 0.75 / S))
+        mm, sites = e.mismatch()
+        assert sites == S
+        # expected distance along the tree path
+        def path_rate(a, b):
+            da, db = {}, 0.0
+            v, acc = a, 0.0
+            while v != -1:
+                da[v] = acc
+                acc += rate[v]
+                v = parent[v]
+            v = b
+            while v not in da:
+                db += rate[v]
+                v = parent[v]
+            return da[v] + db
+        pairs = n * (n - 1) // 2
+        z = norm.ppf(1 - 0.01 / (2 * pairs))
+        for i in range(n):
+            for j in range(i + 1, n):
+                d = path_rate(i, j)
+                p = 0.75 * (1 - np.exp(-4.0 / 3.0 * d))
+                assert abs(mm[i, j] / S - p) <= z * np.sqrt(p * (1 - p) / S) + 1e-12, (i, j)
+
+
+def test_mismatch_matches_numpy(oracle):
+    n, L, G, seed = 70, 130, 33, 8
+    parent, rate, leaf = treegen.coalescent(n, seed=13, mut_rate=0.4)
+    root = len(parent) - 1
+    with build(seed, L, parent, rate, leaf, core_table(G, root)) as e:
+        mm, sites = e.mismatch()
+        assert sites == G * L
+        codes = np.stack([oracle.unpack_codes(e.copy_dense(v, G), L).ravel() for v in range(n)])
+        want = (codes[:, None, :] != codes[None, :, :]).sum(-1).astype(np.uint32)
+        assert np.array_equal(mm, want)
+        assert oracle.mismatch(e.copy_dense(0, G).ravel(), e.copy_dense(1, G).ravel()) == want[0, 1]
+
+
+def test_error_behaviour():
+    e = Engine(1, 100)
+    with pytest.raises(PgsError) as ex:
+        e.sweep()
+    assert ex.value.code == -2
+    with pytest.raises(PgsError):
+        e.set_tree([-1, -1, 0], [0, 0, 0.1], [-1, -1, 0])  # two roots
+    with pytest.raises(PgsError):
+        e.set_tree([1, 0], [0.1, 0.1], [0, 1])  # cycle, no root
+    e.set_tree([2, 2, -1], [0.1, 0.2, 0.0], [0, 1, -1])
+    with pytest.raises(PgsError):  # carrier outside the origin's subtree
+        e.set_genes([5], [0], [0, 1], [1])
+    with pytest.raises(PgsError):  # duplicate gene id
+        e.set_genes([5, 5], [2, 2], [0, 1, 2], [-1, -1])
+    e.set_genes([5], [2], [0, 1], [-1])
+    e.sweep()
+    assert e.copy_packed(0, 0) is not None
+    e.close()
