@@ -83,6 +83,12 @@ uint32_t ref_uniform_int(ref_engine *e, uint32_t hi);
 /* std::uniform_real_distribution<double>(0,1)(engine) = generate_canonical<double,53> (random.tcc) */
 double ref_uniform_real(ref_engine *e);
 
+/* std::exponential_distribution<double>(lambda)(engine) */
+double ref_exponential(ref_engine *e, double lambda);
+/* create_coalescent(n) -- reference img.cxx:71-116; arrays of 2n-1 entries (root = 2n-2). */
+void ref_coalescent(ref_engine *global, int64_t n, int32_t *parent, int32_t *left, int32_t *right,
+					double *time);
+
 /* gene::gene(len, ...) -- reference gene.cxx:13-25.  Writes len chars. */
 void ref_gene_root(ref_engine *global, int64_t len, char *dst);
 /* gene::mutate(rate) -- reference gene.cxx:27-61.  src/dst len chars; returns number of hits. */
@@ -100,7 +106,8 @@ void ref_sim_core_gene(ref_engine *global, int32_t root, const int32_t *left, co
 					   char *root_out, char *leaves_out);
 
 /* E[#substituted sites] of one gene::mutate(rate) call on a gene of length len (selection
- * sampling with fractional quota): exact dynamic programme. */
+ * sampling with fractional quota): exact dynamic programme for quotas up to 64
+ * hits, floor(quota)+1/2 beyond (the count is floor or ceil of the quota there). */
 double ref_expected_hits(double rate, int64_t len);
 
 #ifdef __cplusplus

@@ -58,6 +58,10 @@ def lib():
     L.ref_uniform_int.restype = u32
     L.ref_uniform_real.argtypes = [vp]
     L.ref_uniform_real.restype = dbl
+    L.ref_exponential.argtypes = [vp, dbl]
+    L.ref_exponential.restype = dbl
+    L.ref_coalescent.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.ref_coalescent.restype = None
     L.ref_gene_root.argtypes = [vp, i64, vp]
     L.ref_gene_root.restype = None
     L.ref_gene_mutate.argtypes = [vp, vp, i64, dbl, vp]
@@ -157,6 +161,16 @@ class RefEngine:
 
     def uniform_real(self) -> float:
         return lib().ref_uniform_real(self.ptr())
+
+    def coalescent(self, n: int):
+        """parent, left, right (int32) and branch time (float64) in the reference's pool layout"""
+        m = 2 * n - 1
+        parent = np.zeros(m, np.int32)
+        left = np.zeros(m, np.int32)
+        right = np.zeros(m, np.int32)
+        time = np.zeros(m, np.float64)
+        lib().ref_coalescent(self.ptr(), n, _p(parent), _p(left), _p(right), _p(time))
+        return parent, left, right, time
 
     def gene_root(self, length: int) -> bytes:
         buf = C.create_string_buffer(length)

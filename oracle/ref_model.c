@@ -61,6 +61,51 @@ double ref_uniform_real(ref_engine *e)
 	return ret;
 }
 
+/* std::exponential_distribution<double>(lambda)(engine): -log(1 - canonical) / lambda (random.h) */
+double ref_exponential(ref_engine *e, double lambda)
+{
+	return -log(1.0 - ref_uniform_real(e)) / lambda;
+}
+
+/* create_coalescent(n) -- reference img.cxx:71-116.  Pool layout: slots [0,n) leaves, slot n+i
+ * the i-th merger, root last.  Topology: two rand_int picks per merger over a shrinking
+ * indirection table (img.cxx:87-96); times: cumulative Exp(k(k-1)/2) waits (img.cxx:103-107);
+ * branch time = parent abs time - own abs time (img.cxx:111-113, img.h:165-171).
+ * All output arrays have 2n-1 entries. */
+void ref_coalescent(ref_engine *global, int64_t n, int32_t *parent, int32_t *left, int32_t *right,
+					double *time)
+{
+	const int64_t m = 2 * n - 1;
+	int32_t *indirect = (int32_t *)malloc(sizeof(int32_t) * (size_t)m);
+	double *abs_time = (double *)calloc((size_t)m, sizeof(double));
+	for (int64_t i = 0; i < m; i++) {
+		indirect[i] = (int32_t)i;
+		parent[i] = left[i] = right[i] = -1;
+		time[i] = 0.0;
+	}
+	for (int64_t i = 0; i + 1 < n; i++) {
+		const int32_t p = (int32_t)(n + i);
+		const uint32_t c = ref_uniform_int(global, (uint32_t)(n - i - 1)); /* rand_int(0, n-i) */
+		left[indirect[p]] = indirect[c];
+		parent[indirect[c]] = indirect[p];
+		indirect[c] = indirect[n - i - 1];
+		const uint32_t d = ref_uniform_int(global, (uint32_t)(n - i - 2)); /* rand_int(0, n-i-1) */
+		right[indirect[p]] = indirect[d];
+		parent[indirect[d]] = indirect[p];
+		indirect[d] = indirect[p];
+	}
+	double t = 0.0;
+	uint64_t sample = (uint64_t)n;
+	for (int64_t i = 0; i + 1 < n; i++, sample--) {
+		const uint64_t pairs = sample * (sample - 1) / 2;
+		t += ref_exponential(global, (double)pairs);
+		abs_time[n + i] = t;
+	}
+	for (int64_t i = 0; i + 1 < m; i++) time[i] = abs_time[parent[i]] - abs_time[i];
+	free(indirect);
+	free(abs_time);
+}
+
 /* reference gene.cxx:13-25 -- one uniform_int(0,3) draw per site on the global engine */
 void ref_gene_root(ref_engine *global, int64_t len, char *dst)
 {
@@ -177,6 +222,12 @@ double ref_expected_hits(double rate, int64_t len)
 {
 	const double quota = rate * (double)len;
 	if (!(quota > 0.0)) return 0.0;
+	if (quota >= (double)len) return (double)len;
+	if (quota > 64.0) {
+		/* the programme is O(len * quota); for large quotas the count is floor or ceil of the quota
+		 * (+0.3..+0.6 hits), so return the midpoint: relative error < 8e-3 of one branch, absolute < 0.5 hit */
+		return quota == floor(quota) ? quota : floor(quota) + 0.5;
+	}
 	int64_t hmax = (int64_t)ceil(quota) + 1;
 	if (hmax > len) hmax = len;
 	double *dist = (double *)calloc((size_t)hmax + 2, sizeof(double));

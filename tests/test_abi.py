@@ -1,0 +1,65 @@
+"""CPU tests of the drop-in boundary: libpgs.so loads, exports every symbol include/pgs.h
+declares, and refuses to run without a CUDA device (there is no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_functions():
+    text = (ROOT / "include" / "pgs.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("pgs_create", "pgs_destroy", "pgs_set_tree", "pgs_set_genes", "pgs_sweep",
+                 "pgs_mismatch", "pgs_write_outputs", "pgs_copy_packed", "pgs_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from pangenomesim_b200 import load_library
+    lib = load_library()
+    for name in declared_functions():
+        assert hasattr(lib, name), f"libpgs.so does not export {name}"
+    assert lib.pgs_abi_version() == 1
+
+
+def test_signatures_are_plain_c():
+    text = (ROOT / "include" / "pgs.h").read_text()
+    assert "torch" not in text and "std::" not in text and "extern \"C\"" in text
+
+
+def test_genome_name_matches_reference_and_survives_1000_genomes():
+    from pangenomesim_b200.capi import genome_name
+    assert genome_name(-1) == "genomeref"       # reference util.cxx:17-18
+    assert genome_name(0) == "genome001"
+    assert genome_name(98) == "genome099"
+    assert genome_name(998) == "genome999"
+    assert genome_name(999) == "genome1000"     # the reference throws std::length_error here
+    assert genome_name(49999) == "genome50000"
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from pangenomesim_b200 import Engine, PgsError
+    with pytest.raises(PgsError) as ex:
+        Engine(1, 100)
+    assert ex.value.code == -6 and "no CPU path" in ex.value.message
+
+
+def test_product_does_not_reference_the_oracle():
+    """the product path must not import, link or call anything under oracle/"""
+    for path in list((ROOT / "pangenomesim_b200").rglob("*")):
+        if path.suffix in (".py", ".cu", ".cuh", ".cpp", ".h", ".cxx"):
+            text = path.read_text()
+            assert "oracle_" not in text and "liboracle" not in text and "ref_model" not in text, path
+    so = ROOT / "pangenomesim_b200" / "lib" / "libpgs.so"
+    assert b"liboracle" not in so.read_bytes()
