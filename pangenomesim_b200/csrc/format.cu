@@ -1,8 +1,26 @@
-// format.cu -- K3: 2-bit -> ASCII FASTA / MAF text on the device, streamed through pinned buffers.
+// format.cu -- K3: 2-bit rows -> ASCII FASTA / MAF text on the device, streamed to the host
+// through double-buffered pinned memory.
+//
+// Replaces gene::to_fasta (reference gene.h:42-52), the FASTA writers pangenomesim.cxx:117-157
+// and the MAF writer pangenomesim.cxx:236-293.  The reference builds every record as a
+// std::string on the host; here the whole text (headers included) is produced by the GPU in
+// file order, so the host only hands contiguous chunks to write(2) or to a sink callback.
+//
+// Record offsets are closed-form (no per-record descriptor tables): inside genomeNNN.fasta the
+// k-th record of a genome starts at  k * (name_len + L + 4) + sum of decimal digits of the
+// gene ids before it, and both terms come from two small prefix tables; a MAF block is laid out
+// the same way from a per-gene block offset and a per-carrier prefix.
 #include "engine.h"
 
+#include <algorithm>
+#include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <string>
+#include <unistd.h>
+#include <vector>
 
 namespace pgs {
 
@@ -11,17 +29,737 @@ int format_genome_name(int64_t genome_index, char *dst, size_t cap)
 	// reference util.cxx:15-27: "genome" + zero padding to 3 digits + (index + 1); "genomeref"
 	// for -1.  The reference aborts for >= 1000 genomes (negative padding length); here the
 	// padding is clamped at zero, which leaves every name below 1000 unchanged.
-	int len;
-	if (genome_index < 0)
-		len = std::snprintf(dst, cap, "genomeref");
-	else
-		len = std::snprintf(dst, cap, "genome%03lld", (long long)(genome_index + 1));
-	return len;
+	if (genome_index < 0) return std::snprintf(dst, cap, "genomeref");
+	return std::snprintf(dst, cap, "genome%03lld", (long long)(genome_index + 1));
 }
 
-int write_outputs(Engine &e, const pgs_output_spec *, pgs_output_report *)
+// ---------------------------------------------------------------------------------------------
+// device text helpers
+
+__host__ __device__ inline int dec_digits(uint64_t x)
 {
-	return e.fail(PGS_ERR_STATE, "pgs_write_outputs: formatter not built yet");
+	int d = 1;
+	while (x >= 10) {
+		x /= 10;
+		d++;
+	}
+	return d;
+}
+
+__host__ __device__ inline int genome_name_len(int64_t genome)
+{
+	if (genome < 0) return 9; // "genomeref"
+	const int d = dec_digits((uint64_t)genome + 1);
+	return 6 + (d < 3 ? 3 : d);
+}
+
+__device__ inline char *put_uint(char *p, uint64_t x, int min_digits)
+{
+	int d = dec_digits(x);
+	if (d < min_digits) d = min_digits;
+	for (int i = d - 1; i >= 0; i--) {
+		p[i] = (char)('0' + (int)(x % 10));
+		x /= 10;
+	}
+	return p + d;
+}
+
+__device__ inline char *put_str(char *p, const char *s)
+{
+	while (*s) *p++ = *s++;
+	return p;
+}
+
+__device__ inline char *put_genome_name(char *p, int64_t genome)
+{
+	p = put_str(p, "genome");
+	if (genome < 0) return put_str(p, "ref");
+	return put_uint(p, (uint64_t)genome + 1, 3);
+}
+
+// four sites (8 bits) -> four ASCII bytes: spread the 2-bit codes to nibbles, then let PRMT pick
+// the bytes of "ACGT"
+__device__ __forceinline__ uint32_t ascii4(uint32_t bits8)
+{
+	uint32_t t = (bits8 | (bits8 << 4)) & 0x0F0Fu;
+	t = (t | (t << 2)) & 0x3333u;
+	return __byte_perm(0x54474341u, 0u, t);
+}
+
+// Warp-cooperative: prefix text (prefix_len bytes, staged in shared memory by lane 0), then L
+// bases of `row`, then `tail_len` bytes of tail ("\n" or "\n\n").  dst has any alignment; the
+// body is written with aligned 16-byte stores.
+__device__ void emit_record(char *__restrict__ dst, const char *prefix, int prefix_len,
+							const uint32_t *__restrict__ row, int64_t L, int tail_len, int lane)
+{
+	for (int i = lane; i < prefix_len; i += 32) dst[i] = prefix[i];
+	char *seq = dst + prefix_len;
+	const int64_t head = min((int64_t)((16 - ((uintptr_t)seq & 15)) & 15), L);
+	for (int64_t s = lane; s < head; s += 32) seq[s] = "ACGT"[(row[s >> 4] >> (2 * (s & 15))) & 3u];
+	const int64_t chunks = (L - head) / 16;
+	const int sh = 2 * (int)head; // bit offset of the first body site inside word 0 (head < 16)
+	uint4 *body = reinterpret_cast<uint4 *>(seq + head);
+	for (int64_t c = lane; c < chunks; c += 32) {
+		const uint32_t lo = __ldg(row + c);
+		const uint32_t hi = sh ? __ldg(row + c + 1) : 0u;
+		const uint32_t bits = __funnelshift_r(lo, hi, sh);
+		uint4 v;
+		v.x = ascii4(bits & 0xFFu);
+		v.y = ascii4((bits >> 8) & 0xFFu);
+		v.z = ascii4((bits >> 16) & 0xFFu);
+		v.w = ascii4(bits >> 24);
+		body[c] = v;
+	}
+	const int64_t done = head + chunks * 16;
+	for (int64_t s = done + lane; s < L; s += 32) seq[s] = "ACGT"[(row[s >> 4] >> (2 * (s & 15))) & 3u];
+	if (lane < tail_len) seq[L + lane] = '\n';
+}
+
+struct FormatTables {
+	const uint4 *rows;
+	const int64_t *row_base;     // [N]
+	const int32_t *genome_leaf;  // [n]
+	const int64_t *genome_count; // [n] genes carried by genome
+	const int64_t *sp_off;       // [N+1]
+	const int64_t *sp_gene;      // sparse gene table index per sparse row
+	const int64_t *sp_digits;    // [sp rows + N] per node ms+1 entries: digits of earlier sparse rows
+	const int32_t *dense_slot;   // [G]
+	const int64_t *dense_gene;   // [D]
+	const int32_t *dense_before; // [G+1]
+	const int64_t *dense_digits_before; // [G+1]
+	const int64_t *gene_id;      // [G]
+	const uint32_t *origin_row;  // [G] row of the gene at its origin (kNoRow: no rows)
+	int64_t n_dense, blocks, L;
+};
+
+__device__ inline int64_t sparse_rank(const FormatTables &t, int32_t node, int64_t g)
+{
+	const int64_t *b = t.sp_gene + t.sp_off[node];
+	int64_t lo = 0, hi = t.sp_off[node + 1] - t.sp_off[node];
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (b[mid] < g)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
+constexpr int kFmtWarps = 8;
+
+// ---- genomeNNN.fasta: one warp per leaf row.  rows_prefix[i] = number of leaf rows of the
+// chunk's genomes before genome first_genome + i; file_off[i] = offset of that genome's file
+// in the staging buffer.
+__global__ void __launch_bounds__(kFmtWarps * 32)
+k3_genome_fasta(const __grid_constant__ FormatTables t, char *__restrict__ out, int32_t first_genome,
+				int32_t n_chunk_genomes, const int64_t *__restrict__ rows_prefix,
+				const int64_t *__restrict__ file_off)
+{
+	__shared__ char text[kFmtWarps][64];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t item = (int64_t)blockIdx.x * kFmtWarps + warp;
+	if (item >= rows_prefix[n_chunk_genomes]) return;
+	int lo = 0, hi = n_chunk_genomes - 1; // last i with rows_prefix[i] <= item
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (rows_prefix[mid] <= item)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	const int32_t genome = first_genome + lo;
+	const int64_t slot = item - rows_prefix[lo];
+	const int32_t leaf = t.genome_leaf[genome];
+	int64_t g, srank;
+	if (slot < t.n_dense) {
+		g = t.dense_gene[slot];
+		srank = sparse_rank(t, leaf, g);
+	} else {
+		srank = slot - t.n_dense;
+		g = t.sp_gene[t.sp_off[leaf] + srank];
+	}
+	const int64_t k = t.dense_before[g] + srank;
+	const int name_len = genome_name_len(genome);
+	const int64_t off = k * (name_len + t.L + 4) + t.dense_digits_before[g] +
+						t.sp_digits[t.sp_off[leaf] + leaf + srank];
+	int plen = 0;
+	if (lane == 0) {
+		char *p = text[warp];
+		*p++ = '>';
+		p = put_genome_name(p, genome);
+		*p++ = '.';
+		p = put_uint(p, (uint64_t)t.gene_id[g], 1);
+		*p++ = '\n';
+		plen = (int)(p - text[warp]);
+	}
+	plen = __shfl_sync(0xFFFFFFFFu, plen, 0);
+	__syncwarp();
+	const uint32_t *row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
+	emit_record(out + file_off[lo] + off, text[warp], plen, row, t.L, 1, lane);
+}
+
+// ---- ref.fasta / core.fasta / accessory.fasta: one warp per listed gene, offsets from the host.
+__global__ void __launch_bounds__(kFmtWarps * 32)
+k3_ref_fasta(const __grid_constant__ FormatTables t, char *__restrict__ out, const int64_t *__restrict__ genes,
+			 const int64_t *__restrict__ offs, int64_t n_records)
+{
+	__shared__ char text[kFmtWarps][64];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t item = (int64_t)blockIdx.x * kFmtWarps + warp;
+	if (item >= n_records) return;
+	const int64_t g = genes[item];
+	int plen = 0;
+	if (lane == 0) {
+		char *p = text[warp];
+		*p++ = '>';
+		p = put_genome_name(p, -1);
+		*p++ = '.';
+		p = put_uint(p, (uint64_t)t.gene_id[g], 1);
+		*p++ = '\n';
+		plen = (int)(p - text[warp]);
+	}
+	plen = __shfl_sync(0xFFFFFFFFu, plen, 0);
+	__syncwarp();
+	const uint32_t *row = reinterpret_cast<const uint32_t *>(t.rows + (int64_t)t.origin_row[g] * t.blocks);
+	emit_record(out + offs[item], text[warp], plen, row, t.L, 1, lane);
+}
+
+// ---- alignment.maf: one warp per `s` line.  The chunk covers table genes [first, first + n);
+// lines_prefix[i] = lines of the chunk's genes before gene i (1 + carriers each, 0 for genes
+// without carriers); block_off[i] = offset of the gene's block in the staging buffer.
+struct MafTables {
+	const int64_t *carrier_off;    // [G+1] sparse genes: into carrier_genome
+	const int32_t *carrier_genome;
+	const int64_t *carrier_prefix; // [carriers + G] per gene nc+1 entries: sum(name_len + digits(size))
+	const int32_t *all_order;      // [n]
+	const int64_t *all_prefix;     // [n+1]
+	int64_t ref_size;              // (#reference genes) * L
+	int32_t n_genomes;
+};
+
+__global__ void __launch_bounds__(kFmtWarps * 32)
+k3_maf(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables m, char *__restrict__ out,
+	   int64_t first_gene, int32_t n_chunk_genes, const int64_t *__restrict__ lines_prefix,
+	   const int64_t *__restrict__ block_off)
+{
+	__shared__ char text[kFmtWarps][96];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t item = (int64_t)blockIdx.x * kFmtWarps + warp;
+	if (item >= lines_prefix[n_chunk_genes]) return;
+	int lo = 0, hi = n_chunk_genes - 1;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (lines_prefix[mid] <= item)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	const int64_t g = first_gene + lo;
+	const int64_t j = item - lines_prefix[lo]; // 0 = reference line, 1.. = carriers
+	const int64_t lines = lines_prefix[lo + 1] - lines_prefix[lo];
+	const uint64_t gid = (uint64_t)t.gene_id[g];
+	const bool dense = t.dense_slot[g] >= 0;
+	const int idd = dec_digits(gid), ld = dec_digits((uint64_t)t.L);
+	const int64_t ref_len = 2 + 9 + 1 + idd + 3 + ld + 3 + dec_digits((uint64_t)m.ref_size) + 1 + t.L + 1;
+
+	int64_t off, genome = -1, size;
+	const uint32_t *row;
+	if (j == 0) {
+		off = 0; // "a\n" is part of this line's prefix
+		size = m.ref_size;
+		row = reinterpret_cast<const uint32_t *>(t.rows + (int64_t)t.origin_row[g] * t.blocks);
+	} else {
+		const int64_t c = j - 1;
+		int64_t pre;
+		if (dense) {
+			genome = m.all_order[c];
+			pre = m.all_prefix[c];
+		} else {
+			genome = m.carrier_genome[m.carrier_off[g] + c];
+			pre = m.carrier_prefix[m.carrier_off[g] + g + c];
+		}
+		off = 2 + ref_len + c * (idd + ld + t.L + 11) + pre;
+		size = t.genome_count[genome] * t.L;
+		const int32_t leaf = t.genome_leaf[genome];
+		const int64_t slot = dense ? t.dense_slot[g] : t.n_dense + sparse_rank(t, leaf, g);
+		row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
+	}
+	int plen = 0;
+	if (lane == 0) {
+		char *p = text[warp];
+		if (j == 0) p = put_str(p, "a\n");
+		p = put_str(p, "s ");
+		p = put_genome_name(p, genome);
+		*p++ = '.';
+		p = put_uint(p, gid, 1);
+		p = put_str(p, " 0 ");
+		p = put_uint(p, (uint64_t)t.L, 1);
+		p = put_str(p, " + ");
+		p = put_uint(p, (uint64_t)size, 1);
+		*p++ = ' ';
+		plen = (int)(p - text[warp]);
+	}
+	plen = __shfl_sync(0xFFFFFFFFu, plen, 0);
+	__syncwarp();
+	// the last line of a block is followed by the blank line (std::endl at pangenomesim.cxx:289)
+	emit_record(out + block_off[lo] + off, text[warp], plen, row, t.L, (j == lines - 1) ? 2 : 1, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tables, chunking, pinned double buffering, sinks
+
+namespace {
+
+struct Pinned {
+	char *p = nullptr;
+	~Pinned()
+	{
+		if (p) cudaFreeHost(p);
+	}
+};
+
+struct Writer {
+	Engine &e;
+	const pgs_output_spec *spec;
+	pgs_output_report rep{};
+	int fd = -1;
+	std::string open_name;
+	std::string error;
+
+	explicit Writer(Engine &eng, const pgs_output_spec *s) : e(eng), spec(s) {}
+	~Writer() { close_file(); }
+
+	void close_file()
+	{
+		if (fd >= 0) ::close(fd);
+		fd = -1;
+	}
+	// deliver len bytes of file `name` starting at file offset `offset`
+	bool put(const std::string &name, int64_t offset, const char *data, int64_t len)
+	{
+		if (offset == 0) rep.files++;
+		rep.bytes += len;
+		if (spec->sink) {
+			if (spec->sink(spec->sink_user, name.c_str(), offset, data, len) != 0) {
+				error = "sink aborted at " + name;
+				return false;
+			}
+			return true;
+		}
+		if (open_name != name) {
+			close_file();
+			const std::string path = std::string(spec->out_dir) + "/" + name;
+			fd = ::open(path.c_str(), O_WRONLY | O_CREAT | (offset == 0 ? O_TRUNC : 0), 0644);
+			if (fd < 0) {
+				error = path + ": " + std::strerror(errno);
+				return false;
+			}
+			open_name = name;
+		}
+		while (len > 0) {
+			const ssize_t w = ::pwrite(fd, data, (size_t)len, (off_t)offset);
+			if (w < 0) {
+				if (errno == EINTR) continue;
+				error = open_name + ": " + std::strerror(errno);
+				return false;
+			}
+			data += w;
+			offset += w;
+			len -= w;
+		}
+		return true;
+	}
+};
+
+struct FilePiece {
+	std::string name;
+	int64_t file_offset; // offset inside the file
+	int64_t buf_offset;  // offset inside the staging buffer
+	int64_t len;
+};
+
+} // namespace
+
+int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report)
+{
+	const auto wall0 = std::chrono::steady_clock::now();
+	if (!spec->sink && !spec->out_dir) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: neither out_dir nor sink");
+	const int64_t G = e.n_genes, D = (int64_t)e.dense_gid.size(), L = e.cfg.gene_length;
+	const int32_t N = e.n_nodes, n = e.n_genomes;
+	for (int pass = 0; pass < 2; pass++) {
+		const int64_t cnt = pass ? spec->n_ref_acc : spec->n_ref_core;
+		const int64_t *lst = pass ? spec->ref_acc : spec->ref_core;
+		if (cnt < 0 || (cnt > 0 && !lst)) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: bad reference list");
+		for (int64_t i = 0; i < cnt; i++)
+			if (lst[i] < 0 || lst[i] >= G) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: reference gene index out of range");
+	}
+
+	// ---- tables (host), uploaded once per call
+	std::vector<int32_t> dense_before(G + 1, 0);
+	std::vector<int64_t> dense_digits_before(G + 1, 0);
+	std::vector<uint32_t> origin_row(G, kNoRow);
+	std::vector<int> id_digits(G);
+	for (int64_t g = 0; g < G; g++) {
+		id_digits[g] = dec_digits((uint64_t)e.gene_id[g]);
+		const bool dn = e.dense_slot[g] >= 0;
+		dense_before[g + 1] = dense_before[g] + (dn ? 1 : 0);
+		dense_digits_before[g + 1] = dense_digits_before[g] + (dn ? id_digits[g] : 0);
+		const int64_t r = e.row_index(e.origin[g], g);
+		if (r >= 0) origin_row[g] = (uint32_t)r;
+	}
+	std::vector<int64_t> sp_digits(e.sp_gene.size() + N, 0);
+	for (int32_t v = 0; v < N; v++) {
+		int64_t acc = 0;
+		const int64_t base = e.sp_off[v] + v;
+		for (int64_t j = e.sp_off[v]; j < e.sp_off[v + 1]; j++) {
+			sp_digits[base + (j - e.sp_off[v])] = acc;
+			acc += id_digits[e.sp_gene[j]];
+		}
+		sp_digits[base + (e.sp_off[v + 1] - e.sp_off[v])] = acc;
+	}
+	// MAF tables
+	auto carrier_term = [&](int32_t genome) {
+		return (int64_t)genome_name_len(genome) + dec_digits((uint64_t)(e.genome_gene_count[genome] * L));
+	};
+	std::vector<int64_t> all_prefix(n + 1, 0);
+	for (int32_t i = 0; i < n; i++) all_prefix[i + 1] = all_prefix[i] + carrier_term(e.all_order[i]);
+	std::vector<int64_t> carrier_prefix(e.carrier_genome.size() + G + 1, 0);
+	for (int64_t g = 0; g < G; g++) {
+		int64_t acc = 0;
+		const int64_t base = e.carrier_off[g] + g;
+		for (int64_t k = e.carrier_off[g]; k < e.carrier_off[g + 1]; k++) {
+			carrier_prefix[base + (k - e.carrier_off[g])] = acc;
+			acc += carrier_term(e.carrier_genome[k]);
+		}
+		carrier_prefix[base + (e.carrier_off[g + 1] - e.carrier_off[g])] = acc;
+	}
+	const int64_t ref_size = (spec->n_ref_core + spec->n_ref_acc) * L;
+
+	DevBuf d_genome_leaf, d_genome_count, d_sp_off, d_sp_gene, d_sp_digits, d_dense_slot, d_dense_gene,
+		d_dense_before, d_dense_digits_before, d_gene_id, d_origin_row, d_carrier_off, d_carrier_genome,
+		d_carrier_prefix, d_all_order, d_all_prefix;
+	int rc;
+#define UP(buf, vec) \
+	if ((rc = e.upload(buf, (vec).data(), sizeof((vec)[0]) * (vec).size(), #vec))) return rc
+	UP(d_genome_leaf, e.genome_leaf);
+	UP(d_genome_count, e.genome_gene_count);
+	UP(d_sp_off, e.sp_off);
+	UP(d_sp_gene, e.sp_gene);
+	UP(d_sp_digits, sp_digits);
+	UP(d_dense_slot, e.dense_slot);
+	UP(d_dense_gene, e.dense_gene);
+	UP(d_dense_before, dense_before);
+	UP(d_dense_digits_before, dense_digits_before);
+	UP(d_gene_id, e.gene_id);
+	UP(d_origin_row, origin_row);
+	UP(d_carrier_off, e.carrier_off);
+	UP(d_carrier_genome, e.carrier_genome);
+	UP(d_carrier_prefix, carrier_prefix);
+	UP(d_all_order, e.all_order);
+	UP(d_all_prefix, all_prefix);
+#undef UP
+	FormatTables t{};
+	t.rows = e.tables.rows;
+	t.row_base = e.d_row_base.as<int64_t>();
+	t.genome_leaf = d_genome_leaf.as<int32_t>();
+	t.genome_count = d_genome_count.as<int64_t>();
+	t.sp_off = d_sp_off.as<int64_t>();
+	t.sp_gene = d_sp_gene.as<int64_t>();
+	t.sp_digits = d_sp_digits.as<int64_t>();
+	t.dense_slot = d_dense_slot.as<int32_t>();
+	t.dense_gene = d_dense_gene.as<int64_t>();
+	t.dense_before = d_dense_before.as<int32_t>();
+	t.dense_digits_before = d_dense_digits_before.as<int64_t>();
+	t.gene_id = d_gene_id.as<int64_t>();
+	t.origin_row = d_origin_row.as<uint32_t>();
+	t.n_dense = D;
+	t.blocks = e.blocks;
+	t.L = L;
+	MafTables mt{};
+	mt.carrier_off = d_carrier_off.as<int64_t>();
+	mt.carrier_genome = d_carrier_genome.as<int32_t>();
+	mt.carrier_prefix = d_carrier_prefix.as<int64_t>();
+	mt.all_order = d_all_order.as<int32_t>();
+	mt.all_prefix = d_all_prefix.as<int64_t>();
+	mt.ref_size = ref_size;
+	mt.n_genomes = n;
+
+	// ---- sizes of the big files
+	// genome i: every carried gene contributes name_len + L + 4 + digits(gene_id)
+	std::vector<int64_t> genome_bytes(n), genome_rows(n);
+	for (int32_t i = 0; i < n; i++) {
+		const int32_t v = e.genome_leaf[i];
+		const int64_t ms = e.sp_off[v + 1] - e.sp_off[v];
+		genome_rows[i] = D + ms;
+		genome_bytes[i] = (D + ms) * (genome_name_len(i) + L + 4) + dense_digits_before[G] + sp_digits[e.sp_off[v] + v + ms];
+	}
+	// MAF block of gene g (only genes carried by at least one genome and having rows)
+	const int ld = dec_digits((uint64_t)L);
+	const int rsd = dec_digits((uint64_t)ref_size);
+	std::vector<int64_t> maf_lines(G, 0), maf_bytes(G, 0);
+	for (int64_t g = 0; g < G; g++) {
+		const bool dn = e.dense_slot[g] >= 0;
+		const int64_t nc = dn ? n : e.carrier_off[g + 1] - e.carrier_off[g];
+		if (nc == 0 || origin_row[g] == kNoRow) continue;
+		const int64_t pre = dn ? all_prefix[n] : carrier_prefix[e.carrier_off[g] + g + nc];
+		const int64_t ref_len = 2 + 9 + 1 + id_digits[g] + 3 + ld + 3 + rsd + 1 + L + 1;
+		maf_lines[g] = nc + 1;
+		maf_bytes[g] = 2 + ref_len + nc * (id_digits[g] + ld + L + 11) + pre + 1;
+	}
+
+	// ---- staging: two device buffers + two pinned buffers
+	int64_t stage = (int64_t)64 << 20;
+	if (spec->what & PGS_OUT_GENOMES)
+		for (auto b : genome_bytes) stage = std::max(stage, b);
+	if (spec->what & PGS_OUT_MAF)
+		for (auto b : maf_bytes) stage = std::max(stage, b + 64);
+	{
+		int64_t refs = 0;
+		for (int pass = 0; pass < 2; pass++) {
+			const int64_t cnt = pass ? spec->n_ref_acc : spec->n_ref_core;
+			const int64_t *lst = pass ? spec->ref_acc : spec->ref_core;
+			for (int64_t i = 0; i < cnt; i++) refs += 9 + id_digits[lst[i]] + L + 4;
+		}
+		stage = std::max(stage, refs);
+	}
+	stage = (stage + 255) & ~(int64_t)255;
+	DevBuf d_stage[2], d_aux_a[2], d_aux_b[2];
+	Pinned h_stage[2];
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t formatted[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+	cudaEvent_t k0 = nullptr, k1 = nullptr;
+	auto cleanup = [&]() {
+		for (int i = 0; i < 2; i++) {
+			if (formatted[i]) cudaEventDestroy(formatted[i]);
+			if (copied[i]) cudaEventDestroy(copied[i]);
+			if (consumed[i]) cudaEventDestroy(consumed[i]);
+		}
+		if (k0) cudaEventDestroy(k0);
+		if (k1) cudaEventDestroy(k1);
+		if (copy_stream) cudaStreamDestroy(copy_stream);
+	};
+	cudaError_t ce = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 2 && ce == cudaSuccess; i++) {
+		if ((rc = e.alloc(d_stage[i], (size_t)stage, "format staging"))) {
+			cleanup();
+			return rc;
+		}
+		ce = cudaHostAlloc((void **)&h_stage[i].p, (size_t)stage, cudaHostAllocDefault);
+		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&formatted[i], cudaEventDisableTiming);
+		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming);
+	}
+	if (ce == cudaSuccess) ce = cudaEventCreate(&k0);
+	if (ce == cudaSuccess) ce = cudaEventCreate(&k1);
+	if (ce != cudaSuccess) {
+		cleanup();
+		return e.cuda_fail(ce, "pgs_write_outputs setup");
+	}
+	// small per-chunk index tables live in preallocated buffers (no cudaMalloc/cudaFree, which
+	// would synchronise the device, inside the pipeline)
+	const size_t aux_entries = (size_t)std::max<int64_t>(65537, spec->n_ref_core + spec->n_ref_acc + 1);
+	for (int i = 0; i < 2; i++) {
+		if ((rc = e.alloc(d_aux_a[i], aux_entries * sizeof(int64_t), "format aux")) ||
+			(rc = e.alloc(d_aux_b[i], aux_entries * sizeof(int64_t), "format aux"))) {
+			cleanup();
+			return rc;
+		}
+	}
+	auto h2d = [&](DevBuf &dst, const std::vector<int64_t> &src) -> int {
+		cudaError_t err2 = cudaMemcpyAsync(dst.p, src.data(), sizeof(int64_t) * src.size(), cudaMemcpyHostToDevice, e.stream);
+		return err2 == cudaSuccess ? 0 : e.cuda_fail(err2, "format aux upload");
+	};
+
+	Writer w(e, spec);
+	double device_ms = 0.0;
+	int64_t records = 0;
+
+	// A chunk = kernels writing into d_stage[slot] + the list of file pieces it holds.  The chunk
+	// is copied to pinned memory on copy_stream; the previous chunk is handed to the writer while
+	// this one is formatted and copied.
+	struct Pending {
+		bool live = false;
+		std::vector<FilePiece> pieces;
+		int64_t bytes = 0;
+	} pending[2];
+	int slot = 0;
+	auto drain = [&](int s) -> bool {
+		if (!pending[s].live) return true;
+		cudaError_t err2 = cudaEventSynchronize(copied[s]);
+		if (err2 != cudaSuccess) {
+			w.error = std::string("D2H copy: ") + cudaGetErrorString(err2);
+			return false;
+		}
+		for (const auto &pc : pending[s].pieces)
+			if (!w.put(pc.name, pc.file_offset, h_stage[s].p + pc.buf_offset, pc.len)) return false;
+		pending[s].live = false;
+		return true;
+	};
+	// submit: record kernel-done, copy used bytes, mark pending; then drain the OTHER slot
+	auto submit = [&](int s, int64_t bytes, std::vector<FilePiece> &&pieces) -> bool {
+		cudaEventRecord(k1, e.stream);
+		cudaEventRecord(formatted[s], e.stream);
+		cudaStreamWaitEvent(copy_stream, formatted[s], 0);
+		cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream);
+		cudaEventRecord(copied[s], copy_stream);
+		pending[s].live = true;
+		pending[s].pieces = std::move(pieces);
+		pending[s].bytes = bytes;
+		if (!drain(s ^ 1)) return false;
+		// kernel time of this chunk (the stream is idle by the time the next chunk needs the slot)
+		if (cudaEventSynchronize(k1) == cudaSuccess) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) device_ms += ms;
+		}
+		return true;
+	};
+	auto begin_chunk = [&](int s) {
+		// the staging buffer of slot s is free once its previous copy finished
+		cudaStreamWaitEvent(e.stream, copied[s], 0);
+	};
+	auto fail_out = [&](int code, const std::string &msg) {
+		cudaStreamSynchronize(e.stream);
+		cudaStreamSynchronize(copy_stream);
+		cleanup();
+		return e.fail(code, msg);
+	};
+	// make cudaStreamWaitEvent on never-recorded events harmless
+	for (int i = 0; i < 2; i++) cudaEventRecord(copied[i], copy_stream);
+
+	// ---- ref.fasta, core.fasta, accessory.fasta
+	struct RefFile {
+		uint32_t flag;
+		const char *name;
+		std::vector<int64_t> genes;
+	} ref_files[3] = {{PGS_OUT_REF, "ref.fasta", {}}, {PGS_OUT_CORE, "core.fasta", {}}, {PGS_OUT_ACCESSORY, "accessory.fasta", {}}};
+	ref_files[0].genes.assign(spec->ref_core, spec->ref_core + spec->n_ref_core);
+	ref_files[0].genes.insert(ref_files[0].genes.end(), spec->ref_acc, spec->ref_acc + spec->n_ref_acc);
+	ref_files[1].genes.assign(spec->ref_core, spec->ref_core + spec->n_ref_core);
+	ref_files[2].genes.assign(spec->ref_acc, spec->ref_acc + spec->n_ref_acc);
+	for (auto &rf : ref_files) {
+		if (!(spec->what & rf.flag)) continue;
+		std::vector<int64_t> offs(rf.genes.size());
+		int64_t total = 0;
+		for (size_t i = 0; i < rf.genes.size(); i++) {
+			if (origin_row[rf.genes[i]] == kNoRow) return fail_out(PGS_ERR_ARG, "pgs_write_outputs: reference gene has no rows");
+			offs[i] = total;
+			total += 9 + id_digits[rf.genes[i]] + L + 4;
+		}
+		begin_chunk(slot);
+		cudaEventRecord(k0, e.stream);
+		if (!rf.genes.empty()) {
+			if ((rc = h2d(d_aux_a[slot], rf.genes)) || (rc = h2d(d_aux_b[slot], offs))) {
+				cleanup();
+				return rc;
+			}
+			const int64_t nrec = (int64_t)rf.genes.size();
+			cudaEventRecord(k0, e.stream);
+			k3_ref_fasta<<<(unsigned)((nrec + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
+				t, d_stage[slot].as<char>(), d_aux_a[slot].as<int64_t>(), d_aux_b[slot].as<int64_t>(), nrec);
+			records += nrec;
+		}
+		std::vector<FilePiece> pieces{{rf.name, 0, 0, total}};
+		if (!submit(slot, total, std::move(pieces))) return fail_out(PGS_ERR_IO, w.error);
+		slot ^= 1;
+	}
+
+	// ---- genomeNNN.fasta
+	if (spec->what & PGS_OUT_GENOMES) {
+		int32_t i = 0;
+		while (i < n) {
+			int32_t j = i;
+			int64_t bytes = 0;
+			std::vector<int64_t> rows_prefix{0}, file_off;
+			std::vector<FilePiece> pieces;
+			while (j < n && bytes + genome_bytes[j] <= stage && (j - i) < 65536) {
+				char name[64];
+				format_genome_name(j, name, sizeof name);
+				file_off.push_back(bytes);
+				pieces.push_back({std::string(name) + ".fasta", 0, bytes, genome_bytes[j]});
+				bytes += genome_bytes[j];
+				rows_prefix.push_back(rows_prefix.back() + genome_rows[j]);
+				j++;
+			}
+			begin_chunk(slot);
+			if ((rc = h2d(d_aux_a[slot], rows_prefix)) || (rc = h2d(d_aux_b[slot], file_off))) {
+				cleanup();
+				return rc;
+			}
+			const int64_t items = rows_prefix.back();
+			cudaEventRecord(k0, e.stream);
+			if (items > 0)
+				k3_genome_fasta<<<(unsigned)((items + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
+					t, d_stage[slot].as<char>(), i, j - i, d_aux_a[slot].as<int64_t>(), d_aux_b[slot].as<int64_t>());
+			records += items;
+			if (!submit(slot, bytes, std::move(pieces))) return fail_out(PGS_ERR_IO, w.error);
+			slot ^= 1;
+			i = j;
+		}
+	}
+
+	// ---- alignment.maf
+	if (spec->what & PGS_OUT_MAF) {
+		static const char header[] = "##maf version=1 program=pangenomesim\n"; // pangenomesim.cxx:240
+		const int64_t hlen = (int64_t)sizeof(header) - 1;
+		int64_t file_pos = 0;
+		int64_t g = 0;
+		bool first = true;
+		while (g < G || first) {
+			int64_t bytes = first ? hlen : 0;
+			int64_t g2 = g;
+			std::vector<int64_t> lines_prefix{0}, block_off;
+			while (g2 < G && bytes + maf_bytes[g2] <= stage && (g2 - g) < 65536) {
+				block_off.push_back(bytes);
+				bytes += maf_bytes[g2];
+				lines_prefix.push_back(lines_prefix.back() + maf_lines[g2]);
+				g2++;
+			}
+			begin_chunk(slot);
+			if (first) {
+				ce = cudaMemcpyAsync(d_stage[slot].p, header, (size_t)hlen, cudaMemcpyHostToDevice, e.stream);
+				if (ce != cudaSuccess) {
+					cleanup();
+					return e.cuda_fail(ce, "maf header");
+				}
+			}
+			const int64_t items = lines_prefix.back();
+			cudaEventRecord(k0, e.stream);
+			if (items > 0) {
+				if ((rc = h2d(d_aux_a[slot], lines_prefix)) || (rc = h2d(d_aux_b[slot], block_off))) {
+					cleanup();
+					return rc;
+				}
+				cudaEventRecord(k0, e.stream);
+				k3_maf<<<(unsigned)((items + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
+					t, mt, d_stage[slot].as<char>(), g, (int32_t)(g2 - g), d_aux_a[slot].as<int64_t>(),
+					d_aux_b[slot].as<int64_t>());
+				records += items;
+			}
+			std::vector<FilePiece> pieces{{"alignment.maf", file_pos, 0, bytes}};
+			file_pos += bytes;
+			if (!submit(slot, bytes, std::move(pieces))) return fail_out(PGS_ERR_IO, w.error);
+			slot ^= 1;
+			g = g2;
+			first = false;
+		}
+	}
+
+	if (!drain(slot) || !drain(slot ^ 1)) return fail_out(PGS_ERR_IO, w.error);
+	ce = cudaStreamSynchronize(e.stream);
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(copy_stream);
+	if (ce == cudaSuccess) ce = cudaGetLastError();
+	cleanup();
+	w.close_file();
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_write_outputs");
+	e.format_ms = device_ms;
+	if (report) {
+		*report = w.rep;
+		report->records = records;
+		report->device_ms = device_ms;
+		report->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+	}
+	return PGS_OK;
 }
 
 } // namespace pgs
