@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the pangenomesim sequence path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
+    python bench.py --impl reference [--steps K] [--warmup W]     # the reference's CPU code
+
+Metric (BASELINE.json): simulated leaf nucleotides per second.  Workload at N=1: BASELINE config 4
+(num-genomes=10000, core-size=5000, gene-length=1000, default mut-rate) -- 25.6 GB of 2-bit rows,
+far larger than L2, so no flush is needed between steps.  One step = one pgs_sweep (kernel K0 root
+rows + kernel K1 level sweep over every branch of the coalescent) with tree and tables resident.
+With N > 1 (torchrun, one rank per GPU) every rank sweeps its own 5000-gene shard of a 5000*N
+gene alignment (weak scaling; genes are independent, no collective in the sweep).
+
+Besides the contract keys the line carries
+  roofline      K1's achieved algorithmic HBM GB/s against MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference code (oracle/_ref/ref_seqpath) on one host core, bounded sample
+  e2e           the same metric through the C ABI from host tables to host text: pgs_set_tree +
+                pgs_set_genes (H2D) + pgs_sweep + pgs_write_outputs (K3 formatter, D2H of every
+                genomeNNN.fasta and alignment.maf byte into pinned host memory)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "simulated_leaf_nucleotides_per_sec"
+UNIT = "leaf-nt/s"
+CFG = {"num_genomes": 10000, "core_size": 5000, "gene_length": 1000, "mut_rate": 0.01, "seed": 1}
+
+
+def workload_name(n_gpus):
+    return (f"config4: num-genomes={CFG['num_genomes']} core-size={CFG['core_size']}"
+            f"{'x%d (one shard per GPU)' % n_gpus if n_gpus > 1 else ''} gene-length={CFG['gene_length']}"
+            f" mut-rate={CFG['mut_rate']} seed={CFG['seed']}")
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs: Kingman coalescent in the reference's pool layout (img.cxx:65-116)
+
+def coalescent(n, seed, mut_rate):
+    rng = np.random.default_rng(seed)
+    N = 2 * n - 1
+    parent = np.full(N, -1, dtype=np.int32)
+    abs_time = np.zeros(N)
+    active = list(range(n))
+    t = 0.0
+    for i in range(n - 1):
+        k = n - i
+        p = n + i
+        a = active.pop(int(rng.integers(len(active))))
+        b = active.pop(int(rng.integers(len(active))))
+        parent[a] = parent[b] = p
+        active.append(p)
+        t += rng.exponential(1.0 / (k * (k - 1) / 2))
+        abs_time[p] = t
+    rate = np.zeros(N)
+    rate[:-1] = (abs_time[parent[:-1]] - abs_time[:-1]) * mut_rate
+    leaf = np.full(N, -1, dtype=np.int32)
+    leaf[:n] = np.arange(n)
+    return parent, rate, leaf
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baselines: the reference's own code (never this repo's kernels)
+
+def ref_seqpath_run(n, length, genes, mut_rate, seed, procs=1):
+    """Run `procs` copies of oracle/_ref/ref_seqpath (unmodified reference objects).  Returns
+    (leaf_nt_total, seconds_wall, per-process json)."""
+    exe = ROOT / "oracle" / "_ref" / "ref_seqpath"
+    cmd = [str(exe), str(n), str(length), str(genes), str(mut_rate), str(seed)]
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True) for _ in range(procs)]
+    outs = [json.loads(p.communicate()[0]) for p in ps]
+    wall = time.perf_counter() - t0
+    return sum(o["leaf_nt"] for o in outs), wall, outs
+
+
+def port_run(n, length, genes, mut_rate, seed):
+    """Fallback when the compiled reference did not travel: the plain-C restatement in oracle/."""
+    from oracle import oracle_py
+    e = oracle_py.RefEngine(seed)
+    parent, left, right, tm = e.coalescent(n)
+    leaf_index = np.where(np.arange(2 * n - 1) < n, np.arange(2 * n - 1), -1)
+    t0 = time.perf_counter()
+    for _ in range(genes):
+        e.sim_core_gene(2 * n - 2, left, right, tm, leaf_index, mut_rate, length, n)
+    return float(n) * length * genes, time.perf_counter() - t0
+
+
+def cpu_baseline(sample_genes):
+    n, L = CFG["num_genomes"], CFG["gene_length"]
+    have_ref = (ROOT / "oracle" / "_ref" / "ref_seqpath").exists()
+    if have_ref:
+        nt, wall, outs = ref_seqpath_run(n, L, sample_genes, CFG["mut_rate"], CFG["seed"])
+        sec = outs[0]["seconds"]  # simulate-only time inside the process (excludes tree setup)
+        kind = "reference"
+    else:
+        nt, sec = port_run(n, L, sample_genes, CFG["mut_rate"], CFG["seed"])
+        kind = "port"
+    return {"value": nt / sec, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{sample_genes} of {CFG['core_size']} core genes over the full {n}-genome coalescent "
+                      f"(gene::gene + gene::mutate per branch, leaves discarded), {sec:.1f} s"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, L = CFG["num_genomes"], CFG["gene_length"]
+    have_ref = (ROOT / "oracle" / "_ref" / "ref_seqpath").exists()
+    cores = os.cpu_count() or 1
+    genes_per_proc = args.ref_genes
+    times = []
+    nt = 0.0
+    for step in range(args.warmup + args.steps):
+        if have_ref:
+            nt, wall, _ = ref_seqpath_run(n, L, genes_per_proc, CFG["mut_rate"], CFG["seed"], procs=cores)
+        else:
+            nt, wall = port_run(n, L, genes_per_proc, CFG["mut_rate"], CFG["seed"])
+        if step >= args.warmup:
+            times.append(wall)
+    total = sum(times)
+    value = nt * len(times) / total
+    used = cores if have_ref else 1
+    sample = (f"{used} independent processes x {genes_per_proc} core genes each per step "
+              f"(the reference is single-threaded: global engine, global.h:6), full {n}-genome coalescent, "
+              f"wall clock incl. create_coalescent")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(1), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference" if have_ref else "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2, help="end-to-end steps (each moves ~100 GB over PCIe)")
+    ap.add_argument("--cpu-genes", type=int, default=60, help="gene sample of the cpu_baseline leg (~0.2 s per gene)")
+    ap.add_argument("--ref-genes", type=int, default=8, help="genes per process per step of --impl reference")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--small", action="store_true", help="debug: config 2 sized workload")
+    args = ap.parse_args()
+    if args.small:
+        CFG.update(num_genomes=100, core_size=1000)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from pangenomesim_b200 import Engine
+    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_MAF, PGS_ALL_GENOMES
+    from pangenomesim_b200.sharding import shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, L, G = CFG["num_genomes"], CFG["gene_length"], CFG["core_size"]
+    parent, rate, leaf = coalescent(n, CFG["seed"], CFG["mut_rate"])
+    root = 2 * n - 2
+    # weak scaling: the alignment has G*world genes, rank r owns the contiguous shard [r*G, (r+1)*G)
+    g0, g1 = shard_range(G * world, rank, world)
+    gene_id = np.arange(g0, g1, dtype=np.int64)
+    origin = np.full(len(gene_id), root, np.int32)
+    car_off = np.arange(len(gene_id) + 1, dtype=np.int64)
+    car = np.full(len(gene_id), PGS_ALL_GENOMES, np.int32)
+
+    stream = torch.cuda.Stream()
+    flags = 1 if os.environ.get("PGS_NO_GRAPH") else 0  # PGS_FLAG_NO_GRAPH: plain launches (profiling)
+    eng = Engine(CFG["seed"], L, device=local, flags=flags)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_tree(parent, rate, leaf)
+    eng.set_genes(gene_id, origin, car_off, car)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident steps
+    for _ in range(args.warmup):
+        eng.sweep()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1_ms = []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        eng.sweep()
+    ev1.record(stream)
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    # per-kernel split (CUDA events recorded by the library around K0 and around the K1 level graph)
+    for _ in range(3):
+        eng.sweep()
+        st = eng.stats()
+        k1_ms.append(st["sweep_ms"])
+    if rank == 0:
+        time.sleep(0.15)
+        clocks = sampler.stop()
+    st = eng.stats()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    leaf_nt_all = float(st["leaf_nucleotides"]) * world
+    value = leaf_nt_all * args.steps / (total_ms * 1e-3)
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = (st["rows_written"] + st["rows_read"]) * L / 4.0
+    k1 = float(np.mean(k1_ms))
+    achieved = alg_bytes / (k1 * 1e-3) / 1e9
+    traffic = None
+    tr = ROOT / "profiles" / "k1_traffic.json"
+    if tr.exists():
+        try:
+            traffic = json.loads(tr.read_text()).get("dram_bytes_per_sweep")
+        except ValueError:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k1_sweep_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_sweep": alg_bytes, "k1_ms_per_sweep": k1,
+                "launches_per_sweep": st["kernel_launches"] - 1}
+
+    # ---- end to end through the C ABI with host tables in, host text out
+    e2e = None
+    if not args.no_e2e:
+        what = OUT_GENOMES | OUT_MAF | OUT_DISCARD
+        ref_core = np.arange(len(gene_id), dtype=np.int64)
+        h2d = parent.nbytes + rate.nbytes + leaf.nbytes + gene_id.nbytes + origin.nbytes + car_off.nbytes + car.nbytes
+
+        def e2e_step():
+            eng.set_tree(parent, rate, leaf)
+            eng.set_genes(gene_id, origin, car_off, car)
+            eng.sweep()
+            return eng.write_outputs(None, what, ref_core, [])
+        e2e_step()  # warm-up (allocations, pinned buffers, graph capture)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        rep = None
+        for _ in range(args.e2e_steps):
+            rep = e2e_step()
+        ev1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        e2e = {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(rep["bytes"]), "steps": args.e2e_steps, "ms_per_step": 1e3 * wall / args.e2e_steps,
+               "k3_device_ms_per_step": rep["device_ms"], "files_per_step": int(rep["files"]),
+               "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) "
+                       "into pinned host memory, bytes discarded (no filesystem)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.cpu_genes if not args.small else 200)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(world), "l2": "inputs_larger_than_l2 (25.6 GB of rows per GPU)",
+                       "rng": "Philox4x32-10 keyed (seed, edge, gene, 64-site block)", "rows_per_gpu": st["rows_total"],
+                       "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(st["kernel_launches"]) * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

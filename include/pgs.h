@@ -134,9 +134,10 @@ int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
 #define PGS_OUT_GENOMES 8u
 #define PGS_OUT_MAF 16u
 #define PGS_OUT_ALL 31u
+#define PGS_OUT_DISCARD 32u /* produce, copy to pinned host memory, then drop (benchmarking) */
 
 typedef struct pgs_output_spec {
-	const char *out_dir;      /* files are created in out_dir (must exist); NULL with a sink */
+	const char *out_dir;      /* files are created in out_dir (must exist); NULL with a sink / DISCARD */
 	uint32_t what;            /* PGS_OUT_* */
 	int64_t n_ref_core;       /* reference: img_model::get_core(), img.cxx:381-384 */
 	const int64_t *ref_core;  /* gene table indices */

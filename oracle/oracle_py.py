@@ -40,7 +40,9 @@ def lib():
     L.oracle_jc_p.restype = dbl
     L.oracle_root_block.argtypes = [u64, u32, u32, i64, vp]
     L.oracle_root_block.restype = None
-    L.oracle_mutate_block.argtypes = [u64, u32, u32, u32, i64, vp, vp]
+    L.oracle_mutate_block.argtypes = [u64, u32, u32, u32, u32, u32, i64, vp, vp]
+    L.oracle_sibling_pairs.argtypes = [i32, vp, vp, vp]
+    L.oracle_sibling_pairs.restype = None
     L.oracle_mutate_block.restype = None
     L.oracle_row.argtypes = [u64, i32, vp, vp, i32, i32, u32, i64, vp]
     L.oracle_row.restype = C.c_int

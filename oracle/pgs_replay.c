@@ -104,7 +104,35 @@ void oracle_root_block(uint64_t seed, uint32_t gene_id, uint32_t blk, int64_t ge
 	for (int w = 0; w < 4; w++) out[w] &= v[w];
 }
 
-/* word stream of one (edge, gene, block): words 2,3 of stream 0, then 0..3 of stream 1, 2, ... */
+/* Sibling pairs: the children of a node in ascending index are paired (c0,c1), (c2,c3), ...;
+ * leader[v] = first node of v's pair, side[v] = 0 for the leader, 1 for the other.  Root: itself. */
+void oracle_sibling_pairs(int32_t n_nodes, const int32_t *parent, int32_t *leader, int32_t *side)
+{
+	/* rank of v among its siblings = number of smaller-index nodes with the same parent */
+	int32_t *seen = (int32_t *)calloc((size_t)n_nodes, sizeof(int32_t));   /* children met so far */
+	int32_t *last = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_nodes); /* previous child met */
+	for (int32_t v = 0; v < n_nodes; v++) {
+		const int32_t p = parent[v];
+		if (p < 0) {
+			leader[v] = v;
+			side[v] = 0;
+			continue;
+		}
+		if (seen[p] % 2 == 0) {
+			leader[v] = v;
+			side[v] = 0;
+		} else {
+			leader[v] = last[p];
+			side[v] = 1;
+		}
+		last[p] = v;
+		seen[p]++;
+	}
+	free(seen);
+	free(last);
+}
+
+/* word stream of one (edge, gene, block): words 0..3 of stream 1, then of stream 2, ... */
 typedef struct {
 	uint32_t ctr[4];
 	uint32_t key[2];
@@ -122,19 +150,26 @@ static uint32_t stream_next(word_stream *s)
 	return s->buf[s->next++];
 }
 
-void oracle_mutate_block(uint64_t seed, uint32_t edge, uint32_t gene_id, uint32_t blk,
-						 int64_t gene_length, const uint64_t H[65], uint32_t x[4])
+void oracle_mutate_block(uint64_t seed, uint32_t leader, uint32_t side, uint32_t edge, uint32_t gene_id,
+						 uint32_t blk, int64_t gene_length, const uint64_t H[65], uint32_t x[4])
 {
+	/* decision word: shared by the sibling pair and by blocks 2q, 2q+1 */
+	const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+	const uint32_t pctr[4] = {leader, gene_id, blk / 2u, 0u};
+	uint32_t pw[4];
+	oracle_philox4x32_10(pctr, key, pw);
+	const uint32_t D = pw[2u * side + (blk % 2u)];
+	if (D > (uint32_t)(H[1] >> 32)) return; /* U >= H[1] whatever the low half: no substitution */
+
 	word_stream s;
 	s.ctr[0] = edge;
 	s.ctr[1] = gene_id;
 	s.ctr[2] = blk;
-	s.ctr[3] = 0u;
-	s.key[0] = (uint32_t)seed;
-	s.key[1] = (uint32_t)(seed >> 32);
-	oracle_philox4x32_10(s.ctr, s.key, s.buf);
-	s.next = 2;
-	const uint64_t U = ((uint64_t)s.buf[1] << 32) | s.buf[0];
+	s.ctr[3] = 0u; /* stream_next pre-increments: the first call is stream 1 */
+	s.key[0] = key[0];
+	s.key[1] = key[1];
+	s.next = 4;
+	const uint64_t U = ((uint64_t)D << 32) | stream_next(&s);
 
 	int K = 0;
 	while (K < 64 && U < H[K + 1]) K++;
@@ -190,14 +225,20 @@ int oracle_row(uint64_t seed, int32_t n_nodes, const int32_t *parent, const doub
 	for (int64_t b = 0; b < nb; b++) {
 		oracle_root_block(seed, gene_id, (uint32_t)b, gene_length, dst + 4 * b);
 	}
+	int32_t *leader = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_nodes);
+	int32_t *side = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_nodes);
+	oracle_sibling_pairs(n_nodes, parent, leader, side);
 	uint64_t H[65];
 	for (int i = len - 1; i >= 0; i--) {
 		const int32_t e = path[i];
 		oracle_edge_table(rate[e], H);
 		for (int64_t b = 0; b < nb; b++) {
-			oracle_mutate_block(seed, (uint32_t)e, gene_id, (uint32_t)b, gene_length, H, dst + 4 * b);
+			oracle_mutate_block(seed, (uint32_t)leader[e], (uint32_t)side[e], (uint32_t)e, gene_id, (uint32_t)b,
+								gene_length, H, dst + 4 * b);
 		}
 	}
+	free(leader);
+	free(side);
 	free(path);
 	return 0;
 }
@@ -225,6 +266,9 @@ int oracle_gene_all_nodes(uint64_t seed, int32_t n_nodes, const int32_t *parent,
 	for (int64_t b = 0; b < nb; b++) {
 		oracle_root_block(seed, gene_id, (uint32_t)b, gene_length, dst + words * (size_t)origin + 4 * b);
 	}
+	int32_t *leader = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_nodes);
+	int32_t *side = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_nodes);
+	oracle_sibling_pairs(n_nodes, parent, leader, side);
 	uint64_t H[65];
 	for (int32_t d = 1; d <= maxd; d++) {
 		for (int32_t v = 0; v < n_nodes; v++) {
@@ -233,10 +277,13 @@ int oracle_gene_all_nodes(uint64_t seed, int32_t n_nodes, const int32_t *parent,
 			memcpy(row, dst + words * (size_t)parent[v], sizeof(uint32_t) * words);
 			oracle_edge_table(rate[v], H);
 			for (int64_t b = 0; b < nb; b++) {
-				oracle_mutate_block(seed, (uint32_t)v, gene_id, (uint32_t)b, gene_length, H, row + 4 * b);
+				oracle_mutate_block(seed, (uint32_t)leader[v], (uint32_t)side[v], (uint32_t)v, gene_id,
+									(uint32_t)b, gene_length, H, row + 4 * b);
 			}
 		}
 	}
+	free(leader);
+	free(side);
 	free(order);
 	free(depth);
 	return 0;

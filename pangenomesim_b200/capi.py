@@ -17,7 +17,7 @@ _LIB = None
 
 PGS_ALL_GENOMES = -1
 PGS_FLAG_NO_GRAPH = 1
-OUT_REF, OUT_CORE, OUT_ACCESSORY, OUT_GENOMES, OUT_MAF, OUT_ALL = 1, 2, 4, 8, 16, 31
+OUT_REF, OUT_CORE, OUT_ACCESSORY, OUT_GENOMES, OUT_MAF, OUT_ALL, OUT_DISCARD = 1, 2, 4, 8, 16, 31, 32
 
 
 class PgsError(RuntimeError):

@@ -5,6 +5,7 @@
 #include "edge_table.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -183,6 +184,7 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 		return PGS_ERR_CUDA;
 	}
 	e.stream = e.own_stream;
+	if (const char *v = std::getenv("PGS_K1_VARIANT")) pgs::g_dense_variant = std::atoi(v);
 	e.blocks = (cfg->gene_length + 63) / 64;
 	e.last_valid = (int32_t)(cfg->gene_length - (e.blocks - 1) * 64);
 	*out = h;
@@ -496,7 +498,9 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	// ---- device
 	int rc;
 	const size_t row_bytes = (size_t)e.blocks * 16;
-	if ((rc = e.alloc(e.d_rows, (size_t)rows * row_bytes, "rows (HBM sequence store)"))) return rc;
+	// the sequence store is by far the largest allocation: keep it when a re-plan fits
+	if (e.d_rows.bytes < (size_t)rows * row_bytes || e.d_rows.bytes > 2 * (size_t)rows * row_bytes + (64u << 20))
+		if ((rc = e.alloc(e.d_rows, (size_t)rows * row_bytes, "rows (HBM sequence store)"))) return rc;
 	if ((rc = e.upload(e.d_row_base, e.row_base.data(), sizeof(int64_t) * N, "row_base"))) return rc;
 	if ((rc = e.upload(e.d_h1, e.h1_host.data(), sizeof(uint64_t) * N, "h1"))) return rc;
 	if ((rc = e.upload(e.d_tab, e.tab_host.data(), sizeof(uint64_t) * e.tab_host.size(), "tab"))) return rc;

@@ -340,6 +340,7 @@ struct Writer {
 	{
 		if (offset == 0) rep.files++;
 		rep.bytes += len;
+		if (spec->what & PGS_OUT_DISCARD) return true;
 		if (spec->sink) {
 			if (spec->sink(spec->sink_user, name.c_str(), offset, data, len) != 0) {
 				error = "sink aborted at " + name;
@@ -384,7 +385,8 @@ struct FilePiece {
 int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report)
 {
 	const auto wall0 = std::chrono::steady_clock::now();
-	if (!spec->sink && !spec->out_dir) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: neither out_dir nor sink");
+	if (!spec->sink && !spec->out_dir && !(spec->what & PGS_OUT_DISCARD))
+		return e.fail(PGS_ERR_ARG, "pgs_write_outputs: neither out_dir nor sink");
 	const int64_t G = e.n_genes, D = (int64_t)e.dense_gid.size(), L = e.cfg.gene_length;
 	const int32_t N = e.n_nodes, n = e.n_genomes;
 	for (int pass = 0; pass < 2; pass++) {

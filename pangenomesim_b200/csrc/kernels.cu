@@ -63,79 +63,185 @@ void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_task
 // ---------------------------------------------------------------------------------------------
 // K1, dense region.  The dense genes (carried by every genome, origin = root) occupy the first
 // n_dense rows of every node, in the same order, so a (parent, left, right) triple is a plain
-// 1-D stream: item i of the parent region produces item i of both child regions.  Each thread
-// takes kItems blocks: all loads are issued first (kItems x 16 B in flight per thread), each
-// parent block is read once and both children are produced from it -- the read-once /
-// write-once traffic of SURVEY.md §8(d): 48 bytes per (block, parent).
+// 1-D stream: item i of the parent region produces item i of both child regions.  Each parent
+// block is read once and both children are produced from it -- the read-once / write-once
+// traffic of SURVEY.md §8(d): 48 bytes per (block, parent).
 // Replaces the inner loop of img_model::sim_core_gene, reference img.cxx:215-231, whose
 // per-edge body is gene::mutate, gene.cxx:27-61.
+//
+// Main variant (even number of blocks per gene): a thread owns PAIRS pairs of adjacent blocks,
+// moved with 256-bit loads/stores (LDG.256 / STG.256).  One Philox call yields the four decision
+// words of {left, right} x {even block, odd block}; the fast path is branch-free (all loads
+// first, PAIRS independent Philox chains, compares folded into a bit mask) and substitutions --
+// rare events -- are applied afterwards.
 
-constexpr int kItems = 4;
-constexpr int kTile = kThreads * kItems;
+struct __align__(32) U32x8 {
+	uint4 lo, hi; // blocks 2p and 2p+1
+};
 
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ U32x8 ld_stream256(const U32x8 *p)
+{
+	U32x8 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				 : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y),
+				   "=r"(r.hi.z), "=r"(r.hi.w)
+				 : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void st_stream256(U32x8 *p, const U32x8 &v)
+{
+	asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.lo.x),
+				 "r"(v.lo.y), "r"(v.lo.z), "r"(v.lo.w), "r"(v.hi.x), "r"(v.hi.y), "r"(v.hi.z), "r"(v.hi.w)
+				 : "memory");
+}
+
+template <int PAIRS, int MINB, bool COPY_ONLY = false>
+__global__ void __launch_bounds__(kThreads, MINB)
 k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restrict__ tasks,
-			   uint32_t tiles_per_task, uint32_t items_per_task)
+			   uint32_t tiles_per_task, uint32_t pairs_per_task)
+{
+	constexpr uint32_t kTile = kThreads * PAIRS;
+	const uint32_t task = blockIdx.x / tiles_per_task;
+	const uint32_t tile = blockIdx.x - task * tiles_per_task;
+	const DenseTask dt = tasks[task];
+	const bool has_right = dt.right >= 0;
+	const int32_t right = has_right ? dt.right : dt.left;
+
+	const U32x8 *__restrict__ src = reinterpret_cast<const U32x8 *>(t.rows + __ldg(t.row_base + dt.parent) * t.blocks);
+	const uint32_t first = tile * kTile + threadIdx.x;
+	const bool full = (tile + 1) * kTile <= pairs_per_task; // CTA-uniform
+
+	U32x8 x[PAIRS];
+#pragma unroll
+	for (int j = 0; j < PAIRS; j++) {
+		const uint32_t p = first + j * kThreads;
+		if (full || p < pairs_per_task) x[j] = ld_stream256(src + p);
+	}
+
+	// Copy first: in the common case a child block equals its parent block, so the stores do not
+	// wait for the random numbers at all.  Blocks that do change are rewritten below (the second
+	// store of the same thread to the same address lands in L2 long before the line is evicted).
+	U32x8 *__restrict__ dl = reinterpret_cast<U32x8 *>(t.rows + __ldg(t.row_base + dt.left) * t.blocks);
+	U32x8 *__restrict__ dr = reinterpret_cast<U32x8 *>(t.rows + __ldg(t.row_base + right) * t.blocks);
+#pragma unroll
+	for (int j = 0; j < PAIRS; j++) {
+		const uint32_t p = first + j * kThreads;
+		if (full || p < pairs_per_task) {
+			st_stream256(dl + p, x[j]);
+			if (has_right) st_stream256(dr + p, x[j]);
+		}
+	}
+	if (COPY_ONLY) return;
+
+	const uint32_t h32l = (uint32_t)(__ldg(t.h1 + dt.left) >> 32);
+	const uint32_t h32r = (uint32_t)(__ldg(t.h1 + right) >> 32);
+	uint32_t hits = 0;
+#pragma unroll
+	for (int j = 0; j < PAIRS; j++) {
+		const uint32_t idx = 2u * (first + j * kThreads); // even block index inside the region
+		const uint32_t slot = fastdiv(idx, t.div_blocks);
+		const uint32_t blk = idx - slot * t.blocks;
+		const uint32_t gid = (full || idx < 2u * pairs_per_task) ? __ldg(t.dense_gid + slot) : 0u;
+		const uint4 w = pair_words((uint32_t)dt.left, gid, blk, t.keys);
+		const uint32_t m = (w.x <= h32l ? 1u : 0u) | (w.y <= h32l ? 2u : 0u) | (w.z <= h32r ? 4u : 0u) |
+						   (w.w <= h32r ? 8u : 0u);
+		hits |= (full || idx < 2u * pairs_per_task) ? (m << (4 * j)) : 0u;
+	}
+	if (!has_right) hits &= 0x33333333u;
+	if (hits == 0) return;
+
+	// rare: some of this thread's child blocks (may) change
+	const EdgeDecision el = load_edge(t, dt.left), er = load_edge(t, right);
+#pragma unroll
+	for (int j = 0; j < PAIRS; j++) {
+		const uint32_t m = (hits >> (4 * j)) & 15u;
+		if (m == 0) continue;
+		const uint32_t p = first + j * kThreads;
+		const uint32_t idx = 2u * p;
+		const uint32_t slot = fastdiv(idx, t.div_blocks);
+		const uint32_t blk = idx - slot * t.blocks;
+		const uint32_t gid = __ldg(t.dense_gid + slot);
+		const uint4 w = pair_words((uint32_t)dt.left, gid, blk, t.keys);
+		const int valid_hi = (blk + 2 == t.blocks) ? t.last_valid : 64;
+		uint4 *ol = reinterpret_cast<uint4 *>(dl + p), *orr = reinterpret_cast<uint4 *>(dr + p);
+		if (m & 1u) st_stream(ol, mutate_block_slow(x[j].lo, (uint32_t)dt.left, gid, blk, w.x, el.tab, el.kmax, 64, t.keys));
+		if (m & 2u) st_stream(ol + 1, mutate_block_slow(x[j].hi, (uint32_t)dt.left, gid, blk + 1, w.y, el.tab, el.kmax, valid_hi, t.keys));
+		if (m & 4u) st_stream(orr, mutate_block_slow(x[j].lo, (uint32_t)right, gid, blk, w.z, er.tab, er.kmax, 64, t.keys));
+		if (m & 8u) st_stream(orr + 1, mutate_block_slow(x[j].hi, (uint32_t)right, gid, blk + 1, w.w, er.tab, er.kmax, valid_hi, t.keys));
+	}
+}
+
+// Fallback for an odd number of blocks per gene (adjacent blocks may straddle genes and rows are
+// only 16-byte aligned): one block per thread, each computing its pair's Philox call itself.
+__global__ void __launch_bounds__(kThreads)
+k1_sweep_dense_single(const __grid_constant__ DeviceTables t, const DenseTask *__restrict__ tasks,
+					  uint32_t tiles_per_task, uint32_t items_per_task)
 {
 	const uint32_t task = blockIdx.x / tiles_per_task;
 	const uint32_t tile = blockIdx.x - task * tiles_per_task;
 	const DenseTask dt = tasks[task];
-
-	const uint4 *__restrict__ src = t.rows + __ldg(t.row_base + dt.parent) * t.blocks;
-	const uint32_t first = tile * kTile + threadIdx.x;
-
-	uint4 x[kItems];
-#pragma unroll
-	for (int j = 0; j < kItems; j++) {
-		const uint32_t idx = first + j * kThreads;
-		if (idx < items_per_task) x[j] = ld_stream(src + idx);
-	}
-
-	uint32_t gid[kItems], blk[kItems];
-#pragma unroll
-	for (int j = 0; j < kItems; j++) {
-		const uint32_t idx = first + j * kThreads;
-		const uint32_t slot = fastdiv(idx, t.div_blocks);
-		blk[j] = idx - slot * t.blocks;
-		gid[j] = (idx < items_per_task) ? __ldg(t.dense_gid + slot) : 0u;
-	}
-
+	const uint32_t idx = tile * kThreads + threadIdx.x;
+	if (idx >= items_per_task) return;
+	const uint4 x = ld_stream(t.rows + __ldg(t.row_base + dt.parent) * t.blocks + idx);
+	const uint32_t slot = fastdiv(idx, t.div_blocks);
+	const uint32_t blk = idx - slot * t.blocks;
+	const uint32_t gid = __ldg(t.dense_gid + slot);
+	const int valid = (blk + 1 == t.blocks) ? t.last_valid : 64;
 	{
 		const EdgeDecision d = load_edge(t, dt.left);
-		uint4 *__restrict__ dst = t.rows + __ldg(t.row_base + dt.left) * t.blocks;
-#pragma unroll
-		for (int j = 0; j < kItems; j++) {
-			const uint32_t idx = first + j * kThreads;
-			if (idx < items_per_task) {
-				const int valid = (blk[j] + 1 == t.blocks) ? t.last_valid : 64;
-				st_stream(dst + idx, mutate_block(x[j], (uint32_t)dt.left, gid[j], blk[j], d, valid, t.keys));
-			}
-		}
+		st_stream(t.rows + __ldg(t.row_base + dt.left) * t.blocks + idx,
+				  mutate_block(x, (uint32_t)dt.left, 0u, (uint32_t)dt.left, gid, blk, d, valid, t.keys));
 	}
 	if (dt.right >= 0) {
 		const EdgeDecision d = load_edge(t, dt.right);
-		uint4 *__restrict__ dst = t.rows + __ldg(t.row_base + dt.right) * t.blocks;
-#pragma unroll
-		for (int j = 0; j < kItems; j++) {
-			const uint32_t idx = first + j * kThreads;
-			if (idx < items_per_task) {
-				const int valid = (blk[j] + 1 == t.blocks) ? t.last_valid : 64;
-				st_stream(dst + idx, mutate_block(x[j], (uint32_t)dt.right, gid[j], blk[j], d, valid, t.keys));
-			}
-		}
+		st_stream(t.rows + __ldg(t.row_base + dt.right) * t.blocks + idx,
+				  mutate_block(x, (uint32_t)dt.left, 1u, (uint32_t)dt.right, gid, blk, d, valid, t.keys));
 	}
 }
 
-void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s)
+template <int PAIRS, int MINB, bool COPY_ONLY = false>
+static void launch_dense_variant(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s)
 {
-	if (n_tasks == 0 || t.n_dense == 0) return;
-	const uint32_t items = t.n_dense * t.blocks;
-	const uint32_t tiles = (items + kTile - 1) / kTile;
+	const uint32_t pairs = t.n_dense * t.blocks / 2;
+	const uint32_t tile = kThreads * PAIRS;
+	const uint32_t tiles = (pairs + tile - 1) / tile;
 	// one launch covers at most 2^31-1 CTAs; chunk the task list beyond that
 	const int64_t max_tasks = (int64_t)0x7FFFFFFF / tiles;
 	for (int64_t done = 0; done < n_tasks; done += max_tasks) {
 		const int64_t now = (n_tasks - done < max_tasks) ? (n_tasks - done) : max_tasks;
-		k1_sweep_dense<<<(unsigned)(now * tiles), kThreads, 0, s>>>(t, tasks + done, tiles, items);
+		k1_sweep_dense<PAIRS, MINB, COPY_ONLY><<<(unsigned)(now * tiles), kThreads, 0, s>>>(t, tasks + done, tiles, pairs);
+	}
+}
+
+int g_dense_variant = -1; // development knob (PGS_K1_VARIANT); -1 = default
+
+void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s)
+{
+	if (n_tasks == 0 || t.n_dense == 0) return;
+	if (t.blocks & 1u) {
+		const uint32_t items = t.n_dense * t.blocks;
+		const uint32_t tiles = (items + kThreads - 1) / kThreads;
+		const int64_t max_tasks = (int64_t)0x7FFFFFFF / tiles;
+		for (int64_t done = 0; done < n_tasks; done += max_tasks) {
+			const int64_t now = (n_tasks - done < max_tasks) ? (n_tasks - done) : max_tasks;
+			k1_sweep_dense_single<<<(unsigned)(now * tiles), kThreads, 0, s>>>(t, tasks + done, tiles, items);
+		}
+		return;
+	}
+	switch (g_dense_variant) {
+		case 1: launch_dense_variant<1, 4>(t, tasks, n_tasks, s); break;
+		case 2: launch_dense_variant<1, 6>(t, tasks, n_tasks, s); break;
+		case 3: launch_dense_variant<1, 8>(t, tasks, n_tasks, s); break;
+		case 4: launch_dense_variant<2, 3>(t, tasks, n_tasks, s); break;
+		case 5: launch_dense_variant<2, 4>(t, tasks, n_tasks, s); break;
+		case 6: launch_dense_variant<2, 5>(t, tasks, n_tasks, s); break;
+		case 7: launch_dense_variant<2, 6>(t, tasks, n_tasks, s); break;
+		case 8: launch_dense_variant<4, 2>(t, tasks, n_tasks, s); break;
+		case 9: launch_dense_variant<4, 3>(t, tasks, n_tasks, s); break;
+		case 10: launch_dense_variant<4, 4>(t, tasks, n_tasks, s); break;
+		case 11: launch_dense_variant<2, 4, true>(t, tasks, n_tasks, s); break; // memory ceiling probe: no RNG
+		case 12: launch_dense_variant<4, 4, true>(t, tasks, n_tasks, s); break;
+		default: launch_dense_variant<2, 4>(t, tasks, n_tasks, s); break;
 	}
 }
 
@@ -155,15 +261,22 @@ k1_sweep_sparse(const __grid_constant__ DeviceTables t, const SparseTask *__rest
 	const SparseTask st = tasks[task];
 	const uint4 x = ld_stream(t.rows + (int64_t)st.src * t.blocks + blk);
 	const int valid = (blk + 1 == t.blocks) ? t.last_valid : 64;
+	const uint4 w = pair_words((uint32_t)st.edge_left, st.gid, blk, t.keys);
 	if (st.dst_left != kNoRow) {
 		const EdgeDecision d = load_edge(t, st.edge_left);
-		st_stream(t.rows + (int64_t)st.dst_left * t.blocks + blk,
-				  mutate_block(x, (uint32_t)st.edge_left, st.gid, blk, d, valid, t.keys));
+		const uint32_t D = pick_word(w, 0u, blk);
+		uint4 y = x;
+		if (D <= (uint32_t)(d.h1 >> 32))
+			y = mutate_block_slow(x, (uint32_t)st.edge_left, st.gid, blk, D, d.tab, d.kmax, valid, t.keys);
+		st_stream(t.rows + (int64_t)st.dst_left * t.blocks + blk, y);
 	}
 	if (st.dst_right != kNoRow) {
 		const EdgeDecision d = load_edge(t, st.edge_right);
-		st_stream(t.rows + (int64_t)st.dst_right * t.blocks + blk,
-				  mutate_block(x, (uint32_t)st.edge_right, st.gid, blk, d, valid, t.keys));
+		const uint32_t D = pick_word(w, 1u, blk);
+		uint4 y = x;
+		if (D <= (uint32_t)(d.h1 >> 32))
+			y = mutate_block_slow(x, (uint32_t)st.edge_right, st.gid, blk, D, d.tab, d.kmax, valid, t.keys);
+		st_stream(t.rows + (int64_t)st.dst_right * t.blocks + blk, y);
 	}
 }
 

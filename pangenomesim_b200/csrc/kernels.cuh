@@ -63,6 +63,7 @@ struct DeviceTables {
 	PhiloxKeys keys;
 };
 
+extern int g_dense_variant;
 void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_tasks, cudaStream_t s);
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);

@@ -5,8 +5,11 @@
 // a pure function of (seed, edge, gene_id, site-block, stream), so results do not depend on
 // thread order, grid shape or gene sharding.
 //
-//   ctr = (edge, gene_id, block, stream)   edge = child node index, 0xFFFFFFFF for origin rows
 //   key = (seed_lo, seed_hi); the ten round keys are launch constants (PhiloxKeys)
+//   ctr = (0xFFFFFFFF, gene_id, block, 0)            origin rows
+//   ctr = (leader edge, gene_id, block >> 1, 0)      decision words of a sibling pair (see below)
+//   ctr = (edge, gene_id, block, stream >= 1)        everything else a branch needs for a block
+// edge = child node index of the branch.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -62,21 +65,44 @@ struct EdgeDecision {
 	int kmax;
 };
 
-// Rare path: the block has K >= 1 substitutions.  w is Philox(edge, gid, blk, stream 0), of which
-// words x,y formed U.  K-1 further thresholds are scanned, then K distinct sites are drawn
-// (r-th free site, r = mulhi(word, 64-j)) each with a uniform non-zero 2-bit delta; XOR with a
-// non-zero delta is "uniform pick among the 3 other bases".  valid = number of real sites in
-// this block (64 except for the last block of a gene); padding stays zero.
-static __device__ __noinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
-												uint4 w, uint64_t U, const uint64_t *__restrict__ tab,
-												int kmax, int valid, const PhiloxKeys &keys)
+// ---- decision words -----------------------------------------------------------------------
+// The branches below a node are taken in sibling pairs (children in ascending node index:
+// (c0,c1), (c2,c3), ...); the first of a pair is its `leader`, side = 0 for the leader and 1 for
+// the other.  One Philox call serves the four (edge, block) decisions of a sibling pair and two
+// adjacent blocks:
+//     D(edge, gid, blk) = word[2*side + (blk & 1)] of Philox(leader, gid, blk >> 1, stream 0)
+// D is the HIGH half of the 64-bit uniform U = D * 2^32 + lo that is compared with the branch's
+// thresholds H[k] = floor(2^64 P(K >= k)).  With h32 = H[1] >> 32:  D > h32  =>  U >= H[1]  =>
+// no substitution in the block (the common case: one compare).  Otherwise the low half and
+// everything else comes from the branch's own stream Philox(edge, gid, blk, stream >= 1).
+__device__ __forceinline__ uint4 pair_words(uint32_t leader, uint32_t gid, uint32_t blk, const PhiloxKeys &keys)
 {
-	int K = 1;
+	return philox4x32_10(leader, gid, blk >> 1, 0u, keys);
+}
+__device__ __forceinline__ uint32_t pick_word(const uint4 &w, uint32_t side, uint32_t blk)
+{
+	const uint32_t i = 2u * side + (blk & 1u);
+	return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
+}
+
+// Rare path (D <= h32): the block may change.  Stream 1 of the branch gives lo, then the words
+// for K distinct sites (r-th free site, r = mulhi(word, 64-j)) each with a uniform non-zero
+// 2-bit delta; XOR with a non-zero delta is "uniform pick among the 3 other bases".  Words are
+// consumed in order: x (= lo), y, z, w of stream 1, then x, y, z, w of stream 2, ...
+// valid = number of real sites in this block (64 except for the last block of a gene); padding
+// stays zero.
+static __device__ __noinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
+													   uint32_t D, const uint64_t *__restrict__ tab, int kmax,
+													   int valid, const PhiloxKeys &keys)
+{
+	uint32_t stream = 1;
+	uint4 w = philox4x32_10(edge, gid, blk, stream, keys);
+	const uint64_t U = ((uint64_t)D << 32) | w.x;
+	int K = 0;
 	while (K < kmax && U < tab[K]) K++;
 
 	uint64_t taken = 0, mlo = 0, mhi = 0;
-	uint32_t stream = 0;
-	int have = 2; // unread words of the current call; stream 0 has w.z, w.w left
+	int have = 3; // unread words of the current call
 	for (int j = 0; j < K; j++) {
 		if (have == 0) {
 			stream++;
@@ -84,7 +110,7 @@ static __device__ __noinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, u
 			have = 4;
 		}
 		uint32_t word;
-		switch (have) { // words are consumed in index order x,y,z,w
+		switch (have) {
 			case 4: word = w.x; break;
 			case 3: word = w.y; break;
 			case 2: word = w.z; break;
@@ -95,9 +121,11 @@ static __device__ __noinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, u
 		const uint32_t r = __umulhi(word, m);
 		const uint32_t lo = word * m;
 		const uint64_t delta = 1u + __umulhi(lo, 3u);
-		uint64_t freebits = ~taken;
-		for (uint32_t i = 0; i < r; i++) freebits &= freebits - 1; // drop the r lowest free sites
-		const int pos = __ffsll((long long)freebits) - 1;
+		// r-th (0-based, ascending) site not yet taken
+		const uint64_t freebits = ~taken;
+		const uint32_t flo = (uint32_t)freebits, fhi = (uint32_t)(freebits >> 32);
+		const uint32_t nlo = __popc(flo);
+		const int pos = r < nlo ? (int)__fns(flo, 0u, (int)r + 1) : 32 + (int)__fns(fhi, 0u, (int)(r - nlo) + 1);
 		taken |= 1ull << pos;
 		if (pos < 32)
 			mlo |= delta << (2 * pos);
@@ -119,13 +147,13 @@ static __device__ __noinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, u
 	return x;
 }
 
-// Carry one 64-site block across one edge.
-__device__ __forceinline__ uint4 mutate_block(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
-											  const EdgeDecision &d, int valid, const PhiloxKeys &keys)
+// Carry one 64-site block across one edge (generic form used where blocks are handled singly).
+__device__ __forceinline__ uint4 mutate_block(uint4 x, uint32_t leader, uint32_t side, uint32_t edge, uint32_t gid,
+											  uint32_t blk, const EdgeDecision &d, int valid, const PhiloxKeys &keys)
 {
-	const uint4 w = philox4x32_10(edge, gid, blk, 0u, keys);
-	const uint64_t U = ((uint64_t)w.y << 32) | w.x;
-	if (U < d.h1) return mutate_block_slow(x, edge, gid, blk, w, U, d.tab, d.kmax, valid, keys);
+	const uint4 w = pair_words(leader, gid, blk, keys);
+	const uint32_t D = pick_word(w, side, blk);
+	if (D <= (uint32_t)(d.h1 >> 32)) return mutate_block_slow(x, edge, gid, blk, D, d.tab, d.kmax, valid, keys);
 	return x;
 }
 

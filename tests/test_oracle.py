@@ -72,7 +72,7 @@ def test_mutate_block_statistics(oracle):
     x = np.zeros(4, dtype=np.uint32)
     for b in range(nblk):
         x[:] = 0
-        L.oracle_mutate_block(77, 5, 9, b, gene_length, H.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+        L.oracle_mutate_block(77, 4 + (b % 2), b % 2, 5, 9, b, gene_length, H.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
         codes = oracle.unpack_codes(x, 64)
         counts += codes != 0
         per_block[b] = (codes != 0).sum()
@@ -100,7 +100,7 @@ def test_root_block_uniform_and_padded(oracle):
     assert not oracle.unpack_codes(out, 64)[36:].any()
     H, _ = oracle.edge_table(50.0)
     for e in range(50):
-        L.oracle_mutate_block(3, e, 1, 1, 100, H.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        L.oracle_mutate_block(3, e, 0, e, 1, 1, 100, H.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         assert not oracle.unpack_codes(out, 64)[36:].any()
 
 
