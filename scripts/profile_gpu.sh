@@ -1,14 +1,18 @@
 #!/bin/bash
 # Run on the GPU box (under gpurun): plain run first, then the ncu launch list and one
-# --set full capture of the dominant kernel (recipe: /opt/skills/guides/B200_PROFILING.md).
+# --set full capture per kernel (recipe: /opt/skills/guides/B200_PROFILING.md).
 set -u
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
 export PGS_NO_GRAPH=1
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 37 -c 108 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 108 -c 144 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k1_sweep_dense -s 44 -c 8 \
+ncu --set full --clock-control none --import-source on -k regex:k1_sweep_dense -s 114 -c 10 \
     -o gpurun_out/k1_full $CMD > gpurun_out/ncu_full.log 2>&1
+AUX="python scripts/profile_aux.py"
+$AUX > gpurun_out/aux_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"k2_mismatch|k3_genome_fasta|k3_maf" -c 6 \
+    -o gpurun_out/aux_full $AUX > gpurun_out/ncu_aux.log 2>&1
 ls -la gpurun_out
