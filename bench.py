@@ -205,6 +205,48 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 
+def mismatch_allreduce_leg(torch, dist, Engine, rank, world, local):
+    """K2 on every rank's gene shard, partial n x n counts summed with NCCL over NVLink; checked
+    against the sum of the partials gathered on rank 0 and against the JC expectation."""
+    n, L, genes = 2000, 1000, 250
+    parent, rate, leaf = coalescent(n, 3, 0.05)
+    eng = Engine(7, L, device=local)
+    eng.set_tree(parent, rate, leaf)
+    eng.set_core_genes(genes, 2 * n - 2, first_id=rank * genes)
+    eng.sweep()
+    part = torch.zeros((n, n), dtype=torch.int32, device="cuda")
+    sites = eng.mismatch_device(part.data_ptr())
+    torch.cuda.synchronize()
+    k2_ms = eng.stats()["mismatch_ms"]
+    before = part.to(torch.int64).sum()
+    dist.all_reduce(before)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)
+    ev1.record()
+    torch.cuda.synchronize()
+    ok = bool(part.to(torch.int64).sum().item() == before.item())
+    # JC check of one distant pair on the summed matrix
+    S = sites * world
+    d, v, seen = 0.0, 0, {}
+    acc = 0.0
+    while v != -1:
+        seen[v] = acc
+        acc += rate[v]
+        v = int(parent[v])
+    v, accb = 1, 0.0
+    while v not in seen:
+        accb += rate[v]
+        v = int(parent[v])
+    d = seen[v] + accb
+    p = 0.75 * (1 - np.exp(-4 * d / 3))
+    obs = part[0, 1].item() / S
+    ok = ok and abs(obs - p) < 5 * np.sqrt(p * (1 - p) / S) + 1e-9
+    eng.close()
+    return {"ok": ok, "n_genomes": n, "genes_per_rank": genes, "k2_ms": k2_ms, "allreduce_ms": ev0.elapsed_time(ev1),
+            "bytes": int(part.numel() * 4), "pair01_observed": obs, "pair01_jc_expected": float(p)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,6 +389,12 @@ def main():
                "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) "
                        "into pinned host memory, bytes discarded (no filesystem)"}
 
+    # ---- the path's only collective: all-reduce of the per-rank partial mismatch counts (K2),
+    # untimed verification leg on a reduced problem (2000 genomes, 250 genes per rank)
+    mm_leg = None
+    if world > 1:
+        mm_leg = mismatch_allreduce_leg(torch, dist, Engine, rank, world, local)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.cpu_genes if not args.small else 200)
@@ -360,7 +408,8 @@ def main():
                        "rng": "Philox4x32-10 keyed (seed, edge, gene, 64-site block)", "rows_per_gpu": st["rows_total"],
                        "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(st["kernel_launches"]) * args.steps, "clocks": clocks,
+            "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
+            "mismatch_allreduce": mm_leg,
         }
         print(json.dumps(line), flush=True)
     eng.close()
