@@ -70,7 +70,8 @@ int Engine::upload(DevBuf &b, const void *src, size_t bytes, const char *what)
 int64_t Engine::device_bytes() const
 {
 	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
-						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch};
+						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch,
+						   &d_tab8};
 	int64_t s = 0;
 	for (auto b : all) s += (int64_t)b->bytes;
 	return s;
@@ -514,6 +515,12 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	for (int32_t g = 0; g < n; g++) leaf_words[g] = e.row_base[e.genome_leaf[g]] * e.blocks * 4;
 	if ((rc = e.upload(e.d_leaf_base_words, leaf_words.data(), sizeof(int64_t) * n, "leaf bases"))) return rc;
 	e.d_mismatch.release();
+	{ // first eight thresholds of every branch at a fixed stride, for the kernels' shared-memory copy
+		std::vector<uint64_t> tab8((size_t)N * 8, 0);
+		for (int32_t v = 0; v < N; v++)
+			for (int k = 0; k < 8 && k < e.kmax_host[v]; k++) tab8[(size_t)v * 8 + k] = e.tab_host[e.tab_off_host[v] + k];
+		if ((rc = e.upload(e.d_tab8, tab8.data(), sizeof(uint64_t) * tab8.size(), "tab8"))) return rc;
+	}
 
 	pgs::DeviceTables &t = e.tables;
 	t.rows = e.d_rows.as<uint4>();
@@ -527,6 +534,7 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	t.blocks = (uint32_t)e.blocks;
 	t.last_valid = e.last_valid;
 	t.div_blocks = pgs::make_fastdiv((uint32_t)e.blocks);
+	t.tab8 = e.d_tab8.as<uint64_t>();
 	t.keys = pgs::make_philox_keys(e.cfg.seed);
 	e.have_genes = true;
 	return PGS_OK;

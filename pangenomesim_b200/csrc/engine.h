@@ -64,7 +64,7 @@ struct Engine {
 
 	// ---- device
 	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
-	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch;
+	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8;
 	DeviceTables tables{};
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t graph_exec = nullptr;

@@ -148,26 +148,48 @@ k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restri
 		hits |= (full || idx < 2u * pairs_per_task) ? (m << (4 * j)) : 0u;
 	}
 	if (!has_right) hits &= 0x33333333u;
-	if (hits == 0) return;
 
-	// rare: some of this thread's child blocks (may) change
-	const EdgeDecision el = load_edge(t, dt.left), er = load_edge(t, right);
-#pragma unroll
-	for (int j = 0; j < PAIRS; j++) {
-		const uint32_t m = (hits >> (4 * j)) & 15u;
-		if (m == 0) continue;
+	if (!__any_sync(0xFFFFFFFFu, hits != 0)) return;
+
+	// This warp has work on the rare path.  Its lanes fetch the two branches' first thresholds
+	// (H[1..8] each) and table lengths in ONE round trip into a per-warp shared-memory copy, so
+	// the per-block work below has no dependent global load.
+	__shared__ uint64_t s_tab[kThreads / 32][2][8];
+	__shared__ int s_kmax[kThreads / 32][2];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane < 16)
+		s_tab[warp][lane >> 3][lane & 7] = __ldg(t.tab8 + (size_t)(lane < 8 ? dt.left : right) * 8 + (lane & 7));
+	else if (lane < 18)
+		s_kmax[warp][lane - 16] = __ldg(t.kmax + (lane == 16 ? dt.left : right));
+	__syncwarp();
+
+	// rare: some of this thread's child blocks (may) change.  Every lane works through its own
+	// flagged blocks one at a time, so a warp needs as many passes as its busiest lane has hits
+	// (usually one).  The thresholds come from this warp's shared-memory copy: no dependent global
+	// load sits between the decision and the rewrite.
+	while (hits) {
+		const uint32_t b = (uint32_t)__ffs((int)hits) - 1u;
+		hits &= hits - 1u;
+		const uint32_t j = b >> 2, side = (b >> 1) & 1u, odd = b & 1u;
 		const uint32_t p = first + j * kThreads;
 		const uint32_t idx = 2u * p;
 		const uint32_t slot = fastdiv(idx, t.div_blocks);
-		const uint32_t blk = idx - slot * t.blocks;
+		const uint32_t blk0 = idx - slot * t.blocks;
 		const uint32_t gid = __ldg(t.dense_gid + slot);
-		const uint4 w = pair_words((uint32_t)dt.left, gid, blk, t.keys);
-		const int valid_hi = (blk + 2 == t.blocks) ? t.last_valid : 64;
-		uint4 *ol = reinterpret_cast<uint4 *>(dl + p), *orr = reinterpret_cast<uint4 *>(dr + p);
-		if (m & 1u) st_stream(ol, mutate_block_slow(x[j].lo, (uint32_t)dt.left, gid, blk, w.x, el.tab, el.kmax, 64, t.keys));
-		if (m & 2u) st_stream(ol + 1, mutate_block_slow(x[j].hi, (uint32_t)dt.left, gid, blk + 1, w.y, el.tab, el.kmax, valid_hi, t.keys));
-		if (m & 4u) st_stream(orr, mutate_block_slow(x[j].lo, (uint32_t)right, gid, blk, w.z, er.tab, er.kmax, 64, t.keys));
-		if (m & 8u) st_stream(orr + 1, mutate_block_slow(x[j].hi, (uint32_t)right, gid, blk + 1, w.w, er.tab, er.kmax, valid_hi, t.keys));
+		const uint4 w = pair_words((uint32_t)dt.left, gid, blk0, t.keys);
+		const uint32_t D = pick_word(w, side, odd);
+		const uint32_t blk = blk0 + odd;
+		const int valid = (blk + 1 == t.blocks) ? t.last_valid : 64;
+		uint4 xin = x[0].lo;
+#pragma unroll
+		for (int jj = 0; jj < PAIRS; jj++)
+			if (j == (uint32_t)jj) xin = odd ? x[jj].hi : x[jj].lo;
+		const int kmax = s_kmax[warp][side];
+		const uint32_t edge = side ? (uint32_t)right : (uint32_t)dt.left;
+		// the full table is only touched when more than eight sites of one block change
+		const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
+		uint4 *dst = reinterpret_cast<uint4 *>((side ? dr : dl) + p) + odd;
+		st_stream(dst, mutate_block_slow(xin, edge, gid, blk, D, s_tab[warp][side], tab, kmax, valid, t.keys));
 	}
 }
 
@@ -241,7 +263,7 @@ void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n
 		case 10: launch_dense_variant<4, 4>(t, tasks, n_tasks, s); break;
 		case 11: launch_dense_variant<2, 4, true>(t, tasks, n_tasks, s); break; // memory ceiling probe: no RNG
 		case 12: launch_dense_variant<4, 4, true>(t, tasks, n_tasks, s); break;
-		default: launch_dense_variant<2, 4>(t, tasks, n_tasks, s); break;
+		default: launch_dense_variant<4, 3>(t, tasks, n_tasks, s); break;
 	}
 }
 
@@ -267,7 +289,7 @@ k1_sweep_sparse(const __grid_constant__ DeviceTables t, const SparseTask *__rest
 		const uint32_t D = pick_word(w, 0u, blk);
 		uint4 y = x;
 		if (D <= (uint32_t)(d.h1 >> 32))
-			y = mutate_block_slow(x, (uint32_t)st.edge_left, st.gid, blk, D, d.tab, d.kmax, valid, t.keys);
+			y = mutate_block_slow(x, (uint32_t)st.edge_left, st.gid, blk, D, d.tab, d.tab, d.kmax, valid, t.keys);
 		st_stream(t.rows + (int64_t)st.dst_left * t.blocks + blk, y);
 	}
 	if (st.dst_right != kNoRow) {
@@ -275,7 +297,7 @@ k1_sweep_sparse(const __grid_constant__ DeviceTables t, const SparseTask *__rest
 		const uint32_t D = pick_word(w, 1u, blk);
 		uint4 y = x;
 		if (D <= (uint32_t)(d.h1 >> 32))
-			y = mutate_block_slow(x, (uint32_t)st.edge_right, st.gid, blk, D, d.tab, d.kmax, valid, t.keys);
+			y = mutate_block_slow(x, (uint32_t)st.edge_right, st.gid, blk, D, d.tab, d.tab, d.kmax, valid, t.keys);
 		st_stream(t.rows + (int64_t)st.dst_right * t.blocks + blk, y);
 	}
 }

@@ -60,6 +60,7 @@ struct DeviceTables {
 	uint32_t blocks;          // blocks per gene (Bg)
 	int32_t last_valid;       // real sites in the last block of a gene (1..64)
 	FastDiv div_blocks;
+	const uint64_t *tab8;     // [N][8] first eight thresholds H[1..8] of every branch (0 beyond kmax)
 	PhiloxKeys keys;
 };
 

@@ -91,15 +91,18 @@ __device__ __forceinline__ uint32_t pick_word(const uint4 &w, uint32_t side, uin
 // consumed in order: x (= lo), y, z, w of stream 1, then x, y, z, w of stream 2, ...
 // valid = number of real sites in this block (64 except for the last block of a gene); padding
 // stays zero.
-static __device__ __noinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
-													   uint32_t D, const uint64_t *__restrict__ tab, int kmax,
-													   int valid, const PhiloxKeys &keys)
+// tab8 = H[1..8] of the branch (any address space, e.g. a shared-memory copy), tab = H[1..kmax].
+static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
+													   uint32_t D, const uint64_t *tab8, const uint64_t *__restrict__ tab,
+													   int kmax, int valid, const PhiloxKeys &keys)
 {
 	uint32_t stream = 1;
 	uint4 w = philox4x32_10(edge, gid, blk, stream, keys);
 	const uint64_t U = ((uint64_t)D << 32) | w.x;
 	int K = 0;
-	while (K < kmax && U < tab[K]) K++;
+	while (K < kmax && K < 8 && U < tab8[K]) K++;
+	if (K == 8)
+		while (K < kmax && U < tab[K]) K++;
 
 	uint64_t taken = 0, mlo = 0, mhi = 0;
 	int have = 3; // unread words of the current call
@@ -153,7 +156,7 @@ __device__ __forceinline__ uint4 mutate_block(uint4 x, uint32_t leader, uint32_t
 {
 	const uint4 w = pair_words(leader, gid, blk, keys);
 	const uint32_t D = pick_word(w, side, blk);
-	if (D <= (uint32_t)(d.h1 >> 32)) return mutate_block_slow(x, edge, gid, blk, D, d.tab, d.kmax, valid, keys);
+	if (D <= (uint32_t)(d.h1 >> 32)) return mutate_block_slow(x, edge, gid, blk, D, d.tab, d.tab, d.kmax, valid, keys);
 	return x;
 }
 
