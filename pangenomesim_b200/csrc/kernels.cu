@@ -311,18 +311,27 @@ void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: observed pairwise mismatch counts (popcount of folded XOR) over the dense regions of the
-// leaves.  A CTA owns a 64 x 64 tile of genome pairs and a slice of the columns; 32-bit words
-// (16 sites) are staged through shared memory in chunks, each thread accumulates a 4 x 4
-// sub-tile in registers.  Bound by the integer pipes (n^2 S / 2 site pairs), not by HBM.
+// K2: observed pairwise mismatch counts over the dense regions of the leaves.  A CTA owns a
+// 64 x 64 tile of genome pairs and a slice of the columns.  While a chunk of 512 sites is staged
+// into shared memory each row is split into its two BIT PLANES (low bit / high bit of every
+// 2-bit base, 32 sites per word), so that the inner loop per pair and 32 sites is
+//     mismatch mask = (lo_i ^ lo_j) | (hi_i ^ hi_j)      -> XOR + LOP3
+//     count        += popc(mask)                         -> POPC + IADD
+// i.e. 4 instructions per 32 site pairs instead of 5 per 16 on the packed form.  Each thread keeps
+// a 4 x 4 sub-tile in registers.  Bound by the integer pipes (n^2 S / 2 site pairs), not by HBM.
 
-constexpr int kMmTile = 64;   // genomes per tile side
-constexpr int kMmChunk = 32;  // 32-bit words per staged chunk
+constexpr int kMmTile = 64;    // genomes per tile side
+constexpr int kMmGroups = 16;  // 32-site groups per staged chunk (= 32 packed words per row)
 
-__device__ __forceinline__ uint32_t mismatch16(uint32_t a, uint32_t b)
+// even bits of x -> low 16 bits
+__device__ __forceinline__ uint32_t even_bits(uint32_t x)
 {
-	const uint32_t d = a ^ b;
-	return __popc((d | (d >> 1)) & 0x55555555u);
+	x &= 0x55555555u;
+	x = (x | (x >> 1)) & 0x33333333u;
+	x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+	x = (x | (x >> 4)) & 0x00FF00FFu;
+	x = (x | (x >> 8)) & 0x0000FFFFu;
+	return x;
 }
 
 __global__ void __launch_bounds__(256)
@@ -338,10 +347,11 @@ k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf
 	}
 	const int tj = ti + rem;
 
-	__shared__ uint32_t sa[kMmTile][kMmChunk + 1];
-	__shared__ uint32_t sb[kMmTile][kMmChunk + 1];
+	// [side a/b][plane lo/hi][row][group], row stride 17 words: rows r, r+16, .. and r+1 fall in
+	// different banks for the access pattern below
+	__shared__ uint32_t sm[2][2][kMmTile][kMmGroups + 1];
 
-	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // 16 x 16 threads, 4 x 4 pairs each
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // pairs (ty + 16 i, tx + 16 j)
 	uint32_t acc[4][4];
 #pragma unroll
 	for (int i = 0; i < 4; i++)
@@ -352,27 +362,34 @@ k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf
 	int64_t w_end = w_begin + words_per_split;
 	if (w_end > words_per_leaf) w_end = words_per_leaf;
 
-	for (int64_t w0 = w_begin; w0 < w_end; w0 += kMmChunk) {
-		// stage 64 rows x 32 words of each side: 2048 words per side, 8 per thread, coalesced in w
-		for (int e = threadIdx.x; e < kMmTile * kMmChunk; e += 256) {
-			const int row = e / kMmChunk, col = e % kMmChunk;
-			const int64_t w = w0 + col;
-			const int ga = ti * kMmTile + row, gb = tj * kMmTile + row;
-			sa[row][col] = (ga < n && w < w_end) ? __ldg(words + leaf_base_words[ga] + w) : 0u;
-			sb[row][col] = (gb < n && w < w_end) ? __ldg(words + leaf_base_words[gb] + w) : 0u;
+	for (int64_t w0 = w_begin; w0 < w_end; w0 += 2 * kMmGroups) {
+		// stage: 2 sides x 64 rows x 16 groups = 2048 (row, group) items, 8 per thread; a group is two
+		// packed words (8 bytes, aligned: rows start at multiples of 4 words and w0 is even)
+		for (int e = threadIdx.x; e < 2 * kMmTile * kMmGroups; e += 256) {
+			const int side = e / (kMmTile * kMmGroups);
+			const int row = (e / kMmGroups) % kMmTile, grp = e % kMmGroups;
+			const int g = (side ? tj : ti) * kMmTile + row;
+			const int64_t w = w0 + 2 * grp;
+			uint2 v = make_uint2(0u, 0u);
+			if (g < n && w < w_end) v = __ldg(reinterpret_cast<const uint2 *>(words + leaf_base_words[g] + w));
+			sm[side][0][row][grp] = even_bits(v.x) | (even_bits(v.y) << 16);
+			sm[side][1][row][grp] = even_bits(v.x >> 1) | (even_bits(v.y >> 1) << 16);
 		}
 		__syncthreads();
 #pragma unroll 4
-		for (int k = 0; k < kMmChunk; k++) {
-			uint32_t a[4], b[4];
+		for (int k = 0; k < kMmGroups; k++) {
+			uint32_t alo[4], ahi[4], blo[4], bhi[4];
 #pragma unroll
-			for (int i = 0; i < 4; i++) a[i] = sa[ty * 4 + i][k];
-#pragma unroll
-			for (int j = 0; j < 4; j++) b[j] = sb[tx * 4 + j][k];
+			for (int i = 0; i < 4; i++) {
+				alo[i] = sm[0][0][ty + 16 * i][k];
+				ahi[i] = sm[0][1][ty + 16 * i][k];
+				blo[i] = sm[1][0][tx + 16 * i][k];
+				bhi[i] = sm[1][1][tx + 16 * i][k];
+			}
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
-				for (int j = 0; j < 4; j++) acc[i][j] += mismatch16(a[i], b[j]);
+				for (int j = 0; j < 4; j++) acc[i][j] += __popc((alo[i] ^ blo[j]) | (ahi[i] ^ bhi[j]));
 		}
 		__syncthreads();
 	}
@@ -381,7 +398,7 @@ k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf
 	for (int i = 0; i < 4; i++) {
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			const int gi = ti * kMmTile + ty * 4 + i, gj = tj * kMmTile + tx * 4 + j;
+			const int gi = ti * kMmTile + ty + 16 * i, gj = tj * kMmTile + tx + 16 * j;
 			if (gi < n && gj < n && gi < gj && acc[i][j]) {
 				atomicAdd(out + (int64_t)gi * n + gj, acc[i][j]);
 			}
@@ -406,6 +423,7 @@ void launch_mismatch(const uint4 *rows, const int64_t *leaf_base_words, int32_t 
 	const int64_t tri = (int64_t)tiles * (tiles + 1) / 2;
 	// split the columns so that small n still fills the 148 SMs (4 CTAs each)
 	int64_t splits = (148 * 4 + tri - 1) / tri;
+	constexpr int kMmChunk = 2 * kMmGroups; // packed words per staged chunk
 	const int64_t chunks = (words_per_leaf + kMmChunk - 1) / kMmChunk;
 	if (splits > chunks) splits = chunks;
 	if (splits > 65535) splits = 65535;
