@@ -18,7 +18,7 @@ LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/kernels.o $(OBJDIR)/format.o $(OBJDIR)/
 all: lib cli oracle
 
 lib: $(LIBDIR)/libpgs.so
-cli: $(BINDIR)/pangenomesim-b200
+cli: $(BINDIR)/pangenomesim-b200 $(LIBDIR)/libpgshost.so
 oracle:
 	$(MAKE) -C oracle
 
@@ -35,12 +35,16 @@ $(LIBDIR)/libpgs.so: $(LIB_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart shared -Xlinker -rpath,/usr/local/cuda/lib64
 
-HOST_SRCS := $(wildcard $(HOST)/*.cpp)
-$(BINDIR)/pangenomesim-b200: $(HOST_SRCS) $(wildcard $(HOST)/*.h) include/pgs.h $(LIBDIR)/libpgs.so
+HOST_HDRS := $(wildcard $(HOST)/*.h) include/pgs.h
+$(BINDIR)/pangenomesim-b200: $(HOST)/main.cpp $(HOST)/model.cpp $(HOST_HDRS) $(LIBDIR)/libpgs.so
 	@mkdir -p $(BINDIR)
-	@if [ -n "$(HOST_SRCS)" ]; then \
-	  $(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude $(HOST_SRCS) -o $@ -L$(LIBDIR) -lpgs -Wl,-rpath,'$$ORIGIN/../lib' -lpthread ; \
-	else echo "host CLI sources not present yet"; fi
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude $(HOST)/main.cpp $(HOST)/model.cpp -o $@ -L$(LIBDIR) -lpgs \
+		-Wl,-rpath,'$$ORIGIN/../lib' -lpthread
+
+# the host model as a small shared library for Python callers (bench.py, tests): no CUDA inside
+$(LIBDIR)/libpgshost.so: $(HOST)/capi_host.cpp $(HOST)/model.cpp $(HOST_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -Wextra -Iinclude $(HOST)/capi_host.cpp $(HOST)/model.cpp -o $@
 
 clean:
 	rm -rf build $(LIBDIR) $(BINDIR)

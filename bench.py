@@ -46,29 +46,13 @@ def workload_name(n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic inputs: Kingman coalescent in the reference's pool layout (img.cxx:65-116)
+# synthetic inputs: the reference's own coalescent (create_coalescent, img.cxx:71-116) as drawn by
+# the retained host code for seed 1 (pangenomesim_b200/host/model.cpp, bit-exact against the
+# reference: tests/test_host_cli.py)
 
 def coalescent(n, seed, mut_rate):
-    rng = np.random.default_rng(seed)
-    N = 2 * n - 1
-    parent = np.full(N, -1, dtype=np.int32)
-    abs_time = np.zeros(N)
-    active = list(range(n))
-    t = 0.0
-    for i in range(n - 1):
-        k = n - i
-        p = n + i
-        a = active.pop(int(rng.integers(len(active))))
-        b = active.pop(int(rng.integers(len(active))))
-        parent[a] = parent[b] = p
-        active.append(p)
-        t += rng.exponential(1.0 / (k * (k - 1) / 2))
-        abs_time[p] = t
-    rate = np.zeros(N)
-    rate[:-1] = (abs_time[parent[:-1]] - abs_time[:-1]) * mut_rate
-    leaf = np.full(N, -1, dtype=np.int32)
-    leaf[:n] = np.arange(n)
-    return parent, rate, leaf
+    from pangenomesim_b200.capi import host_coalescent
+    return host_coalescent(n, seed, mut_rate)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -160,9 +144,29 @@ def cpu_baseline(sample_genes):
     else:
         nt, sec = port_run(n, L, sample_genes, CFG["mut_rate"], CFG["seed"])
         kind = "port"
-    return {"value": nt / sec, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"{sample_genes} of {CFG['core_size']} core genes over the full {n}-genome coalescent "
-                      f"(gene::gene + gene::mutate per branch, leaves discarded), {sec:.1f} s"}
+    out = {"value": nt / sec, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{sample_genes} of {CFG['core_size']} core genes over the full {n}-genome coalescent "
+                     f"(gene::gene + gene::mutate per branch, leaves discarded), {sec:.1f} s"}
+    # T1 of SURVEY.md §8d: the unmodified reference CLI end to end (all 104 output files) at config 2,
+    # the largest BASELINE config it can run
+    exe = ROOT / "oracle" / "_ref" / "pangenomesim"
+    if exe.exists():
+        import shutil
+        import tempfile
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        tmp = tempfile.mkdtemp(prefix="pgs_ref_", dir=base)
+        try:
+            t0 = time.perf_counter()
+            subprocess.run([str(exe), "-o", tmp, "-p", "num-genomes=100,core-size=1000,gene-length=1000,seed=1"],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+            wall = time.perf_counter() - t0
+            out["reference_cli_config2"] = {"value": 1e8 / wall, "unit": UNIT, "seconds": wall,
+                                            "what": "unmodified reference binary, end to end incl. 200 MB of output"}
+        except (subprocess.SubprocessError, OSError):
+            pass
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 def run_reference_arm(args):

@@ -237,3 +237,23 @@ class Engine:
         rep = OutputReport()
         self._check(self._lib.pgs_write_outputs(self._h, C.byref(spec), C.byref(rep)))
         return rep.as_dict()
+
+
+def host_coalescent(n: int, seed: int, mut_rate: float = 0.01, return_time: bool = False):
+    """The reference's coalescent (img.cxx:71-116) as drawn by the host program for `seed`:
+    returns parent[int32], rate[float64] = branch time * mut_rate, leaf_genome[int32]."""
+    path = _HERE / "lib" / "libpgshost.so"
+    if not path.exists():
+        raise PgsError(-6, f"{path} is missing: build it with `make cli`")
+    lib = C.CDLL(str(path))
+    lib.pgsh_coalescent.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    N = 2 * n - 1
+    parent = np.zeros(N, dtype=np.int32)
+    time = np.zeros(N, dtype=np.float64)
+    if lib.pgsh_coalescent(n, seed, _ptr(parent), _ptr(time)) != 0:
+        raise PgsError(-1, "pgsh_coalescent: bad arguments (n >= 1, seed >= 1)")
+    leaf = np.full(N, -1, dtype=np.int32)
+    leaf[:n] = np.arange(n)
+    if return_time:
+        return parent, time, leaf
+    return parent, time * float(np.float32(mut_rate)), leaf

@@ -17,8 +17,14 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <fcntl.h>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unistd.h>
 #include <vector>
 
@@ -319,24 +325,113 @@ struct Pinned {
 	}
 };
 
+// Small pool of writer threads: a chunk that has arrived in pinned memory is cut into ranges that
+// are pwrite()n in parallel (one thread cannot keep up with PCIe: ~3 GB/s into the page cache).
+class WritePool {
+  public:
+	explicit WritePool(unsigned n)
+	{
+		for (unsigned i = 0; i < n; i++) threads.emplace_back([this] { run(); });
+	}
+	~WritePool()
+	{
+		{
+			std::lock_guard<std::mutex> l(m);
+			stop = true;
+		}
+		cv.notify_all();
+		for (auto &t : threads) t.join();
+	}
+	void submit(std::function<void()> f)
+	{
+		{
+			std::lock_guard<std::mutex> l(m);
+			q.push_back(std::move(f));
+			pending++;
+		}
+		cv.notify_one();
+	}
+	void wait_all()
+	{
+		std::unique_lock<std::mutex> l(m);
+		done_cv.wait(l, [this] { return pending == 0; });
+	}
+
+  private:
+	void run()
+	{
+		for (;;) {
+			std::function<void()> f;
+			{
+				std::unique_lock<std::mutex> l(m);
+				cv.wait(l, [this] { return stop || !q.empty(); });
+				if (q.empty()) return;
+				f = std::move(q.front());
+				q.pop_front();
+			}
+			f();
+			{
+				std::lock_guard<std::mutex> l(m);
+				if (--pending == 0) done_cv.notify_all();
+			}
+		}
+	}
+	std::vector<std::thread> threads;
+	std::mutex m;
+	std::condition_variable cv, done_cv;
+	std::deque<std::function<void()>> q;
+	int pending = 0;
+	bool stop = false;
+};
+
 struct Writer {
 	Engine &e;
 	const pgs_output_spec *spec;
 	pgs_output_report rep{};
-	int fd = -1;
-	std::string open_name;
+	std::unique_ptr<WritePool> pool;
+	std::mutex err_mutex;
 	std::string error;
+	int maf_fd = -1; // a file that spans chunks stays open
+	std::string maf_name;
 
-	explicit Writer(Engine &eng, const pgs_output_spec *s) : e(eng), spec(s) {}
+	explicit Writer(Engine &eng, const pgs_output_spec *s) : e(eng), spec(s)
+	{
+		if (!(s->what & PGS_OUT_DISCARD) && !s->sink) {
+			unsigned n = std::thread::hardware_concurrency();
+			pool.reset(new WritePool(n < 2 ? 1 : (n > 8 ? 8 : n)));
+		}
+	}
 	~Writer() { close_file(); }
 
 	void close_file()
 	{
-		if (fd >= 0) ::close(fd);
-		fd = -1;
+		if (pool) pool->wait_all();
+		if (maf_fd >= 0) ::close(maf_fd);
+		maf_fd = -1;
 	}
-	// deliver len bytes of file `name` starting at file offset `offset`
-	bool put(const std::string &name, int64_t offset, const char *data, int64_t len)
+	void fail(const std::string &msg)
+	{
+		std::lock_guard<std::mutex> l(err_mutex);
+		if (error.empty()) error = msg;
+	}
+	static bool write_range(int fd, const char *data, int64_t len, int64_t offset, std::string &msg)
+	{
+		while (len > 0) {
+			const ssize_t w = ::pwrite(fd, data, (size_t)len, (off_t)offset);
+			if (w < 0) {
+				if (errno == EINTR) continue;
+				msg = std::strerror(errno);
+				return false;
+			}
+			data += w;
+			offset += w;
+			len -= w;
+		}
+		return true;
+	}
+	// deliver len bytes of file `name` starting at file offset `offset`; `whole` = the piece is the
+	// complete file.  File output is asynchronous: finish() waits for the chunk's writes.
+	bool put(const std::string &name, int64_t offset, const char *data, int64_t len, bool whole)
 	{
 		if (offset == 0) rep.files++;
 		rep.bytes += len;
@@ -348,28 +443,44 @@ struct Writer {
 			}
 			return true;
 		}
-		if (open_name != name) {
-			close_file();
-			const std::string path = std::string(spec->out_dir) + "/" + name;
-			fd = ::open(path.c_str(), O_WRONLY | O_CREAT | (offset == 0 ? O_TRUNC : 0), 0644);
-			if (fd < 0) {
+		const std::string path = std::string(spec->out_dir) + "/" + name;
+		constexpr int64_t kSlice = (int64_t)8 << 20;
+		if (whole && len <= 2 * kSlice) { // small complete file: one task opens, writes, closes
+			pool->submit([this, path, data, len] {
+				const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+				std::string msg;
+				if (fd < 0) return fail(path + ": " + std::strerror(errno));
+				if (!write_range(fd, data, len, 0, msg)) fail(path + ": " + msg);
+				::close(fd);
+			});
+			return true;
+		}
+		if (maf_name != name) { // a file that arrives in several pieces / slices
+			pool->wait_all();
+			if (maf_fd >= 0) ::close(maf_fd);
+			maf_fd = ::open(path.c_str(), O_WRONLY | O_CREAT | (offset == 0 ? O_TRUNC : 0), 0644);
+			if (maf_fd < 0) {
 				error = path + ": " + std::strerror(errno);
 				return false;
 			}
-			open_name = name;
+			maf_name = name;
 		}
-		while (len > 0) {
-			const ssize_t w = ::pwrite(fd, data, (size_t)len, (off_t)offset);
-			if (w < 0) {
-				if (errno == EINTR) continue;
-				error = open_name + ": " + std::strerror(errno);
-				return false;
-			}
-			data += w;
-			offset += w;
-			len -= w;
+		for (int64_t at = 0; at < len; at += kSlice) {
+			const int64_t now = std::min(kSlice, len - at);
+			const int fd = maf_fd;
+			pool->submit([this, fd, path, data, at, now, offset] {
+				std::string msg;
+				if (!write_range(fd, data + at, now, offset + at, msg)) fail(path + ": " + msg);
+			});
 		}
 		return true;
+	}
+	// all writes of the chunk have reached the kernel; its pinned buffer may be reused
+	bool finish()
+	{
+		if (pool) pool->wait_all();
+		std::lock_guard<std::mutex> l(err_mutex);
+		return error.empty();
 	}
 };
 
@@ -378,6 +489,7 @@ struct FilePiece {
 	int64_t file_offset; // offset inside the file
 	int64_t buf_offset;  // offset inside the staging buffer
 	int64_t len;
+	bool whole;          // the piece is the complete file
 };
 
 } // namespace
@@ -594,9 +706,9 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			return false;
 		}
 		for (const auto &pc : pending[s].pieces)
-			if (!w.put(pc.name, pc.file_offset, h_stage[s].p + pc.buf_offset, pc.len)) return false;
+			if (!w.put(pc.name, pc.file_offset, h_stage[s].p + pc.buf_offset, pc.len, pc.whole)) return false;
 		pending[s].live = false;
-		return true;
+		return w.finish();
 	};
 	// submit: record kernel-done, copy used bytes, mark pending; then drain the OTHER slot
 	auto submit = [&](int s, int64_t bytes, std::vector<FilePiece> &&pieces) -> bool {
@@ -661,7 +773,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				t, d_stage[slot].as<char>(), d_aux_a[slot].as<int64_t>(), d_aux_b[slot].as<int64_t>(), nrec);
 			records += nrec;
 		}
-		std::vector<FilePiece> pieces{{rf.name, 0, 0, total}};
+		std::vector<FilePiece> pieces{{rf.name, 0, 0, total, true}};
 		if (!submit(slot, total, std::move(pieces))) return fail_out(PGS_ERR_IO, w.error);
 		slot ^= 1;
 	}
@@ -678,7 +790,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				char name[64];
 				format_genome_name(j, name, sizeof name);
 				file_off.push_back(bytes);
-				pieces.push_back({std::string(name) + ".fasta", 0, bytes, genome_bytes[j]});
+				pieces.push_back({std::string(name) + ".fasta", 0, bytes, genome_bytes[j], true});
 				bytes += genome_bytes[j];
 				rows_prefix.push_back(rows_prefix.back() + genome_rows[j]);
 				j++;
@@ -738,7 +850,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 					d_aux_b[slot].as<int64_t>());
 				records += items;
 			}
-			std::vector<FilePiece> pieces{{"alignment.maf", file_pos, 0, bytes}};
+			std::vector<FilePiece> pieces{{"alignment.maf", file_pos, 0, bytes, false}};
 			file_pos += bytes;
 			if (!submit(slot, bytes, std::move(pieces))) return fail_out(PGS_ERR_IO, w.error);
 			slot ^= 1;

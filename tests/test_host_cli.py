@@ -118,3 +118,13 @@ def test_sequence_files_have_the_reference_layout(tmp_path, run, oracle):
         rate = time * float(np.float32(d.get("mut-rate", 0.01)))
         row = oracle.row(d["seed"], parent, rate, 0, len(parent) - 1, 0, L)
         assert seqs["genome001.0"] == oracle.unpack_ascii(row, L).decode()
+
+
+def test_host_library_coalescent_matches_reference_dump():
+    from pangenomesim_b200.capi import host_coalescent
+    trees = json.loads((GOLD / "trees.json").read_text())
+    for key, t in trees.items():
+        parent, time, leaf = host_coalescent(t["n"], t["seed"], return_time=True)
+        assert [int(x) for x in parent] == t["parent"], key
+        assert [float(x) for x in time] == [float.fromhex(h) for h in t["time_hex"]], key
+        assert list(leaf[:t["n"]]) == list(range(t["n"])) and (leaf[t["n"]:] == -1).all()
