@@ -217,3 +217,32 @@ def test_error_behaviour():
     e.sweep()
     assert e.copy_packed(0, 0) is not None
     e.close()
+
+
+def test_non_binary_trees_and_degenerate_inputs(oracle):
+    """the ABI takes any rooted tree: children are swept in sibling pairs (c0,c1), (c2,c3), (c4)"""
+    # root 0 with five children 1..5; node 2 has three children 6,7,8; node 8 has one child 9
+    parent = np.array([-1, 0, 0, 0, 0, 0, 2, 2, 2, 8], dtype=np.int32)
+    rate = np.array([0, 0.3, 0.2, 0.01, 1.5, 0.0, 0.4, 0.05, 0.6, 0.9])
+    leaf = np.array([-1, 0, -1, 1, 2, 3, 4, 5, -1, 6], dtype=np.int32)
+    seed, L = 77, 200
+    genes = (np.array([3, 9, 11], np.int64), np.array([0, 0, 2], np.int32), np.array([0, 1, 2, 4], np.int64),
+             np.array([-1, -1, 4, 6], np.int32))
+    with build(seed, L, parent, rate, leaf, genes) as e:
+        assert e.stats()["n_genomes"] == 7 and e.stats()["n_dense_genes"] == 2
+        check_all_nodes(e, oracle, seed, parent, rate, genes[0], genes[1], L, range(3))
+        assert e.copy_packed(1, 2) is None and e.copy_packed(9, 2) is not None and e.copy_packed(7, 2) is None
+    # a single genome: the tree is one node, nothing to sweep
+    with build(5, 100, [-1], [0.0], [0], core_table(3, 0)) as e:
+        assert e.stats()["levels"] == 0 and e.stats()["rows_written"] == 0
+        assert np.array_equal(e.copy_packed(0, 1), oracle.row(5, [-1], [0.0], 0, 0, 1, 100))
+        mm, sites = e.mismatch()
+        assert mm.shape == (1, 1) and mm[0, 0] == 0
+    # an empty gene table is legal and sweeps nothing
+    parent, rate, leaf = treegen.coalescent(4, seed=1)
+    with Engine(1, 64) as e:
+        e.set_tree(parent, rate, leaf)
+        e.set_genes([], [], [0], [])
+        e.sweep()
+        assert e.stats()["rows_total"] == 0
+        assert e.write_outputs(None, 31 | 32, [], [])["records"] == 0
