@@ -393,6 +393,26 @@ def main():
                "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) "
                        "into pinned host memory, bytes discarded (no filesystem)"}
 
+    # ---- strong-scaling leg (BASELINE config 4 as written: its 5000 genes sharded over the GPUs)
+    strong = None
+    if world > 1:
+        s0, s1 = shard_range(G, rank, world)
+        eng.set_genes(np.arange(s0, s1, dtype=np.int64), np.full(s1 - s0, root, np.int32),
+                      np.arange(s1 - s0 + 1, dtype=np.int64), np.full(s1 - s0, PGS_ALL_GENOMES, np.int32))
+        for _ in range(args.warmup):
+            eng.sweep()
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            eng.sweep()
+        ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / args.steps
+        strong = {"value": float(n) * G * L / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                  "what": f"the same {G} genes sharded {world}-way ({s1 - s0} genes on rank 0), no collective"}
+
     # ---- the path's only collective: all-reduce of the per-rank partial mismatch counts (K2),
     # untimed verification leg on a reduced problem (2000 genomes, 250 genes per rank)
     mm_leg = None
@@ -413,7 +433,7 @@ def main():
                        "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
-            "mismatch_allreduce": mm_leg,
+            "mismatch_allreduce": mm_leg, "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -68,6 +68,8 @@ void pgs_destroy(pgs_engine *h);
 /* Message of the last failing call on h (h may be NULL: last pgs_create failure of this thread). */
 const char *pgs_last_error(const pgs_engine *h);
 int pgs_abi_version(void);
+/* Number of usable CUDA devices (0 if none: there is no CPU path). */
+int pgs_device_count(void);
 
 /* Use a caller-owned stream (a cudaStream_t cast to void*; NULL = the engine's own stream). */
 int pgs_set_stream(pgs_engine *h, void *cuda_stream);
@@ -136,6 +138,18 @@ int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
 #define PGS_OUT_ALL 31u
 #define PGS_OUT_DISCARD 32u /* produce, copy to pinned host memory, then drop (benchmarking) */
 
+/* Sharded output: engines that each hold a contiguous slice of the gene table fill disjoint byte
+ * ranges of the same genomeNNN.fasta / alignment.maf.  The caller creates (truncates) the files,
+ * asks every engine for its sizes (pgs_output_sizes), prefix-sums them over the engines and
+ * passes the resulting offsets.  ref/core/accessory.fasta are then written by the caller from
+ * pgs_copy_origin_ascii. */
+typedef struct pgs_shard_layout {
+	const int64_t *genome_offset;     /* [n_genomes] offset of this engine's first record in genomeNNN.fasta */
+	int64_t maf_offset;               /* offset of this engine's first block in alignment.maf; 0 = writes the header */
+	const int64_t *genome_gene_total; /* [n_genomes] genes carried by each genome over ALL engines (MAF size field) */
+	int64_t n_ref_total;              /* reference genes over ALL engines (MAF size field of genomeref) */
+} pgs_shard_layout;
+
 typedef struct pgs_output_spec {
 	const char *out_dir;      /* files are created in out_dir (must exist); NULL with a sink / DISCARD */
 	uint32_t what;            /* PGS_OUT_* */
@@ -147,6 +161,7 @@ typedef struct pgs_output_spec {
 	 * data is pinned host memory valid during the call.  Return non-zero to abort. */
 	int (*sink)(void *user, const char *file_name, int64_t offset, const char *data, int64_t len);
 	void *sink_user;
+	const pgs_shard_layout *shard; /* NULL: this engine holds the whole gene table */
 } pgs_output_spec;
 
 typedef struct pgs_output_report {
@@ -156,6 +171,13 @@ typedef struct pgs_output_report {
 } pgs_output_report;
 
 int pgs_write_outputs(pgs_engine *h, const pgs_output_spec *spec, pgs_output_report *report);
+
+/* Bytes this engine will contribute to every genomeNNN.fasta (genome_bytes[n_genomes]) and to
+ * alignment.maf (*maf_bytes, including the file header iff spec->shard is NULL or has maf_offset 0).
+ * spec->shard may carry only genome_gene_total / n_ref_total at this point. */
+int pgs_output_sizes(pgs_engine *h, const pgs_output_spec *spec, int64_t *genome_bytes, int64_t *maf_bytes);
+/* The gene's sequence at its origin node (its genomeref record) as gene_length ASCII bases. */
+int pgs_copy_origin_ascii(pgs_engine *h, int64_t gene_index, char *dst);
 
 /* genome_name of the reference (util.cxx:15-27) with the >= 1000 genomes fix of SURVEY.md H5:
  * "genome" + zero-padded(3) (index+1), "genomeref" for -1.  Returns the length written. */

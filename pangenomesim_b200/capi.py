@@ -45,10 +45,15 @@ class Stats(C.Structure):
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64)
 
 
+class ShardLayout(C.Structure):
+    _fields_ = [("genome_offset", C.POINTER(C.c_int64)), ("maf_offset", C.c_int64),
+                ("genome_gene_total", C.POINTER(C.c_int64)), ("n_ref_total", C.c_int64)]
+
+
 class OutputSpec(C.Structure):
     _fields_ = [("out_dir", C.c_char_p), ("what", C.c_uint32), ("n_ref_core", C.c_int64),
                 ("ref_core", C.POINTER(C.c_int64)), ("n_ref_acc", C.c_int64), ("ref_acc", C.POINTER(C.c_int64)),
-                ("sink", SINK_FN), ("sink_user", C.c_void_p)]
+                ("sink", SINK_FN), ("sink_user", C.c_void_p), ("shard", C.POINTER(ShardLayout))]
 
 
 class OutputReport(C.Structure):
@@ -74,6 +79,7 @@ def load_library():
     lib = C.CDLL(str(path))
     P = C.POINTER
     lib.pgs_abi_version.restype = C.c_int
+    lib.pgs_device_count.restype = C.c_int
     lib.pgs_last_error.restype = C.c_char_p
     lib.pgs_last_error.argtypes = [C.c_void_p]
     lib.pgs_create.argtypes = [P(_Config), P(C.c_void_p)]
@@ -88,6 +94,8 @@ def load_library():
     lib.pgs_mismatch.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
     lib.pgs_mismatch_device.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
     lib.pgs_write_outputs.argtypes = [C.c_void_p, P(OutputSpec), P(OutputReport)]
+    lib.pgs_output_sizes.argtypes = [C.c_void_p, P(OutputSpec), C.c_void_p, P(C.c_int64)]
+    lib.pgs_copy_origin_ascii.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]
     lib.pgs_genome_name.argtypes = [C.c_int64, C.c_char_p, C.c_size_t]
     lib.pgs_copy_packed.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
     lib.pgs_copy_dense.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -215,10 +223,57 @@ class Engine:
         self._check(self._lib.pgs_get_edge_table(self._h, node, _ptr(H), C.byref(k)))
         return H, k.value
 
-    def write_outputs(self, out_dir=None, what=OUT_ALL, ref_core=(), ref_acc=(), sink=None):
+    @staticmethod
+    def _shard(genome_offset, maf_offset, genome_gene_total, n_ref_total):
+        keep = []
+        sh = ShardLayout()
+        if genome_offset is not None:
+            a = np.ascontiguousarray(genome_offset, dtype=np.int64)
+            keep.append(a)
+            sh.genome_offset = a.ctypes.data_as(C.POINTER(C.c_int64))
+        b = np.ascontiguousarray(genome_gene_total, dtype=np.int64)
+        keep.append(b)
+        sh.genome_gene_total = b.ctypes.data_as(C.POINTER(C.c_int64))
+        sh.maf_offset = maf_offset
+        sh.n_ref_total = n_ref_total
+        return sh, keep
+
+    def output_sizes(self, n_ref_core=0, n_ref_acc=0, shard=None):
+        """(bytes per genomeNNN.fasta [n_genomes], bytes of alignment.maf) this engine will write;
+        shard = dict(maf_offset=, genome_gene_total=, n_ref_total=) for a sliced gene table."""
+        spec = OutputSpec()
+        spec.what = OUT_GENOMES | OUT_MAF
+        dummy = np.zeros(max(n_ref_core, n_ref_acc, 1), dtype=np.int64)
+        spec.n_ref_core, spec.n_ref_acc = 0, 0
+        keep = None
+        if shard is not None:
+            sh, keep = self._shard(None, shard.get("maf_offset", 0), shard["genome_gene_total"], shard["n_ref_total"])
+            spec.shard = C.pointer(sh)
+        else:
+            # ref_size only depends on the counts: pass index lists of the right length
+            idx = np.zeros(n_ref_core + n_ref_acc, dtype=np.int64)
+            spec.n_ref_core = len(idx)
+            spec.ref_core = idx.ctypes.data_as(C.POINTER(C.c_int64))
+        gb = np.zeros(self.n_genomes, dtype=np.int64)
+        mb = C.c_int64()
+        self._check(self._lib.pgs_output_sizes(self._h, C.byref(spec), _ptr(gb), C.byref(mb)))
+        del dummy, keep
+        return gb, mb.value
+
+    def copy_origin_ascii(self, gene_index: int) -> bytes:
+        buf = C.create_string_buffer(self.gene_length)
+        self._check(self._lib.pgs_copy_origin_ascii(self._h, gene_index, buf))
+        return buf.raw
+
+    def write_outputs(self, out_dir=None, what=OUT_ALL, ref_core=(), ref_acc=(), sink=None, shard=None):
         rc_arr = np.ascontiguousarray(ref_core, dtype=np.int64)
         ra_arr = np.ascontiguousarray(ref_acc, dtype=np.int64)
         spec = OutputSpec()
+        keep = None
+        if shard is not None:
+            sh, keep = self._shard(shard["genome_offset"], shard["maf_offset"], shard["genome_gene_total"],
+                                   shard["n_ref_total"])
+            spec.shard = C.pointer(sh)
         spec.out_dir = str(out_dir).encode() if out_dir is not None else None
         spec.what = what
         spec.n_ref_core = len(rc_arr)

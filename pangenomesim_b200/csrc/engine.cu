@@ -134,6 +134,16 @@ int pgs_abi_version(void)
 	return PGS_ABI_VERSION;
 }
 
+int pgs_device_count(void)
+{
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return count;
+}
+
 const char *pgs_last_error(const pgs_engine *h)
 {
 	return h ? h->e.err.c_str() : pgs::g_create_error.c_str();
@@ -657,6 +667,31 @@ int pgs_write_outputs(pgs_engine *h, const pgs_output_spec *spec, pgs_output_rep
 	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_write_outputs: call pgs_sweep first");
 	if (!spec) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: null spec");
 	return pgs::write_outputs(e, spec, report);
+}
+
+int pgs_output_sizes(pgs_engine *h, const pgs_output_spec *spec, int64_t *genome_bytes, int64_t *maf_bytes)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.have_genes) return e.fail(PGS_ERR_STATE, "pgs_output_sizes: call pgs_set_genes first");
+	if (!spec) return e.fail(PGS_ERR_ARG, "pgs_output_sizes: null spec");
+	if (spec->shard && !spec->shard->genome_gene_total) return e.fail(PGS_ERR_ARG, "pgs_output_sizes: shard layout without totals");
+	pgs_shard_layout tmp;
+	pgs_output_spec local = *spec;
+	std::vector<int64_t> zeros;
+	if (spec->shard && !spec->shard->genome_offset) { // offsets are not known yet: that is what the caller is computing
+		tmp = *spec->shard;
+		zeros.assign(e.n_genomes, 0);
+		tmp.genome_offset = zeros.data();
+		local.shard = &tmp;
+	}
+	return pgs::output_sizes(e, &local, genome_bytes, maf_bytes);
+}
+
+int pgs_copy_origin_ascii(pgs_engine *h, int64_t gene_index, char *dst)
+{
+	ENGINE_OR_RETURN(h);
+	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_copy_origin_ascii: call pgs_sweep first");
+	return pgs::copy_origin_ascii(e, gene_index, dst);
 }
 
 int pgs_genome_name(int64_t genome_index, char *dst, size_t cap)

@@ -84,6 +84,8 @@ struct Engine {
 
 // format.cu
 int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report);
+int output_sizes(Engine &e, const pgs_output_spec *spec, int64_t *genome_bytes, int64_t *maf_bytes);
+int copy_origin_ascii(Engine &e, int64_t gene_index, char *dst);
 int format_genome_name(int64_t genome_index, char *dst, size_t cap);
 
 } // namespace pgs

@@ -445,12 +445,14 @@ struct Writer {
 		}
 		const std::string path = std::string(spec->out_dir) + "/" + name;
 		constexpr int64_t kSlice = (int64_t)8 << 20;
-		if (whole && len <= 2 * kSlice) { // small complete file: one task opens, writes, closes
-			pool->submit([this, path, data, len] {
-				const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+		// with a shard layout several engines fill one file: never truncate (the caller created it)
+		const int trunc = (offset == 0 && !spec->shard) ? O_TRUNC : 0;
+		if ((whole || spec->shard) && len <= 2 * kSlice) { // small piece: one task opens, writes, closes
+			pool->submit([this, path, data, len, offset, trunc] {
+				const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | trunc, 0644);
 				std::string msg;
 				if (fd < 0) return fail(path + ": " + std::strerror(errno));
-				if (!write_range(fd, data, len, 0, msg)) fail(path + ": " + msg);
+				if (!write_range(fd, data, len, offset, msg)) fail(path + ": " + msg);
 				::close(fd);
 			});
 			return true;
@@ -458,7 +460,7 @@ struct Writer {
 		if (maf_name != name) { // a file that arrives in several pieces / slices
 			pool->wait_all();
 			if (maf_fd >= 0) ::close(maf_fd);
-			maf_fd = ::open(path.c_str(), O_WRONLY | O_CREAT | (offset == 0 ? O_TRUNC : 0), 0644);
+			maf_fd = ::open(path.c_str(), O_WRONLY | O_CREAT | trunc, 0644);
 			if (maf_fd < 0) {
 				error = path + ": " + std::strerror(errno);
 				return false;
@@ -494,13 +496,21 @@ struct FilePiece {
 
 } // namespace
 
-int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report)
+// Host-side layout of the text outputs of one engine: digit tables, closed-form offsets, sizes.
+struct OutputPlan {
+	std::vector<int32_t> dense_before;
+	std::vector<int64_t> dense_digits_before, sp_digits, all_prefix, carrier_prefix, genome_count;
+	std::vector<uint32_t> origin_row;
+	std::vector<int> id_digits;
+	std::vector<int64_t> genome_bytes, genome_rows, maf_lines, maf_bytes;
+	int64_t ref_size = 0;
+};
+
+static int build_output_plan(Engine &e, const pgs_output_spec *spec, OutputPlan &p)
 {
-	const auto wall0 = std::chrono::steady_clock::now();
-	if (!spec->sink && !spec->out_dir && !(spec->what & PGS_OUT_DISCARD))
-		return e.fail(PGS_ERR_ARG, "pgs_write_outputs: neither out_dir nor sink");
 	const int64_t G = e.n_genes, D = (int64_t)e.dense_gid.size(), L = e.cfg.gene_length;
 	const int32_t N = e.n_nodes, n = e.n_genomes;
+	const pgs_shard_layout *shard = spec->shard;
 	for (int pass = 0; pass < 2; pass++) {
 		const int64_t cnt = pass ? spec->n_ref_acc : spec->n_ref_core;
 		const int64_t *lst = pass ? spec->ref_acc : spec->ref_core;
@@ -508,56 +518,139 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		for (int64_t i = 0; i < cnt; i++)
 			if (lst[i] < 0 || lst[i] >= G) return e.fail(PGS_ERR_ARG, "pgs_write_outputs: reference gene index out of range");
 	}
+	if (shard && (!shard->genome_offset || !shard->genome_gene_total))
+		return e.fail(PGS_ERR_ARG, "pgs_write_outputs: incomplete shard layout");
 
-	// ---- tables (host), uploaded once per call
-	std::vector<int32_t> dense_before(G + 1, 0);
-	std::vector<int64_t> dense_digits_before(G + 1, 0);
-	std::vector<uint32_t> origin_row(G, kNoRow);
-	std::vector<int> id_digits(G);
+	p.dense_before.assign(G + 1, 0);
+	p.dense_digits_before.assign(G + 1, 0);
+	p.origin_row.assign(G, kNoRow);
+	p.id_digits.resize(G);
 	for (int64_t g = 0; g < G; g++) {
-		id_digits[g] = dec_digits((uint64_t)e.gene_id[g]);
+		p.id_digits[g] = dec_digits((uint64_t)e.gene_id[g]);
 		const bool dn = e.dense_slot[g] >= 0;
-		dense_before[g + 1] = dense_before[g] + (dn ? 1 : 0);
-		dense_digits_before[g + 1] = dense_digits_before[g] + (dn ? id_digits[g] : 0);
+		p.dense_before[g + 1] = p.dense_before[g] + (dn ? 1 : 0);
+		p.dense_digits_before[g + 1] = p.dense_digits_before[g] + (dn ? p.id_digits[g] : 0);
 		const int64_t r = e.row_index(e.origin[g], g);
-		if (r >= 0) origin_row[g] = (uint32_t)r;
+		if (r >= 0) p.origin_row[g] = (uint32_t)r;
 	}
-	std::vector<int64_t> sp_digits(e.sp_gene.size() + N, 0);
+	p.sp_digits.assign(e.sp_gene.size() + N, 0);
 	for (int32_t v = 0; v < N; v++) {
 		int64_t acc = 0;
 		const int64_t base = e.sp_off[v] + v;
 		for (int64_t j = e.sp_off[v]; j < e.sp_off[v + 1]; j++) {
-			sp_digits[base + (j - e.sp_off[v])] = acc;
-			acc += id_digits[e.sp_gene[j]];
+			p.sp_digits[base + (j - e.sp_off[v])] = acc;
+			acc += p.id_digits[e.sp_gene[j]];
 		}
-		sp_digits[base + (e.sp_off[v + 1] - e.sp_off[v])] = acc;
+		p.sp_digits[base + (e.sp_off[v + 1] - e.sp_off[v])] = acc;
 	}
-	// MAF tables
+	// genes per genome over the whole alignment (all shards): the MAF "source size" field
+	p.genome_count = shard ? std::vector<int64_t>(shard->genome_gene_total, shard->genome_gene_total + n) : e.genome_gene_count;
 	auto carrier_term = [&](int32_t genome) {
-		return (int64_t)genome_name_len(genome) + dec_digits((uint64_t)(e.genome_gene_count[genome] * L));
+		return (int64_t)genome_name_len(genome) + dec_digits((uint64_t)(p.genome_count[genome] * L));
 	};
-	std::vector<int64_t> all_prefix(n + 1, 0);
-	for (int32_t i = 0; i < n; i++) all_prefix[i + 1] = all_prefix[i] + carrier_term(e.all_order[i]);
-	std::vector<int64_t> carrier_prefix(e.carrier_genome.size() + G + 1, 0);
+	p.all_prefix.assign(n + 1, 0);
+	for (int32_t i = 0; i < n; i++) p.all_prefix[i + 1] = p.all_prefix[i] + carrier_term(e.all_order[i]);
+	p.carrier_prefix.assign(e.carrier_genome.size() + G + 1, 0);
 	for (int64_t g = 0; g < G; g++) {
 		int64_t acc = 0;
 		const int64_t base = e.carrier_off[g] + g;
 		for (int64_t k = e.carrier_off[g]; k < e.carrier_off[g + 1]; k++) {
-			carrier_prefix[base + (k - e.carrier_off[g])] = acc;
+			p.carrier_prefix[base + (k - e.carrier_off[g])] = acc;
 			acc += carrier_term(e.carrier_genome[k]);
 		}
-		carrier_prefix[base + (e.carrier_off[g + 1] - e.carrier_off[g])] = acc;
+		p.carrier_prefix[base + (e.carrier_off[g + 1] - e.carrier_off[g])] = acc;
 	}
-	const int64_t ref_size = (spec->n_ref_core + spec->n_ref_acc) * L;
+	p.ref_size = (shard ? shard->n_ref_total : spec->n_ref_core + spec->n_ref_acc) * L;
+
+	// genome i: every carried gene contributes name_len + L + 4 + digits(gene_id)
+	p.genome_bytes.resize(n);
+	p.genome_rows.resize(n);
+	for (int32_t i = 0; i < n; i++) {
+		const int32_t v = e.genome_leaf[i];
+		const int64_t ms = e.sp_off[v + 1] - e.sp_off[v];
+		p.genome_rows[i] = D + ms;
+		p.genome_bytes[i] = (D + ms) * (genome_name_len(i) + L + 4) + p.dense_digits_before[G] + p.sp_digits[e.sp_off[v] + v + ms];
+	}
+	// MAF block of gene g (only genes carried by at least one genome and having rows)
+	const int ld = dec_digits((uint64_t)L);
+	const int rsd = dec_digits((uint64_t)p.ref_size);
+	p.maf_lines.assign(G, 0);
+	p.maf_bytes.assign(G, 0);
+	for (int64_t g = 0; g < G; g++) {
+		const bool dn = e.dense_slot[g] >= 0;
+		const int64_t nc = dn ? n : e.carrier_off[g + 1] - e.carrier_off[g];
+		if (nc == 0 || p.origin_row[g] == kNoRow) continue;
+		const int64_t pre = dn ? p.all_prefix[n] : p.carrier_prefix[e.carrier_off[g] + g + nc];
+		const int64_t ref_len = 2 + 9 + 1 + p.id_digits[g] + 3 + ld + 3 + rsd + 1 + L + 1;
+		p.maf_lines[g] = nc + 1;
+		p.maf_bytes[g] = 2 + ref_len + nc * (p.id_digits[g] + ld + L + 11) + pre + 1;
+	}
+	return PGS_OK;
+}
+
+static const char kMafHeader[] = "##maf version=1 program=pangenomesim\n"; // pangenomesim.cxx:240
+
+int output_sizes(Engine &e, const pgs_output_spec *spec, int64_t *genome_bytes, int64_t *maf_bytes)
+{
+	OutputPlan p;
+	int rc = build_output_plan(e, spec, p);
+	if (rc) return rc;
+	if (genome_bytes) std::copy(p.genome_bytes.begin(), p.genome_bytes.end(), genome_bytes);
+	if (maf_bytes) {
+		int64_t total = (!spec->shard || spec->shard->maf_offset == 0) ? (int64_t)sizeof(kMafHeader) - 1 : 0;
+		for (auto b : p.maf_bytes) total += b;
+		*maf_bytes = total;
+	}
+	return PGS_OK;
+}
+
+int copy_origin_ascii(Engine &e, int64_t gene_index, char *dst)
+{
+	if (gene_index < 0 || gene_index >= e.n_genes || !dst) return e.fail(PGS_ERR_ARG, "pgs_copy_origin_ascii: bad argument");
+	const int64_t row = e.row_index(e.origin[gene_index], gene_index);
+	if (row < 0) return e.fail(PGS_ERR_ARG, "pgs_copy_origin_ascii: the gene has no rows");
+	std::vector<uint32_t> words((size_t)e.blocks * 4);
+	cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce == cudaSuccess)
+		ce = cudaMemcpy(words.data(), e.tables.rows + row * e.blocks, (size_t)e.blocks * 16, cudaMemcpyDeviceToHost);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_copy_origin_ascii");
+	for (int64_t s = 0; s < e.cfg.gene_length; s++) dst[s] = "ACGT"[(words[s >> 4] >> (2 * (s & 15))) & 3u];
+	return PGS_OK;
+}
+
+int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report)
+{
+	const auto wall0 = std::chrono::steady_clock::now();
+	if (!spec->sink && !spec->out_dir && !(spec->what & PGS_OUT_DISCARD))
+		return e.fail(PGS_ERR_ARG, "pgs_write_outputs: neither out_dir nor sink");
+	const int64_t G = e.n_genes, D = (int64_t)e.dense_gid.size(), L = e.cfg.gene_length;
+	const int32_t n = e.n_genomes;
+	const pgs_shard_layout *shard = spec->shard;
+	if (shard && (spec->what & (PGS_OUT_REF | PGS_OUT_CORE | PGS_OUT_ACCESSORY)))
+		return e.fail(PGS_ERR_ARG, "pgs_write_outputs: reference files are written by the host in sharded mode (pgs_copy_origin_ascii)");
+	OutputPlan plan;
+	int rc = build_output_plan(e, spec, plan);
+	if (rc) return rc;
+	auto &dense_before = plan.dense_before;
+	auto &dense_digits_before = plan.dense_digits_before;
+	auto &sp_digits = plan.sp_digits;
+	auto &all_prefix = plan.all_prefix;
+	auto &carrier_prefix = plan.carrier_prefix;
+	auto &origin_row = plan.origin_row;
+	auto &id_digits = plan.id_digits;
+	auto &genome_bytes = plan.genome_bytes;
+	auto &genome_rows = plan.genome_rows;
+	auto &maf_lines = plan.maf_lines;
+	auto &maf_bytes = plan.maf_bytes;
+	const int64_t ref_size = plan.ref_size;
 
 	DevBuf d_genome_leaf, d_genome_count, d_sp_off, d_sp_gene, d_sp_digits, d_dense_slot, d_dense_gene,
 		d_dense_before, d_dense_digits_before, d_gene_id, d_origin_row, d_carrier_off, d_carrier_genome,
 		d_carrier_prefix, d_all_order, d_all_prefix;
-	int rc;
 #define UP(buf, vec) \
 	if ((rc = e.upload(buf, (vec).data(), sizeof((vec)[0]) * (vec).size(), #vec))) return rc
 	UP(d_genome_leaf, e.genome_leaf);
-	UP(d_genome_count, e.genome_gene_count);
+	UP(d_genome_count, plan.genome_count);
 	UP(d_sp_off, e.sp_off);
 	UP(d_sp_gene, e.sp_gene);
 	UP(d_sp_digits, sp_digits);
@@ -598,29 +691,6 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	mt.all_prefix = d_all_prefix.as<int64_t>();
 	mt.ref_size = ref_size;
 	mt.n_genomes = n;
-
-	// ---- sizes of the big files
-	// genome i: every carried gene contributes name_len + L + 4 + digits(gene_id)
-	std::vector<int64_t> genome_bytes(n), genome_rows(n);
-	for (int32_t i = 0; i < n; i++) {
-		const int32_t v = e.genome_leaf[i];
-		const int64_t ms = e.sp_off[v + 1] - e.sp_off[v];
-		genome_rows[i] = D + ms;
-		genome_bytes[i] = (D + ms) * (genome_name_len(i) + L + 4) + dense_digits_before[G] + sp_digits[e.sp_off[v] + v + ms];
-	}
-	// MAF block of gene g (only genes carried by at least one genome and having rows)
-	const int ld = dec_digits((uint64_t)L);
-	const int rsd = dec_digits((uint64_t)ref_size);
-	std::vector<int64_t> maf_lines(G, 0), maf_bytes(G, 0);
-	for (int64_t g = 0; g < G; g++) {
-		const bool dn = e.dense_slot[g] >= 0;
-		const int64_t nc = dn ? n : e.carrier_off[g + 1] - e.carrier_off[g];
-		if (nc == 0 || origin_row[g] == kNoRow) continue;
-		const int64_t pre = dn ? all_prefix[n] : carrier_prefix[e.carrier_off[g] + g + nc];
-		const int64_t ref_len = 2 + 9 + 1 + id_digits[g] + 3 + ld + 3 + rsd + 1 + L + 1;
-		maf_lines[g] = nc + 1;
-		maf_bytes[g] = 2 + ref_len + nc * (id_digits[g] + ld + L + 11) + pre + 1;
-	}
 
 	// ---- staging: two device buffers + two pinned buffers
 	int64_t stage = (int64_t)64 << 20;
@@ -790,7 +860,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				char name[64];
 				format_genome_name(j, name, sizeof name);
 				file_off.push_back(bytes);
-				pieces.push_back({std::string(name) + ".fasta", 0, bytes, genome_bytes[j], true});
+				pieces.push_back({std::string(name) + ".fasta", shard ? shard->genome_offset[j] : 0, bytes, genome_bytes[j], !shard});
 				bytes += genome_bytes[j];
 				rows_prefix.push_back(rows_prefix.back() + genome_rows[j]);
 				j++;
@@ -814,9 +884,10 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 
 	// ---- alignment.maf
 	if (spec->what & PGS_OUT_MAF) {
-		static const char header[] = "##maf version=1 program=pangenomesim\n"; // pangenomesim.cxx:240
-		const int64_t hlen = (int64_t)sizeof(header) - 1;
-		int64_t file_pos = 0;
+		const char *header = kMafHeader;
+		const bool with_header = !shard || shard->maf_offset == 0;
+		const int64_t hlen = with_header ? (int64_t)sizeof(kMafHeader) - 1 : 0;
+		int64_t file_pos = shard ? shard->maf_offset : 0;
 		int64_t g = 0;
 		bool first = true;
 		while (g < G || first) {
@@ -830,7 +901,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				g2++;
 			}
 			begin_chunk(slot);
-			if (first) {
+			if (first && hlen > 0) {
 				ce = cudaMemcpyAsync(d_stage[slot].p, header, (size_t)hlen, cudaMemcpyHostToDevice, e.stream);
 				if (ce != cudaSuccess) {
 					cleanup();

@@ -24,6 +24,7 @@
 #include <regex>
 #include <sstream>
 #include <thread>
+#include <unordered_map>
 
 extern "C" {
 #include <err.h>
@@ -54,7 +55,8 @@ static bool verbose = false;
 		"                           genefrequency.gfs / panmatrix.tsv match the reference bit for bit\n"
 		"      --rng-fast           Never replay (default for large runs)\n"
 		"      --no-sequences       Host-side files only (no GPU needed)\n"
-		"      --device N           CUDA device ordinal\n\n"
+		"      --device N           CUDA device ordinal\n"
+		"      --devices N          Shard the genes over N engines (devices 0..N-1, wrapping around)\n\n"
 		"Simulation Parameters:\n"
 		"  core-size=INT            Minimum size of the core genome\n"
 		"  gene-length=INT          Length of a gene\n"
@@ -166,12 +168,13 @@ int main(int argc, char *argv[])
 		{"param", required_argument, nullptr, 'p'}, {"out-dir", required_argument, nullptr, 'o'},
 		{"verbose", no_argument, nullptr, 'v'},     {"rng-compat", no_argument, nullptr, 0},
 		{"rng-fast", no_argument, nullptr, 0},      {"no-sequences", no_argument, nullptr, 0},
-		{"device", required_argument, nullptr, 0},  {nullptr, 0, nullptr, 0}};
+		{"device", required_argument, nullptr, 0},  {"devices", required_argument, nullptr, 0},
+		{nullptr, 0, nullptr, 0}};
 
 	Model model;
 	std::string out_dir = "./";
 	bool sequences = true;
-	int device = -1;
+	int device = -1, n_devices = 1;
 
 	for (;;) {
 		int index = 0;
@@ -190,6 +193,7 @@ int main(int argc, char *argv[])
 				if (name == "rng-fast") model.rng_mode = pgshost::RngMode::Fast;
 				if (name == "no-sequences") sequences = false;
 				if (name == "device") device = std::atoi(optarg);
+				if (name == "devices") n_devices = std::atoi(optarg);
 				break;
 			}
 			case 'o': out_dir = std::string(optarg) + "/"; break;
@@ -261,64 +265,169 @@ int main(int argc, char *argv[])
 	const auto t2 = std::chrono::steady_clock::now();
 
 	if (sequences) {
-		pgs_config cfg{};
-		cfg.seed = model.seed;
-		cfg.gene_length = (int64_t)model.gene_length;
-		cfg.device = device;
-		pgs_engine *h = nullptr;
-		if (pgs_create(&cfg, &h) != PGS_OK) errx(2, "%s", pgs_last_error(nullptr));
-		auto check = [&](int rc) {
-			if (rc < 0) errx(2, "%s", pgs_last_error(h));
-		};
 		const pgshost::Tree &t = model.tree;
-		const size_t N = t.nodes();
+		const size_t N = t.nodes(), G = model.genes.size();
 		std::vector<double> rate(N, 0.0);
 		std::vector<int32_t> leaf_genome(N, -1);
 		for (size_t v = 0; v < N; v++) {
 			rate[v] = t.time[v] * model.mut_rate; // img.cxx:218,286
 			if (v < n) leaf_genome[v] = (int32_t)v;
 		}
-		check(pgs_set_tree(h, (int32_t)N, t.parent.data(), rate.data(), leaf_genome.data()));
+		const int available = pgs_device_count();
+		if (available < 1) errx(2, "%s", "no usable CUDA device; this program has no CPU path for sequences");
+		if (n_devices < 1) n_devices = 1;
 
-		const size_t G = model.genes.size();
-		std::vector<int64_t> gene_id(G), carrier_off(G + 1, 0);
-		std::vector<int32_t> origin(G), carriers;
-		for (size_t k = 0; k < G; k++) {
-			const auto &g = model.genes[k];
-			gene_id[k] = g.id;
-			origin[k] = g.origin;
-			if (g.all && g.origin == t.root()) {
-				carriers.push_back(PGS_ALL_GENOMES);
-			} else if (g.all) {
-				carriers.insert(carriers.end(), model.all_order.begin(), model.all_order.end());
-			} else {
-				carriers.insert(carriers.end(), g.carriers.begin(), g.carriers.end());
+		// contiguous slices of the gene table, balanced by the rows they occupy
+		std::vector<size_t> cut(n_devices + 1, G);
+		{
+			std::vector<double> weight(G + 1, 0.0);
+			for (size_t k = 0; k < G; k++)
+				weight[k + 1] = weight[k] + (model.genes[k].all ? (double)N : (double)model.genes[k].carriers.size() * 2.0 + 1.0);
+			cut[0] = 0;
+			size_t k = 0;
+			for (int d = 1; d < n_devices; d++) {
+				while (k < G && weight[k] < weight[G] * d / n_devices) k++;
+				cut[d] = k;
 			}
-			carrier_off[k + 1] = (int64_t)carriers.size();
 		}
-		check(pgs_set_genes(h, (int64_t)G, gene_id.data(), origin.data(), carrier_off.data(), carriers.data(),
-							model.all_order.data()));
-		check(pgs_sweep(h));
-		pgs_output_spec spec{};
-		const std::string dir = out_dir.substr(0, out_dir.size() - 1);
-		spec.out_dir = dir.empty() ? "/" : dir.c_str();
-		spec.what = PGS_OUT_ALL;
-		spec.n_ref_core = (int64_t)model.ref_core.size();
-		spec.ref_core = model.ref_core.data();
-		spec.n_ref_acc = (int64_t)model.ref_acc.size();
-		spec.ref_acc = model.ref_acc.data();
-		pgs_output_report rep{};
-		check(pgs_write_outputs(h, &spec, &rep));
-		if (verbose) {
+		struct Shard {
+			pgs_engine *h = nullptr;
+			std::string error;
+			pgs_output_report rep{};
 			pgs_stats st{};
-			pgs_get_stats(h, &st);
-			std::fprintf(stderr,
-						 "sequences: %lld rows, K0 %.3f ms, K1 %.3f ms (%lld launches), K3 %.3f ms, %lld files, "
-						 "%lld bytes, output wall %.1f ms\n",
-						 (long long)st.rows_total, st.rootgen_ms, st.sweep_ms, (long long)st.kernel_launches,
-						 rep.device_ms, (long long)rep.files, (long long)rep.bytes, rep.wall_ms);
+			std::vector<int64_t> genome_bytes, genome_offset, ref_core, ref_acc;
+			int64_t maf_bytes = 0, maf_offset = 0;
+		};
+		std::vector<Shard> shards(n_devices);
+		auto each = [&](auto fn) { // run fn(d) for every shard on its own thread, stop on the first error
+			std::vector<std::thread> pool;
+			for (int d = 0; d < n_devices; d++) pool.emplace_back([&, d] { fn(d); });
+			for (auto &th : pool) th.join();
+			for (int d = 0; d < n_devices; d++)
+				if (!shards[d].error.empty()) errx(2, "device %d: %s", d, shards[d].error.c_str());
+		};
+		std::unordered_map<int64_t, std::pair<int, int64_t>> where; // gene table index -> (shard, local index)
+		each([&](int d) {
+			Shard &s = shards[d];
+			auto check = [&](int rc) {
+				if (rc < 0 && s.error.empty()) s.error = pgs_last_error(s.h);
+				return rc >= 0;
+			};
+			pgs_config cfg{};
+			cfg.seed = model.seed;
+			cfg.gene_length = (int64_t)model.gene_length;
+			cfg.device = device >= 0 && n_devices == 1 ? device : d % available;
+			if (pgs_create(&cfg, &s.h) != PGS_OK) {
+				s.error = pgs_last_error(nullptr);
+				return;
+			}
+			if (!check(pgs_set_tree(s.h, (int32_t)N, t.parent.data(), rate.data(), leaf_genome.data()))) return;
+			const size_t lo = cut[d], hi = cut[d + 1];
+			std::vector<int64_t> gene_id(hi - lo), carrier_off(hi - lo + 1, 0);
+			std::vector<int32_t> origin(hi - lo), carriers;
+			for (size_t k = lo; k < hi; k++) {
+				const auto &g = model.genes[k];
+				gene_id[k - lo] = g.id;
+				origin[k - lo] = g.origin;
+				if (g.all && g.origin == t.root())
+					carriers.push_back(PGS_ALL_GENOMES);
+				else if (g.all)
+					carriers.insert(carriers.end(), model.all_order.begin(), model.all_order.end());
+				else
+					carriers.insert(carriers.end(), g.carriers.begin(), g.carriers.end());
+				carrier_off[k - lo + 1] = (int64_t)carriers.size();
+			}
+			if (!check(pgs_set_genes(s.h, (int64_t)(hi - lo), gene_id.data(), origin.data(), carrier_off.data(),
+									 carriers.data(), model.all_order.data())))
+				return;
+			check(pgs_sweep(s.h));
+		});
+		for (int d = 0; d < n_devices; d++)
+			for (size_t k = cut[d]; k < cut[d + 1]; k++) where[(int64_t)k] = {d, (int64_t)(k - cut[d])};
+
+		const std::string dir = out_dir.substr(0, out_dir.size() - 1);
+		const std::string dir_c = dir.empty() ? "/" : dir;
+		if (n_devices == 1) {
+			Shard &s = shards[0];
+			pgs_output_spec spec{};
+			spec.out_dir = dir_c.c_str();
+			spec.what = PGS_OUT_ALL;
+			spec.n_ref_core = (int64_t)model.ref_core.size();
+			spec.ref_core = model.ref_core.data();
+			spec.n_ref_acc = (int64_t)model.ref_acc.size();
+			spec.ref_acc = model.ref_acc.data();
+			if (pgs_write_outputs(s.h, &spec, &s.rep) < 0) errx(2, "%s", pgs_last_error(s.h));
+		} else {
+			// several engines fill disjoint byte ranges of the same files
+			const int64_t n_ref_total = (int64_t)(model.ref_core.size() + model.ref_acc.size());
+			each([&](int d) {
+				Shard &s = shards[d];
+				pgs_shard_layout lay{};
+				lay.genome_gene_total = model.genome_gene_count.data();
+				lay.n_ref_total = n_ref_total;
+				lay.maf_offset = d; // only "is this the first shard" matters for the size
+				pgs_output_spec spec{};
+				spec.what = PGS_OUT_GENOMES | PGS_OUT_MAF;
+				spec.shard = &lay;
+				s.genome_bytes.assign(n, 0);
+				if (pgs_output_sizes(s.h, &spec, s.genome_bytes.data(), &s.maf_bytes) < 0) s.error = pgs_last_error(s.h);
+			});
+			std::vector<int64_t> at(n, 0);
+			int64_t maf_at = 0;
+			for (int d = 0; d < n_devices; d++) {
+				shards[d].genome_offset = at;
+				shards[d].maf_offset = maf_at;
+				for (size_t i = 0; i < n; i++) at[i] += shards[d].genome_bytes[i];
+				maf_at += shards[d].maf_bytes;
+			}
+			for (size_t i = 0; i < n; i++) open_out(out_dir + pgshost::genome_name((ssize_t)i) + ".fasta");
+			open_out(out_dir + "alignment.maf");
+			each([&](int d) {
+				Shard &s = shards[d];
+				pgs_shard_layout lay{};
+				lay.genome_offset = s.genome_offset.data();
+				lay.maf_offset = s.maf_offset;
+				lay.genome_gene_total = model.genome_gene_count.data();
+				lay.n_ref_total = n_ref_total;
+				pgs_output_spec spec{};
+				spec.out_dir = dir_c.c_str();
+				spec.what = PGS_OUT_GENOMES | PGS_OUT_MAF;
+				spec.shard = &lay;
+				if (pgs_write_outputs(s.h, &spec, &s.rep) < 0) s.error = pgs_last_error(s.h);
+			});
+			// ref.fasta = core.fasta + accessory.fasta, gene::to_fasta layout (gene.h:42-52)
+			std::string seq(model.gene_length, 'N');
+			auto record = [&](int64_t k) {
+				const auto w = where.at(k);
+				if (pgs_copy_origin_ascii(shards[w.first].h, w.second, &seq[0]) < 0) errx(2, "%s", pgs_last_error(shards[w.first].h));
+				return ">genomeref." + std::to_string(model.genes[k].id) + "\n" + seq + "\n";
+			};
+			std::ofstream ref = open_out(out_dir + "ref.fasta"), cor = open_out(out_dir + "core.fasta"),
+						  acc = open_out(out_dir + "accessory.fasta");
+			for (int64_t k : model.ref_core) {
+				const std::string r = record(k);
+				ref << r;
+				cor << r;
+			}
+			for (int64_t k : model.ref_acc) {
+				const std::string r = record(k);
+				ref << r;
+				acc << r;
+			}
 		}
-		pgs_destroy(h);
+		for (int d = 0; d < n_devices; d++) {
+			Shard &s = shards[d];
+			if (verbose) {
+				pgs_get_stats(s.h, &s.st);
+				std::fprintf(stderr,
+							 "device %d: genes [%zu,%zu), %lld rows, K0 %.3f ms, K1 %.3f ms (%lld launches), K3 %.3f ms, "
+							 "%lld files, %lld bytes, output wall %.1f ms\n",
+							 d, cut[d], cut[d + 1], (long long)s.st.rows_total, s.st.rootgen_ms, s.st.sweep_ms,
+							 (long long)s.st.kernel_launches, s.rep.device_ms, (long long)s.rep.files, (long long)s.rep.bytes,
+							 s.rep.wall_ms);
+			}
+			pgs_destroy(s.h);
+		}
 	}
 	if (verbose) {
 		const auto t3 = std::chrono::steady_clock::now();

@@ -137,3 +137,56 @@ def test_more_than_999_genomes_and_many_chunks(oracle):
     recs = got["genome1101.fasta"].split(b"\n")
     assert recs[2 * 37] == b">genome1101.37" and recs[2 * 37 + 1] == want
     e.close()
+
+
+def test_sharded_outputs_equal_single_engine(oracle, tmp_path):
+    """two engines that each hold a slice of the gene table fill disjoint byte ranges of the same
+    files (pgs_shard_layout); the result is byte-identical to one engine holding everything"""
+    n, L, seed = 13, 90, 21
+    parent, rate, leaf = treegen.coalescent(n, seed=5, mut_rate=0.2)
+    gene_id, origin, off, car = treegen.gene_table(parent, leaf, n_core=7, n_acc=20, seed=8)
+    G = len(gene_id)
+    below = treegen.leaves_below(parent, leaf)
+    total = np.zeros(n, dtype=np.int64)
+    for g in range(G):
+        c = car[off[g]:off[g + 1]]
+        for x in (below[int(origin[g])] if list(c) == [-1] else c):
+            total[int(x)] += 1
+    order = np.random.default_rng(3).permutation(n).astype(np.int32)
+    what = OUT_GENOMES | OUT_MAF
+
+    single = tmp_path / "single"
+    single.mkdir()
+    with Engine(seed, L) as e:
+        e.set_tree(parent, rate, leaf)
+        e.set_genes(gene_id, origin, off, car, all_order=order)
+        e.sweep()
+        e.write_outputs(single, what, list(range(G)), [])
+        ref_seq = {int(gene_id[g]): e.copy_origin_ascii(g) for g in range(G)}
+
+    cut = 11
+    parts = []
+    for lo, hi in ((0, cut), (cut, G)):
+        e = Engine(seed, L)
+        e.set_tree(parent, rate, leaf)
+        e.set_genes(gene_id[lo:hi], origin[lo:hi], off[lo:hi + 1] - off[lo], car[off[lo]:off[hi]], all_order=order)
+        e.sweep()
+        parts.append(e)
+    shard0 = dict(maf_offset=0, genome_gene_total=total, n_ref_total=G)
+    gb0, mb0 = parts[0].output_sizes(shard=shard0)
+    gb1, mb1 = parts[1].output_sizes(shard=dict(shard0, maf_offset=mb0))
+    sharded = tmp_path / "sharded"
+    sharded.mkdir()
+    for name in [genome_name(i) + ".fasta" for i in range(n)] + ["alignment.maf"]:
+        (sharded / name).write_bytes(b"")
+    parts[1].write_outputs(sharded, what, [], [], shard=dict(shard0, genome_offset=gb0, maf_offset=mb0))
+    parts[0].write_outputs(sharded, what, [], [], shard=dict(shard0, genome_offset=np.zeros(n, np.int64)))
+    for p in sorted(single.iterdir()):
+        assert (sharded / p.name).read_bytes() == p.read_bytes(), p.name
+    assert (sharded / "alignment.maf").stat().st_size == mb0 + mb1
+    # the host writes the reference files itself in sharded mode
+    for g in range(G):
+        eng, idx = (parts[0], g) if g < cut else (parts[1], g - cut)
+        assert eng.copy_origin_ascii(idx) == ref_seq[int(gene_id[g])]
+    for e in parts:
+        e.close()

@@ -128,3 +128,17 @@ def test_host_library_coalescent_matches_reference_dump():
         assert [int(x) for x in parent] == t["parent"], key
         assert [float(x) for x in time] == [float.fromhex(h) for h in t["time_hex"]], key
         assert list(leaf[:t["n"]]) == list(range(t["n"])) and (leaf[t["n"]:] == -1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("run,devices", [("acc_seed3", 2), ("safeguard_like", 3), ("config1_seed42", 8)])
+def test_sharded_cli_is_byte_identical(tmp_path, run, devices):
+    """--devices N shards the gene table over N engines (wrapping around the available GPUs);
+    every output file must equal the single-engine run byte for byte"""
+    params, _ = param_string(run)
+    run_cli(tmp_path / "one", params)
+    run_cli(tmp_path / "many", params, "--devices", str(devices))
+    names = sorted(p.name for p in (tmp_path / "one").iterdir())
+    assert sorted(p.name for p in (tmp_path / "many").iterdir()) == names
+    for name in names:
+        assert (tmp_path / "many" / name).read_bytes() == (tmp_path / "one" / name).read_bytes(), name
