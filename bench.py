@@ -39,6 +39,15 @@ UNIT = "leaf-nt/s"
 CFG = {"num_genomes": 10000, "core_size": 5000, "gene_length": 1000, "mut_rate": 0.01, "seed": 1}
 
 
+def _jsonable(x):
+    """numpy scalars / arrays that slipped into the result line"""
+    if isinstance(x, np.generic):
+        return x.item()
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    return str(x)
+
+
 def workload_name(n_gpus):
     return (f"config4: num-genomes={CFG['num_genomes']} core-size={CFG['core_size']}"
             f"{'x%d (one shard per GPU)' % n_gpus if n_gpus > 1 else ''} gene-length={CFG['gene_length']}"
@@ -245,7 +254,7 @@ def mismatch_allreduce_leg(torch, dist, Engine, rank, world, local):
     d = seen[v] + accb
     p = 0.75 * (1 - np.exp(-4 * d / 3))
     obs = part[0, 1].item() / S
-    ok = ok and abs(obs - p) < 5 * np.sqrt(p * (1 - p) / S) + 1e-9
+    ok = bool(ok and abs(obs - p) < 5 * np.sqrt(p * (1 - p) / S) + 1e-9)
     eng.close()
     return {"ok": ok, "n_genomes": n, "genes_per_rank": genes, "k2_ms": k2_ms, "allreduce_ms": ev0.elapsed_time(ev1),
             "bytes": int(part.numel() * 4), "pair01_observed": obs, "pair01_jc_expected": float(p)}
@@ -435,7 +444,7 @@ def main():
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
             "mismatch_allreduce": mm_leg, "strong_scaling": strong,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=_jsonable), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
