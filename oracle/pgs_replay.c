@@ -3,9 +3,10 @@
  * Host replay of the Philox-keyed Jukes-Cantor substitution scheme of DESIGN.md §3, written
  * from the specification; shares no source with the CUDA engine.  It replaces, for checking
  * purposes, the reference's gene::gene (gene.cxx:13-25) and gene::mutate (gene.cxx:27-61) by the
- * north_star's scheme: a counter-based generator keyed by (seed, edge, gene, site-block) and a
- * per-branch substitution probability p = 3/4 (1 - exp(-4/3 mu t)), uniform among the 3 other
- * bases.  Pinned by the Random123 Philox4x32-10 known-answer vectors (tests/test_oracle.py).
+ * north_star's scheme: a counter-based generator keyed by (seed, edge, gene, site-block) -- the
+ * decision word of a block is shared by a sibling pair of branches and two adjacent blocks, see
+ * oracle_mutate_block -- and a per-branch substitution probability p = 3/4 (1 - exp(-4/3 mu t)),
+ * uniform among the 3 other bases.  Pinned by the Random123 Philox4x32-10 known-answer vectors (tests/test_oracle.py).
  */
 #include "oracle.h"
 
