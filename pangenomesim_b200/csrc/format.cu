@@ -44,9 +44,15 @@ int format_genome_name(int64_t genome_index, char *dst, size_t cap)
 
 __host__ __device__ inline int dec_digits(uint64_t x)
 {
+	// 64-bit division is a long software routine on the GPU: stay in 32 bits whenever possible
 	int d = 1;
-	while (x >= 10) {
+	while (x > 0xFFFFFFFFull) {
 		x /= 10;
+		d++;
+	}
+	uint32_t y = (uint32_t)x;
+	while (y >= 10) {
+		y /= 10;
 		d++;
 	}
 	return d;
@@ -63,9 +69,16 @@ __device__ inline char *put_uint(char *p, uint64_t x, int min_digits)
 {
 	int d = dec_digits(x);
 	if (d < min_digits) d = min_digits;
-	for (int i = d - 1; i >= 0; i--) {
-		p[i] = (char)('0' + (int)(x % 10));
+	int i = d - 1;
+	while (x > 0xFFFFFFFFull) {
+		p[i--] = (char)('0' + (int)(x % 10));
 		x /= 10;
+	}
+	uint32_t y = (uint32_t)x; // division by the constant 10 is a multiply and a shift here
+	for (; i >= 0; i--) {
+		const uint32_t q = y / 10u;
+		p[i] = (char)('0' + (int)(y - q * 10u));
+		y = q;
 	}
 	return p + d;
 }
