@@ -56,6 +56,11 @@ typedef struct pgs_config {
 } pgs_config;
 
 #define PGS_FLAG_NO_GRAPH 1u /* launch the level sweep kernel by kernel instead of one CUDA graph */
+/* Keep the row of every internal node in memory (level-synchronous sweep).  Without this flag
+ * the dense genes are swept by the fused column walk, which only materialises what the outputs
+ * need: the rows of the genomes (leaves) and of the origins; pgs_copy_packed / pgs_copy_dense on
+ * any other node then fail with PGS_ERR_STATE. */
+#define PGS_FLAG_KEEP_INTERNAL 2u
 
 /* sentinel carrier entry: "every genome below the origin node carries the gene" */
 #define PGS_ALL_GENOMES (-1)
@@ -113,6 +118,9 @@ typedef struct pgs_stats {
 	int64_t levels;              /* tree levels below the root */
 	int64_t kernel_launches;     /* kernels launched by the last pgs_sweep */
 	int64_t device_bytes;        /* bytes of HBM held by the engine */
+	int64_t sweep_mode;          /* 0 = level-synchronous, 1 = fused column walk (dense genes) */
+	int64_t rows_stored;         /* rows K1 actually writes to memory */
+	int64_t rows_loaded;         /* rows K1 actually reads from memory */
 	double sweep_ms, rootgen_ms; /* device time of the last completed pgs_sweep (CUDA events) */
 	double mismatch_ms, format_ms;
 } pgs_stats;

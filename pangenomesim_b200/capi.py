@@ -17,6 +17,7 @@ _LIB = None
 
 PGS_ALL_GENOMES = -1
 PGS_FLAG_NO_GRAPH = 1
+PGS_FLAG_KEEP_INTERNAL = 2
 OUT_REF, OUT_CORE, OUT_ACCESSORY, OUT_GENOMES, OUT_MAF, OUT_ALL, OUT_DISCARD = 1, 2, 4, 8, 16, 31, 32
 
 
@@ -35,7 +36,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in (
         "n_nodes", "n_genomes", "n_genes", "n_dense_genes", "blocks_per_gene", "rows_total",
         "rows_written", "rows_read", "rows_origin", "leaf_nucleotides", "site_edges", "levels",
-        "kernel_launches", "device_bytes")] + [(k, C.c_double) for k in (
+        "kernel_launches", "device_bytes", "sweep_mode", "rows_stored", "rows_loaded")] + [(k, C.c_double) for k in (
         "sweep_ms", "rootgen_ms", "mismatch_ms", "format_ms")]
 
     def as_dict(self):

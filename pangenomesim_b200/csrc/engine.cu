@@ -71,7 +71,7 @@ int64_t Engine::device_bytes() const
 {
 	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
 						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch,
-						   &d_tab8};
+						   &d_tab8, &d_walk_steps, &d_walk_off};
 	int64_t s = 0;
 	for (auto b : all) s += (int64_t)b->bytes;
 	return s;
@@ -101,9 +101,17 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 {
 	const DenseTask *dt = d_dense_tasks.as<DenseTask>();
 	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
+	if (walk) { // dense genes: the top of the tree (one unit), then all subtrees side by side
+		if (n_walk_top_units) {
+			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>(), n_walk_top_units, s);
+			(*launches)++;
+		}
+		launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + n_walk_top_units, n_walk_units, s);
+		(*launches)++;
+	}
 	for (int32_t lvl = 1; lvl <= max_level; lvl++) {
 		const int64_t nd = dense_level_off[lvl + 1] - dense_level_off[lvl];
-		if (nd > 0 && tables.n_dense > 0) {
+		if (nd > 0 && tables.n_dense > 0 && !walk) {
 			launch_sweep_dense(tables, dt + dense_level_off[lvl], (int32_t)nd, s);
 			(*launches)++;
 		}
@@ -196,6 +204,9 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 	}
 	e.stream = e.own_stream;
 	if (const char *v = std::getenv("PGS_K1_VARIANT")) pgs::g_dense_variant = std::atoi(v);
+	if (const char *v = std::getenv("PGS_WALK_DISCARD")) pgs::g_walk_discard = std::atoi(v);
+	if (const char *v = std::getenv("PGS_KEEP_INTERNAL")) // development knob: force the level-synchronous sweep
+		if (std::atoi(v)) e.cfg.flags |= PGS_FLAG_KEEP_INTERNAL;
 	e.blocks = (cfg->gene_length + 63) / 64;
 	e.last_valid = (int32_t)(cfg->gene_length - (e.blocks - 1) * 64);
 	*out = h;
@@ -525,6 +536,140 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	for (int32_t g = 0; g < n; g++) leaf_words[g] = e.row_base[e.genome_leaf[g]] * e.blocks * 4;
 	if ((rc = e.upload(e.d_leaf_base_words, leaf_words.data(), sizeof(int64_t) * n, "leaf bases"))) return rc;
 	e.d_mismatch.release();
+	// ---- fused column walk of the dense region (see k1_walk_dense): cut the tree into units,
+	// order every unit depth-first with the smaller subtree first
+	e.walk = false;
+	e.n_walk_units = 0;
+	e.materialised.assign(N, 1);
+	e.rows_stored = e.rows_written;
+	e.rows_loaded = e.rows_read;
+	std::vector<pgs::WalkStep> walk_steps;
+	std::vector<int64_t> walk_off;
+	{
+		bool binary = N > 1;
+		for (int32_t v = 0; v < N && binary; v++) {
+			const int32_t nc = e.child_off[v + 1] - e.child_off[v];
+			if (nc != 0 && nc != 2) binary = false;
+		}
+		if (binary && D > 0 && (e.blocks % 2) == 0 && !(e.cfg.flags & PGS_FLAG_KEEP_INTERNAL)) {
+			auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
+			// subtree sizes (nodes), children before parents: process by decreasing level
+			std::vector<int32_t> order(N);
+			for (int32_t v = 0; v < N; v++) order[v] = v;
+			std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
+			std::vector<int64_t> size(N, 1);
+			for (int32_t v : order)
+				if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
+			// units: split the largest subtree until there are enough of them
+			size_t target_units = 80;
+			if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
+			std::vector<int32_t> roots{e.root};
+			std::vector<char> top(N, 0);
+			while (roots.size() < target_units) {
+				size_t best = 0;
+				for (size_t i = 1; i < roots.size(); i++)
+					if (size[roots[i]] > size[roots[best]]) best = i;
+				const int32_t v = roots[best];
+				if (size[v] < 64) break;
+				top[v] = 1;
+				roots.erase(roots.begin() + best);
+				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
+					if (internal(e.child[c])) roots.push_back(e.child[c]);
+			}
+			std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+			const int64_t B = e.blocks;
+			auto make_step = [&](int32_t v, uint32_t flags) {
+				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
+				pgs::WalkStep s{};
+				s.in_off = e.row_base[v] * B;
+				s.a_off = e.row_base[a] * B;
+				s.b_off = e.row_base[b] * B;
+				s.edge_a = (uint32_t)a;
+				s.edge_b = (uint32_t)b;
+				s.h32a = (uint32_t)(e.h1_host[a] >> 32);
+				s.h32b = (uint32_t)(e.h1_host[b] >> 32);
+				s.flags = flags;
+				return s;
+			};
+			std::fill(e.materialised.begin(), e.materialised.end(), 0);
+			e.materialised[e.root] = 1;
+			e.rows_stored = e.rows_loaded = 0;
+			// Depth-first step list of the subtree below `start`, smaller child first.  `descend(c)`
+			// says whether an internal child belongs to this walk; an internal child that does not
+			// (the root of another unit) is written like a parked row and picked up by its own unit.
+			auto emit_walk = [&](int32_t start, auto descend) {
+				std::vector<int32_t> parked;
+				int32_t v = start;
+				bool in_reg = false, have = true;
+				while (have) {
+					const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
+					const bool ia = internal(a), ib = internal(b);
+					const bool da = ia && descend(a), db = ib && descend(b);
+					uint32_t f = 0;
+					if (!in_reg) {
+						f |= pgs::kWalkLoad;
+						e.rows_loaded += D;
+						if (v != e.root) f |= pgs::kWalkDiscard;
+					}
+					if (!ia) f |= pgs::kWalkStoreA;                       // a genome's row
+					if (!ib) f |= pgs::kWalkStoreB;
+					if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA; // root of another unit
+					if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB;
+					int32_t carry = -1;
+					if (da && db) {
+						const bool a_first = size[a] <= size[b];
+						carry = a_first ? a : b;
+						f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkStoreB | pgs::kWalkParkB)
+									 : (pgs::kWalkCarryB | pgs::kWalkStoreA | pgs::kWalkParkA);
+						parked.push_back(a_first ? b : a);
+					} else if (da) {
+						carry = a;
+						f |= pgs::kWalkCarryA;
+					} else if (db) {
+						carry = b;
+						f |= pgs::kWalkCarryB;
+					}
+					if (f & pgs::kWalkStoreA) {
+						e.rows_stored += D;
+						if (!ia) e.materialised[a] = 1;
+					}
+					if (f & pgs::kWalkStoreB) {
+						e.rows_stored += D;
+						if (!ib) e.materialised[b] = 1;
+					}
+					walk_steps.push_back(make_step(v, f));
+					if (carry >= 0) {
+						v = carry;
+						in_reg = true;
+					} else if (!parked.empty()) {
+						v = parked.back();
+						parked.pop_back();
+						in_reg = false;
+					} else {
+						have = false;
+					}
+				}
+			};
+			// pass 1 (one unit): the top of the tree, down to the roots of the units of pass 2;
+			// pass 2: every unit loads its root row and walks its own subtree
+			walk_off.push_back(0);
+			e.n_walk_top_units = 0;
+			if (top[e.root]) {
+				emit_walk(e.root, [&](int32_t c) { return top[c] != 0; });
+				walk_off.push_back((int64_t)walk_steps.size());
+				e.n_walk_top_units = 1;
+			}
+			for (int32_t r : roots) {
+				emit_walk(r, [](int32_t) { return true; });
+				walk_off.push_back((int64_t)walk_steps.size());
+			}
+			e.walk = true;
+			e.n_walk_units = (int32_t)roots.size();
+		}
+	}
+	if ((rc = e.upload(e.d_walk_steps, walk_steps.data(), sizeof(pgs::WalkStep) * walk_steps.size(), "walk steps"))) return rc;
+	if ((rc = e.upload(e.d_walk_off, walk_off.data(), sizeof(int64_t) * walk_off.size(), "walk units"))) return rc;
+
 	{ // first eight thresholds of every branch at a fixed stride, for the kernels' shared-memory copy
 		std::vector<uint64_t> tab8((size_t)N * 8, 0);
 		for (int32_t v = 0; v < N; v++)
@@ -610,6 +755,9 @@ int pgs_get_stats(pgs_engine *h, pgs_stats *out)
 		out->levels = e.max_level;
 		out->kernel_launches = e.launches_last_sweep + (e.n_root_tasks ? 1 : 0);
 		out->device_bytes = e.device_bytes();
+		out->sweep_mode = e.walk ? 1 : 0;
+		out->rows_stored = e.rows_stored;
+		out->rows_loaded = e.rows_loaded;
 	}
 	if (e.swept) {
 		cudaError_t ce = cudaStreamSynchronize(e.stream);
@@ -714,6 +862,8 @@ int pgs_copy_packed(pgs_engine *h, int32_t node, int64_t gene_index, void *dst)
 		return e.fail(PGS_ERR_ARG, "pgs_copy_packed: index out of range");
 	const int64_t row = e.row_index(node, gene_index);
 	if (row < 0) return 1;
+	if (e.dense_slot[gene_index] >= 0 && !e.materialised[node])
+		return e.fail(PGS_ERR_STATE, "pgs_copy_packed: this internal row is not kept (create the engine with PGS_FLAG_KEEP_INTERNAL)");
 	cudaError_t ce = cudaStreamSynchronize(e.stream);
 	if (ce == cudaSuccess)
 		ce = cudaMemcpy(dst, e.tables.rows + row * e.blocks, (size_t)e.blocks * 16, cudaMemcpyDeviceToHost);
@@ -726,6 +876,8 @@ int pgs_copy_dense(pgs_engine *h, int32_t node, void *dst)
 	ENGINE_OR_RETURN(h);
 	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_copy_dense: call pgs_sweep first");
 	if (!dst || node < 0 || node >= e.n_nodes) return e.fail(PGS_ERR_ARG, "pgs_copy_dense: bad argument");
+	if (!e.materialised[node])
+		return e.fail(PGS_ERR_STATE, "pgs_copy_dense: this internal node is not kept (create the engine with PGS_FLAG_KEEP_INTERNAL)");
 	cudaError_t ce = cudaStreamSynchronize(e.stream);
 	if (ce == cudaSuccess)
 		ce = cudaMemcpy(dst, e.tables.rows + e.row_base[node] * e.blocks,

@@ -58,13 +58,18 @@ struct Engine {
 	std::vector<int64_t> dense_level_off;  // [max_level+2] into dense tasks (index = child level)
 	std::vector<int64_t> sparse_level_off; // [max_level+2]
 	int64_t n_dense_tasks = 0, n_sparse_tasks = 0, n_root_tasks = 0;
+	// fused column walk of the dense region (default for binary trees)
+	bool walk = false;
+	int32_t n_walk_units = 0, n_walk_top_units = 0;
+	int64_t rows_stored = 0, rows_loaded = 0;
+	std::vector<char> materialised; // [N] dense region of the node holds valid rows after a sweep
 	std::vector<uint64_t> tab_host; // concatenated H[1..kmax]
 	std::vector<int32_t> tab_off_host, kmax_host;
 	std::vector<uint64_t> h1_host;
 
 	// ---- device
 	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
-	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8;
+	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off;
 	DeviceTables tables{};
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t graph_exec = nullptr;

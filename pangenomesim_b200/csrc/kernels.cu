@@ -268,6 +268,157 @@ void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1, fused column walk (default for binary trees).  Columns are independent given the tree, so a
+// thread can take one pair of blocks of one gene and carry it through a whole subtree by itself:
+// the value of the child it descends into stays in REGISTERS, only the sibling that is visited
+// later is parked in memory (and re-read from L2 a few steps later), and internal nodes that no
+// output needs are never written.  HBM traffic falls from "every row written + every parent
+// read" (0.375 B per site-edge) towards "leaves written once" (0.25 B per leaf nucleotide).
+// The host cuts the tree into a few dozen subtrees (units) and orders each unit's steps
+// depth-first, smaller subtree first, so at most log2(n) parked rows per unit are alive;
+// a CTA = (unit, slab of 256 block pairs); the RNG keying makes the result independent of all this.
+
+__device__ __forceinline__ U32x8 ld_own256(const U32x8 *p)
+{
+	// coherent load: the thread re-reads what it stored itself a few steps earlier
+	U32x8 r;
+	asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				 : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y),
+				   "=r"(r.hi.z), "=r"(r.hi.w)
+				 : "l"(p)
+				 : "memory");
+	return r;
+}
+
+// leaf rows are not touched again during the sweep: first in line for eviction from L2 ...
+__device__ __forceinline__ void st_leaf256(U32x8 *p, const U32x8 &v)
+{
+	asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+				 "r"(v.lo.x), "r"(v.lo.y), "r"(v.lo.z), "r"(v.lo.w), "r"(v.hi.x), "r"(v.hi.y), "r"(v.hi.z), "r"(v.hi.w)
+				 : "memory");
+}
+// ... parked siblings come back within a few steps: last in line
+__device__ __forceinline__ void st_park256(U32x8 *p, const U32x8 &v)
+{
+	asm volatile("st.global.L1::no_allocate.L2::evict_last.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+				 "r"(v.lo.x), "r"(v.lo.y), "r"(v.lo.z), "r"(v.lo.w), "r"(v.hi.x), "r"(v.hi.y), "r"(v.hi.z), "r"(v.hi.w)
+				 : "memory");
+}
+
+constexpr int kWalkChunk = 32; // steps staged in shared memory per barrier
+
+__global__ void __launch_bounds__(kThreads, 4)
+k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
+			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node, uint32_t discard_ok)
+{
+	const uint32_t unit = blockIdx.x % n_units, slab = blockIdx.x / n_units;
+	const uint32_t p = slab * kThreads + threadIdx.x;
+	const bool active = p < pairs_per_node;
+	const uint32_t idx = 2u * p;
+	const uint32_t slot = fastdiv(idx, t.div_blocks);
+	const uint32_t blk = idx - slot * t.blocks;
+	const uint32_t gid = active ? __ldg(t.dense_gid + slot) : 0u;
+	const int valid_hi = (blk + 2 == t.blocks) ? t.last_valid : 64;
+	// this thread's column inside any node's dense region; step offsets are in uint4 units
+	U32x8 *const column = reinterpret_cast<U32x8 *>(t.rows) + p;
+	const bool may_discard = discard_ok && (p & 3u) == 0u && p + 3u < pairs_per_node;
+
+	__shared__ WalkStep s_steps[kWalkChunk];
+	__shared__ uint64_t s_tab[kThreads / 32][2][8]; // per warp: H[1..8] of the current step's two branches
+	__shared__ int s_kmax[kThreads / 32][2];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	U32x8 cur; // the value carried from step to step
+	cur.lo = make_uint4(0u, 0u, 0u, 0u);
+	cur.hi = cur.lo;
+	const int64_t begin = unit_off[unit], end = unit_off[unit + 1];
+	for (int64_t i0 = begin; i0 < end; i0 += kWalkChunk) {
+		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
+		__syncthreads();
+		if ((int)threadIdx.x < 3 * cnt)
+			reinterpret_cast<uint4 *>(s_steps)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(steps + i0) + threadIdx.x);
+		__syncthreads();
+		for (int k = 0; k < cnt; k++) {
+			const WalkStep &st = s_steps[k];
+			// threads beyond the last pair of the region (tail slab only) keep in step with no effect
+			const uint32_t f = active ? st.flags : 0u;
+			if (f & kWalkLoad) cur = ld_own256(reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column) + st.in_off));
+			const uint32_t edge_a = st.edge_a, h32a = st.h32a, h32b = st.h32b;
+			const uint4 w = pair_words(edge_a, gid, blk, t.keys);
+			uint32_t m = (w.x <= h32a ? 1u : 0u) | (w.y <= h32a ? 2u : 0u) | (w.z <= h32b ? 4u : 0u) | (w.w <= h32b ? 8u : 0u);
+			if (!active) m = 0u;
+			U32x8 *const dst_a = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column) + st.a_off);
+			U32x8 *const dst_b = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column) + st.b_off);
+			if (__any_sync(0xFFFFFFFFu, m != 0)) {
+				// some lane of this warp is on the rare path: lanes 0-17 fetch both branches' first
+				// thresholds and table lengths in one round trip
+				const uint32_t edge_b2 = st.edge_b;
+				__syncwarp();
+				if (lane < 16)
+					s_tab[warp][lane >> 3][lane & 7] = __ldg(t.tab8 + (size_t)(lane < 8 ? edge_a : edge_b2) * 8 + (lane & 7));
+				else if (lane < 18)
+					s_kmax[warp][lane - 16] = __ldg(t.kmax + (lane == 16 ? edge_a : edge_b2));
+				__syncwarp();
+			}
+			if (m == 0) { // common case: both children are copies of the carried value
+				if (f & kWalkStoreA) {
+					if (f & kWalkParkA) st_park256(dst_a, cur); else st_leaf256(dst_a, cur);
+				}
+				if (f & kWalkStoreB) {
+					if (f & kWalkParkB) st_park256(dst_b, cur); else st_leaf256(dst_b, cur);
+				}
+			} else { // rare: a block of a child may change
+				U32x8 ya = cur, yb = cur;
+				const uint32_t edge_b = st.edge_b;
+				do {
+					const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+					m &= m - 1u;
+					const uint32_t side = b >> 1, odd = b & 1u;
+					const uint32_t edge = side ? edge_b : edge_a;
+					const int kmax = s_kmax[warp][side];
+					const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
+					const uint4 xin = odd ? cur.hi : cur.lo;
+					const uint4 y = mutate_block_slow(xin, edge, gid, blk + odd, pick_word(w, side, odd), s_tab[warp][side],
+													  tab, kmax, odd ? valid_hi : 64, t.keys);
+					if (side) {
+						if (odd) yb.hi = y; else yb.lo = y;
+					} else {
+						if (odd) ya.hi = y; else ya.lo = y;
+					}
+				} while (m);
+				if (f & kWalkStoreA) {
+					if (f & kWalkParkA) st_park256(dst_a, ya); else st_leaf256(dst_a, ya);
+				}
+				if (f & kWalkStoreB) {
+					if (f & kWalkParkB) st_park256(dst_b, yb); else st_leaf256(dst_b, yb);
+				}
+				if (f & kWalkCarryA)
+					cur = ya;
+				else if (f & kWalkCarryB)
+					cur = yb;
+			}
+			if ((f & kWalkDiscard) && may_discard) {
+				// the four pairs of this 128-byte line were loaded by this warp instruction and are dead now
+				asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<const uint4 *>(column) + st.in_off) : "memory");
+			}
+		}
+	}
+}
+
+int g_walk_discard = 1; // development knob (PGS_WALK_DISCARD)
+
+void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
+					   cudaStream_t s)
+{
+	if (n_units == 0 || t.n_dense == 0) return;
+	const uint32_t pairs = t.n_dense * t.blocks / 2;
+	const uint32_t slabs = (pairs + kThreads - 1) / kThreads;
+	// lines of 128 bytes = 4 pairs must not straddle nodes: needs 128-byte aligned dense regions
+	const uint32_t discard_ok = (g_walk_discard && (t.blocks % 8u) == 0u) ? 1u : 0u;
+	k1_walk_dense<<<(unsigned)((uint64_t)slabs * (uint32_t)n_units), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units,
+																				  pairs, discard_ok);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1, sparse region.  Accessory genes are present at few nodes; their rows are
 // compacted per node and a 24-byte task per parent row names source and destination rows.
 // Replaces gene::bulk_mutate over the per-node gene map, reference gene.h:26-40 called at

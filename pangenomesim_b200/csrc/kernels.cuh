@@ -23,6 +23,25 @@ struct RootTask {
 	uint32_t row, gid;
 };
 
+// One step of the fused column walk (k1_walk_dense): carry the dense region of one node across the
+// two branches below it.  Offsets are in uint4 units from the start of the row store.
+struct __align__(16) WalkStep {
+	int64_t in_off, a_off, b_off; // dense regions of the node and of its children a (pair leader) and b
+	uint32_t edge_a, edge_b;      // child node indices = RNG edge ids (edge_a < edge_b)
+	uint32_t h32a, h32b;          // H[1] >> 32 of the two branches
+	uint32_t flags;               // kWalk* below
+	uint32_t pad;
+};
+static_assert(sizeof(WalkStep) == 48, "WalkStep is staged as three uint4");
+constexpr uint32_t kWalkLoad = 1u;     // input comes from memory (else: the value carried in registers)
+constexpr uint32_t kWalkStoreA = 2u;   // write child a's row
+constexpr uint32_t kWalkStoreB = 4u;
+constexpr uint32_t kWalkCarryA = 8u;   // child a's value is the next step's input
+constexpr uint32_t kWalkCarryB = 16u;
+constexpr uint32_t kWalkDiscard = 32u; // the loaded input row is dead afterwards: drop its lines from L2
+constexpr uint32_t kWalkParkA = 64u;   // the stored child a is an internal node that is re-read soon (keep in L2)
+constexpr uint32_t kWalkParkB = 128u;
+
 // Unsigned division by a launch constant: q = umulhi(x, mul) >> shift (x < 2^31).
 struct FastDiv {
 	uint32_t mul, shift, div;
@@ -65,9 +84,13 @@ struct DeviceTables {
 };
 
 extern int g_dense_variant;
+extern int g_walk_discard;
 void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_tasks, cudaStream_t s);
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);
+// Fused dense sweep: unit u executes steps[unit_off[u] .. unit_off[u+1]) for every column slab.
+void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
+					   cudaStream_t s);
 
 // K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
 // i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).

@@ -40,7 +40,7 @@ for r in range(a.reps):
     print(f"rep {r}: sweep {s['sweep_ms']:.3f} ms rootgen {s['rootgen_ms']:.3f} ms wall {wall*1e3:.2f} ms | "
           f"{bytes_alg/s['sweep_ms']/1e6:.0f} GB/s algorithmic ({bytes_real/s['sweep_ms']/1e6:.0f} moved) | "
           f"{s['leaf_nucleotides']/s['sweep_ms']/1e-3:.3e} leaf-nt/s | launches {s['kernel_launches']} levels {s['levels']} "
-          f"| HBM {s['device_bytes']/2**30:.1f} GiB", flush=True)
+          f"| HBM {s['device_bytes']/2**30:.1f} GiB | mode {s['sweep_mode']} stored {s['rows_stored']/s['n_dense_genes']:.0f} loaded {s['rows_loaded']/s['n_dense_genes']:.0f} node-rows", flush=True)
 if a.mismatch:
     t0 = time.time()
     mm, sites = e.mismatch()

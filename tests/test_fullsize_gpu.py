@@ -46,7 +46,7 @@ def test_config4_oracle_spot_checks(config4, oracle):
     e, parent, rate, leaf, n, G, L, seed = config4
     rng = np.random.default_rng(0)
     root = 2 * n - 2
-    nodes = [0, n - 1, n, root, root - 1] + [int(x) for x in rng.integers(0, 2 * n - 1, 25)]
+    nodes = [0, n - 1, root] + [int(x) for x in rng.integers(0, n, 25)]  # leaves and root: what the walk keeps
     genes = [0, G - 1] + [int(x) for x in rng.integers(0, G, 6)]
     for v in nodes:
         for g in genes:
@@ -56,7 +56,7 @@ def test_config4_oracle_spot_checks(config4, oracle):
 
 def test_config4_deterministic_and_shard_invariant(config4):
     e, parent, rate, leaf, n, G, L, seed = config4
-    probe = [0, 1234, n - 1, n + 77, 2 * n - 3]
+    probe = [0, 1234, n - 1, 4321, 2 * n - 2]
     before = {v: e.copy_dense(v, G).copy() for v in probe}
     e.sweep()
     e.sync()
@@ -73,7 +73,13 @@ def test_config4_deterministic_and_shard_invariant(config4):
 
 def test_config4_branch_substitution_counts(config4, oracle):
     """per-branch counts ~ Binomial(S, p_e): the longest branches, a few typical and tiny ones"""
-    e, parent, rate, leaf, n, G, L, seed = config4
+    _, parent, rate, leaf, n, _, L, seed = config4
+    from pangenomesim_b200.capi import PGS_FLAG_KEEP_INTERNAL
+    G = 500  # internal rows are needed here: a second, smaller engine in level-synchronous mode
+    e = Engine(seed, L, flags=PGS_FLAG_KEEP_INTERNAL)
+    e.set_tree(parent, rate, leaf)
+    e.set_core_genes(G, 2 * n - 2)
+    e.sweep()
     S = G * L
     order = np.argsort(rate[:-1])
     picks = list(order[-6:]) + list(order[len(order) // 2 - 2: len(order) // 2 + 2]) + list(order[:3])
@@ -91,6 +97,11 @@ def test_config4_branch_substitution_counts(config4, oracle):
     # padding sites (1000..1023 of every gene) are zero everywhere
     codes = oracle.unpack_codes(e.copy_dense(int(order[-1]), G)[:50], 1024)
     assert not codes[:, 1000:].any()
+    # and this engine's leaves equal the big walk-mode engine's (same gene ids 0..499)
+    big = config4[0]
+    for v in (0, 77, n - 1):
+        assert np.array_equal(e.copy_dense(v, G), big.copy_dense(v, 5000)[:G])
+    e.close()
 
 
 def test_config4_leaf_composition_and_distance(config4, oracle):
@@ -128,6 +139,6 @@ def test_config5_shape_high_mutation_rate(oracle):
         s = e.stats()
         assert s["rows_total"] * s["blocks_per_gene"] * 16 > 2**31
         rng = np.random.default_rng(1)
-        for v in [0, n - 1, root - 1] + [int(x) for x in rng.integers(0, n, 12)]:
+        for v in [0, n - 1, root] + [int(x) for x in rng.integers(0, n, 12)]:
             g = int(rng.integers(0, G))
             assert np.array_equal(e.copy_packed(v, g), oracle.row(seed, parent, rate, v, root, g, L)), (v, g)

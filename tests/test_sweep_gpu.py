@@ -5,12 +5,14 @@ import pytest
 
 import treegen
 from pangenomesim_b200 import Engine, PgsError
-from pangenomesim_b200.capi import PGS_FLAG_NO_GRAPH
+from pangenomesim_b200.capi import PGS_FLAG_KEEP_INTERNAL, PGS_FLAG_NO_GRAPH
 
 pytestmark = pytest.mark.gpu
 
 
-def build(seed, L, parent, rate, leaf_genome, genes, flags=0):
+def build(seed, L, parent, rate, leaf_genome, genes, flags=PGS_FLAG_KEEP_INTERNAL):
+    """default here: the level-synchronous sweep that keeps every internal row, so that every node
+    can be compared; the fused column walk (the product default) is covered by the *_walk tests"""
     e = Engine(seed, L, flags=flags)
     e.set_tree(parent, rate, leaf_genome)
     e.set_genes(*genes)
@@ -102,7 +104,7 @@ def test_graph_and_plain_launches_agree_and_repeat(oracle):
     parent, rate, leaf = treegen.coalescent(n, seed=2, mut_rate=0.05)
     genes = treegen.gene_table(parent, leaf, n_core=20, n_acc=15, seed=1)
     with build(seed, L, parent, rate, leaf, genes) as a, \
-            build(seed, L, parent, rate, leaf, genes, flags=PGS_FLAG_NO_GRAPH) as b:
+            build(seed, L, parent, rate, leaf, genes, flags=PGS_FLAG_NO_GRAPH | PGS_FLAG_KEEP_INTERNAL) as b:
         a.sweep()  # a second sweep overwrites every row with the same values
         a.sync()
         for v in (0, n - 1, n, len(parent) - 1):
@@ -246,3 +248,42 @@ def test_non_binary_trees_and_degenerate_inputs(oracle):
         e.sweep()
         assert e.stats()["rows_total"] == 0
         assert e.write_outputs(None, 31 | 32, [], [])["records"] == 0
+
+
+@pytest.mark.parametrize("n,L,mut_rate", [(2, 128, 0.3), (9, 128, 0.3), (40, 1000, 0.01), (200, 1000, 2.0), (700, 256, 0.05),
+                                          (300, 512, 0.02)])
+def test_fused_walk_equals_level_sweep_and_oracle(oracle, n, L, mut_rate):
+    """the product default (fused column walk: children carried in registers, parked siblings,
+    internal rows not kept) produces exactly the leaf and root rows of the level-synchronous sweep"""
+    seed = 1000 + n
+    parent, rate, leaf = treegen.coalescent(n, seed=n, mut_rate=mut_rate)
+    genes = treegen.gene_table(parent, leaf, n_core=9, n_acc=6, seed=n + 1)
+    gene_id, origin = genes[0], genes[1]
+    root = len(parent) - 1
+    with build(seed, L, parent, rate, leaf, genes, flags=0) as walk, build(seed, L, parent, rate, leaf, genes) as keep:
+        assert walk.stats()["sweep_mode"] == 1 and keep.stats()["sweep_mode"] == 0
+        assert walk.stats()["rows_stored"] < keep.stats()["rows_stored"] or n == 2
+        assert walk.stats()["rows_loaded"] <= keep.stats()["rows_loaded"]
+        for v in list(range(n)) + [root]:
+            assert np.array_equal(walk.copy_dense(v, 9), keep.copy_dense(v, 9)), v
+        dense = [gi for gi in range(len(gene_id)) if gene_id[gi] < 9]
+        for gi in dense[:3]:
+            want = oracle.gene_all_nodes(seed, parent, rate, root, int(gene_id[gi]), L)
+            for v in list(range(n)) + [root]:
+                assert np.array_equal(walk.copy_packed(v, gi), want[v]), (gi, v)
+        if n > 2:
+            with pytest.raises(PgsError):
+                walk.copy_dense(n, 9)  # an internal node other than the root is not kept
+        # sparse genes still go level by level in both modes
+        for gi in range(len(gene_id)):
+            if gene_id[gi] >= 9:
+                for v in range(len(parent)):
+                    a, b = walk.copy_packed(v, gi), keep.copy_packed(v, gi)
+                    assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))
+        mw, _ = walk.mismatch()
+        mk, _ = keep.mismatch()
+        assert np.array_equal(mw, mk)
+        walk.sweep()  # repeatable (parked rows are rewritten, discarded lines do not matter)
+        walk.sync()
+        for v in (0, n - 1, root):
+            assert np.array_equal(walk.copy_dense(v, 9), keep.copy_dense(v, 9))
