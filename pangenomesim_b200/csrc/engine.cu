@@ -205,6 +205,7 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 	e.stream = e.own_stream;
 	if (const char *v = std::getenv("PGS_K1_VARIANT")) pgs::g_dense_variant = std::atoi(v);
 	if (const char *v = std::getenv("PGS_WALK_DISCARD")) pgs::g_walk_discard = std::atoi(v);
+	if (const char *v = std::getenv("PGS_WALK_VARIANT")) pgs::g_walk_variant = std::atoi(v);
 	if (const char *v = std::getenv("PGS_KEEP_INTERNAL")) // development knob: force the level-synchronous sweep
 		if (std::atoi(v)) e.cfg.flags |= PGS_FLAG_KEEP_INTERNAL;
 	e.blocks = (cfg->gene_length + 63) / 64;

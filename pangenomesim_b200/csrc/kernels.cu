@@ -307,29 +307,40 @@ __device__ __forceinline__ void st_park256(U32x8 *p, const U32x8 &v)
 
 constexpr int kWalkChunk = 32; // steps staged in shared memory per barrier
 
-__global__ void __launch_bounds__(kThreads, 4)
+template <int MINB, int PAIRS>
+__global__ void __launch_bounds__(kThreads, MINB)
 k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
 			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node, uint32_t discard_ok)
 {
 	const uint32_t unit = blockIdx.x % n_units, slab = blockIdx.x / n_units;
-	const uint32_t p = slab * kThreads + threadIdx.x;
-	const bool active = p < pairs_per_node;
-	const uint32_t idx = 2u * p;
-	const uint32_t slot = fastdiv(idx, t.div_blocks);
-	const uint32_t blk = idx - slot * t.blocks;
-	const uint32_t gid = active ? __ldg(t.dense_gid + slot) : 0u;
-	const int valid_hi = (blk + 2 == t.blocks) ? t.last_valid : 64;
-	// this thread's column inside any node's dense region; step offsets are in uint4 units
-	U32x8 *const column = reinterpret_cast<U32x8 *>(t.rows) + p;
-	const bool may_discard = discard_ok && (p & 3u) == 0u && p + 3u < pairs_per_node;
+	// this thread's PAIRS columns (block pairs) inside any node's dense region
+	uint32_t p[PAIRS], gid[PAIRS], blk[PAIRS];
+	bool active[PAIRS], may_discard[PAIRS];
+	int valid_hi[PAIRS];
+	U32x8 *column[PAIRS];
+#pragma unroll
+	for (int j = 0; j < PAIRS; j++) {
+		p[j] = (slab * PAIRS + j) * kThreads + threadIdx.x;
+		active[j] = p[j] < pairs_per_node;
+		const uint32_t idx = 2u * p[j];
+		const uint32_t slot = fastdiv(idx, t.div_blocks);
+		blk[j] = idx - slot * t.blocks;
+		gid[j] = active[j] ? __ldg(t.dense_gid + slot) : 0u;
+		valid_hi[j] = (blk[j] + 2 == t.blocks) ? t.last_valid : 64;
+		column[j] = reinterpret_cast<U32x8 *>(t.rows) + p[j]; // step offsets are in uint4 units
+		may_discard[j] = discard_ok && (p[j] & 3u) == 0u && p[j] + 3u < pairs_per_node;
+	}
 
 	__shared__ WalkStep s_steps[kWalkChunk];
 	__shared__ uint64_t s_tab[kThreads / 32][2][8]; // per warp: H[1..8] of the current step's two branches
 	__shared__ int s_kmax[kThreads / 32][2];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	U32x8 cur; // the value carried from step to step
-	cur.lo = make_uint4(0u, 0u, 0u, 0u);
-	cur.hi = cur.lo;
+	U32x8 cur[PAIRS]; // the values carried from step to step
+#pragma unroll
+	for (int j = 0; j < PAIRS; j++) {
+		cur[j].lo = make_uint4(0u, 0u, 0u, 0u);
+		cur[j].hi = cur[j].lo;
+	}
 	const int64_t begin = unit_off[unit], end = unit_off[unit + 1];
 	for (int64_t i0 = begin; i0 < end; i0 += kWalkChunk) {
 		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
@@ -339,15 +350,23 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 		__syncthreads();
 		for (int k = 0; k < cnt; k++) {
 			const WalkStep &st = s_steps[k];
+			const uint32_t f = st.flags;
 			// threads beyond the last pair of the region (tail slab only) keep in step with no effect
-			const uint32_t f = active ? st.flags : 0u;
-			if (f & kWalkLoad) cur = ld_own256(reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column) + st.in_off));
+			if (f & kWalkLoad) {
+#pragma unroll
+				for (int j = 0; j < PAIRS; j++)
+					if (active[j]) cur[j] = ld_own256(reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off));
+			}
 			const uint32_t edge_a = st.edge_a, h32a = st.h32a, h32b = st.h32b;
-			const uint4 w = pair_words(edge_a, gid, blk, t.keys);
-			uint32_t m = (w.x <= h32a ? 1u : 0u) | (w.y <= h32a ? 2u : 0u) | (w.z <= h32b ? 4u : 0u) | (w.w <= h32b ? 8u : 0u);
-			if (!active) m = 0u;
-			U32x8 *const dst_a = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column) + st.a_off);
-			U32x8 *const dst_b = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column) + st.b_off);
+			uint4 w[PAIRS];
+			uint32_t m = 0;
+#pragma unroll
+			for (int j = 0; j < PAIRS; j++) {
+				w[j] = pair_words(edge_a, gid[j], blk[j], t.keys);
+				const uint32_t mj = (w[j].x <= h32a ? 1u : 0u) | (w[j].y <= h32a ? 2u : 0u) | (w[j].z <= h32b ? 4u : 0u) |
+									(w[j].w <= h32b ? 8u : 0u);
+				if (active[j]) m |= mj << (4 * j);
+			}
 			if (__any_sync(0xFFFFFFFFu, m != 0)) {
 				// some lane of this warp is on the rare path: lanes 0-17 fetch both branches' first
 				// thresholds and table lengths in one round trip
@@ -359,63 +378,80 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 					s_kmax[warp][lane - 16] = __ldg(t.kmax + (lane == 16 ? edge_a : edge_b2));
 				__syncwarp();
 			}
-			if (m == 0) { // common case: both children are copies of the carried value
-				if (f & kWalkStoreA) {
-					if (f & kWalkParkA) st_park256(dst_a, cur); else st_leaf256(dst_a, cur);
-				}
-				if (f & kWalkStoreB) {
-					if (f & kWalkParkB) st_park256(dst_b, cur); else st_leaf256(dst_b, cur);
-				}
-			} else { // rare: a block of a child may change
-				U32x8 ya = cur, yb = cur;
-				const uint32_t edge_b = st.edge_b;
-				do {
-					const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-					m &= m - 1u;
-					const uint32_t side = b >> 1, odd = b & 1u;
-					const uint32_t edge = side ? edge_b : edge_a;
-					const int kmax = s_kmax[warp][side];
-					const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
-					const uint4 xin = odd ? cur.hi : cur.lo;
-					const uint4 y = mutate_block_slow(xin, edge, gid, blk + odd, pick_word(w, side, odd), s_tab[warp][side],
-													  tab, kmax, odd ? valid_hi : 64, t.keys);
-					if (side) {
-						if (odd) yb.hi = y; else yb.lo = y;
-					} else {
-						if (odd) ya.hi = y; else ya.lo = y;
+#pragma unroll
+			for (int j = 0; j < PAIRS; j++) {
+				if (!active[j]) continue;
+				uint32_t mj = (m >> (4 * j)) & 15u;
+				U32x8 *const dst_a = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + st.a_off);
+				U32x8 *const dst_b = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + st.b_off);
+				if (mj == 0) { // common case: both children are copies of the carried value
+					if (f & kWalkStoreA) {
+						if (f & kWalkParkA) st_park256(dst_a, cur[j]); else st_leaf256(dst_a, cur[j]);
 					}
-				} while (m);
-				if (f & kWalkStoreA) {
-					if (f & kWalkParkA) st_park256(dst_a, ya); else st_leaf256(dst_a, ya);
+					if (f & kWalkStoreB) {
+						if (f & kWalkParkB) st_park256(dst_b, cur[j]); else st_leaf256(dst_b, cur[j]);
+					}
+				} else { // rare: a block of a child may change
+					U32x8 ya = cur[j], yb = cur[j];
+					const uint32_t edge_b = st.edge_b;
+					do {
+						const uint32_t b = (uint32_t)__ffs((int)mj) - 1u;
+						mj &= mj - 1u;
+						const uint32_t side = b >> 1, odd = b & 1u;
+						const uint32_t edge = side ? edge_b : edge_a;
+						const int kmax = s_kmax[warp][side];
+						const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
+						const uint4 xin = odd ? cur[j].hi : cur[j].lo;
+						const uint4 y = mutate_block_slow(xin, edge, gid[j], blk[j] + odd, pick_word(w[j], side, odd),
+														  s_tab[warp][side], tab, kmax, odd ? valid_hi[j] : 64, t.keys);
+						if (side) {
+							if (odd) yb.hi = y; else yb.lo = y;
+						} else {
+							if (odd) ya.hi = y; else ya.lo = y;
+						}
+					} while (mj);
+					if (f & kWalkStoreA) {
+						if (f & kWalkParkA) st_park256(dst_a, ya); else st_leaf256(dst_a, ya);
+					}
+					if (f & kWalkStoreB) {
+						if (f & kWalkParkB) st_park256(dst_b, yb); else st_leaf256(dst_b, yb);
+					}
+					if (f & kWalkCarryA)
+						cur[j] = ya;
+					else if (f & kWalkCarryB)
+						cur[j] = yb;
 				}
-				if (f & kWalkStoreB) {
-					if (f & kWalkParkB) st_park256(dst_b, yb); else st_leaf256(dst_b, yb);
+				if ((f & kWalkDiscard) && may_discard[j]) {
+					// the four pairs of this 128-byte line were loaded by this warp instruction and are dead now
+					asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<const uint4 *>(column[j]) + st.in_off) : "memory");
 				}
-				if (f & kWalkCarryA)
-					cur = ya;
-				else if (f & kWalkCarryB)
-					cur = yb;
-			}
-			if ((f & kWalkDiscard) && may_discard) {
-				// the four pairs of this 128-byte line were loaded by this warp instruction and are dead now
-				asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<const uint4 *>(column) + st.in_off) : "memory");
 			}
 		}
 	}
 }
 
 int g_walk_discard = 1; // development knob (PGS_WALK_DISCARD)
+int g_walk_variant = 0; // development knob (PGS_WALK_VARIANT)
 
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
 					   cudaStream_t s)
 {
 	if (n_units == 0 || t.n_dense == 0) return;
 	const uint32_t pairs = t.n_dense * t.blocks / 2;
-	const uint32_t slabs = (pairs + kThreads - 1) / kThreads;
 	// lines of 128 bytes = 4 pairs must not straddle nodes: needs 128-byte aligned dense regions
 	const uint32_t discard_ok = (g_walk_discard && (t.blocks % 8u) == 0u) ? 1u : 0u;
-	k1_walk_dense<<<(unsigned)((uint64_t)slabs * (uint32_t)n_units), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units,
-																				  pairs, discard_ok);
+	auto grid = [&](int pairs_per_thread) {
+		const uint32_t per_cta = kThreads * pairs_per_thread;
+		return (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
+	};
+	switch (g_walk_variant) {
+		case 1: k1_walk_dense<4, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+		case 2: k1_walk_dense<2, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+		case 3: k1_walk_dense<2, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+		case 4: k1_walk_dense<1, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+		case 5: k1_walk_dense<3, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+		default: k1_walk_dense<3, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------

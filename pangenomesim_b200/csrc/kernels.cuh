@@ -85,6 +85,7 @@ struct DeviceTables {
 
 extern int g_dense_variant;
 extern int g_walk_discard;
+extern int g_walk_variant;
 void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_tasks, cudaStream_t s);
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);
