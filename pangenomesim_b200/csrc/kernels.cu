@@ -305,6 +305,20 @@ __device__ __forceinline__ void st_park256(U32x8 *p, const U32x8 &v)
 				 : "memory");
 }
 
+// Predicated re-load of a parked row straight into the registers that carry the running value
+// (read-write operands, two 128-bit loads: a 256-bit load wants an 8-aligned register octet, which
+// made ptxas keep a second copy of the value and shuffle 16 registers per step).
+__device__ __forceinline__ void ld_own256_if(U32x8 &v, const U32x8 *p, uint32_t pred)
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+				 "@q ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%8];\n\t"
+				 "@q ld.global.L1::no_allocate.v4.u32 {%4,%5,%6,%7}, [%8+16];\n\t}"
+				 : "+r"(v.lo.x), "+r"(v.lo.y), "+r"(v.lo.z), "+r"(v.lo.w), "+r"(v.hi.x), "+r"(v.hi.y), "+r"(v.hi.z),
+				   "+r"(v.hi.w)
+				 : "l"(p), "r"(pred)
+				 : "memory");
+}
+
 constexpr int kWalkChunk = 32; // steps staged in shared memory per barrier
 
 template <int MINB, int PAIRS>
@@ -331,7 +345,9 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 		may_discard[j] = discard_ok && (p[j] & 3u) == 0u && p[j] + 3u < pairs_per_node;
 	}
 
-	__shared__ WalkStep s_steps[kWalkChunk];
+	// every warp stages its own copy of the next steps: warps of a CTA drift apart (rare path) and
+	// must not wait for each other at a block barrier
+	__shared__ WalkStep s_steps_all[kThreads / 32][kWalkChunk];
 	__shared__ uint64_t s_tab[kThreads / 32][2][8]; // per warp: H[1..8] of the current step's two branches
 	__shared__ int s_kmax[kThreads / 32][2];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -344,19 +360,19 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	const int64_t begin = unit_off[unit], end = unit_off[unit + 1];
 	for (int64_t i0 = begin; i0 < end; i0 += kWalkChunk) {
 		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
-		__syncthreads();
-		if ((int)threadIdx.x < 3 * cnt)
-			reinterpret_cast<uint4 *>(s_steps)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(steps + i0) + threadIdx.x);
-		__syncthreads();
+		WalkStep *const s_steps = s_steps_all[warp];
+		__syncwarp();
+		for (int q = lane; q < 3 * cnt; q += 32)
+			reinterpret_cast<uint4 *>(s_steps)[q] = __ldg(reinterpret_cast<const uint4 *>(steps + i0) + q);
+		__syncwarp();
 		for (int k = 0; k < cnt; k++) {
 			const WalkStep &st = s_steps[k];
 			const uint32_t f = st.flags;
 			// threads beyond the last pair of the region (tail slab only) keep in step with no effect
-			if (f & kWalkLoad) {
 #pragma unroll
-				for (int j = 0; j < PAIRS; j++)
-					if (active[j]) cur[j] = ld_own256(reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off));
-			}
+			for (int j = 0; j < PAIRS; j++)
+				ld_own256_if(cur[j], reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off),
+							 (f & kWalkLoad) && active[j] ? 1u : 0u);
 			const uint32_t edge_a = st.edge_a, h32a = st.h32a, h32b = st.h32b;
 			uint4 w[PAIRS];
 			uint32_t m = 0;
