@@ -566,13 +566,15 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 			if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
 			std::vector<int32_t> roots{e.root};
 			std::vector<char> top(N, 0);
-			while (roots.size() < target_units) {
+			size_t n_top = 0;
+			while (roots.size() < target_units && n_top < 4 * target_units) { // (a caterpillar never widens)
 				size_t best = 0;
 				for (size_t i = 1; i < roots.size(); i++)
 					if (size[roots[i]] > size[roots[best]]) best = i;
 				const int32_t v = roots[best];
 				if (size[v] < 64) break;
 				top[v] = 1;
+				n_top++;
 				roots.erase(roots.begin() + best);
 				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
 					if (internal(e.child[c])) roots.push_back(e.child[c]);

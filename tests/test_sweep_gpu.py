@@ -287,3 +287,54 @@ def test_fused_walk_equals_level_sweep_and_oracle(oracle, n, L, mut_rate):
         walk.sync()
         for v in (0, n - 1, root):
             assert np.array_equal(walk.copy_dense(v, 9), keep.copy_dense(v, 9))
+
+
+def _caterpillar(n, rate):
+    """leaves 0..n-1; internal node n+i joins leaf i+1 with the previous internal node (or leaf 0)"""
+    N = 2 * n - 1
+    parent = np.full(N, -1, dtype=np.int32)
+    prev = 0
+    for i in range(n - 1):
+        p = n + i
+        parent[prev] = p
+        parent[i + 1] = p
+        prev = p
+    r = np.full(N, rate)
+    r[-1] = 0.0
+    leaf = np.full(N, -1, dtype=np.int32)
+    leaf[:n] = np.arange(n)
+    return parent, r, leaf
+
+
+def _balanced(depth, rate):
+    n = 2 ** depth
+    N = 2 * n - 1
+    parent = np.full(N, -1, dtype=np.int32)
+    level = list(range(n))
+    nxt = n
+    while len(level) > 1:
+        up = []
+        for i in range(0, len(level), 2):
+            parent[level[i]] = parent[level[i + 1]] = nxt
+            up.append(nxt)
+            nxt += 1
+        level = up
+    r = np.full(N, rate)
+    r[-1] = 0.0
+    leaf = np.full(N, -1, dtype=np.int32)
+    leaf[:n] = np.arange(n)
+    return parent, r, leaf
+
+
+@pytest.mark.parametrize("shape", ["caterpillar", "balanced"])
+def test_fused_walk_on_extreme_tree_shapes(oracle, shape):
+    parent, rate, leaf = _caterpillar(700, 0.004) if shape == "caterpillar" else _balanced(9, 0.02)
+    n, L, seed, G = int((leaf >= 0).sum()), 256, 31, 12
+    root = len(parent) - 1
+    genes = core_table(G, root)
+    with build(seed, L, parent, rate, leaf, genes, flags=0) as walk, build(seed, L, parent, rate, leaf, genes) as keep:
+        assert walk.stats()["sweep_mode"] == 1
+        for v in list(range(0, n, 7)) + [n - 1, root]:
+            assert np.array_equal(walk.copy_dense(v, G), keep.copy_dense(v, G)), v
+        for v in (0, n // 2, n - 1):
+            assert np.array_equal(walk.copy_packed(v, 3), oracle.row(seed, parent, rate, v, root, 3, L))
