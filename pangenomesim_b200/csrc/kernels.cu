@@ -408,34 +408,49 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 						if (f & kWalkParkB) st_park256(dst_b, cur[j]); else st_leaf256(dst_b, cur[j]);
 					}
 				} else { // rare: a block of a child may change
-					U32x8 ya = cur[j], yb = cur[j];
+					// The child that is NOT carried on goes first, into a temporary; the carried child (or
+					// b when nothing is carried: the value is dead after this step) is then changed in
+					// place, so the running value never lives in two register sets.
 					const uint32_t edge_b = st.edge_b;
-					do {
-						const uint32_t b = (uint32_t)__ffs((int)mj) - 1u;
-						mj &= mj - 1u;
-						const uint32_t side = b >> 1, odd = b & 1u;
-						const uint32_t edge = side ? edge_b : edge_a;
-						const int kmax = s_kmax[warp][side];
-						const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
-						const uint4 xin = odd ? cur[j].hi : cur[j].lo;
-						const uint4 y = mutate_block_slow(xin, edge, gid[j], blk[j] + odd, pick_word(w[j], side, odd),
-														  s_tab[warp][side], tab, kmax, odd ? valid_hi[j] : 64, t.keys);
-						if (side) {
-							if (odd) yb.hi = y; else yb.lo = y;
-						} else {
-							if (odd) ya.hi = y; else ya.lo = y;
+					const uint32_t second = (f & kWalkCarryA) ? 0u : 1u, first = second ^ 1u;
+					{
+						U32x8 y = cur[j];
+						uint32_t mf = (mj >> (2 * first)) & 3u;
+						while (mf) {
+							const uint32_t odd = (mf & 1u) ? 0u : 1u;
+							mf &= mf - 1u;
+							const uint32_t edge = first ? edge_b : edge_a;
+							const int kmax = s_kmax[warp][first];
+							const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
+							const uint4 out = mutate_block_slow(odd ? cur[j].hi : cur[j].lo, edge, gid[j], blk[j] + odd,
+																pick_word(w[j], first, odd), s_tab[warp][first], tab, kmax,
+																odd ? valid_hi[j] : 64, t.keys);
+							if (odd) y.hi = out; else y.lo = out;
 						}
-					} while (mj);
-					if (f & kWalkStoreA) {
-						if (f & kWalkParkA) st_park256(dst_a, ya); else st_leaf256(dst_a, ya);
+						if (f & (first ? kWalkStoreB : kWalkStoreA)) {
+							U32x8 *const dst = first ? dst_b : dst_a;
+							if (f & (first ? kWalkParkB : kWalkParkA)) st_park256(dst, y); else st_leaf256(dst, y);
+						}
 					}
-					if (f & kWalkStoreB) {
-						if (f & kWalkParkB) st_park256(dst_b, yb); else st_leaf256(dst_b, yb);
+					{
+						uint32_t ms = (mj >> (2 * second)) & 3u;
+						const uint4 lo0 = cur[j].lo, hi0 = cur[j].hi;
+						while (ms) {
+							const uint32_t odd = (ms & 1u) ? 0u : 1u;
+							ms &= ms - 1u;
+							const uint32_t edge = second ? edge_b : edge_a;
+							const int kmax = s_kmax[warp][second];
+							const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
+							const uint4 out = mutate_block_slow(odd ? hi0 : lo0, edge, gid[j], blk[j] + odd,
+																pick_word(w[j], second, odd), s_tab[warp][second], tab, kmax,
+																odd ? valid_hi[j] : 64, t.keys);
+							if (odd) cur[j].hi = out; else cur[j].lo = out;
+						}
+						if (f & (second ? kWalkStoreB : kWalkStoreA)) {
+							U32x8 *const dst = second ? dst_b : dst_a;
+							if (f & (second ? kWalkParkB : kWalkParkA)) st_park256(dst, cur[j]); else st_leaf256(dst, cur[j]);
+						}
 					}
-					if (f & kWalkCarryA)
-						cur[j] = ya;
-					else if (f & kWalkCarryB)
-						cur[j] = yb;
 				}
 				if ((f & kWalkDiscard) && may_discard[j]) {
 					// the four pairs of this 128-byte line were loaded by this warp instruction and are dead now
