@@ -24,6 +24,8 @@ void DevBuf::release()
 Engine::~Engine()
 {
 	drop_graph();
+	for (auto &p : h_stage)
+		if (p) cudaFreeHost(p);
 	for (auto &x : ev)
 		if (x) cudaEventDestroy(x);
 	if (own_stream) cudaStreamDestroy(own_stream);

@@ -70,6 +70,9 @@ struct Engine {
 	// ---- device
 	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
 	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off;
+	DevBuf d_stage[2];          // K3 staging, kept between pgs_write_outputs calls
+	char *h_stage[2] = {nullptr, nullptr}; // pinned
+	int64_t stage_bytes = 0;
 	DeviceTables tables{};
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t graph_exec = nullptr;

@@ -16,6 +16,7 @@
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <deque>
@@ -707,6 +708,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 
 	// ---- staging: two device buffers + two pinned buffers
 	int64_t stage = (int64_t)64 << 20;
+	if (const char *v = std::getenv("PGS_STAGE_MB")) stage = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
 	if (spec->what & PGS_OUT_GENOMES)
 		for (auto b : genome_bytes) stage = std::max(stage, b);
 	if (spec->what & PGS_OUT_MAF)
@@ -721,8 +723,21 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		stage = std::max(stage, refs);
 	}
 	stage = (stage + 255) & ~(int64_t)255;
-	DevBuf d_stage[2], d_aux_a[2], d_aux_b[2];
-	Pinned h_stage[2];
+	// staging buffers (2 device + 2 pinned) are kept by the engine between calls: cudaHostAlloc of
+	// tens of megabytes costs milliseconds each time
+	DevBuf d_aux_a[2], d_aux_b[2];
+	DevBuf *d_stage = e.d_stage;
+	struct HostView {
+		char *p;
+	} h_stage[2];
+	if (e.stage_bytes < stage) {
+		for (int i = 0; i < 2; i++) {
+			if (e.h_stage[i]) cudaFreeHost(e.h_stage[i]);
+			e.h_stage[i] = nullptr;
+			e.d_stage[i].release();
+		}
+		e.stage_bytes = 0;
+	}
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t formatted[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
 	cudaEvent_t k0 = nullptr, k1 = nullptr;
@@ -738,11 +753,15 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	};
 	cudaError_t ce = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
 	for (int i = 0; i < 2 && ce == cudaSuccess; i++) {
-		if ((rc = e.alloc(d_stage[i], (size_t)stage, "format staging"))) {
-			cleanup();
-			return rc;
+		if (e.stage_bytes < stage) {
+			if ((rc = e.alloc(d_stage[i], (size_t)stage, "format staging"))) {
+				cleanup();
+				return rc;
+			}
+			ce = cudaHostAlloc((void **)&e.h_stage[i], (size_t)stage, cudaHostAllocDefault);
+			if (ce != cudaSuccess) e.h_stage[i] = nullptr;
 		}
-		ce = cudaHostAlloc((void **)&h_stage[i].p, (size_t)stage, cudaHostAllocDefault);
+		h_stage[i].p = e.h_stage[i];
 		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&formatted[i], cudaEventDisableTiming);
 		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
 		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming);
@@ -753,6 +772,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		cleanup();
 		return e.cuda_fail(ce, "pgs_write_outputs setup");
 	}
+	if (e.stage_bytes < stage) e.stage_bytes = stage;
 	// small per-chunk index tables live in preallocated buffers (no cudaMalloc/cudaFree, which
 	// would synchronise the device, inside the pipeline)
 	const size_t aux_entries = (size_t)std::max<int64_t>(65537, spec->n_ref_core + spec->n_ref_acc + 1);
