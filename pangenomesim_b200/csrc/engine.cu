@@ -90,11 +90,11 @@ void Engine::drop_graph()
 int64_t Engine::row_index(int32_t node, int64_t g) const
 {
 	if (!have_genes || node < 0 || node >= n_nodes || g < 0 || g >= n_genes) return -1;
-	if (dense_slot[g] >= 0) return row_base[node] + dense_slot[g];
+	if (dense_slot[g] >= 0) return materialised[node] ? row_base[node] + dense_slot[g] : -1;
 	const int64_t *b = sp_gene.data() + sp_off[node], *e = sp_gene.data() + sp_off[node + 1];
 	const int64_t *it = std::lower_bound(b, e, g);
 	if (it == e || *it != g) return -1;
-	return row_base[node] + (int64_t)dense_gid.size() + (it - b);
+	return row_base[node] + (materialised[node] ? (int64_t)dense_gid.size() : 0) + (it - b);
 }
 
 // K1 for every level below the root: dense region, then sparse region.  Levels are separated by
@@ -206,7 +206,6 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 	}
 	e.stream = e.own_stream;
 	if (const char *v = std::getenv("PGS_K1_VARIANT")) pgs::g_dense_variant = std::atoi(v);
-	if (const char *v = std::getenv("PGS_WALK_DISCARD")) pgs::g_walk_discard = std::atoi(v);
 	if (const char *v = std::getenv("PGS_WALK_VARIANT")) pgs::g_walk_variant = std::atoi(v);
 	if (const char *v = std::getenv("PGS_KEEP_INTERNAL")) // development knob: force the level-synchronous sweep
 		if (std::atoi(v)) e.cfg.flags |= PGS_FLAG_KEEP_INTERNAL;
@@ -422,16 +421,27 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	at_node.clear();
 	at_node.shrink_to_fit();
 
-	// ---- row layout: node-major, dense region first
+	// ---- sweep mode.  The fused column walk (k1_walk_dense) needs a binary tree and an even number
+	// of blocks per gene; it keeps dense rows only where an output reads them (genomes and the root).
+	bool walk_mode = N > 1 && D > 0 && (e.blocks % 2) == 0 && !(e.cfg.flags & PGS_FLAG_KEEP_INTERNAL);
+	for (int32_t v = 0; v < N && walk_mode; v++) {
+		const int32_t nc = e.child_off[v + 1] - e.child_off[v];
+		if (nc != 0 && nc != 2) walk_mode = false;
+	}
+	e.materialised.assign(N, 1);
+	if (walk_mode)
+		for (int32_t v = 0; v < N; v++) e.materialised[v] = (e.child_off[v + 1] == e.child_off[v] || v == e.root) ? 1 : 0;
+	auto dense_rows = [&](int32_t v) -> int64_t { return e.materialised[v] ? D : 0; };
+
+	// ---- row layout: node-major, dense region (where kept) first, then the node's sparse rows;
+	// the walk's transient rows (parked siblings, unit roots) live in a small pool behind the nodes
 	e.row_base.assign(N, 0);
 	int64_t rows = 0;
 	for (int32_t v = 0; v < N; v++) {
 		e.row_base[v] = rows;
-		rows += D + (e.sp_off[v + 1] - e.sp_off[v]);
+		rows += dense_rows(v) + (e.sp_off[v + 1] - e.sp_off[v]);
 	}
-	if (rows >= (int64_t)pgs::kNoRow) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32-2 rows on one engine; shard the genes");
 	if (D * e.blocks >= (int64_t)1 << 31) return e.fail(PGS_ERR_ARG, "pgs_set_genes: dense region of a node exceeds 2^31 blocks; shard the genes");
-	e.rows_total = rows;
 
 	// ---- tasks, grouped by the level of the children
 	const int32_t ML = e.max_level;
@@ -465,9 +475,9 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 				const bool hl = il < nl && lg[il] == g, hr = ir < nr && rg[ir] == g;
 				if (!hl && !hr) continue;
 				pgs::SparseTask t;
-				t.src = (uint32_t)(e.row_base[p] + D + ip);
-				t.dst_left = hl ? (uint32_t)(e.row_base[l] + D + il) : pgs::kNoRow;
-				t.dst_right = hr ? (uint32_t)(e.row_base[r] + D + ir) : pgs::kNoRow;
+				t.src = (uint32_t)(e.row_base[p] + dense_rows(p) + ip);
+				t.dst_left = hl ? (uint32_t)(e.row_base[l] + dense_rows(l) + il) : pgs::kNoRow;
+				t.dst_right = hr ? (uint32_t)(e.row_base[r] + dense_rows(r) + ir) : pgs::kNoRow;
 				t.gid = (uint32_t)e.gene_id[g];
 				t.edge_left = l;
 				t.edge_right = r;
@@ -501,7 +511,7 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 		const int64_t *b = e.sp_gene.data() + e.sp_off[v], *en = e.sp_gene.data() + e.sp_off[v + 1];
 		const int64_t *it = std::lower_bound(b, en, g);
 		if (it == en || *it != g) continue; // gene carried by no genome: no rows at all
-		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + D + (it - b)), (uint32_t)e.gene_id[g]});
+		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + dense_rows(v) + (it - b)), (uint32_t)e.gene_id[g]});
 	}
 	e.n_root_tasks = (int64_t)root_tasks.size();
 	e.rows_origin = e.n_root_tasks;
@@ -520,8 +530,144 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 		for (int k = 1; k <= km; k++) e.tab_host.push_back(H[k]);
 	}
 
+	// ---- fused column walk of the dense region (see k1_walk_dense): cut the tree into units,
+	// order every unit depth-first with the smaller subtree first
+	int rc = 0;
+	e.walk = false;
+	e.n_walk_units = e.n_walk_top_units = 0;
+	e.rows_stored = e.rows_written;
+	e.rows_loaded = e.rows_read;
+	std::vector<pgs::WalkStep> walk_steps;
+	std::vector<int64_t> walk_off;
+	int64_t pool_slots = 0; // transient dense regions (D rows each) behind the node regions
+	if (walk_mode) {
+		auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
+		// subtree sizes (nodes), children before parents: process by decreasing level
+		std::vector<int32_t> order(N);
+		for (int32_t v = 0; v < N; v++) order[v] = v;
+		std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
+		std::vector<int64_t> size(N, 1);
+		for (int32_t v : order)
+			if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
+		// units: split the largest subtree until there are enough of them
+		size_t target_units = 80;
+		if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
+		std::vector<int32_t> roots{e.root};
+		std::vector<char> top(N, 0);
+		size_t n_top = 0;
+		while (roots.size() < target_units && n_top < 4 * target_units) { // (a caterpillar never widens)
+			size_t best = 0;
+			for (size_t i = 1; i < roots.size(); i++)
+				if (size[roots[i]] > size[roots[best]]) best = i;
+			const int32_t v = roots[best];
+			if (size[v] < 64) break;
+			top[v] = 1;
+			n_top++;
+			roots.erase(roots.begin() + best);
+			for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
+				if (internal(e.child[c])) roots.push_back(e.child[c]);
+		}
+		std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+		const int64_t B = e.blocks;
+		// where a node's dense region lives (uint4 units): its own region for genomes and the root,
+		// a pool slot for unit roots (written by pass 1, read by pass 2) and parked siblings
+		std::vector<int64_t> loc(N, -1);
+		for (int32_t v = 0; v < N; v++)
+			if (e.materialised[v]) loc[v] = e.row_base[v] * B;
+		auto slot_off = [&](int64_t slot) { return (rows + slot * D) * B; };
+		for (size_t u = 0; u < roots.size(); u++)
+			if (roots[u] != e.root) loc[roots[u]] = slot_off(pool_slots++);
+		auto make_step = [&](int32_t v, uint32_t flags) {
+			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
+			pgs::WalkStep s{};
+			s.in_off = loc[v] >= 0 ? loc[v] : 0;
+			s.a_off = loc[a] >= 0 ? loc[a] : 0;
+			s.b_off = loc[b] >= 0 ? loc[b] : 0;
+			s.edge_a = (uint32_t)a;
+			s.edge_b = (uint32_t)b;
+			s.h32a = (uint32_t)(e.h1_host[a] >> 32);
+			s.h32b = (uint32_t)(e.h1_host[b] >> 32);
+			s.flags = flags;
+			return s;
+		};
+		e.rows_stored = e.rows_loaded = 0;
+		// Depth-first step list of the subtree below `start`, smaller child first.  `descend(c)`
+		// says whether an internal child belongs to this walk; an internal child that does not
+		// (the root of another unit) is written to its pool slot and picked up by its own unit.
+		auto emit_walk = [&](int32_t start, auto descend) {
+			const int64_t stack_base = pool_slots; // this walk's parked rows: slots stack_base + depth
+			int64_t deepest = 0;
+			std::vector<int32_t> parked;
+			int32_t v = start;
+			bool in_reg = false, have = true;
+			while (have) {
+				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
+				const bool ia = internal(a), ib = internal(b);
+				const bool da = ia && descend(a), db = ib && descend(b);
+				uint32_t f = 0;
+				if (!in_reg) {
+					f |= pgs::kWalkLoad;
+					e.rows_loaded += D;
+				}
+				if (!ia) f |= pgs::kWalkStoreA;                       // a genome's row
+				if (!ib) f |= pgs::kWalkStoreB;
+				if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA; // root of another unit
+				if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB;
+				int32_t carry = -1;
+				if (da && db) {
+					const bool a_first = size[a] <= size[b];
+					carry = a_first ? a : b;
+					const int32_t later = a_first ? b : a;
+					f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkStoreB | pgs::kWalkParkB)
+								 : (pgs::kWalkCarryB | pgs::kWalkStoreA | pgs::kWalkParkA);
+					loc[later] = slot_off(stack_base + (int64_t)parked.size());
+					parked.push_back(later);
+					deepest = std::max(deepest, (int64_t)parked.size());
+				} else if (da) {
+					carry = a;
+					f |= pgs::kWalkCarryA;
+				} else if (db) {
+					carry = b;
+					f |= pgs::kWalkCarryB;
+				}
+				if (f & pgs::kWalkStoreA) e.rows_stored += D;
+				if (f & pgs::kWalkStoreB) e.rows_stored += D;
+				walk_steps.push_back(make_step(v, f));
+				if (carry >= 0) {
+					v = carry;
+					in_reg = true;
+				} else if (!parked.empty()) {
+					v = parked.back();
+					parked.pop_back();
+					in_reg = false;
+				} else {
+					have = false;
+				}
+			}
+			pool_slots += deepest;
+		};
+		// pass 1 (one unit): the top of the tree, down to the roots of the units of pass 2;
+		// pass 2: every unit loads its root row and walks its own subtree
+		walk_off.push_back(0);
+		if (top[e.root]) {
+			emit_walk(e.root, [&](int32_t c) { return top[c] != 0; });
+			walk_off.push_back((int64_t)walk_steps.size());
+			e.n_walk_top_units = 1;
+		}
+		for (int32_t r : roots) {
+			emit_walk(r, [](int32_t) { return true; });
+			walk_off.push_back((int64_t)walk_steps.size());
+		}
+		e.walk = true;
+		e.n_walk_units = (int32_t)roots.size();
+	}
+	rows += pool_slots * D;
+	if (rows >= (int64_t)pgs::kNoRow) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32-2 rows on one engine; shard the genes");
+	e.rows_total = rows;
+	if ((rc = e.upload(e.d_walk_steps, walk_steps.data(), sizeof(pgs::WalkStep) * walk_steps.size(), "walk steps"))) return rc;
+	if ((rc = e.upload(e.d_walk_off, walk_off.data(), sizeof(int64_t) * walk_off.size(), "walk units"))) return rc;
+
 	// ---- device
-	int rc;
 	const size_t row_bytes = (size_t)e.blocks * 16;
 	// the sequence store is by far the largest allocation: keep it when a re-plan fits
 	if (e.d_rows.bytes < (size_t)rows * row_bytes || e.d_rows.bytes > 2 * (size_t)rows * row_bytes + (64u << 20))
@@ -539,142 +685,6 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	for (int32_t g = 0; g < n; g++) leaf_words[g] = e.row_base[e.genome_leaf[g]] * e.blocks * 4;
 	if ((rc = e.upload(e.d_leaf_base_words, leaf_words.data(), sizeof(int64_t) * n, "leaf bases"))) return rc;
 	e.d_mismatch.release();
-	// ---- fused column walk of the dense region (see k1_walk_dense): cut the tree into units,
-	// order every unit depth-first with the smaller subtree first
-	e.walk = false;
-	e.n_walk_units = 0;
-	e.materialised.assign(N, 1);
-	e.rows_stored = e.rows_written;
-	e.rows_loaded = e.rows_read;
-	std::vector<pgs::WalkStep> walk_steps;
-	std::vector<int64_t> walk_off;
-	{
-		bool binary = N > 1;
-		for (int32_t v = 0; v < N && binary; v++) {
-			const int32_t nc = e.child_off[v + 1] - e.child_off[v];
-			if (nc != 0 && nc != 2) binary = false;
-		}
-		if (binary && D > 0 && (e.blocks % 2) == 0 && !(e.cfg.flags & PGS_FLAG_KEEP_INTERNAL)) {
-			auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
-			// subtree sizes (nodes), children before parents: process by decreasing level
-			std::vector<int32_t> order(N);
-			for (int32_t v = 0; v < N; v++) order[v] = v;
-			std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
-			std::vector<int64_t> size(N, 1);
-			for (int32_t v : order)
-				if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
-			// units: split the largest subtree until there are enough of them
-			size_t target_units = 80;
-			if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
-			std::vector<int32_t> roots{e.root};
-			std::vector<char> top(N, 0);
-			size_t n_top = 0;
-			while (roots.size() < target_units && n_top < 4 * target_units) { // (a caterpillar never widens)
-				size_t best = 0;
-				for (size_t i = 1; i < roots.size(); i++)
-					if (size[roots[i]] > size[roots[best]]) best = i;
-				const int32_t v = roots[best];
-				if (size[v] < 64) break;
-				top[v] = 1;
-				n_top++;
-				roots.erase(roots.begin() + best);
-				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
-					if (internal(e.child[c])) roots.push_back(e.child[c]);
-			}
-			std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
-			const int64_t B = e.blocks;
-			auto make_step = [&](int32_t v, uint32_t flags) {
-				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
-				pgs::WalkStep s{};
-				s.in_off = e.row_base[v] * B;
-				s.a_off = e.row_base[a] * B;
-				s.b_off = e.row_base[b] * B;
-				s.edge_a = (uint32_t)a;
-				s.edge_b = (uint32_t)b;
-				s.h32a = (uint32_t)(e.h1_host[a] >> 32);
-				s.h32b = (uint32_t)(e.h1_host[b] >> 32);
-				s.flags = flags;
-				return s;
-			};
-			std::fill(e.materialised.begin(), e.materialised.end(), 0);
-			e.materialised[e.root] = 1;
-			e.rows_stored = e.rows_loaded = 0;
-			// Depth-first step list of the subtree below `start`, smaller child first.  `descend(c)`
-			// says whether an internal child belongs to this walk; an internal child that does not
-			// (the root of another unit) is written like a parked row and picked up by its own unit.
-			auto emit_walk = [&](int32_t start, auto descend) {
-				std::vector<int32_t> parked;
-				int32_t v = start;
-				bool in_reg = false, have = true;
-				while (have) {
-					const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
-					const bool ia = internal(a), ib = internal(b);
-					const bool da = ia && descend(a), db = ib && descend(b);
-					uint32_t f = 0;
-					if (!in_reg) {
-						f |= pgs::kWalkLoad;
-						e.rows_loaded += D;
-						if (v != e.root) f |= pgs::kWalkDiscard;
-					}
-					if (!ia) f |= pgs::kWalkStoreA;                       // a genome's row
-					if (!ib) f |= pgs::kWalkStoreB;
-					if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA; // root of another unit
-					if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB;
-					int32_t carry = -1;
-					if (da && db) {
-						const bool a_first = size[a] <= size[b];
-						carry = a_first ? a : b;
-						f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkStoreB | pgs::kWalkParkB)
-									 : (pgs::kWalkCarryB | pgs::kWalkStoreA | pgs::kWalkParkA);
-						parked.push_back(a_first ? b : a);
-					} else if (da) {
-						carry = a;
-						f |= pgs::kWalkCarryA;
-					} else if (db) {
-						carry = b;
-						f |= pgs::kWalkCarryB;
-					}
-					if (f & pgs::kWalkStoreA) {
-						e.rows_stored += D;
-						if (!ia) e.materialised[a] = 1;
-					}
-					if (f & pgs::kWalkStoreB) {
-						e.rows_stored += D;
-						if (!ib) e.materialised[b] = 1;
-					}
-					walk_steps.push_back(make_step(v, f));
-					if (carry >= 0) {
-						v = carry;
-						in_reg = true;
-					} else if (!parked.empty()) {
-						v = parked.back();
-						parked.pop_back();
-						in_reg = false;
-					} else {
-						have = false;
-					}
-				}
-			};
-			// pass 1 (one unit): the top of the tree, down to the roots of the units of pass 2;
-			// pass 2: every unit loads its root row and walks its own subtree
-			walk_off.push_back(0);
-			e.n_walk_top_units = 0;
-			if (top[e.root]) {
-				emit_walk(e.root, [&](int32_t c) { return top[c] != 0; });
-				walk_off.push_back((int64_t)walk_steps.size());
-				e.n_walk_top_units = 1;
-			}
-			for (int32_t r : roots) {
-				emit_walk(r, [](int32_t) { return true; });
-				walk_off.push_back((int64_t)walk_steps.size());
-			}
-			e.walk = true;
-			e.n_walk_units = (int32_t)roots.size();
-		}
-	}
-	if ((rc = e.upload(e.d_walk_steps, walk_steps.data(), sizeof(pgs::WalkStep) * walk_steps.size(), "walk steps"))) return rc;
-	if ((rc = e.upload(e.d_walk_off, walk_off.data(), sizeof(int64_t) * walk_off.size(), "walk units"))) return rc;
-
 	{ // first eight thresholds of every branch at a fixed stride, for the kernels' shared-memory copy
 		std::vector<uint64_t> tab8((size_t)N * 8, 0);
 		for (int32_t v = 0; v < N; v++)

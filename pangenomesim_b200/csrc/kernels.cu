@@ -324,12 +324,12 @@ constexpr int kWalkChunk = 32; // steps staged in shared memory per barrier
 template <int MINB, int PAIRS>
 __global__ void __launch_bounds__(kThreads, MINB)
 k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
-			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node, uint32_t discard_ok)
+			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node)
 {
 	const uint32_t unit = blockIdx.x % n_units, slab = blockIdx.x / n_units;
 	// this thread's PAIRS columns (block pairs) inside any node's dense region
 	uint32_t p[PAIRS], gid[PAIRS], blk[PAIRS];
-	bool active[PAIRS], may_discard[PAIRS];
+	bool active[PAIRS];
 	int valid_hi[PAIRS];
 	U32x8 *column[PAIRS];
 #pragma unroll
@@ -342,7 +342,6 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 		gid[j] = active[j] ? __ldg(t.dense_gid + slot) : 0u;
 		valid_hi[j] = (blk[j] + 2 == t.blocks) ? t.last_valid : 64;
 		column[j] = reinterpret_cast<U32x8 *>(t.rows) + p[j]; // step offsets are in uint4 units
-		may_discard[j] = discard_ok && (p[j] & 3u) == 0u && p[j] + 3u < pairs_per_node;
 	}
 
 	// every warp stages its own copy of the next steps: warps of a CTA drift apart (rare path) and
@@ -452,16 +451,11 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 						}
 					}
 				}
-				if ((f & kWalkDiscard) && may_discard[j]) {
-					// the four pairs of this 128-byte line were loaded by this warp instruction and are dead now
-					asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<const uint4 *>(column[j]) + st.in_off) : "memory");
-				}
 			}
 		}
 	}
 }
 
-int g_walk_discard = 1; // development knob (PGS_WALK_DISCARD)
 int g_walk_variant = 0; // development knob (PGS_WALK_VARIANT)
 
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
@@ -469,19 +463,17 @@ void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64
 {
 	if (n_units == 0 || t.n_dense == 0) return;
 	const uint32_t pairs = t.n_dense * t.blocks / 2;
-	// lines of 128 bytes = 4 pairs must not straddle nodes: needs 128-byte aligned dense regions
-	const uint32_t discard_ok = (g_walk_discard && (t.blocks % 8u) == 0u) ? 1u : 0u;
 	auto grid = [&](int pairs_per_thread) {
 		const uint32_t per_cta = kThreads * pairs_per_thread;
 		return (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
 	};
 	switch (g_walk_variant) {
-		case 1: k1_walk_dense<4, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
-		case 2: k1_walk_dense<2, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
-		case 3: k1_walk_dense<2, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
-		case 4: k1_walk_dense<1, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
-		case 5: k1_walk_dense<3, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
-		default: k1_walk_dense<3, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs, discard_ok); break;
+		case 1: k1_walk_dense<4, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+		case 2: k1_walk_dense<2, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+		case 3: k1_walk_dense<2, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+		case 4: k1_walk_dense<1, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+		case 5: k1_walk_dense<3, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+		default: k1_walk_dense<3, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
 	}
 }
 

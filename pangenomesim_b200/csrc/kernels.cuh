@@ -38,7 +38,6 @@ constexpr uint32_t kWalkStoreA = 2u;   // write child a's row
 constexpr uint32_t kWalkStoreB = 4u;
 constexpr uint32_t kWalkCarryA = 8u;   // child a's value is the next step's input
 constexpr uint32_t kWalkCarryB = 16u;
-constexpr uint32_t kWalkDiscard = 32u; // the loaded input row is dead afterwards: drop its lines from L2
 constexpr uint32_t kWalkParkA = 64u;   // the stored child a is an internal node that is re-read soon (keep in L2)
 constexpr uint32_t kWalkParkB = 128u;
 
@@ -84,7 +83,6 @@ struct DeviceTables {
 };
 
 extern int g_dense_variant;
-extern int g_walk_discard;
 extern int g_walk_variant;
 void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_tasks, cudaStream_t s);
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);

@@ -37,9 +37,11 @@ def test_config4_counts_and_stats(config4):
     s = e.stats()
     assert s["leaf_nucleotides"] == n * G * L == 5 * 10**10
     assert s["site_edges"] == (2 * n - 2) * G * L
-    assert s["rows_total"] == (2 * n - 1) * G
-    assert s["rows_read"] == (n - 1) * G and s["rows_written"] == (2 * n - 2) * G
-    assert s["device_bytes"] > 25e9
+    assert s["rows_read"] == (n - 1) * G and s["rows_written"] == (2 * n - 2) * G   # algorithmic (level-synchronous) counts
+    # the fused walk keeps rows for the genomes and the root plus a small pool of transient rows
+    assert s["sweep_mode"] == 1 and (n + 1) * G <= s["rows_total"] < 1.3 * n * G
+    assert s["rows_stored"] < 1.4 * n * G and s["rows_loaded"] < 0.4 * n * G
+    assert 12.8e9 < s["device_bytes"] < 17e9
 
 
 def test_config4_oracle_spot_checks(config4, oracle):
@@ -129,7 +131,7 @@ def test_config4_leaf_composition_and_distance(config4, oracle):
 def test_config5_shape_high_mutation_rate(oracle):
     """config 5's tree (50000 genomes, gene-length 2000, high mut-rate) at a reduced gene count:
     memory layout beyond 2^31 bytes, 38+ levels, dense rare path; oracle spot checks."""
-    n, G, L, seed = 50000, 60, 2000, 3
+    n, G, L, seed = 50000, 120, 2000, 3
     parent, rate, leaf = host_coalescent(n, seed, 0.5)
     root = 2 * n - 2
     with Engine(seed, L) as e:

@@ -338,3 +338,21 @@ def test_fused_walk_on_extreme_tree_shapes(oracle, shape):
             assert np.array_equal(walk.copy_dense(v, G), keep.copy_dense(v, G)), v
         for v in (0, n // 2, n - 1):
             assert np.array_equal(walk.copy_packed(v, 3), oracle.row(seed, parent, rate, v, root, 3, L))
+
+
+def test_fused_walk_is_race_free_under_repetition(oracle):
+    """pool slots of parked rows are reused inside a sweep; repeat a mid-sized sweep and compare
+    every genome with the level-synchronous engine each time"""
+    n, L, seed, G = 3000, 1024, 77, 64
+    parent, rate, leaf = treegen.coalescent(n, seed=12, mut_rate=0.02)
+    root = len(parent) - 1
+    genes = core_table(G, root)
+    with build(seed, L, parent, rate, leaf, genes) as keep:
+        want = np.stack([keep.copy_dense(v, G) for v in range(n)])
+    with build(seed, L, parent, rate, leaf, genes, flags=0) as walk:
+        for rep in range(6):
+            if rep:
+                walk.sweep()
+                walk.sync()
+            got = np.stack([walk.copy_dense(v, G) for v in range(n)])
+            assert np.array_equal(got, want), f"repetition {rep}"
