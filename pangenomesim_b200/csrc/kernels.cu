@@ -321,7 +321,7 @@ __device__ __forceinline__ void ld_own256_if(U32x8 &v, const U32x8 *p, uint32_t 
 
 constexpr int kWalkChunk = 32; // steps staged in shared memory per barrier
 
-template <int MINB, int PAIRS>
+template <int MINB, int PAIRS, bool HINTS = true>
 __global__ void __launch_bounds__(kThreads, MINB)
 k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
 			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node)
@@ -401,10 +401,10 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 				U32x8 *const dst_b = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + st.b_off);
 				if (mj == 0) { // common case: both children are copies of the carried value
 					if (f & kWalkStoreA) {
-						if (f & kWalkParkA) st_park256(dst_a, cur[j]); else st_leaf256(dst_a, cur[j]);
+						if (!HINTS) st_stream256(dst_a, cur[j]); else if (f & kWalkParkA) st_park256(dst_a, cur[j]); else st_leaf256(dst_a, cur[j]);
 					}
 					if (f & kWalkStoreB) {
-						if (f & kWalkParkB) st_park256(dst_b, cur[j]); else st_leaf256(dst_b, cur[j]);
+						if (!HINTS) st_stream256(dst_b, cur[j]); else if (f & kWalkParkB) st_park256(dst_b, cur[j]); else st_leaf256(dst_b, cur[j]);
 					}
 				} else { // rare: a block of a child may change
 					// The child that is NOT carried on goes first, into a temporary; the carried child (or
@@ -428,7 +428,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 						}
 						if (f & (first ? kWalkStoreB : kWalkStoreA)) {
 							U32x8 *const dst = first ? dst_b : dst_a;
-							if (f & (first ? kWalkParkB : kWalkParkA)) st_park256(dst, y); else st_leaf256(dst, y);
+							if (!HINTS) st_stream256(dst, y); else if (f & (first ? kWalkParkB : kWalkParkA)) st_park256(dst, y); else st_leaf256(dst, y);
 						}
 					}
 					{
@@ -447,7 +447,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 						}
 						if (f & (second ? kWalkStoreB : kWalkStoreA)) {
 							U32x8 *const dst = second ? dst_b : dst_a;
-							if (f & (second ? kWalkParkB : kWalkParkA)) st_park256(dst, cur[j]); else st_leaf256(dst, cur[j]);
+							if (!HINTS) st_stream256(dst, cur[j]); else if (f & (second ? kWalkParkB : kWalkParkA)) st_park256(dst, cur[j]); else st_leaf256(dst, cur[j]);
 						}
 					}
 				}
@@ -468,7 +468,7 @@ void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64
 		return (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
 	};
 	switch (g_walk_variant) {
-		case 1: k1_walk_dense<4, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+		case 1: k1_walk_dense<3, 1, false><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
 		case 2: k1_walk_dense<2, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
 		case 3: k1_walk_dense<2, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
 		case 4: k1_walk_dense<1, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
