@@ -412,7 +412,9 @@ struct Writer {
 	{
 		if (!(s->what & PGS_OUT_DISCARD) && !s->sink) {
 			unsigned n = std::thread::hardware_concurrency();
-			pool.reset(new WritePool(n < 2 ? 1 : (n > 8 ? 8 : n)));
+			n = n < 2 ? 1 : (n > 8 ? 8 : n);
+			if (const char *v = std::getenv("PGS_WRITE_THREADS")) n = (unsigned)std::max(1, std::atoi(v)); // tuning knob
+			pool.reset(new WritePool(n));
 		}
 	}
 	~Writer() { close_file(); }
