@@ -2,7 +2,6 @@
 // tables, launches.  There is no CPU path: every compute entry point ends in a CUDA kernel of
 // kernels.cu / format.cu and fails with PGS_ERR_NO_DEVICE / PGS_ERR_CUDA otherwise.
 #include "engine.h"
-#include "edge_table.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -329,383 +328,8 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 		return e.fail(PGS_ERR_ARG, "pgs_set_genes: null table");
 	e.have_genes = e.swept = false;
 	e.drop_graph();
-	const int32_t N = e.n_nodes, n = e.n_genomes;
-
-	// ---- copy and validate the gene table
-	e.n_genes = n_genes;
-	e.gene_id.assign(gene_id, gene_id + n_genes);
-	e.origin.assign(origin_node, origin_node + n_genes);
-	e.all_order.resize(n);
-	if (all_order) {
-		std::vector<char> seen(n, 0);
-		for (int32_t i = 0; i < n; i++) {
-			const int32_t g = all_order[i];
-			if (g < 0 || g >= n || seen[g]) return e.fail(PGS_ERR_ARG, "pgs_set_genes: all_order is not a permutation");
-			seen[g] = 1;
-			e.all_order[i] = g;
-		}
-	} else {
-		for (int32_t i = 0; i < n; i++) e.all_order[i] = i;
-	}
-	e.dense_slot.assign(n_genes, -1);
-	std::vector<std::pair<uint32_t, int64_t>> dense; // (gene_id, table index)
-	for (int64_t g = 0; g < n_genes; g++) {
-		if (gene_id[g] < 0 || gene_id[g] >= (int64_t)0xFFFFFFFFll)
-			return e.fail(PGS_ERR_ARG, "pgs_set_genes: gene_id outside [0, 2^32-1)");
-		if (origin_node[g] < 0 || origin_node[g] >= N) return e.fail(PGS_ERR_ARG, "pgs_set_genes: origin out of range");
-		const int64_t b = carrier_off[g], c = carrier_off[g + 1];
-		if (b < 0 || c < b) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier_off not monotone");
-		if (c - b == 1 && carrier_genome[b] == PGS_ALL_GENOMES && origin_node[g] == e.root)
-			dense.emplace_back((uint32_t)gene_id[g], g);
-	}
-	std::sort(dense.begin(), dense.end());
-	const int64_t D = (int64_t)dense.size();
-	e.dense_gid.resize(D);
-	e.dense_gene.resize(D);
-	for (int64_t s = 0; s < D; s++) {
-		e.dense_gid[s] = dense[s].first;
-		e.dense_gene[s] = dense[s].second;
-		e.dense_slot[dense[s].second] = (int32_t)s;
-	}
-
-	// ---- sparse genes: expand carriers, mark the nodes on the paths carrier -> origin
-	e.carrier_off.assign(n_genes + 1, 0);
-	e.carrier_genome.clear();
-	std::vector<std::vector<int64_t>> at_node(N);
-	std::vector<int64_t> stamp(N, -1);
-	e.genome_gene_count.assign(n, D);
-	for (int64_t g = 0; g < n_genes; g++) {
-		e.carrier_off[g] = (int64_t)e.carrier_genome.size();
-		if (e.dense_slot[g] >= 0) continue;
-		const int64_t b = carrier_off[g], c = carrier_off[g + 1];
-		const int32_t org = origin_node[g];
-		if (c - b == 1 && carrier_genome[b] == PGS_ALL_GENOMES) {
-			// every genome below a non-root origin, in all_order
-			for (int32_t i = 0; i < n; i++) {
-				int32_t v = e.genome_leaf[e.all_order[i]];
-				while (v != -1 && v != org) v = e.parent[v];
-				if (v == org) e.carrier_genome.push_back(e.all_order[i]);
-			}
-		} else {
-			for (int64_t k = b; k < c; k++) {
-				const int32_t cg = carrier_genome[k];
-				if (cg < 0 || cg >= n) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier genome out of range");
-				e.carrier_genome.push_back(cg);
-			}
-		}
-		for (int64_t k = e.carrier_off[g]; k < (int64_t)e.carrier_genome.size(); k++) {
-			int32_t v = e.genome_leaf[e.carrier_genome[k]];
-			if (stamp[v] == g) return e.fail(PGS_ERR_ARG, "pgs_set_genes: genome listed twice for a gene");
-			e.genome_gene_count[e.carrier_genome[k]]++;
-			while (stamp[v] != g) {
-				stamp[v] = g;
-				at_node[v].push_back(g);
-				if (v == org) break;
-				v = e.parent[v];
-				if (v < 0) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier is not below the gene's origin");
-			}
-		}
-	}
-	e.carrier_off[n_genes] = (int64_t)e.carrier_genome.size();
-	{ // gene ids must be unique across the whole table
-		std::vector<int64_t> ids(e.gene_id);
-		std::sort(ids.begin(), ids.end());
-		if (std::adjacent_find(ids.begin(), ids.end()) != ids.end())
-			return e.fail(PGS_ERR_ARG, "pgs_set_genes: duplicate gene_id");
-	}
-
-	e.sp_off.assign(N + 1, 0);
-	for (int32_t v = 0; v < N; v++) e.sp_off[v + 1] = e.sp_off[v] + (int64_t)at_node[v].size();
-	e.sp_gene.resize(e.sp_off[N]);
-	for (int32_t v = 0; v < N; v++) std::copy(at_node[v].begin(), at_node[v].end(), e.sp_gene.begin() + e.sp_off[v]);
-	at_node.clear();
-	at_node.shrink_to_fit();
-
-	// ---- sweep mode.  The fused column walk (k1_walk_dense) needs a binary tree and an even number
-	// of blocks per gene; it keeps dense rows only where an output reads them (genomes and the root).
-	bool walk_mode = N > 1 && D > 0 && (e.blocks % 2) == 0 && !(e.cfg.flags & PGS_FLAG_KEEP_INTERNAL);
-	for (int32_t v = 0; v < N && walk_mode; v++) {
-		const int32_t nc = e.child_off[v + 1] - e.child_off[v];
-		if (nc != 0 && nc != 2) walk_mode = false;
-	}
-	e.materialised.assign(N, 1);
-	if (walk_mode)
-		for (int32_t v = 0; v < N; v++) e.materialised[v] = (e.child_off[v + 1] == e.child_off[v] || v == e.root) ? 1 : 0;
-	auto dense_rows = [&](int32_t v) -> int64_t { return e.materialised[v] ? D : 0; };
-
-	// ---- row layout: node-major, dense region (where kept) first, then the node's sparse rows;
-	// the walk's transient rows (parked siblings, unit roots) live in a small pool behind the nodes
-	e.row_base.assign(N, 0);
-	int64_t rows = 0;
-	for (int32_t v = 0; v < N; v++) {
-		e.row_base[v] = rows;
-		rows += dense_rows(v) + (e.sp_off[v + 1] - e.sp_off[v]);
-	}
-	if (D * e.blocks >= (int64_t)1 << 31) return e.fail(PGS_ERR_ARG, "pgs_set_genes: dense region of a node exceeds 2^31 blocks; shard the genes");
-
-	// ---- tasks, grouped by the level of the children
-	const int32_t ML = e.max_level;
-	std::vector<std::vector<pgs::DenseTask>> dl(ML + 2);
-	std::vector<std::vector<pgs::SparseTask>> sl(ML + 2);
-	e.rows_written = e.rows_read = 0;
-	for (int32_t p = 0; p < N; p++) {
-		const int32_t nc = e.child_off[p + 1] - e.child_off[p];
-		if (nc == 0) continue;
-		const int32_t lvl = e.level[p] + 1;
-		const int64_t *pg = e.sp_gene.data() + e.sp_off[p];
-		const int64_t np = e.sp_off[p + 1] - e.sp_off[p];
-		for (int32_t ci = 0; ci < nc; ci += 2) {
-			const int32_t l = e.child[e.child_off[p] + ci];
-			const int32_t r = (ci + 1 < nc) ? e.child[e.child_off[p] + ci + 1] : -1;
-			if (D > 0) {
-				dl[lvl].push_back(pgs::DenseTask{p, l, r});
-				e.rows_read += D;
-				e.rows_written += D * (r >= 0 ? 2 : 1);
-			}
-			// merge the parent's sparse list with the children's (all ascending)
-			const int64_t *lg = e.sp_gene.data() + e.sp_off[l];
-			const int64_t nl = e.sp_off[l + 1] - e.sp_off[l];
-			const int64_t *rg = r >= 0 ? e.sp_gene.data() + e.sp_off[r] : nullptr;
-			const int64_t nr = r >= 0 ? e.sp_off[r + 1] - e.sp_off[r] : 0;
-			int64_t il = 0, ir = 0;
-			for (int64_t ip = 0; ip < np; ip++) {
-				const int64_t g = pg[ip];
-				while (il < nl && lg[il] < g) il++;
-				while (ir < nr && rg[ir] < g) ir++;
-				const bool hl = il < nl && lg[il] == g, hr = ir < nr && rg[ir] == g;
-				if (!hl && !hr) continue;
-				pgs::SparseTask t;
-				t.src = (uint32_t)(e.row_base[p] + dense_rows(p) + ip);
-				t.dst_left = hl ? (uint32_t)(e.row_base[l] + dense_rows(l) + il) : pgs::kNoRow;
-				t.dst_right = hr ? (uint32_t)(e.row_base[r] + dense_rows(r) + ir) : pgs::kNoRow;
-				t.gid = (uint32_t)e.gene_id[g];
-				t.edge_left = l;
-				t.edge_right = r;
-				sl[lvl].push_back(t);
-				e.rows_read += 1;
-				e.rows_written += (hl ? 1 : 0) + (hr ? 1 : 0);
-			}
-		}
-	}
-	std::vector<pgs::DenseTask> dense_tasks;
-	std::vector<pgs::SparseTask> sparse_tasks;
-	e.dense_level_off.assign(ML + 2, 0);
-	e.sparse_level_off.assign(ML + 2, 0);
-	for (int32_t lvl = 0; lvl <= ML; lvl++) {
-		e.dense_level_off[lvl] = (int64_t)dense_tasks.size();
-		e.sparse_level_off[lvl] = (int64_t)sparse_tasks.size();
-		dense_tasks.insert(dense_tasks.end(), dl[lvl].begin(), dl[lvl].end());
-		sparse_tasks.insert(sparse_tasks.end(), sl[lvl].begin(), sl[lvl].end());
-	}
-	e.dense_level_off[ML + 1] = (int64_t)dense_tasks.size();
-	e.sparse_level_off[ML + 1] = (int64_t)sparse_tasks.size();
-	e.n_dense_tasks = (int64_t)dense_tasks.size();
-	e.n_sparse_tasks = (int64_t)sparse_tasks.size();
-
-	std::vector<pgs::RootTask> root_tasks;
-	root_tasks.reserve(n_genes);
-	for (int64_t s = 0; s < D; s++) root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[e.root] + s), e.dense_gid[s]});
-	for (int64_t g = 0; g < n_genes; g++) {
-		if (e.dense_slot[g] >= 0) continue;
-		const int32_t v = e.origin[g];
-		const int64_t *b = e.sp_gene.data() + e.sp_off[v], *en = e.sp_gene.data() + e.sp_off[v + 1];
-		const int64_t *it = std::lower_bound(b, en, g);
-		if (it == en || *it != g) continue; // gene carried by no genome: no rows at all
-		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + dense_rows(v) + (it - b)), (uint32_t)e.gene_id[g]});
-	}
-	e.n_root_tasks = (int64_t)root_tasks.size();
-	e.rows_origin = e.n_root_tasks;
-
-	// ---- per-branch decision tables
-	e.h1_host.assign(N, 0);
-	e.tab_off_host.assign(N, 0);
-	e.kmax_host.assign(N, 0);
-	e.tab_host.clear();
-	for (int32_t v = 0; v < N; v++) {
-		uint64_t H[65];
-		const int km = (v == e.root) ? 0 : pgs::build_edge_table(e.rate[v], H);
-		e.tab_off_host[v] = (int32_t)e.tab_host.size();
-		e.kmax_host[v] = km;
-		e.h1_host[v] = km > 0 ? H[1] : 0;
-		for (int k = 1; k <= km; k++) e.tab_host.push_back(H[k]);
-	}
-
-	// ---- fused column walk of the dense region (see k1_walk_dense): cut the tree into units,
-	// order every unit depth-first with the smaller subtree first
-	int rc = 0;
-	e.walk = false;
-	e.n_walk_units = e.n_walk_top_units = 0;
-	e.rows_stored = e.rows_written;
-	e.rows_loaded = e.rows_read;
-	std::vector<pgs::WalkStep> walk_steps;
-	std::vector<int64_t> walk_off;
-	int64_t pool_slots = 0; // transient dense regions (D rows each) behind the node regions
-	if (walk_mode) {
-		auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
-		// subtree sizes (nodes), children before parents: process by decreasing level
-		std::vector<int32_t> order(N);
-		for (int32_t v = 0; v < N; v++) order[v] = v;
-		std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
-		std::vector<int64_t> size(N, 1);
-		for (int32_t v : order)
-			if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
-		// units: split the largest subtree until there are enough of them
-		size_t target_units = 80;
-		if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
-		std::vector<int32_t> roots{e.root};
-		std::vector<char> top(N, 0);
-		size_t n_top = 0;
-		while (roots.size() < target_units && n_top < 4 * target_units) { // (a caterpillar never widens)
-			size_t best = 0;
-			for (size_t i = 1; i < roots.size(); i++)
-				if (size[roots[i]] > size[roots[best]]) best = i;
-			const int32_t v = roots[best];
-			if (size[v] < 64) break;
-			top[v] = 1;
-			n_top++;
-			roots.erase(roots.begin() + best);
-			for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
-				if (internal(e.child[c])) roots.push_back(e.child[c]);
-		}
-		std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
-		const int64_t B = e.blocks;
-		// where a node's dense region lives (uint4 units): its own region for genomes and the root,
-		// a pool slot for unit roots (written by pass 1, read by pass 2) and parked siblings
-		std::vector<int64_t> loc(N, -1);
-		for (int32_t v = 0; v < N; v++)
-			if (e.materialised[v]) loc[v] = e.row_base[v] * B;
-		auto slot_off = [&](int64_t slot) { return (rows + slot * D) * B; };
-		for (size_t u = 0; u < roots.size(); u++)
-			if (roots[u] != e.root) loc[roots[u]] = slot_off(pool_slots++);
-		auto make_step = [&](int32_t v, uint32_t flags) {
-			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
-			pgs::WalkStep s{};
-			s.in_off = loc[v] >= 0 ? loc[v] : 0;
-			s.a_off = loc[a] >= 0 ? loc[a] : 0;
-			s.b_off = loc[b] >= 0 ? loc[b] : 0;
-			s.edge_a = (uint32_t)a;
-			s.edge_b = (uint32_t)b;
-			s.h32a = (uint32_t)(e.h1_host[a] >> 32);
-			s.h32b = (uint32_t)(e.h1_host[b] >> 32);
-			s.flags = flags;
-			return s;
-		};
-		e.rows_stored = e.rows_loaded = 0;
-		// Depth-first step list of the subtree below `start`, smaller child first.  `descend(c)`
-		// says whether an internal child belongs to this walk; an internal child that does not
-		// (the root of another unit) is written to its pool slot and picked up by its own unit.
-		auto emit_walk = [&](int32_t start, auto descend) {
-			const int64_t stack_base = pool_slots; // this walk's parked rows: slots stack_base + depth
-			int64_t deepest = 0;
-			std::vector<int32_t> parked;
-			int32_t v = start;
-			bool in_reg = false, have = true;
-			while (have) {
-				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
-				const bool ia = internal(a), ib = internal(b);
-				const bool da = ia && descend(a), db = ib && descend(b);
-				uint32_t f = 0;
-				if (!in_reg) {
-					f |= pgs::kWalkLoad;
-					e.rows_loaded += D;
-				}
-				if (!ia) f |= pgs::kWalkStoreA;                       // a genome's row
-				if (!ib) f |= pgs::kWalkStoreB;
-				if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA; // root of another unit
-				if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB;
-				int32_t carry = -1;
-				if (da && db) {
-					const bool a_first = size[a] <= size[b];
-					carry = a_first ? a : b;
-					const int32_t later = a_first ? b : a;
-					f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkStoreB | pgs::kWalkParkB)
-								 : (pgs::kWalkCarryB | pgs::kWalkStoreA | pgs::kWalkParkA);
-					loc[later] = slot_off(stack_base + (int64_t)parked.size());
-					parked.push_back(later);
-					deepest = std::max(deepest, (int64_t)parked.size());
-				} else if (da) {
-					carry = a;
-					f |= pgs::kWalkCarryA;
-				} else if (db) {
-					carry = b;
-					f |= pgs::kWalkCarryB;
-				}
-				if (f & pgs::kWalkStoreA) e.rows_stored += D;
-				if (f & pgs::kWalkStoreB) e.rows_stored += D;
-				walk_steps.push_back(make_step(v, f));
-				if (carry >= 0) {
-					v = carry;
-					in_reg = true;
-				} else if (!parked.empty()) {
-					v = parked.back();
-					parked.pop_back();
-					in_reg = false;
-				} else {
-					have = false;
-				}
-			}
-			pool_slots += deepest;
-		};
-		// pass 1 (one unit): the top of the tree, down to the roots of the units of pass 2;
-		// pass 2: every unit loads its root row and walks its own subtree
-		walk_off.push_back(0);
-		if (top[e.root]) {
-			emit_walk(e.root, [&](int32_t c) { return top[c] != 0; });
-			walk_off.push_back((int64_t)walk_steps.size());
-			e.n_walk_top_units = 1;
-		}
-		for (int32_t r : roots) {
-			emit_walk(r, [](int32_t) { return true; });
-			walk_off.push_back((int64_t)walk_steps.size());
-		}
-		e.walk = true;
-		e.n_walk_units = (int32_t)roots.size();
-	}
-	rows += pool_slots * D;
-	if (rows >= (int64_t)pgs::kNoRow) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32-2 rows on one engine; shard the genes");
-	e.rows_total = rows;
-	if ((rc = e.upload(e.d_walk_steps, walk_steps.data(), sizeof(pgs::WalkStep) * walk_steps.size(), "walk steps"))) return rc;
-	if ((rc = e.upload(e.d_walk_off, walk_off.data(), sizeof(int64_t) * walk_off.size(), "walk units"))) return rc;
-
-	// ---- device
-	const size_t row_bytes = (size_t)e.blocks * 16;
-	// the sequence store is by far the largest allocation: keep it when a re-plan fits
-	if (e.d_rows.bytes < (size_t)rows * row_bytes || e.d_rows.bytes > 2 * (size_t)rows * row_bytes + (64u << 20))
-		if ((rc = e.alloc(e.d_rows, (size_t)rows * row_bytes, "rows (HBM sequence store)"))) return rc;
-	if ((rc = e.upload(e.d_row_base, e.row_base.data(), sizeof(int64_t) * N, "row_base"))) return rc;
-	if ((rc = e.upload(e.d_h1, e.h1_host.data(), sizeof(uint64_t) * N, "h1"))) return rc;
-	if ((rc = e.upload(e.d_tab, e.tab_host.data(), sizeof(uint64_t) * e.tab_host.size(), "tab"))) return rc;
-	if ((rc = e.upload(e.d_tab_off, e.tab_off_host.data(), sizeof(int32_t) * N, "tab_off"))) return rc;
-	if ((rc = e.upload(e.d_kmax, e.kmax_host.data(), sizeof(int32_t) * N, "kmax"))) return rc;
-	if ((rc = e.upload(e.d_dense_gid, e.dense_gid.data(), sizeof(uint32_t) * D, "dense_gid"))) return rc;
-	if ((rc = e.upload(e.d_dense_tasks, dense_tasks.data(), sizeof(pgs::DenseTask) * dense_tasks.size(), "dense tasks"))) return rc;
-	if ((rc = e.upload(e.d_sparse_tasks, sparse_tasks.data(), sizeof(pgs::SparseTask) * sparse_tasks.size(), "sparse tasks"))) return rc;
-	if ((rc = e.upload(e.d_root_tasks, root_tasks.data(), sizeof(pgs::RootTask) * root_tasks.size(), "root tasks"))) return rc;
-	std::vector<int64_t> leaf_words(n);
-	for (int32_t g = 0; g < n; g++) leaf_words[g] = e.row_base[e.genome_leaf[g]] * e.blocks * 4;
-	if ((rc = e.upload(e.d_leaf_base_words, leaf_words.data(), sizeof(int64_t) * n, "leaf bases"))) return rc;
-	e.d_mismatch.release();
-	{ // first eight thresholds of every branch at a fixed stride, for the kernels' shared-memory copy
-		std::vector<uint64_t> tab8((size_t)N * 8, 0);
-		for (int32_t v = 0; v < N; v++)
-			for (int k = 0; k < 8 && k < e.kmax_host[v]; k++) tab8[(size_t)v * 8 + k] = e.tab_host[e.tab_off_host[v] + k];
-		if ((rc = e.upload(e.d_tab8, tab8.data(), sizeof(uint64_t) * tab8.size(), "tab8"))) return rc;
-	}
-
-	pgs::DeviceTables &t = e.tables;
-	t.rows = e.d_rows.as<uint4>();
-	t.row_base = e.d_row_base.as<int64_t>();
-	t.h1 = e.d_h1.as<uint64_t>();
-	t.tab = e.d_tab.as<uint64_t>();
-	t.tab_off = e.d_tab_off.as<int32_t>();
-	t.kmax = e.d_kmax.as<int32_t>();
-	t.dense_gid = e.d_dense_gid.as<uint32_t>();
-	t.n_dense = (uint32_t)D;
-	t.blocks = (uint32_t)e.blocks;
-	t.last_valid = e.last_valid;
-	t.div_blocks = pgs::make_fastdiv((uint32_t)e.blocks);
-	t.tab8 = e.d_tab8.as<uint64_t>();
-	t.keys = pgs::make_philox_keys(e.cfg.seed);
+	const int rc = pgs::plan_genes(e, n_genes, gene_id, origin_node, carrier_off, carrier_genome, all_order); // plan.cu
+	if (rc) return rc;
 	e.have_genes = true;
 	return PGS_OK;
 }

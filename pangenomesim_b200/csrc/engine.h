@@ -90,6 +90,10 @@ struct Engine {
 	void enqueue_levels(cudaStream_t s, int64_t *launches);
 };
 
+// plan.cu: everything behind pgs_set_genes (validation, layout, tasks, tables, uploads)
+int plan_genes(Engine &e, int64_t n_genes, const int64_t *gene_id, const int32_t *origin_node,
+			   const int64_t *carrier_off, const int32_t *carrier_genome, const int32_t *all_order);
+
 // format.cu
 int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report);
 int output_sizes(Engine &e, const pgs_output_spec *spec, int64_t *genome_bytes, int64_t *maf_bytes);
