@@ -206,6 +206,8 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 	e.stream = e.own_stream;
 	if (const char *v = std::getenv("PGS_K1_VARIANT")) pgs::g_dense_variant = std::atoi(v);
 	if (const char *v = std::getenv("PGS_WALK_VARIANT")) pgs::g_walk_variant = std::atoi(v);
+	if (const char *v = std::getenv("PGS_NO_GRAPH")) // development knob: plain launches (profiling, first-sweep timing)
+		if (std::atoi(v)) e.cfg.flags |= PGS_FLAG_NO_GRAPH;
 	if (const char *v = std::getenv("PGS_KEEP_INTERNAL")) // development knob: force the level-synchronous sweep
 		if (std::atoi(v)) e.cfg.flags |= PGS_FLAG_KEEP_INTERNAL;
 	e.blocks = (cfg->gene_length + 63) / 64;
@@ -327,6 +329,7 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 	if (n_genes < 0 || (n_genes > 0 && (!gene_id || !origin_node || !carrier_off || !carrier_genome)))
 		return e.fail(PGS_ERR_ARG, "pgs_set_genes: null table");
 	e.have_genes = e.swept = false;
+	e.sweeps_done = 0;
 	e.drop_graph();
 	const int rc = pgs::plan_genes(e, n_genes, gene_id, origin_node, carrier_off, carrier_genome, all_order); // plan.cu
 	if (rc) return rc;
@@ -344,7 +347,11 @@ int pgs_sweep(pgs_engine *h)
 	pgs::launch_rootgen(e.tables, e.d_root_tasks.as<pgs::RootTask>(), e.n_root_tasks, e.stream);
 	if (e.n_root_tasks) launches++;
 	cudaEventRecord(e.ev[1], e.stream);
-	if (e.cfg.flags & PGS_FLAG_NO_GRAPH) {
+	// The first sweep of a plan is launched kernel by kernel (capturing and instantiating a graph
+	// costs more than it saves for a single sweep, e.g. the CLI); repeated sweeps replay a graph.
+	const bool plain = (e.cfg.flags & PGS_FLAG_NO_GRAPH) || e.sweeps_done == 0;
+	e.sweeps_done++;
+	if (plain) {
 		e.enqueue_levels(e.stream, &launches);
 	} else {
 		if (!e.graph_exec) {
@@ -366,7 +373,7 @@ int pgs_sweep(pgs_engine *h)
 	cudaEventRecord(e.ev[2], e.stream);
 	ce = cudaGetLastError();
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_sweep launch");
-	if (e.cfg.flags & PGS_FLAG_NO_GRAPH) e.launches_last_sweep = launches - (e.n_root_tasks ? 1 : 0);
+	if (plain) e.launches_last_sweep = launches - (e.n_root_tasks ? 1 : 0);
 	(void)launches;
 	e.swept = true;
 	return PGS_OK;

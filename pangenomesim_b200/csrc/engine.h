@@ -76,7 +76,7 @@ struct Engine {
 	DeviceTables tables{};
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t graph_exec = nullptr;
-	int64_t launches_last_sweep = 0;
+	int64_t launches_last_sweep = 0, sweeps_done = 0;
 	double mismatch_ms = 0.0, format_ms = 0.0;
 
 	~Engine();

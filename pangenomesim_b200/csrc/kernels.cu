@@ -458,41 +458,58 @@ void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64
 // Replaces gene::bulk_mutate over the per-node gene map, reference gene.h:26-40 called at
 // img.cxx:285-286.
 
+// PAIR: a thread takes two adjacent blocks (256-bit accesses, one Philox call for the four
+// decisions); used whenever the number of blocks per gene is even.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads)
 k1_sweep_sparse(const __grid_constant__ DeviceTables t, const SparseTask *__restrict__ tasks, int64_t n_items)
 {
 	const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
 	if (idx >= n_items) return;
-	const uint32_t task = (uint32_t)(idx / t.blocks);
-	const uint32_t blk = (uint32_t)(idx - (int64_t)task * t.blocks);
+	const uint32_t per_row = PAIR ? t.blocks / 2 : t.blocks;
+	const uint32_t task = (uint32_t)(idx / per_row);
+	const uint32_t blk = (uint32_t)(idx - (int64_t)task * per_row) * (PAIR ? 2u : 1u);
 	const SparseTask st = tasks[task];
-	const uint4 x = ld_stream(t.rows + (int64_t)st.src * t.blocks + blk);
-	const int valid = (blk + 1 == t.blocks) ? t.last_valid : 64;
-	const uint4 w = pair_words((uint32_t)st.edge_left, st.gid, blk, t.keys);
-	if (st.dst_left != kNoRow) {
-		const EdgeDecision d = load_edge(t, st.edge_left);
-		const uint32_t D = pick_word(w, 0u, blk);
-		uint4 y = x;
-		if (D <= (uint32_t)(d.h1 >> 32))
-			y = mutate_block_slow(x, (uint32_t)st.edge_left, st.gid, blk, D, d.tab, d.tab, d.kmax, valid, t.keys);
-		st_stream(t.rows + (int64_t)st.dst_left * t.blocks + blk, y);
+	U32x8 x;
+	if (PAIR) {
+		x = ld_stream256(reinterpret_cast<const U32x8 *>(t.rows + (int64_t)st.src * t.blocks + blk));
+	} else {
+		x.lo = ld_stream(t.rows + (int64_t)st.src * t.blocks + blk);
+		x.hi = x.lo;
 	}
-	if (st.dst_right != kNoRow) {
-		const EdgeDecision d = load_edge(t, st.edge_right);
-		const uint32_t D = pick_word(w, 1u, blk);
-		uint4 y = x;
-		if (D <= (uint32_t)(d.h1 >> 32))
-			y = mutate_block_slow(x, (uint32_t)st.edge_right, st.gid, blk, D, d.tab, d.tab, d.kmax, valid, t.keys);
-		st_stream(t.rows + (int64_t)st.dst_right * t.blocks + blk, y);
+	const uint32_t last = PAIR ? blk + 1 : blk;
+	const int valid_last = (last + 1 == t.blocks) ? t.last_valid : 64;
+	const uint4 w = pair_words((uint32_t)st.edge_left, st.gid, blk, t.keys);
+#pragma unroll
+	for (uint32_t side = 0; side < 2; side++) {
+		const uint32_t dst = side ? st.dst_right : st.dst_left;
+		if (dst == kNoRow) continue;
+		const uint32_t edge = (uint32_t)(side ? st.edge_right : st.edge_left);
+		const EdgeDecision d = load_edge(t, (int32_t)edge);
+		const uint32_t h32 = (uint32_t)(d.h1 >> 32);
+		U32x8 y = x;
+		const uint32_t D0 = pick_word(w, side, blk);
+		if (D0 <= h32) y.lo = mutate_block_slow(x.lo, edge, st.gid, blk, D0, d.tab, d.tab, d.kmax, PAIR ? 64 : valid_last, t.keys);
+		if (PAIR) {
+			const uint32_t D1 = pick_word(w, side, blk + 1);
+			if (D1 <= h32) y.hi = mutate_block_slow(x.hi, edge, st.gid, blk + 1, D1, d.tab, d.tab, d.kmax, valid_last, t.keys);
+			st_stream256(reinterpret_cast<U32x8 *>(t.rows + (int64_t)dst * t.blocks + blk), y);
+		} else {
+			st_stream(t.rows + (int64_t)dst * t.blocks + blk, y.lo);
+		}
 	}
 }
 
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s)
 {
-	const int64_t items = n_tasks * t.blocks;
+	const bool pair = (t.blocks & 1u) == 0;
+	const int64_t items = n_tasks * (pair ? t.blocks / 2 : t.blocks);
 	if (items == 0) return;
 	const int64_t grid = (items + kThreads - 1) / kThreads;
-	k1_sweep_sparse<<<(unsigned)grid, kThreads, 0, s>>>(t, tasks, items);
+	if (pair)
+		k1_sweep_sparse<true><<<(unsigned)grid, kThreads, 0, s>>>(t, tasks, items);
+	else
+		k1_sweep_sparse<false><<<(unsigned)grid, kThreads, 0, s>>>(t, tasks, items);
 }
 
 // ---------------------------------------------------------------------------------------------
