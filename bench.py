@@ -233,6 +233,9 @@ def mismatch_allreduce_leg(torch, dist, Engine, rank, world, local):
     k2_ms = eng.stats()["mismatch_ms"]
     before = part.to(torch.int64).sum()
     dist.all_reduce(before)
+    warm = torch.zeros_like(part)
+    dist.all_reduce(warm, op=dist.ReduceOp.SUM)  # NCCL sets up its channels for this size on first use
+    torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     dist.all_reduce(part, op=dist.ReduceOp.SUM)
