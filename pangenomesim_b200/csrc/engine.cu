@@ -102,13 +102,13 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 {
 	const DenseTask *dt = d_dense_tasks.as<DenseTask>();
 	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
-	if (walk) { // dense genes: the top of the tree (one unit), then all subtrees side by side
-		if (n_walk_top_units) {
-			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>(), n_walk_top_units, s);
+	if (walk) { // dense genes: crown, rest of the top, then all subtrees side by side (k1_walk_dense)
+		int64_t first_unit = 0;
+		for (int32_t units : walk_pass_units) {
+			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + first_unit, units, s);
 			(*launches)++;
+			first_unit += units;
 		}
-		launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + n_walk_top_units, n_walk_units, s);
-		(*launches)++;
 	}
 	for (int32_t lvl = 1; lvl <= max_level; lvl++) {
 		const int64_t nd = dense_level_off[lvl + 1] - dense_level_off[lvl];

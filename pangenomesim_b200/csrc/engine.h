@@ -60,7 +60,7 @@ struct Engine {
 	int64_t n_dense_tasks = 0, n_sparse_tasks = 0, n_root_tasks = 0;
 	// fused column walk of the dense region (default for binary trees)
 	bool walk = false;
-	int32_t n_walk_units = 0, n_walk_top_units = 0;
+	std::vector<int32_t> walk_pass_units; // units per pass (crown, rest of the top, subtrees)
 	int64_t rows_stored = 0, rows_loaded = 0;
 	std::vector<char> materialised; // [N] dense region of the node holds valid rows after a sweep
 	std::vector<uint64_t> tab_host; // concatenated H[1..kmax]

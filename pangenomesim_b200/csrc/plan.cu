@@ -273,7 +273,7 @@ int plan_walk(Engine &e, SweepPlan &p)
 	// ---- fused column walk of the dense region (see k1_walk_dense): cut the tree into units,
 	// order every unit depth-first with the smaller subtree first
 	e.walk = false;
-	e.n_walk_units = e.n_walk_top_units = 0;
+	e.walk_pass_units.clear();
 	e.rows_stored = e.rows_written;
 	e.rows_loaded = e.rows_read;
 	int64_t pool_slots = 0; // transient dense regions (D rows each) behind the node regions
@@ -312,6 +312,35 @@ int plan_walk(Engine &e, SweepPlan &p)
 		for (int32_t v = 0; v < N; v++)
 			if (e.materialised[v]) loc[v] = e.row_base[v] * B;
 		auto slot_off = [&](int64_t slot) { return (rows + slot * D) * B; };
+		// The top part is cut once more: its own top ("crown", pass A: one unit) and the subtrees of
+		// top nodes below it (pass B), so that the serial chain before the big pass C is ~2 sqrt(n_top)
+		// steps instead of n_top.
+		std::vector<char> crown(N, 0);
+		std::vector<int32_t> mid_roots; // roots of the pass-B units (top nodes)
+		{
+			std::vector<int64_t> top_size(N, 0); // top nodes in the subtree
+			for (int32_t v : order) {
+				if (top[v]) top_size[v] += 1;
+				if (e.parent[v] >= 0) top_size[e.parent[v]] += top_size[v];
+			}
+			if (top[e.root]) mid_roots.push_back(e.root);
+			size_t want = 1;
+			while (want * want < n_top) want++;
+			if (n_top < 24) want = 1; // a small top is walked in one go
+			while (!mid_roots.empty() && mid_roots.size() < want) {
+				size_t best = 0;
+				for (size_t i = 1; i < mid_roots.size(); i++)
+					if (top_size[mid_roots[i]] > top_size[mid_roots[best]]) best = i;
+				const int32_t v = mid_roots[best];
+				if (top_size[v] < 4) break;
+				crown[v] = 1;
+				mid_roots.erase(mid_roots.begin() + best);
+				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
+					if (top[e.child[c]]) mid_roots.push_back(e.child[c]);
+			}
+		}
+		for (int32_t r : mid_roots)
+			if (r != e.root) loc[r] = slot_off(pool_slots++);
 		for (size_t u = 0; u < roots.size(); u++)
 			if (roots[u] != e.root) loc[roots[u]] = slot_off(pool_slots++);
 		auto make_step = [&](int32_t v, uint32_t flags) {
@@ -383,20 +412,29 @@ int plan_walk(Engine &e, SweepPlan &p)
 			}
 			pool_slots += deepest;
 		};
-		// pass 1 (one unit): the top of the tree, down to the roots of the units of pass 2;
-		// pass 2: every unit loads its root row and walks its own subtree
+		// pass A (one unit): the crown; pass B: the rest of the top, one unit per subtree below the
+		// crown; pass C: every final unit loads its root row and walks its own subtree.  A pass only
+		// reads rows written by earlier passes (stream order).
 		walk_off.push_back(0);
-		if (top[e.root]) {
-			emit_walk(e.root, [&](int32_t c) { return top[c] != 0; });
+		e.walk_pass_units.clear();
+		if (crown[e.root]) {
+			emit_walk(e.root, [&](int32_t c) { return crown[c] != 0; });
 			walk_off.push_back((int64_t)walk_steps.size());
-			e.n_walk_top_units = 1;
+			e.walk_pass_units.push_back(1);
+		}
+		if (!mid_roots.empty()) {
+			for (int32_t r : mid_roots) {
+				emit_walk(r, [&](int32_t c) { return top[c] != 0; });
+				walk_off.push_back((int64_t)walk_steps.size());
+			}
+			e.walk_pass_units.push_back((int32_t)mid_roots.size());
 		}
 		for (int32_t r : roots) {
 			emit_walk(r, [](int32_t) { return true; });
 			walk_off.push_back((int64_t)walk_steps.size());
 		}
+		e.walk_pass_units.push_back((int32_t)roots.size());
 		e.walk = true;
-		e.n_walk_units = (int32_t)roots.size();
 	}
 	rows += pool_slots * D;
 	if (rows >= (int64_t)pgs::kNoRow) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32-2 rows on one engine; shard the genes");
