@@ -5,15 +5,15 @@ set -u
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
 export PGS_NO_GRAPH=1
-# default sweep (fused column walk): 3 launches per sweep (K0, walk pass 1, walk pass 2)
+# default sweep (fused column walk): 4 launches per sweep (K0, walk passes A, B, C)
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 9 -c 15 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 20 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k1_walk_dense -s 6 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:k1_walk_dense -s 9 -c 3 \
     -o gpurun_out/k1_walk_full $CMD > gpurun_out/ncu_full.log 2>&1
 AUX="python scripts/profile_aux.py"
 $AUX > gpurun_out/aux_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k2_mismatch|k3_genome_fasta|k3_maf" -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:"k0_rootgen|k1_sweep_sparse|k2_mismatch|k3_genome_fasta|k3_maf" -c 40 \
     -o gpurun_out/aux_full $AUX > gpurun_out/ncu_aux.log 2>&1
 ls -la gpurun_out
