@@ -167,19 +167,21 @@ __device__ inline int64_t sparse_rank(const FormatTables &t, int32_t node, int64
 }
 
 constexpr int kFmtWarps = 8;
+constexpr int kRecPerCta = 32; // records per CTA: headers are built by 32 lanes side by side (phase 1),
+							   // then every warp expands four of the records (phase 2)
 
-// ---- genomeNNN.fasta: one warp per leaf row.  rows_prefix[i] = number of leaf rows of the
-// chunk's genomes before genome first_genome + i; file_off[i] = offset of that genome's file
-// in the staging buffer.
-__global__ void __launch_bounds__(kFmtWarps * 32)
-k3_genome_fasta(const __grid_constant__ FormatTables t, char *__restrict__ out, int32_t first_genome,
-				int32_t n_chunk_genomes, const int64_t *__restrict__ rows_prefix,
-				const int64_t *__restrict__ file_off)
+struct Record {
+	char *dst;           // start of the record in the staging buffer
+	const uint32_t *row; // packed sequence
+	int plen, tail;      // header bytes, trailing newlines
+};
+
+// ---- genomeNNN.fasta.  rows_prefix[i] = number of leaf rows of the chunk's genomes before genome
+// first_genome + i; file_off[i] = offset of that genome's file in the staging buffer.
+__device__ Record genome_fasta_record(const FormatTables &t, char *out, int32_t first_genome, int32_t n_chunk_genomes,
+									  const int64_t *__restrict__ rows_prefix, const int64_t *__restrict__ file_off,
+									  int64_t item, char *text)
 {
-	__shared__ char text[kFmtWarps][64];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int64_t item = (int64_t)blockIdx.x * kFmtWarps + warp;
-	if (item >= rows_prefix[n_chunk_genomes]) return;
 	int lo = 0, hi = n_chunk_genomes - 1; // last i with rows_prefix[i] <= item
 	while (lo < hi) {
 		const int mid = (lo + hi + 1) >> 1;
@@ -203,20 +205,35 @@ k3_genome_fasta(const __grid_constant__ FormatTables t, char *__restrict__ out, 
 	const int name_len = genome_name_len(genome);
 	const int64_t off = k * (name_len + t.L + 4) + t.dense_digits_before[g] +
 						t.sp_digits[t.sp_off[leaf] + leaf + srank];
-	int plen = 0;
-	if (lane == 0) {
-		char *p = text[warp];
-		*p++ = '>';
-		p = put_genome_name(p, genome);
-		*p++ = '.';
-		p = put_uint(p, (uint64_t)t.gene_id[g], 1);
-		*p++ = '\n';
-		plen = (int)(p - text[warp]);
-	}
-	plen = __shfl_sync(0xFFFFFFFFu, plen, 0);
-	__syncwarp();
-	const uint32_t *row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
-	emit_record(out + file_off[lo] + off, text[warp], plen, row, t.L, 1, lane);
+	char *p = text;
+	*p++ = '>';
+	p = put_genome_name(p, genome);
+	*p++ = '.';
+	p = put_uint(p, (uint64_t)t.gene_id[g], 1);
+	*p++ = '\n';
+	Record r;
+	r.dst = out + file_off[lo] + off;
+	r.row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
+	r.plen = (int)(p - text);
+	r.tail = 1;
+	return r;
+}
+
+__global__ void __launch_bounds__(kFmtWarps * 32)
+k3_genome_fasta(const __grid_constant__ FormatTables t, char *__restrict__ out, int32_t first_genome,
+				int32_t n_chunk_genomes, const int64_t *__restrict__ rows_prefix,
+				const int64_t *__restrict__ file_off)
+{
+	__shared__ char s_text[kRecPerCta][64];
+	__shared__ Record s_rec[kRecPerCta];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t item0 = (int64_t)blockIdx.x * kRecPerCta, total = rows_prefix[n_chunk_genomes];
+	if (threadIdx.x < kRecPerCta && item0 + threadIdx.x < total)
+		s_rec[threadIdx.x] = genome_fasta_record(t, out, first_genome, n_chunk_genomes, rows_prefix, file_off,
+												 item0 + threadIdx.x, s_text[threadIdx.x]);
+	__syncthreads();
+	for (int r = warp; r < kRecPerCta && item0 + r < total; r += kFmtWarps)
+		emit_record(s_rec[r].dst, s_text[r], s_rec[r].plen, s_rec[r].row, t.L, s_rec[r].tail, lane);
 }
 
 // ---- ref.fasta / core.fasta / accessory.fasta: one warp per listed gene, offsets from the host.
@@ -258,15 +275,10 @@ struct MafTables {
 	int32_t n_genomes;
 };
 
-__global__ void __launch_bounds__(kFmtWarps * 32)
-k3_maf(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables m, char *__restrict__ out,
-	   int64_t first_gene, int32_t n_chunk_genes, const int64_t *__restrict__ lines_prefix,
-	   const int64_t *__restrict__ block_off)
+__device__ Record maf_record(const FormatTables &t, const MafTables &m, char *out, int64_t first_gene, int32_t n_chunk_genes,
+							 const int64_t *__restrict__ lines_prefix, const int64_t *__restrict__ block_off, int64_t item,
+							 char *text)
 {
-	__shared__ char text[kFmtWarps][96];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int64_t item = (int64_t)blockIdx.x * kFmtWarps + warp;
-	if (item >= lines_prefix[n_chunk_genes]) return;
 	int lo = 0, hi = n_chunk_genes - 1;
 	while (lo < hi) {
 		const int mid = (lo + hi + 1) >> 1;
@@ -283,12 +295,12 @@ k3_maf(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables
 	const int idd = dec_digits(gid), ld = dec_digits((uint64_t)t.L);
 	const int64_t ref_len = 2 + 9 + 1 + idd + 3 + ld + 3 + dec_digits((uint64_t)m.ref_size) + 1 + t.L + 1;
 
+	Record r;
 	int64_t off, genome = -1, size;
-	const uint32_t *row;
 	if (j == 0) {
 		off = 0; // "a\n" is part of this line's prefix
 		size = m.ref_size;
-		row = reinterpret_cast<const uint32_t *>(t.rows + (int64_t)t.origin_row[g] * t.blocks);
+		r.row = reinterpret_cast<const uint32_t *>(t.rows + (int64_t)t.origin_row[g] * t.blocks);
 	} else {
 		const int64_t c = j - 1;
 		int64_t pre;
@@ -303,27 +315,41 @@ k3_maf(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables
 		size = t.genome_count[genome] * t.L;
 		const int32_t leaf = t.genome_leaf[genome];
 		const int64_t slot = dense ? t.dense_slot[g] : t.n_dense + sparse_rank(t, leaf, g);
-		row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
+		r.row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
 	}
-	int plen = 0;
-	if (lane == 0) {
-		char *p = text[warp];
-		if (j == 0) p = put_str(p, "a\n");
-		p = put_str(p, "s ");
-		p = put_genome_name(p, genome);
-		*p++ = '.';
-		p = put_uint(p, gid, 1);
-		p = put_str(p, " 0 ");
-		p = put_uint(p, (uint64_t)t.L, 1);
-		p = put_str(p, " + ");
-		p = put_uint(p, (uint64_t)size, 1);
-		*p++ = ' ';
-		plen = (int)(p - text[warp]);
-	}
-	plen = __shfl_sync(0xFFFFFFFFu, plen, 0);
-	__syncwarp();
+	char *p = text;
+	if (j == 0) p = put_str(p, "a\n");
+	p = put_str(p, "s ");
+	p = put_genome_name(p, genome);
+	*p++ = '.';
+	p = put_uint(p, gid, 1);
+	p = put_str(p, " 0 ");
+	p = put_uint(p, (uint64_t)t.L, 1);
+	p = put_str(p, " + ");
+	p = put_uint(p, (uint64_t)size, 1);
+	*p++ = ' ';
+	r.dst = out + block_off[lo] + off;
+	r.plen = (int)(p - text);
 	// the last line of a block is followed by the blank line (std::endl at pangenomesim.cxx:289)
-	emit_record(out + block_off[lo] + off, text[warp], plen, row, t.L, (j == lines - 1) ? 2 : 1, lane);
+	r.tail = (j == lines - 1) ? 2 : 1;
+	return r;
+}
+
+__global__ void __launch_bounds__(kFmtWarps * 32)
+k3_maf(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables m, char *__restrict__ out,
+	   int64_t first_gene, int32_t n_chunk_genes, const int64_t *__restrict__ lines_prefix,
+	   const int64_t *__restrict__ block_off)
+{
+	__shared__ char s_text[kRecPerCta][96];
+	__shared__ Record s_rec[kRecPerCta];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t item0 = (int64_t)blockIdx.x * kRecPerCta, total = lines_prefix[n_chunk_genes];
+	if (threadIdx.x < kRecPerCta && item0 + threadIdx.x < total)
+		s_rec[threadIdx.x] = maf_record(t, m, out, first_gene, n_chunk_genes, lines_prefix, block_off, item0 + threadIdx.x,
+										s_text[threadIdx.x]);
+	__syncthreads();
+	for (int r = warp; r < kRecPerCta && item0 + r < total; r += kFmtWarps)
+		emit_record(s_rec[r].dst, s_text[r], s_rec[r].plen, s_rec[r].row, t.L, s_rec[r].tail, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -908,7 +934,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			const int64_t items = rows_prefix.back();
 			cudaEventRecord(k0, e.stream);
 			if (items > 0)
-				k3_genome_fasta<<<(unsigned)((items + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
+				k3_genome_fasta<<<(unsigned)((items + kRecPerCta - 1) / kRecPerCta), kFmtWarps * 32, 0, e.stream>>>(
 					t, d_stage[slot].as<char>(), i, j - i, d_aux_a[slot].as<int64_t>(), d_aux_b[slot].as<int64_t>());
 			records += items;
 			if (!submit(slot, bytes, std::move(pieces))) return fail_out(PGS_ERR_IO, w.error);
@@ -951,7 +977,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 					return rc;
 				}
 				cudaEventRecord(k0, e.stream);
-				k3_maf<<<(unsigned)((items + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
+				k3_maf<<<(unsigned)((items + kRecPerCta - 1) / kRecPerCta), kFmtWarps * 32, 0, e.stream>>>(
 					t, mt, d_stage[slot].as<char>(), g, (int32_t)(g2 - g), d_aux_a[slot].as<int64_t>(),
 					d_aux_b[slot].as<int64_t>());
 				records += items;
