@@ -52,9 +52,10 @@ void oracle_root_block(uint64_t seed, uint32_t gene_id, uint32_t blk, int64_t ge
  * node of v's pair, side[v] = 0 for the leader and 1 for the other. */
 void oracle_sibling_pairs(int32_t n_nodes, const int32_t *parent, int32_t *leader, int32_t *side);
 
-/* Carry block x across edge `edge` (= child node index) in place.  The high half of the 64-bit
- * uniform is word [2*side + blk%2] of Philox(leader, gene, blk/2, stream 0); the low half and
- * the site/base draws come from Philox(edge, gene, blk, stream 1, 2, ...). */
+/* Carry block x across edge `edge` (= child node index) in place.  The top 16 bits of the 64-bit
+ * uniform are the (blk%2)-th 16-bit field of word [2*side + (blk/2)%2] of
+ * Philox(leader, gene, blk/4, stream 0); the low 48 bits and the site/base draws come from
+ * Philox(edge, gene, blk, stream 1, 2, ...). */
 void oracle_mutate_block(uint64_t seed, uint32_t leader, uint32_t side, uint32_t edge, uint32_t gene_id,
 						 uint32_t blk, int64_t gene_length, const uint64_t H[65], uint32_t x[4]);
 

@@ -4,7 +4,7 @@
  * from the specification; shares no source with the CUDA engine.  It replaces, for checking
  * purposes, the reference's gene::gene (gene.cxx:13-25) and gene::mutate (gene.cxx:27-61) by the
  * north_star's scheme: a counter-based generator keyed by (seed, edge, gene, site-block) -- the
- * decision word of a block is shared by a sibling pair of branches and two adjacent blocks, see
+ * decision call of a block is shared by a sibling pair of branches and four adjacent blocks, see
  * oracle_mutate_block -- and a per-branch substitution probability p = 3/4 (1 - exp(-4/3 mu t)),
  * uniform among the 3 other bases.  Pinned by the Random123 Philox4x32-10 known-answer vectors (tests/test_oracle.py).
  */
@@ -154,13 +154,15 @@ static uint32_t stream_next(word_stream *s)
 void oracle_mutate_block(uint64_t seed, uint32_t leader, uint32_t side, uint32_t edge, uint32_t gene_id,
 						 uint32_t blk, int64_t gene_length, const uint64_t H[65], uint32_t x[4])
 {
-	/* decision word: shared by the sibling pair and by blocks 2q, 2q+1 */
+	/* decision field: one call is shared by the sibling pair and by the quad of blocks 4q..4q+3;
+	 * word 2*side + (pair of the quad), 16-bit field (even block: low half, odd block: high half) */
 	const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-	const uint32_t pctr[4] = {leader, gene_id, blk / 2u, 0u};
+	const uint32_t pctr[4] = {leader, gene_id, blk / 4u, 0u};
 	uint32_t pw[4];
 	oracle_philox4x32_10(pctr, key, pw);
-	const uint32_t D = pw[2u * side + (blk % 2u)];
-	if (D > (uint32_t)(H[1] >> 32)) return; /* U >= H[1] whatever the low half: no substitution */
+	const uint32_t pair_word = pw[2u * side + ((blk / 2u) % 2u)];
+	const uint32_t D = (blk % 2u) ? (pair_word >> 16) : (pair_word & 0xFFFFu);
+	if (D > (uint32_t)(H[1] >> 48)) return; /* U >= H[1] whatever the low 48 bits: no substitution */
 
 	word_stream s;
 	s.ctr[0] = edge;
@@ -170,7 +172,9 @@ void oracle_mutate_block(uint64_t seed, uint32_t leader, uint32_t side, uint32_t
 	s.key[0] = key[0];
 	s.key[1] = key[1];
 	s.next = 4;
-	const uint64_t U = ((uint64_t)D << 32) | stream_next(&s);
+	/* U = D : first word : top half of the second word (the rest of that word is not used) */
+	const uint64_t u1 = stream_next(&s), u2 = stream_next(&s);
+	const uint64_t U = ((uint64_t)D << 48) | (u1 << 16) | (u2 >> 16);
 
 	int K = 0;
 	while (K < 64 && U < H[K + 1]) K++;

@@ -104,8 +104,10 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
 	if (walk) { // dense genes: crown, rest of the top, then all subtrees side by side (k1_walk_dense)
 		int64_t first_unit = 0;
-		for (int32_t units : walk_pass_units) {
-			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + first_unit, units, s);
+		for (size_t pass = 0; pass < walk_pass_units.size(); pass++) {
+			const int32_t units = walk_pass_units[pass];
+			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + first_unit, units,
+							  walk_smem_levels, pass + 1 < walk_pass_units.size(), s);
 			(*launches)++;
 			first_unit += units;
 		}

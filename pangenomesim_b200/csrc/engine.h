@@ -61,6 +61,8 @@ struct Engine {
 	// fused column walk of the dense region (default for binary trees)
 	bool walk = false;
 	std::vector<int32_t> walk_pass_units; // units per pass (crown, rest of the top, subtrees)
+	int32_t walk_smem_levels = 0;         // deepest shared-memory stack level used by any step, plus one
+	int64_t rows_parked_smem = 0;         // rows per sweep parked in shared memory instead of the global pool
 	int64_t rows_stored = 0, rows_loaded = 0;
 	std::vector<char> materialised; // [N] dense region of the node holds valid rows after a sweep
 	std::vector<uint64_t> tab_host; // concatenated H[1..kmax]

@@ -3,6 +3,8 @@
 // so no tensor cores: coalesced 16-byte accesses, several loads in flight per thread, grids that
 // are whole multiples of what the 148 SMs hold.
 #include "kernels.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace pgs {
 
@@ -70,10 +72,12 @@ void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_task
 // per-edge body is gene::mutate, gene.cxx:27-61.
 //
 // Main variant (even number of blocks per gene): a thread owns PAIRS pairs of adjacent blocks,
-// moved with 256-bit loads/stores (LDG.256 / STG.256).  One Philox call yields the four decision
-// words of {left, right} x {even block, odd block}; the fast path is branch-free (all loads
-// first, PAIRS independent Philox chains, compares folded into a bit mask) and substitutions --
-// rare events -- are applied afterwards.
+// moved with 256-bit loads/stores (LDG.256 / STG.256).  One Philox call yields the eight 16-bit
+// decision fields of {left, right} x {four blocks of a quad}.  QUAD (blocks per gene a multiple
+// of four): pairs 2i and 2i+1 of a thread are the two halves of one quad and share the call;
+// otherwise every pair makes the call of its quad itself and uses half of it.  The fast path is
+// branch-free (all loads first, independent Philox chains, compares folded into a bit mask) and
+// substitutions -- rare events -- are applied afterwards.
 
 struct __align__(32) U32x8 {
 	uint4 lo, hi; // blocks 2p and 2p+1
@@ -95,11 +99,20 @@ __device__ __forceinline__ void st_stream256(U32x8 *p, const U32x8 &v)
 				 : "memory");
 }
 
-template <int PAIRS, int MINB, bool COPY_ONLY = false>
+// pair index of a thread's j-th pair inside its tile
+template <int PAIRS, bool QUAD>
+__device__ __forceinline__ uint32_t tile_pair(uint32_t tile, int j)
+{
+	return QUAD ? 2u * ((tile * (PAIRS / 2) + (uint32_t)(j >> 1)) * kThreads + threadIdx.x) + (uint32_t)(j & 1)
+				: (tile * PAIRS + (uint32_t)j) * kThreads + threadIdx.x;
+}
+
+template <int PAIRS, int MINB, bool QUAD, bool COPY_ONLY = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restrict__ tasks,
 			   uint32_t tiles_per_task, uint32_t pairs_per_task)
 {
+	static_assert(!QUAD || PAIRS % 2 == 0, "a quad is two pairs");
 	constexpr uint32_t kTile = kThreads * PAIRS;
 	const uint32_t task = blockIdx.x / tiles_per_task;
 	const uint32_t tile = blockIdx.x - task * tiles_per_task;
@@ -108,13 +121,12 @@ k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restri
 	const int32_t right = has_right ? dt.right : dt.left;
 
 	const U32x8 *__restrict__ src = reinterpret_cast<const U32x8 *>(t.rows + __ldg(t.row_base + dt.parent) * t.blocks);
-	const uint32_t first = tile * kTile + threadIdx.x;
 	const bool full = (tile + 1) * kTile <= pairs_per_task; // CTA-uniform
 
 	U32x8 x[PAIRS];
 #pragma unroll
 	for (int j = 0; j < PAIRS; j++) {
-		const uint32_t p = first + j * kThreads;
+		const uint32_t p = tile_pair<PAIRS, QUAD>(tile, j);
 		if (full || p < pairs_per_task) x[j] = ld_stream256(src + p);
 	}
 
@@ -125,7 +137,7 @@ k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restri
 	U32x8 *__restrict__ dr = reinterpret_cast<U32x8 *>(t.rows + __ldg(t.row_base + right) * t.blocks);
 #pragma unroll
 	for (int j = 0; j < PAIRS; j++) {
-		const uint32_t p = first + j * kThreads;
+		const uint32_t p = tile_pair<PAIRS, QUAD>(tile, j);
 		if (full || p < pairs_per_task) {
 			st_stream256(dl + p, x[j]);
 			if (has_right) st_stream256(dr + p, x[j]);
@@ -133,19 +145,28 @@ k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restri
 	}
 	if (COPY_ONLY) return;
 
-	const uint32_t h32l = (uint32_t)(__ldg(t.h1 + dt.left) >> 32);
-	const uint32_t h32r = (uint32_t)(__ldg(t.h1 + right) >> 32);
-	uint32_t hits = 0;
+	const uint32_t hcl = decision_cmp(__ldg(t.h1 + dt.left));
+	const uint32_t hcr = decision_cmp(__ldg(t.h1 + right));
+	uint32_t hits = 0; // 4 bits per pair: left even, left odd, right even, right odd
+	uint4 w = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
 	for (int j = 0; j < PAIRS; j++) {
-		const uint32_t idx = 2u * (first + j * kThreads); // even block index inside the region
-		const uint32_t slot = fastdiv(idx, t.div_blocks);
-		const uint32_t blk = idx - slot * t.blocks;
-		const uint32_t gid = (full || idx < 2u * pairs_per_task) ? __ldg(t.dense_gid + slot) : 0u;
-		const uint4 w = pair_words((uint32_t)dt.left, gid, blk, t.keys);
-		const uint32_t m = (w.x <= h32l ? 1u : 0u) | (w.y <= h32l ? 2u : 0u) | (w.z <= h32r ? 4u : 0u) |
-						   (w.w <= h32r ? 8u : 0u);
-		hits |= (full || idx < 2u * pairs_per_task) ? (m << (4 * j)) : 0u;
+		const uint32_t idx = 2u * tile_pair<PAIRS, QUAD>(tile, j); // even block index inside the region
+		const bool live = full || idx < 2u * pairs_per_task;
+		uint32_t wl, wr;
+		if (!QUAD || (j & 1) == 0) {
+			const uint32_t slot = fastdiv(idx, t.div_blocks);
+			const uint32_t blk = idx - slot * t.blocks;
+			const uint32_t gid = live ? __ldg(t.dense_gid + slot) : 0u;
+			w = quad_words((uint32_t)dt.left, gid, blk, t.keys);
+			wl = QUAD ? w.x : pick_pair_word(w, 0u, blk);
+			wr = QUAD ? w.z : pick_pair_word(w, 1u, blk);
+		} else {
+			wl = w.y;
+			wr = w.w;
+		}
+		const uint32_t m = pair_hits(wl, hcl) | (pair_hits(wr, hcr) << 2);
+		hits |= live ? (m << (4 * j)) : 0u;
 	}
 	if (!has_right) hits &= 0x33333333u;
 
@@ -171,14 +192,13 @@ k1_sweep_dense(const __grid_constant__ DeviceTables t, const DenseTask *__restri
 		const uint32_t b = (uint32_t)__ffs((int)hits) - 1u;
 		hits &= hits - 1u;
 		const uint32_t j = b >> 2, side = (b >> 1) & 1u, odd = b & 1u;
-		const uint32_t p = first + j * kThreads;
+		const uint32_t p = tile_pair<PAIRS, QUAD>(tile, (int)j);
 		const uint32_t idx = 2u * p;
 		const uint32_t slot = fastdiv(idx, t.div_blocks);
 		const uint32_t blk0 = idx - slot * t.blocks;
 		const uint32_t gid = __ldg(t.dense_gid + slot);
-		const uint4 w = pair_words((uint32_t)dt.left, gid, blk0, t.keys);
-		const uint32_t D = pick_word(w, side, odd);
 		const uint32_t blk = blk0 + odd;
+		const uint32_t D = pick_field(quad_words((uint32_t)dt.left, gid, blk, t.keys), side, blk);
 		const int valid = (blk + 1 == t.blocks) ? t.last_valid : 64;
 		uint4 xin = x[0].lo;
 #pragma unroll
@@ -221,7 +241,7 @@ k1_sweep_dense_single(const __grid_constant__ DeviceTables t, const DenseTask *_
 	}
 }
 
-template <int PAIRS, int MINB, bool COPY_ONLY = false>
+template <int PAIRS, int MINB, bool QUAD, bool COPY_ONLY = false>
 static void launch_dense_variant(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s)
 {
 	const uint32_t pairs = t.n_dense * t.blocks / 2;
@@ -231,7 +251,7 @@ static void launch_dense_variant(const DeviceTables &t, const DenseTask *tasks, 
 	const int64_t max_tasks = (int64_t)0x7FFFFFFF / tiles;
 	for (int64_t done = 0; done < n_tasks; done += max_tasks) {
 		const int64_t now = (n_tasks - done < max_tasks) ? (n_tasks - done) : max_tasks;
-		k1_sweep_dense<PAIRS, MINB, COPY_ONLY><<<(unsigned)(now * tiles), kThreads, 0, s>>>(t, tasks + done, tiles, pairs);
+		k1_sweep_dense<PAIRS, MINB, QUAD, COPY_ONLY><<<(unsigned)(now * tiles), kThreads, 0, s>>>(t, tasks + done, tiles, pairs);
 	}
 }
 
@@ -250,10 +270,14 @@ void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n
 		}
 		return;
 	}
-	switch (g_dense_variant) { // development knob; measured on config 4: <4,3> 6.1 ms, <2,4> 6.2 ms, copy-only 5.8 ms
-		case 1: launch_dense_variant<2, 4>(t, tasks, n_tasks, s); break;
-		case 2: launch_dense_variant<4, 3, true>(t, tasks, n_tasks, s); break; // memory ceiling probe: no RNG
-		default: launch_dense_variant<4, 3>(t, tasks, n_tasks, s); break;
+	if (t.blocks & 3u) { // blocks = 2 mod 4: every pair makes its quad's call itself
+		launch_dense_variant<4, 3, false>(t, tasks, n_tasks, s);
+		return;
+	}
+	switch (g_dense_variant) { // development knob
+		case 1: launch_dense_variant<4, 3, false>(t, tasks, n_tasks, s); break;
+		case 2: launch_dense_variant<4, 3, true, true>(t, tasks, n_tasks, s); break; // memory ceiling probe: no RNG
+		default: launch_dense_variant<4, 3, true>(t, tasks, n_tasks, s); break;
 	}
 }
 
@@ -297,13 +321,19 @@ __device__ __forceinline__ void ld_own256_if(U32x8 &v, const U32x8 *p, uint32_t 
 				 : "memory");
 }
 
-constexpr int kWalkChunk = 32; // steps staged in shared memory per barrier
+#ifndef PGS_WALK_CHUNK
+#define PGS_WALK_CHUNK 16
+#endif
+constexpr int kWalkChunk = PGS_WALK_CHUNK; // steps a warp stages in shared memory at a time
 
-template <int MINB, int PAIRS, bool HINTS = true>
+// QUAD (blocks per gene a multiple of four): pairs 2i, 2i+1 of a thread are the halves of one
+// quad of blocks -- 64 contiguous bytes, one Philox call per step for the eight decisions.
+template <int MINB, int PAIRS, bool QUAD, bool HINTS = true>
 __global__ void __launch_bounds__(kThreads, MINB)
 k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
 			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node)
 {
+	static_assert(!QUAD || PAIRS % 2 == 0, "a quad is two pairs");
 	const uint32_t unit = blockIdx.x % n_units, slab = blockIdx.x / n_units;
 	// this thread's PAIRS columns (block pairs) inside any node's dense region
 	uint32_t p[PAIRS], gid[PAIRS], blk[PAIRS];
@@ -312,7 +342,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	U32x8 *column[PAIRS];
 #pragma unroll
 	for (int j = 0; j < PAIRS; j++) {
-		p[j] = (slab * PAIRS + j) * kThreads + threadIdx.x;
+		p[j] = tile_pair<PAIRS, QUAD>(slab, j);
 		active[j] = p[j] < pairs_per_node;
 		const uint32_t idx = 2u * p[j];
 		const uint32_t slot = fastdiv(idx, t.div_blocks);
@@ -327,6 +357,9 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	__shared__ WalkStep s_steps_all[kThreads / 32][kWalkChunk];
 	__shared__ uint64_t s_tab[kThreads / 32][2][8]; // per warp: H[1..8] of the current step's two branches
 	__shared__ int s_kmax[kThreads / 32][2];
+	// Parked siblings: a thread's own stack, [level][pair][half][thread] (thread-private, so no
+	// synchronisation; consecutive threads hit consecutive 16-byte words: conflict-free).
+	extern __shared__ uint4 s_park[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	U32x8 cur[PAIRS]; // the values carried from step to step
 #pragma unroll
@@ -346,18 +379,34 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 			const WalkStep &st = s_steps[k];
 			const uint32_t f = st.flags;
 			// threads beyond the last pair of the region (tail slab only) keep in step with no effect
+			if (f & kWalkLoadSmem) {
+				const uint4 *src = s_park + ((st.slots >> 8) & 255u) * (PAIRS * 2 * kThreads) + threadIdx.x;
 #pragma unroll
-			for (int j = 0; j < PAIRS; j++)
-				ld_own256_if(cur[j], reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off),
-							 (f & kWalkLoad) && active[j] ? 1u : 0u);
-			const uint32_t edge_a = st.edge_a, h32a = st.h32a, h32b = st.h32b;
-			uint4 w[PAIRS];
+				for (int j = 0; j < PAIRS; j++) {
+					cur[j].lo = src[(2 * j) * kThreads];
+					cur[j].hi = src[(2 * j + 1) * kThreads];
+				}
+			} else {
+#pragma unroll
+				for (int j = 0; j < PAIRS; j++)
+					ld_own256_if(cur[j], reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off),
+								 (f & kWalkLoad) && active[j] ? 1u : 0u);
+			}
+			const uint32_t edge_a = st.edge_a, hca = st.hca, hcb = st.hcb;
+			uint32_t wa[PAIRS], wb[PAIRS]; // the pair words of branch a and branch b
 			uint32_t m = 0;
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++) {
-				w[j] = pair_words(edge_a, gid[j], blk[j], t.keys);
-				const uint32_t mj = (w[j].x <= h32a ? 1u : 0u) | (w[j].y <= h32a ? 2u : 0u) | (w[j].z <= h32b ? 4u : 0u) |
-									(w[j].w <= h32b ? 8u : 0u);
+				if (!QUAD || (j & 1) == 0) {
+					const uint4 w = quad_words(edge_a, gid[j], blk[j], t.keys);
+					wa[j] = QUAD ? w.x : pick_pair_word(w, 0u, blk[j]);
+					wb[j] = QUAD ? w.z : pick_pair_word(w, 1u, blk[j]);
+					if constexpr (QUAD) {
+						wa[j | 1] = w.y;
+						wb[j | 1] = w.w;
+					}
+				}
+				const uint32_t mj = pair_hits(wa[j], hca) | (pair_hits(wb[j], hcb) << 2);
 				if (active[j]) m |= mj << (4 * j);
 			}
 			if (__any_sync(0xFFFFFFFFu, m != 0)) {
@@ -371,19 +420,26 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 					s_kmax[warp][lane - 16] = __ldg(t.kmax + (lane == 16 ? edge_a : edge_b2));
 				__syncwarp();
 			}
+			uint4 *const park = s_park + (st.slots & 255u) * (PAIRS * 2 * kThreads) + threadIdx.x;
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++) {
 				if (!active[j]) continue;
 				uint32_t mj = (m >> (4 * j)) & 15u;
 				U32x8 *const dst_a = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + st.a_off);
 				U32x8 *const dst_b = reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + st.b_off);
+				// child `side` (0 = a, 1 = b) takes value v: to its row, to the global pool or to the stack
+				auto put = [&](uint32_t side, const U32x8 &v) {
+					if (f & (side ? kWalkStoreB : kWalkStoreA)) {
+						U32x8 *const dst = side ? dst_b : dst_a;
+						if (!HINTS) st_stream256(dst, v); else if (f & (side ? kWalkParkB : kWalkParkA)) st_park256(dst, v); else st_leaf256(dst, v);
+					} else if (f & (side ? kWalkSmemB : kWalkSmemA)) {
+						park[(2 * j) * kThreads] = v.lo;
+						park[(2 * j + 1) * kThreads] = v.hi;
+					}
+				};
 				if (mj == 0) { // common case: both children are copies of the carried value
-					if (f & kWalkStoreA) {
-						if (!HINTS) st_stream256(dst_a, cur[j]); else if (f & kWalkParkA) st_park256(dst_a, cur[j]); else st_leaf256(dst_a, cur[j]);
-					}
-					if (f & kWalkStoreB) {
-						if (!HINTS) st_stream256(dst_b, cur[j]); else if (f & kWalkParkB) st_park256(dst_b, cur[j]); else st_leaf256(dst_b, cur[j]);
-					}
+					put(0u, cur[j]);
+					put(1u, cur[j]);
 				} else { // rare: a block of a child may change
 					// The child that is NOT carried on goes first, into a temporary; the carried child (or
 					// b when nothing is carried: the value is dead after this step) is then changed in
@@ -400,14 +456,11 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 							const int kmax = s_kmax[warp][first];
 							const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
 							const uint4 out = mutate_block_slow(odd ? cur[j].hi : cur[j].lo, edge, gid[j], blk[j] + odd,
-																pick_word(w[j], first, odd), s_tab[warp][first], tab, kmax,
+																pair_field(first ? wb[j] : wa[j], odd), s_tab[warp][first], tab, kmax,
 																odd ? valid_hi[j] : 64, t.keys);
 							if (odd) y.hi = out; else y.lo = out;
 						}
-						if (f & (first ? kWalkStoreB : kWalkStoreA)) {
-							U32x8 *const dst = first ? dst_b : dst_a;
-							if (!HINTS) st_stream256(dst, y); else if (f & (first ? kWalkParkB : kWalkParkA)) st_park256(dst, y); else st_leaf256(dst, y);
-						}
+						put(first, y);
 					}
 					{
 						uint32_t ms = (mj >> (2 * second)) & 3u;
@@ -419,14 +472,11 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 							const int kmax = s_kmax[warp][second];
 							const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
 							const uint4 out = mutate_block_slow(odd ? hi0 : lo0, edge, gid[j], blk[j] + odd,
-																pick_word(w[j], second, odd), s_tab[warp][second], tab, kmax,
+																pair_field(second ? wb[j] : wa[j], odd), s_tab[warp][second], tab, kmax,
 																odd ? valid_hi[j] : 64, t.keys);
 							if (odd) cur[j].hi = out; else cur[j].lo = out;
 						}
-						if (f & (second ? kWalkStoreB : kWalkStoreA)) {
-							U32x8 *const dst = second ? dst_b : dst_a;
-							if (!HINTS) st_stream256(dst, cur[j]); else if (f & (second ? kWalkParkB : kWalkParkA)) st_park256(dst, cur[j]); else st_leaf256(dst, cur[j]);
-						}
+						put(second, cur[j]);
 					}
 				}
 			}
@@ -434,21 +484,69 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	}
 }
 
-int g_walk_variant = 0; // development knob (PGS_WALK_VARIANT)
+int g_walk_variant = 2; // development knob (PGS_WALK_VARIANT), see walk_variant_for
+
+// variant actually launched for a gene length: 0 = quads, 2 CTAs/SM; 1 = pairs; 2 = quads, 3 CTAs/SM;
+// 3 = quads without cache hints
+static int walk_variant_for(uint32_t blocks)
+{
+	if (blocks & 3u) return 1; // blocks = 2 mod 4: every pair makes its quad's call itself
+	return (g_walk_variant >= 0 && g_walk_variant <= 3) ? g_walk_variant : 2;
+}
+
+// Shared memory of one SM that the resident CTAs' stacks may take: 227 KB less the static part
+// (steps, thresholds) and the 1 KB the driver reserves per CTA.
+int walk_smem_capacity(uint32_t blocks)
+{
+	const int variant = walk_variant_for(blocks);
+	const int ctas = (variant == 1 || variant == 2) ? 3 : 2, pairs = variant == 1 ? 1 : 2;
+	const int per_cta = (227 * 1024) / ctas - 1024 - (int)(sizeof(WalkStep) * kWalkChunk * (kThreads / 32)) - 1280;
+	int levels = per_cta / (pairs * 2 * 16 * kThreads);
+	if (const char *v = std::getenv("PGS_WALK_SMEM_LEVELS")) levels = std::min(levels, std::max(0, std::atoi(v))); // tuning knob
+	return levels;
+}
+
+template <int MINB, int PAIRS, bool QUAD, bool HINTS>
+static void launch_walk_variant(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
+								int32_t smem_levels, cudaStream_t s)
+{
+	const uint32_t pairs = t.n_dense * t.blocks / 2;
+	const uint32_t per_cta = kThreads * PAIRS;
+	const unsigned grid = (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
+	const size_t dyn = (size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads; // allowed by prepare_walk_dense
+	k1_walk_dense<MINB, PAIRS, QUAD, HINTS><<<grid, kThreads, dyn, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs);
+}
+
+template <int MINB, int PAIRS, bool QUAD, bool HINTS>
+static cudaError_t allow_walk_smem(int32_t smem_levels)
+{
+	return cudaFuncSetAttribute(k1_walk_dense<MINB, PAIRS, QUAD, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+								(int)((size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads));
+}
+
+cudaError_t prepare_walk_dense(uint32_t blocks, int32_t smem_levels)
+{
+	const cudaError_t ce = allow_walk_smem<3, 1, false, true>(smem_levels); // the passes over the top of the tree
+	if (ce != cudaSuccess) return ce;
+	switch (walk_variant_for(blocks)) {
+		case 0: return allow_walk_smem<2, 2, true, true>(smem_levels);
+		case 2: return allow_walk_smem<3, 2, true, true>(smem_levels);
+		case 3: return allow_walk_smem<2, 2, true, false>(smem_levels);
+		default: return allow_walk_smem<3, 1, false, true>(smem_levels);
+	}
+}
 
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-					   cudaStream_t s)
+					   int32_t smem_levels, bool top_pass, cudaStream_t s)
 {
 	if (n_units == 0 || t.n_dense == 0) return;
-	const uint32_t pairs = t.n_dense * t.blocks / 2;
-	auto grid = [&](int pairs_per_thread) {
-		const uint32_t per_cta = kThreads * pairs_per_thread;
-		return (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
-	};
-	switch (g_walk_variant) { // development knob; measured on config 4: <3,1> 2.64 ms, no hints 2.66 ms (+9 % DRAM), <2,2> 3.1 ms
-		case 1: k1_walk_dense<3, 1, false><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
-		case 2: k1_walk_dense<2, 2><<<grid(2), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
-		default: k1_walk_dense<3, 1><<<grid(1), kThreads, 0, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs); break;
+	// The passes over the top of the tree are short serial chains on long branches (most blocks
+	// take the rare path): the finest split of the columns gives them the most threads.
+	switch (top_pass ? 1 : walk_variant_for(t.blocks)) {
+		case 0: launch_walk_variant<2, 2, true, true>(t, steps, unit_off, n_units, smem_levels, s); break;
+		case 2: launch_walk_variant<3, 2, true, true>(t, steps, unit_off, n_units, smem_levels, s); break;
+		case 3: launch_walk_variant<2, 2, true, false>(t, steps, unit_off, n_units, smem_levels, s); break;
+		default: launch_walk_variant<3, 1, false, true>(t, steps, unit_off, n_units, smem_levels, s); break;
 	}
 }
 
@@ -479,20 +577,20 @@ k1_sweep_sparse(const __grid_constant__ DeviceTables t, const SparseTask *__rest
 	}
 	const uint32_t last = PAIR ? blk + 1 : blk;
 	const int valid_last = (last + 1 == t.blocks) ? t.last_valid : 64;
-	const uint4 w = pair_words((uint32_t)st.edge_left, st.gid, blk, t.keys);
+	const uint4 w = quad_words((uint32_t)st.edge_left, st.gid, blk, t.keys);
 #pragma unroll
 	for (uint32_t side = 0; side < 2; side++) {
 		const uint32_t dst = side ? st.dst_right : st.dst_left;
 		if (dst == kNoRow) continue;
 		const uint32_t edge = (uint32_t)(side ? st.edge_right : st.edge_left);
 		const EdgeDecision d = load_edge(t, (int32_t)edge);
-		const uint32_t h32 = (uint32_t)(d.h1 >> 32);
+		const uint32_t h16 = (uint32_t)(d.h1 >> 48);
 		U32x8 y = x;
-		const uint32_t D0 = pick_word(w, side, blk);
-		if (D0 <= h32) y.lo = mutate_block_slow(x.lo, edge, st.gid, blk, D0, d.tab, d.tab, d.kmax, PAIR ? 64 : valid_last, t.keys);
+		const uint32_t D0 = pick_field(w, side, blk);
+		if (D0 <= h16) y.lo = mutate_block_slow(x.lo, edge, st.gid, blk, D0, d.tab, d.tab, d.kmax, PAIR ? 64 : valid_last, t.keys);
 		if (PAIR) {
-			const uint32_t D1 = pick_word(w, side, blk + 1);
-			if (D1 <= h32) y.hi = mutate_block_slow(x.hi, edge, st.gid, blk + 1, D1, d.tab, d.tab, d.kmax, valid_last, t.keys);
+			const uint32_t D1 = pick_field(w, side, blk + 1);
+			if (D1 <= h16) y.hi = mutate_block_slow(x.hi, edge, st.gid, blk + 1, D1, d.tab, d.tab, d.kmax, valid_last, t.keys);
 			st_stream256(reinterpret_cast<U32x8 *>(t.rows + (int64_t)dst * t.blocks + blk), y);
 		} else {
 			st_stream(t.rows + (int64_t)dst * t.blocks + blk, y.lo);

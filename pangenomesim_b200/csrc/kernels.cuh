@@ -28,9 +28,9 @@ struct RootTask {
 struct __align__(16) WalkStep {
 	int64_t in_off, a_off, b_off; // dense regions of the node and of its children a (pair leader) and b
 	uint32_t edge_a, edge_b;      // child node indices = RNG edge ids (edge_a < edge_b)
-	uint32_t h32a, h32b;          // H[1] >> 32 of the two branches
+	uint32_t hca, hcb;            // decision_cmp(H[1]) of the two branches
 	uint32_t flags;               // kWalk* below
-	uint32_t pad;
+	uint32_t slots;               // bits 0-7: shared-memory level the parked child goes to, bits 8-15: level the input comes from
 };
 static_assert(sizeof(WalkStep) == 48, "WalkStep is staged as three uint4");
 constexpr uint32_t kWalkLoad = 1u;     // input comes from memory (else: the value carried in registers)
@@ -40,6 +40,9 @@ constexpr uint32_t kWalkCarryA = 8u;   // child a's value is the next step's inp
 constexpr uint32_t kWalkCarryB = 16u;
 constexpr uint32_t kWalkParkA = 64u;   // the stored child a is an internal node that is re-read soon (keep in L2)
 constexpr uint32_t kWalkParkB = 128u;
+constexpr uint32_t kWalkSmemA = 256u;  // child a is parked in the thread's shared-memory stack (no global store)
+constexpr uint32_t kWalkSmemB = 512u;
+constexpr uint32_t kWalkLoadSmem = 1024u; // input comes from the shared-memory stack
 
 // Unsigned division by a launch constant: q = umulhi(x, mul) >> shift (x < 2^31).
 struct FastDiv {
@@ -88,8 +91,15 @@ void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_task
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);
 // Fused dense sweep: unit u executes steps[unit_off[u] .. unit_off[u+1]) for every column slab.
+// smem_levels = deepest shared-memory stack level any step uses, plus one; top_pass = one of the
+// short passes over the top of the tree that precede the pass over all subtrees.
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-					   cudaStream_t s);
+					   int32_t smem_levels, bool top_pass, cudaStream_t s);
+// How many parked rows per thread the walk kernel selected by (PGS_WALK_VARIANT, blocks per gene)
+// can keep in shared memory; deeper levels of a unit's stack go to the global pool.
+int walk_smem_capacity(uint32_t blocks_per_gene);
+// Once per device and plan, before the first launch: opt in to the dynamic shared memory the stack needs.
+cudaError_t prepare_walk_dense(uint32_t blocks_per_gene, int32_t smem_levels);
 
 // K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
 // i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).

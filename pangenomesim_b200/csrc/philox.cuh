@@ -7,7 +7,7 @@
 //
 //   key = (seed_lo, seed_hi); the ten round keys are launch constants (PhiloxKeys)
 //   ctr = (0xFFFFFFFF, gene_id, block, 0)            origin rows
-//   ctr = (leader edge, gene_id, block >> 1, 0)      decision words of a sibling pair (see below)
+//   ctr = (leader edge, gene_id, block >> 2, 0)      decision fields of a sibling pair (see below)
 //   ctr = (edge, gene_id, block, stream >= 1)        everything else a branch needs for a block
 // edge = child node index of the branch.
 #pragma once
@@ -65,30 +65,53 @@ struct EdgeDecision {
 	int kmax;
 };
 
-// ---- decision words -----------------------------------------------------------------------
+// ---- decision fields ----------------------------------------------------------------------
 // The branches below a node are taken in sibling pairs (children in ascending node index:
 // (c0,c1), (c2,c3), ...); the first of a pair is its `leader`, side = 0 for the leader and 1 for
-// the other.  One Philox call serves the four (edge, block) decisions of a sibling pair and two
-// adjacent blocks:
-//     D(edge, gid, blk) = word[2*side + (blk & 1)] of Philox(leader, gid, blk >> 1, stream 0)
-// D is the HIGH half of the 64-bit uniform U = D * 2^32 + lo that is compared with the branch's
-// thresholds H[k] = floor(2^64 P(K >= k)).  With h32 = H[1] >> 32:  D > h32  =>  U >= H[1]  =>
-// no substitution in the block (the common case: one compare).  Otherwise the low half and
-// everything else comes from the branch's own stream Philox(edge, gid, blk, stream >= 1).
-__device__ __forceinline__ uint4 pair_words(uint32_t leader, uint32_t gid, uint32_t blk, const PhiloxKeys &keys)
+// the other.  One Philox call serves the EIGHT (edge, block) decisions of a sibling pair and a
+// quad of four adjacent blocks (256 sites of both branches), 16 bits each:
+//     W = Philox(leader, gid, blk >> 2, stream 0)
+//     D(edge, gid, blk) = 16-bit field (blk & 1) of word W[2*side + ((blk >> 1) & 1)]
+// (field 0 = low half, field 1 = high half).  D is the TOP 16 bits of the 64-bit uniform
+// U = D * 2^48 + lo48 that is compared with the branch's thresholds H[k] = floor(2^64 P(K >= k)).
+// With h16 = H[1] >> 48:  D > h16  =>  U >= H[1]  =>  no substitution in the block (the common
+// case).  Otherwise the low 48 bits and everything else come from the branch's own stream
+// Philox(edge, gid, blk, stream >= 1).
+__device__ __forceinline__ uint4 quad_words(uint32_t leader, uint32_t gid, uint32_t blk, const PhiloxKeys &keys)
 {
-	return philox4x32_10(leader, gid, blk >> 1, 0u, keys);
+	return philox4x32_10(leader, gid, blk >> 2, 0u, keys);
 }
-__device__ __forceinline__ uint32_t pick_word(const uint4 &w, uint32_t side, uint32_t blk)
+// the word that holds the two fields of blocks (blk & ~1, blk | 1) on one side
+__device__ __forceinline__ uint32_t pick_pair_word(const uint4 &w, uint32_t side, uint32_t blk)
 {
-	const uint32_t i = 2u * side + (blk & 1u);
+	const uint32_t i = 2u * side + ((blk >> 1) & 1u);
 	return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
 }
+__device__ __forceinline__ uint32_t pair_field(uint32_t pair_word, uint32_t odd)
+{
+	return odd ? (pair_word >> 16) : (pair_word & 0xFFFFu);
+}
+__device__ __forceinline__ uint32_t pick_field(const uint4 &w, uint32_t side, uint32_t blk)
+{
+	return pair_field(pick_pair_word(w, side, blk), blk & 1u);
+}
+// Compare constant of a branch: hc = (h16 << 16) | 0xFFFF.  For a pair word v:
+//   block field 1 (high half) decides "may change"  iff  v <= hc
+//   block field 0 (low half)                        iff  (v << 16) <= hc
+__host__ __device__ __forceinline__ uint32_t decision_cmp(uint64_t h1)
+{
+	return ((uint32_t)(h1 >> 48) << 16) | 0xFFFFu;
+}
+// bit 0: even block of the pair may change, bit 1: odd block
+__device__ __forceinline__ uint32_t pair_hits(uint32_t v, uint32_t hc)
+{
+	return ((v << 16) <= hc ? 1u : 0u) | (v <= hc ? 2u : 0u);
+}
 
-// Rare path (D <= h32): the block may change.  Stream 1 of the branch gives lo, then the words
-// for K distinct sites (r-th free site, r = mulhi(word, 64-j)) each with a uniform non-zero
-// 2-bit delta; XOR with a non-zero delta is "uniform pick among the 3 other bases".  Words are
-// consumed in order: x (= lo), y, z, w of stream 1, then x, y, z, w of stream 2, ...
+// Rare path (D <= h16): the block may change.  Stream 1 of the branch gives lo48 = x:y[31:16],
+// then the words for K distinct sites (r-th free site, r = mulhi(word, 64-j)) each with a uniform
+// non-zero 2-bit delta; XOR with a non-zero delta is "uniform pick among the 3 other bases".
+// Words are consumed in order: z, w of stream 1, then x, y, z, w of stream 2, ...
 // valid = number of real sites in this block (64 except for the last block of a gene); padding
 // stays zero.
 // tab8 = H[1..8] of the branch (any address space, e.g. a shared-memory copy), tab = H[1..kmax].
@@ -98,14 +121,14 @@ static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge
 {
 	uint32_t stream = 1;
 	uint4 w = philox4x32_10(edge, gid, blk, stream, keys);
-	const uint64_t U = ((uint64_t)D << 32) | w.x;
+	const uint64_t U = ((uint64_t)D << 48) | ((uint64_t)w.x << 16) | (uint64_t)(w.y >> 16);
 	int K = 0;
 	while (K < kmax && K < 8 && U < tab8[K]) K++;
 	if (K == 8)
 		while (K < kmax && U < tab[K]) K++;
 
 	uint64_t taken = 0, mlo = 0, mhi = 0;
-	int have = 3; // unread words of the current call
+	int have = 2; // unread words of the current call
 	for (int j = 0; j < K; j++) {
 		if (have == 0) {
 			stream++;
@@ -154,9 +177,9 @@ static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge
 __device__ __forceinline__ uint4 mutate_block(uint4 x, uint32_t leader, uint32_t side, uint32_t edge, uint32_t gid,
 											  uint32_t blk, const EdgeDecision &d, int valid, const PhiloxKeys &keys)
 {
-	const uint4 w = pair_words(leader, gid, blk, keys);
-	const uint32_t D = pick_word(w, side, blk);
-	if (D <= (uint32_t)(d.h1 >> 32)) return mutate_block_slow(x, edge, gid, blk, D, d.tab, d.tab, d.kmax, valid, keys);
+	const uint4 w = quad_words(leader, gid, blk, keys);
+	const uint32_t D = pick_field(w, side, blk);
+	if (D <= (uint32_t)(d.h1 >> 48)) return mutate_block_slow(x, edge, gid, blk, D, d.tab, d.tab, d.kmax, valid, keys);
 	return x;
 }
 

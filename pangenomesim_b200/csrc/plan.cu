@@ -277,7 +277,12 @@ int plan_walk(Engine &e, SweepPlan &p)
 	e.rows_stored = e.rows_written;
 	e.rows_loaded = e.rows_read;
 	int64_t pool_slots = 0; // transient dense regions (D rows each) behind the node regions
+	e.walk_smem_levels = 0;
+	e.rows_parked_smem = 0;
 	if (walk_mode) {
+		// a thread's parked siblings go to its shared-memory stack; levels beyond what fits go to the pool
+		const int smem_cap = pgs::walk_smem_capacity((uint32_t)e.blocks);
+		std::vector<int32_t> smem_level(N, -1); // stack level of a node parked in shared memory
 		auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
 		// subtree sizes (nodes), children before parents: process by decreasing level
 		std::vector<int32_t> order(N);
@@ -351,9 +356,12 @@ int plan_walk(Engine &e, SweepPlan &p)
 			s.b_off = loc[b] >= 0 ? loc[b] : 0;
 			s.edge_a = (uint32_t)a;
 			s.edge_b = (uint32_t)b;
-			s.h32a = (uint32_t)(e.h1_host[a] >> 32);
-			s.h32b = (uint32_t)(e.h1_host[b] >> 32);
+			s.hca = decision_cmp(e.h1_host[a]);
+			s.hcb = decision_cmp(e.h1_host[b]);
 			s.flags = flags;
+			if (flags & pgs::kWalkSmemA) s.slots |= (uint32_t)smem_level[a];
+			if (flags & pgs::kWalkSmemB) s.slots |= (uint32_t)smem_level[b];
+			if (flags & pgs::kWalkLoadSmem) s.slots |= (uint32_t)smem_level[v] << 8;
 			return s;
 		};
 		e.rows_stored = e.rows_loaded = 0;
@@ -371,7 +379,9 @@ int plan_walk(Engine &e, SweepPlan &p)
 				const bool ia = internal(a), ib = internal(b);
 				const bool da = ia && descend(a), db = ib && descend(b);
 				uint32_t f = 0;
-				if (!in_reg) {
+				if (!in_reg && smem_level[v] >= 0) {
+					f |= pgs::kWalkLoadSmem;
+				} else if (!in_reg) {
 					f |= pgs::kWalkLoad;
 					e.rows_loaded += D;
 				}
@@ -384,11 +394,19 @@ int plan_walk(Engine &e, SweepPlan &p)
 					const bool a_first = size[a] <= size[b];
 					carry = a_first ? a : b;
 					const int32_t later = a_first ? b : a;
-					f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkStoreB | pgs::kWalkParkB)
-								 : (pgs::kWalkCarryB | pgs::kWalkStoreA | pgs::kWalkParkA);
-					loc[later] = slot_off(stack_base + (int64_t)parked.size());
+					const int64_t depth = (int64_t)parked.size();
+					if (depth < smem_cap) {
+						f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkSmemB) : (pgs::kWalkCarryB | pgs::kWalkSmemA);
+						smem_level[later] = (int32_t)depth;
+						e.walk_smem_levels = std::max(e.walk_smem_levels, (int32_t)depth + 1);
+						e.rows_parked_smem += D;
+					} else {
+						f |= a_first ? (pgs::kWalkCarryA | pgs::kWalkStoreB | pgs::kWalkParkB)
+									 : (pgs::kWalkCarryB | pgs::kWalkStoreA | pgs::kWalkParkA);
+						loc[later] = slot_off(stack_base + depth - smem_cap);
+						deepest = std::max(deepest, depth - smem_cap + 1);
+					}
 					parked.push_back(later);
-					deepest = std::max(deepest, (int64_t)parked.size());
 				} else if (da) {
 					carry = a;
 					f |= pgs::kWalkCarryA;
@@ -456,6 +474,8 @@ int upload_plan(Engine &e, SweepPlan &p)
 	int rc = 0;
 	if ((rc = e.upload(e.d_walk_steps, p.walk_steps.data(), sizeof(WalkStep) * p.walk_steps.size(), "walk steps"))) return rc;
 	if ((rc = e.upload(e.d_walk_off, p.walk_off.data(), sizeof(int64_t) * p.walk_off.size(), "walk units"))) return rc;
+	if (e.walk && pgs::prepare_walk_dense((uint32_t)e.blocks, e.walk_smem_levels) != cudaSuccess)
+		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the walk kernel's shared-memory stack does not fit this device");
 
 	// ---- device
 	const size_t row_bytes = (size_t)e.blocks * 16;

@@ -356,3 +356,29 @@ def test_fused_walk_is_race_free_under_repetition(oracle):
                 walk.sync()
             got = np.stack([walk.copy_dense(v, G) for v in range(n)])
             assert np.array_equal(got, want), f"repetition {rep}"
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("smem_levels", [None, 0, 2])
+def test_fused_walk_kernel_variants_and_stack_placement(oracle, monkeypatch, variant, smem_levels):
+    """every walk kernel (block pairs / quads per thread) and every placement of the parked rows
+    (a thread's shared-memory stack, the global pool, or the first levels here and the rest there)
+    gives the rows of the level-synchronous sweep"""
+    monkeypatch.setenv("PGS_WALK_VARIANT", str(variant))
+    if smem_levels is not None:
+        monkeypatch.setenv("PGS_WALK_SMEM_LEVELS", str(smem_levels))
+    n, seed, G = 600, 5, 20
+    parent, rate, leaf = treegen.coalescent(n, seed=21, mut_rate=0.05)
+    root = len(parent) - 1
+    genes = core_table(G, root)
+    for L in (1000, 400, 100):  # 16 blocks, 7 blocks (level-synchronous fallback), 2 blocks (pairs)
+        with build(seed, L, parent, rate, leaf, genes) as keep:
+            want = np.stack([keep.copy_dense(v, G) for v in list(range(n)) + [root]])
+        with build(seed, L, parent, rate, leaf, genes, flags=0) as walk:
+            assert walk.stats()["sweep_mode"] == (0 if L == 400 else 1)
+            for rep in range(2):
+                if rep:
+                    walk.sweep()
+                    walk.sync()
+                got = np.stack([walk.copy_dense(v, G) for v in list(range(n)) + [root]])
+                assert np.array_equal(got, want), (L, rep)
