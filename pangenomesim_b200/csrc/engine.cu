@@ -107,7 +107,7 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 		for (size_t pass = 0; pass < walk_pass_units.size(); pass++) {
 			const int32_t units = walk_pass_units[pass];
 			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + first_unit, units,
-							  walk_smem_levels, pass + 1 < walk_pass_units.size(), s);
+							  walk_smem_levels, walk_variant, pass + 1 < walk_pass_units.size(), s);
 			(*launches)++;
 			first_unit += units;
 		}

@@ -61,6 +61,7 @@ struct Engine {
 	// fused column walk of the dense region (default for binary trees)
 	bool walk = false;
 	std::vector<int32_t> walk_pass_units; // units per pass (crown, rest of the top, subtrees)
+	int walk_variant = 2;                 // kernel of the pass over the subtrees (choose_walk_variant)
 	int32_t walk_smem_levels = 0;         // deepest shared-memory stack level used by any step, plus one
 	int64_t rows_parked_smem = 0;         // rows per sweep parked in shared memory instead of the global pool
 	int64_t rows_stored = 0, rows_loaded = 0;

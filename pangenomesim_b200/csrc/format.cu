@@ -21,6 +21,8 @@
 #include <condition_variable>
 #include <deque>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -433,6 +435,9 @@ struct Writer {
 	std::string error;
 	int maf_fd = -1; // a file that spans chunks stays open
 	std::string maf_name;
+	int64_t maf_size = 0;                          // current size of that file
+	bool use_mmap = true;                          // PGS_WRITE_MMAP=0: pwrite only
+	std::vector<std::pair<void *, size_t>> mapped; // this chunk's mappings of that file
 
 	explicit Writer(Engine &eng, const pgs_output_spec *s) : e(eng), spec(s)
 	{
@@ -440,14 +445,21 @@ struct Writer {
 			unsigned n = std::thread::hardware_concurrency();
 			n = n < 2 ? 1 : (n > 8 ? 8 : n);
 			if (const char *v = std::getenv("PGS_WRITE_THREADS")) n = (unsigned)std::max(1, std::atoi(v)); // tuning knob
+			if (const char *v = std::getenv("PGS_WRITE_MMAP")) use_mmap = std::atoi(v) != 0;               // tuning knob
 			pool.reset(new WritePool(n));
 		}
 	}
 	~Writer() { close_file(); }
 
+	void unmap_all()
+	{
+		for (auto &m : mapped) ::munmap(m.first, m.second);
+		mapped.clear();
+	}
 	void close_file()
 	{
 		if (pool) pool->wait_all();
+		unmap_all();
 		if (maf_fd >= 0) ::close(maf_fd);
 		maf_fd = -1;
 	}
@@ -501,17 +513,56 @@ struct Writer {
 		}
 		if (maf_name != name) { // a file that arrives in several pieces / slices
 			pool->wait_all();
+			unmap_all();
 			if (maf_fd >= 0) ::close(maf_fd);
-			maf_fd = ::open(path.c_str(), O_WRONLY | O_CREAT | trunc, 0644);
+			maf_fd = ::open(path.c_str(), O_RDWR | O_CREAT | trunc, 0644);
 			if (maf_fd < 0) {
 				error = path + ": " + std::strerror(errno);
 				return false;
 			}
 			maf_name = name;
+			struct stat sb;
+			maf_size = ::fstat(maf_fd, &sb) == 0 ? (int64_t)sb.st_size : 0;
+		}
+		// Buffered pwrite()s to ONE file serialise on the inode lock (one writer at a time, ~3 GB/s);
+		// page faults on a shared mapping do not.  So the piece's range of the file is mapped and the
+		// pool copies slices into the mapping, each thread populating its own pages first
+		// (MADV_POPULATE_WRITE reports a full disk as an error where a plain store would SIGBUS).
+		char *window = nullptr;
+		if (use_mmap && len > 0) {
+			bool sized = maf_size >= offset + len;
+			if (!sized && ::ftruncate(maf_fd, (off_t)(offset + len)) == 0) {
+				maf_size = offset + len;
+				sized = true;
+			}
+			if (sized) {
+				const int64_t page = (int64_t)::sysconf(_SC_PAGESIZE);
+				const int64_t map_start = offset & ~(page - 1);
+				const size_t map_len = (size_t)(offset + len - map_start);
+				void *m = ::mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, maf_fd, (off_t)map_start);
+				if (m != MAP_FAILED) {
+					mapped.emplace_back(m, map_len);
+					window = static_cast<char *>(m) + (offset - map_start);
+				}
+			}
 		}
 		for (int64_t at = 0; at < len; at += kSlice) {
 			const int64_t now = std::min(kSlice, len - at);
 			const int fd = maf_fd;
+			if (window) {
+				pool->submit([this, path, window, data, at, now] {
+#ifdef MADV_POPULATE_WRITE
+					const uintptr_t page = (uintptr_t)::sysconf(_SC_PAGESIZE);
+					const uintptr_t b = (uintptr_t)(window + at) & ~(page - 1);
+					const uintptr_t en = ((uintptr_t)(window + at + now) + page - 1) & ~(page - 1);
+					if (::madvise(reinterpret_cast<void *>(b), (size_t)(en - b), MADV_POPULATE_WRITE) != 0 &&
+						(errno == EFAULT || errno == ENOMEM))
+						return fail(path + ": cannot allocate file pages (file system full?)");
+#endif
+					std::memcpy(window + at, data + at, (size_t)now);
+				});
+				continue;
+			}
 			pool->submit([this, fd, path, data, at, now, offset] {
 				std::string msg;
 				if (!write_range(fd, data + at, now, offset + at, msg)) fail(path + ": " + msg);
@@ -523,6 +574,7 @@ struct Writer {
 	bool finish()
 	{
 		if (pool) pool->wait_all();
+		unmap_all();
 		std::lock_guard<std::mutex> l(err_mutex);
 		return error.empty();
 	}

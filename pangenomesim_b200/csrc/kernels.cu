@@ -484,21 +484,24 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	}
 }
 
-int g_walk_variant = 2; // development knob (PGS_WALK_VARIANT), see walk_variant_for
+int g_walk_variant = -1; // development knob (PGS_WALK_VARIANT): force a kernel, see choose_walk_variant
 
-// variant actually launched for a gene length: 0 = quads, 2 CTAs/SM; 1 = pairs; 2 = quads, 3 CTAs/SM;
-// 3 = quads without cache hints
-static int walk_variant_for(uint32_t blocks)
+// Which walk kernel sweeps the subtrees.  0 = quads, 2 CTAs/SM (six stack levels); 1 = pairs;
+// 2 = quads, 3 CTAs/SM (four stack levels); 3 = quads without cache hints.
+// mean_hit = mean over the branches of P(a 64-site block changes).  Measured on config 4's tree:
+// variant 2 wins while the rare path is rare (2.2 ms against 2.3 / 2.6 for variants 0 / 1 at
+// mut-rate 0.01), variant 0 once it is not (3.6 against 3.85 ms at mut-rate 0.1).
+int choose_walk_variant(uint32_t blocks, double mean_hit)
 {
 	if (blocks & 3u) return 1; // blocks = 2 mod 4: every pair makes its quad's call itself
-	return (g_walk_variant >= 0 && g_walk_variant <= 3) ? g_walk_variant : 2;
+	if (g_walk_variant >= 0 && g_walk_variant <= 3) return g_walk_variant;
+	return mean_hit > 0.003 ? 0 : 2;
 }
 
 // Shared memory of one SM that the resident CTAs' stacks may take: 227 KB less the static part
 // (steps, thresholds) and the 1 KB the driver reserves per CTA.
-int walk_smem_capacity(uint32_t blocks)
+int walk_smem_capacity(int variant)
 {
-	const int variant = walk_variant_for(blocks);
 	const int ctas = (variant == 1 || variant == 2) ? 3 : 2, pairs = variant == 1 ? 1 : 2;
 	const int per_cta = (227 * 1024) / ctas - 1024 - (int)(sizeof(WalkStep) * kWalkChunk * (kThreads / 32)) - 1280;
 	int levels = per_cta / (pairs * 2 * 16 * kThreads);
@@ -524,11 +527,11 @@ static cudaError_t allow_walk_smem(int32_t smem_levels)
 								(int)((size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads));
 }
 
-cudaError_t prepare_walk_dense(uint32_t blocks, int32_t smem_levels)
+cudaError_t prepare_walk_dense(int variant, int32_t smem_levels)
 {
 	const cudaError_t ce = allow_walk_smem<3, 1, false, true>(smem_levels); // the passes over the top of the tree
 	if (ce != cudaSuccess) return ce;
-	switch (walk_variant_for(blocks)) {
+	switch (variant) {
 		case 0: return allow_walk_smem<2, 2, true, true>(smem_levels);
 		case 2: return allow_walk_smem<3, 2, true, true>(smem_levels);
 		case 3: return allow_walk_smem<2, 2, true, false>(smem_levels);
@@ -537,12 +540,12 @@ cudaError_t prepare_walk_dense(uint32_t blocks, int32_t smem_levels)
 }
 
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-					   int32_t smem_levels, bool top_pass, cudaStream_t s)
+					   int32_t smem_levels, int variant, bool top_pass, cudaStream_t s)
 {
 	if (n_units == 0 || t.n_dense == 0) return;
 	// The passes over the top of the tree are short serial chains on long branches (most blocks
 	// take the rare path): the finest split of the columns gives them the most threads.
-	switch (top_pass ? 1 : walk_variant_for(t.blocks)) {
+	switch (top_pass ? 1 : variant) {
 		case 0: launch_walk_variant<2, 2, true, true>(t, steps, unit_off, n_units, smem_levels, s); break;
 		case 2: launch_walk_variant<3, 2, true, true>(t, steps, unit_off, n_units, smem_levels, s); break;
 		case 3: launch_walk_variant<2, 2, true, false>(t, steps, unit_off, n_units, smem_levels, s); break;

@@ -91,15 +91,17 @@ void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_task
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);
 // Fused dense sweep: unit u executes steps[unit_off[u] .. unit_off[u+1]) for every column slab.
-// smem_levels = deepest shared-memory stack level any step uses, plus one; top_pass = one of the
-// short passes over the top of the tree that precede the pass over all subtrees.
+// variant = choose_walk_variant(...); smem_levels = deepest shared-memory stack level any step
+// uses, plus one; top_pass = one of the short passes over the top of the tree that precede the
+// pass over all subtrees.
+int choose_walk_variant(uint32_t blocks_per_gene, double mean_hit);
+// how many parked rows per thread that kernel can keep in shared memory; deeper levels of a unit's
+// stack go to the global pool
+int walk_smem_capacity(int variant);
+// once per device and plan, before the first launch: opt in to the dynamic shared memory the stack needs
+cudaError_t prepare_walk_dense(int variant, int32_t smem_levels);
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-					   int32_t smem_levels, bool top_pass, cudaStream_t s);
-// How many parked rows per thread the walk kernel selected by (PGS_WALK_VARIANT, blocks per gene)
-// can keep in shared memory; deeper levels of a unit's stack go to the global pool.
-int walk_smem_capacity(uint32_t blocks_per_gene);
-// Once per device and plan, before the first launch: opt in to the dynamic shared memory the stack needs.
-cudaError_t prepare_walk_dense(uint32_t blocks_per_gene, int32_t smem_levels);
+					   int32_t smem_levels, int variant, bool top_pass, cudaStream_t s);
 
 // K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
 // i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).

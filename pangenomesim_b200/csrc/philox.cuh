@@ -147,11 +147,15 @@ static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge
 		const uint32_t r = __umulhi(word, m);
 		const uint32_t lo = word * m;
 		const uint64_t delta = 1u + __umulhi(lo, 3u);
-		// r-th (0-based, ascending) site not yet taken
-		const uint64_t freebits = ~taken;
-		const uint32_t flo = (uint32_t)freebits, fhi = (uint32_t)(freebits >> 32);
-		const uint32_t nlo = __popc(flo);
-		const int pos = r < nlo ? (int)__fns(flo, 0u, (int)r + 1) : 32 + (int)__fns(fhi, 0u, (int)(r - nlo) + 1);
+		// r-th (0-based, ascending) site not yet taken; the first pick (most blocks on the rare path
+		// change in exactly one site) needs no search
+		int pos = (int)r;
+		if (j > 0) {
+			const uint64_t freebits = ~taken;
+			const uint32_t flo = (uint32_t)freebits, fhi = (uint32_t)(freebits >> 32);
+			const uint32_t nlo = __popc(flo);
+			pos = r < nlo ? (int)__fns(flo, 0u, (int)r + 1) : 32 + (int)__fns(fhi, 0u, (int)(r - nlo) + 1);
+		}
 		taken |= 1ull << pos;
 		if (pos < 32)
 			mlo |= delta << (2 * pos);

@@ -281,7 +281,10 @@ int plan_walk(Engine &e, SweepPlan &p)
 	e.rows_parked_smem = 0;
 	if (walk_mode) {
 		// a thread's parked siblings go to its shared-memory stack; levels beyond what fits go to the pool
-		const int smem_cap = pgs::walk_smem_capacity((uint32_t)e.blocks);
+		double mean_hit = 0.0; // mean over the branches of P(a block changes) = H[1] / 2^64
+		for (int32_t v = 0; v < N; v++) mean_hit += (double)e.h1_host[v] * 0x1p-64;
+		e.walk_variant = pgs::choose_walk_variant((uint32_t)e.blocks, N > 1 ? mean_hit / (N - 1) : 0.0);
+		const int smem_cap = pgs::walk_smem_capacity(e.walk_variant);
 		std::vector<int32_t> smem_level(N, -1); // stack level of a node parked in shared memory
 		auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
 		// subtree sizes (nodes), children before parents: process by decreasing level
@@ -474,7 +477,7 @@ int upload_plan(Engine &e, SweepPlan &p)
 	int rc = 0;
 	if ((rc = e.upload(e.d_walk_steps, p.walk_steps.data(), sizeof(WalkStep) * p.walk_steps.size(), "walk steps"))) return rc;
 	if ((rc = e.upload(e.d_walk_off, p.walk_off.data(), sizeof(int64_t) * p.walk_off.size(), "walk units"))) return rc;
-	if (e.walk && pgs::prepare_walk_dense((uint32_t)e.blocks, e.walk_smem_levels) != cudaSuccess)
+	if (e.walk && pgs::prepare_walk_dense(e.walk_variant, e.walk_smem_levels) != cudaSuccess)
 		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the walk kernel's shared-memory stack does not fit this device");
 
 	// ---- device

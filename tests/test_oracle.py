@@ -123,3 +123,19 @@ def test_row_equals_all_nodes_and_zero_rate_copies(oracle):
     a = oracle.unpack_ascii(allrows[0], 130)
     assert len(a) == 130 and set(a) <= set(b"ACGT")
     assert oracle.mismatch(allrows[0], allrows[1]) == sum(x != y for x, y in zip(a, oracle.unpack_ascii(allrows[1], 130)))
+
+
+@pytest.mark.parametrize("rate", [3e-6, 2e-5, 4e-4])
+def test_low_rate_substitution_counts_are_binomial(oracle, rate):
+    """the fast path decides on the top 16 bits of the 64-bit uniform (D > H[1] >> 48 means no
+    substitution); the low 48 bits come in on the rare path, so the count over many blocks must
+    still be Binomial(S, p) with p = 3/4 (1 - exp(-4/3 rate)) -- no bias from the 16-bit test"""
+    parent = np.array([2, 2, -1], dtype=np.int32)
+    rates = np.array([rate, rate, 0.0])
+    S = 64 * 1_500_000
+    p = oracle.jc_p(rate)
+    for seed, node in ((11, 0), (12, 1)):
+        root = oracle.row(seed, parent, rates, 2, 2, 7, S)
+        leaf = oracle.row(seed, parent, rates, node, 2, 7, S)
+        diff = oracle.mismatch(root, leaf)
+        assert abs(diff - S * p) < 4.0 * math.sqrt(S * p * (1 - p)), (seed, node, diff, S * p)
