@@ -121,9 +121,9 @@ __device__ void emit_record(char *__restrict__ dst, const char *prefix, int pref
 	const int64_t chunks = (L - head) / 16;
 	const int sh = 2 * (int)head; // bit offset of the first body site inside word 0 (head < 16)
 	uint4 *body = reinterpret_cast<uint4 *>(seq + head);
-	for (int64_t c = lane; c < chunks; c += 32) {
-		const uint32_t lo = __ldg(row + c);
-		const uint32_t hi = sh ? __ldg(row + c + 1) : 0u;
+	// two 16-byte chunks per lane and round: all four loads are in flight before the first is used
+	// (a 1000-site record is 62 chunks: one round)
+	auto expand = [&](int64_t c, uint32_t lo, uint32_t hi) {
 		const uint32_t bits = __funnelshift_r(lo, hi, sh);
 		uint4 v;
 		v.x = ascii4(bits & 0xFFu);
@@ -131,6 +131,16 @@ __device__ void emit_record(char *__restrict__ dst, const char *prefix, int pref
 		v.z = ascii4((bits >> 16) & 0xFFu);
 		v.w = ascii4(bits >> 24);
 		body[c] = v;
+	};
+	for (int64_t c = lane; c < chunks; c += 64) {
+		const int64_t c2 = c + 32;
+		const bool two = c2 < chunks;
+		const uint32_t lo0 = __ldg(row + c);
+		const uint32_t hi0 = sh ? __ldg(row + c + 1) : 0u;
+		const uint32_t lo1 = two ? __ldg(row + c2) : 0u;
+		const uint32_t hi1 = (two && sh) ? __ldg(row + c2 + 1) : 0u;
+		expand(c, lo0, hi0);
+		if (two) expand(c2, lo1, hi1);
 	}
 	const int64_t done = head + chunks * 16;
 	for (int64_t s = done + lane; s < L; s += 32) seq[s] = "ACGT"[(row[s >> 4] >> (2 * (s & 15))) & 3u];
@@ -787,7 +797,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	mt.n_genomes = n;
 
 	// ---- staging: two device buffers + two pinned buffers
-	int64_t stage = (int64_t)64 << 20;
+	int64_t stage = (int64_t)256 << 20; // 64 MB chunks: K3 123 ms per config-4 output, 256 MB: 60 ms (launch-bound below)
 	if (const char *v = std::getenv("PGS_STAGE_MB")) stage = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
 	if (spec->what & PGS_OUT_GENOMES)
 		for (auto b : genome_bytes) stage = std::max(stage, b);
