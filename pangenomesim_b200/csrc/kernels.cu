@@ -619,9 +619,9 @@ void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t
 // into shared memory each row is split into its two BIT PLANES (low bit / high bit of every
 // 2-bit base, 32 sites per word), so that the inner loop per pair and 32 sites is
 //     mismatch mask = (lo_i ^ lo_j) | (hi_i ^ hi_j)      -> XOR + LOP3
-//     count        += popc(mask)                         -> POPC + IADD
-// i.e. 4 instructions per 32 site pairs instead of 5 per 16 on the packed form.  Each thread keeps
-// a 4 x 4 sub-tile in registers.  Bound by the integer pipes (n^2 S / 2 site pairs), not by HBM.
+//     count        += popc(mask) [+ popc(next mask)]      -> POPC + half an IADD3
+// i.e. 3.5 instructions per 32 site pairs instead of 5 per 16 on the packed form.  Each thread
+// keeps a 4 x 4 sub-tile in registers and fetches two groups per shared-memory load.  Bound by the integer pipes (n^2 S / 2 site pairs), not by HBM.
 
 constexpr int kMmTile = 64;    // genomes per tile side
 constexpr int kMmGroups = 16;  // 32-site groups per staged chunk (= 32 packed words per row)
@@ -650,9 +650,9 @@ k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf
 	}
 	const int tj = ti + rem;
 
-	// [side a/b][plane lo/hi][row][group], row stride 17 words: rows r, r+16, .. and r+1 fall in
-	// different banks for the access pattern below
-	__shared__ uint32_t sm[2][2][kMmTile][kMmGroups + 1];
+	// [side a/b][plane lo/hi][row][group], row stride 18 words: the inner loop reads two groups at a
+	// time (LDS.64); 16 consecutive rows at a stride of 18 words start in 16 different even banks
+	__shared__ __align__(8) uint32_t sm[2][2][kMmTile][kMmGroups + 2];
 
 	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // pairs (ty + 16 i, tx + 16 j)
 	uint32_t acc[4][4];
@@ -679,20 +679,22 @@ k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf
 			sm[side][1][row][grp] = even_bits(v.x >> 1) | (even_bits(v.y >> 1) << 16);
 		}
 		__syncthreads();
-#pragma unroll 4
-		for (int k = 0; k < kMmGroups; k++) {
-			uint32_t alo[4], ahi[4], blo[4], bhi[4];
+#pragma unroll 2
+		for (int k = 0; k < kMmGroups; k += 2) {
+			uint2 alo[4], ahi[4], blo[4], bhi[4];
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
-				alo[i] = sm[0][0][ty + 16 * i][k];
-				ahi[i] = sm[0][1][ty + 16 * i][k];
-				blo[i] = sm[1][0][tx + 16 * i][k];
-				bhi[i] = sm[1][1][tx + 16 * i][k];
+				alo[i] = *reinterpret_cast<const uint2 *>(&sm[0][0][ty + 16 * i][k]);
+				ahi[i] = *reinterpret_cast<const uint2 *>(&sm[0][1][ty + 16 * i][k]);
+				blo[i] = *reinterpret_cast<const uint2 *>(&sm[1][0][tx + 16 * i][k]);
+				bhi[i] = *reinterpret_cast<const uint2 *>(&sm[1][1][tx + 16 * i][k]);
 			}
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
-				for (int j = 0; j < 4; j++) acc[i][j] += __popc((alo[i] ^ blo[j]) | (ahi[i] ^ bhi[j]));
+				for (int j = 0; j < 4; j++) // one three-input add per two groups
+					acc[i][j] += __popc((alo[i].x ^ blo[j].x) | (ahi[i].x ^ bhi[j].x)) +
+								 __popc((alo[i].y ^ blo[j].y) | (ahi[i].y ^ bhi[j].y));
 		}
 		__syncthreads();
 	}
