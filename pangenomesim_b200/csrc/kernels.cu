@@ -692,7 +692,9 @@ k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
-				for (int j = 0; j < 4; j++) // one three-input add per two groups
+				for (int j = 0; j < 4; j++) // one three-input add per two groups.  (XOR, LOP3, POPC and the add all
+											// issue on the ALU pipe, which is the bound -- 73 % busy; a carry-save
+											// adder tree that trades POPCs for LOP3s was measured 17 % slower)
 					acc[i][j] += __popc((alo[i].x ^ blo[j].x) | (ahi[i].x ^ bhi[j].x)) +
 								 __popc((alo[i].y ^ blo[j].y) | (ahi[i].y ^ bhi[j].y));
 		}
