@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iomanip>
 #include <iostream>
 #include <regex>
@@ -134,6 +135,7 @@ static void write_distance_matrix(const Model &m, const std::string &name)
 	const size_t batch = 256;
 	unsigned workers = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
 	if (n < 512) workers = 1;
+	std::future<void> writing;
 	for (size_t r0 = 0; r0 < n; r0 += batch) {
 		const size_t r1 = std::min(n, r0 + batch);
 		std::vector<std::string> lines(r1 - r0);
@@ -159,8 +161,13 @@ static void write_distance_matrix(const Model &m, const std::string &name)
 		for (unsigned w = 1; w < workers; w++) pool.emplace_back(work);
 		work();
 		for (auto &th : pool) th.join();
-		for (const auto &l : lines) out << l;
+		// the batch is written while the next one is computed
+		if (writing.valid()) writing.get();
+		writing = std::async(std::launch::async, [&out, done = std::move(lines)] {
+			for (const auto &l : done) out << l;
+		});
 	}
+	if (writing.valid()) writing.get();
 	if (!out.good()) err(errno, "%s: couldn't write to file", name.c_str());
 }
 
