@@ -347,7 +347,7 @@ __device__ Record maf_record(const FormatTables &t, const MafTables &m, char *ou
 	return r;
 }
 
-__global__ void __launch_bounds__(kFmtWarps * 32)
+__global__ void __launch_bounds__(kFmtWarps * 32, 8)
 k3_maf(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables m, char *__restrict__ out,
 	   int64_t first_gene, int32_t n_chunk_genes, const int64_t *__restrict__ lines_prefix,
 	   const int64_t *__restrict__ block_off)

@@ -311,15 +311,30 @@ void Model::simulate()
 	for (ssize_t id : ref_core_ids) ref_core.push_back(index_of.at(id));
 	for (ssize_t id : ref_acc_ids) ref_acc.push_back(index_of.at(id));
 
-	// undirected adjacency with edge weight time * mut_rate (img.cxx:142) for distance rows
-	adj.assign(t.nodes(), {});
-	for (size_t v = 0; v + 1 < t.nodes(); v++) {
+	// undirected adjacency (CSR) with edge weight time * mut_rate (img.cxx:142) for distance rows
+	const size_t N = t.nodes();
+	adj_off.assign(N + 1, 0);
+	for (size_t v = 0; v + 1 < N; v++) {
+		adj_off[v + 1]++;
+		adj_off[(size_t)t.parent[v] + 1]++;
+	}
+	for (size_t v = 0; v < N; v++) adj_off[v + 1] += adj_off[v];
+	adj_to.assign(adj_off[N], 0);
+	adj_w.assign(adj_off[N], 0.0);
+	std::vector<int64_t> fill(adj_off.begin(), adj_off.end() - 1);
+	for (size_t v = 0; v + 1 < N; v++) {
 		const double w = t.time[v] * mut_rate;
-		adj[v].push_back({t.parent[v], w});
-		adj[t.parent[v]].push_back({(int32_t)v, w});
+		const size_t p = (size_t)t.parent[v];
+		adj_to[fill[v]] = (int32_t)p;
+		adj_w[fill[v]++] = w;
+		adj_to[fill[p]] = (int32_t)v;
+		adj_w[fill[p]++] = w;
 	}
 }
 
+// Expected distances from genome i to every genome: the sum of the branch weights along the
+// unique path, accumulated outwards from i (the value the reference's Floyd-Warshall converges to,
+// img.cxx:147-154; identical as printed, tests/test_host_cli.py).
 void Model::distance_row(size_t i, std::vector<double> &row) const
 {
 	const size_t n = num_genomes;
@@ -328,14 +343,15 @@ void Model::distance_row(size_t i, std::vector<double> &row) const
 		int32_t node, from;
 		double dist;
 	};
-	std::vector<Item> todo;
+	thread_local std::vector<Item> todo;
+	todo.clear();
 	todo.push_back({(int32_t)i, -1, 0.0});
 	while (!todo.empty()) {
 		const Item it = todo.back();
 		todo.pop_back();
 		if ((size_t)it.node < n) row[it.node] = it.dist;
-		for (const auto &e : adj[it.node])
-			if (e.first != it.from) todo.push_back({e.first, it.node, it.dist + e.second});
+		for (int64_t k = adj_off[it.node]; k < adj_off[it.node + 1]; k++)
+			if (adj_to[k] != it.from) todo.push_back({adj_to[k], it.node, it.dist + adj_w[k]});
 	}
 }
 

@@ -78,7 +78,9 @@ class Model {
 	void replay_root_draws();
 	void replay_mutate(double rate);
 	void build_children_lists();
-	std::vector<std::vector<std::pair<int32_t, double>>> adj; // undirected tree, for distance rows
+	std::vector<int64_t> adj_off; // undirected tree in CSR form, for distance rows
+	std::vector<int32_t> adj_to;
+	std::vector<double> adj_w;
 };
 
 std::string genome_name(ssize_t index); // util.cxx:15-27 with the >= 1000 fix
