@@ -334,7 +334,11 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node)
 {
 	static_assert(!QUAD || PAIRS % 2 == 0, "a quad is two pairs");
-	const uint32_t unit = blockIdx.x % n_units, slab = blockIdx.x / n_units;
+	// Units are sorted by decreasing length and CTAs start in index order: unit-major numbering
+	// (all slabs of the longest unit first, the shortest units last) keeps the tail of the launch short.
+	// (config 4: 2.28 -> 2.11 ms against slab-major numbering; 625 genes: 0.49 -> 0.36 ms)
+	const uint32_t n_slabs = gridDim.x / n_units;
+	const uint32_t unit = blockIdx.x / n_slabs, slab = blockIdx.x - unit * n_slabs;
 	// this thread's PAIRS columns (block pairs) inside any node's dense region
 	uint32_t p[PAIRS], gid[PAIRS], blk[PAIRS];
 	bool active[PAIRS];
@@ -500,6 +504,13 @@ int choose_walk_variant(uint32_t blocks, double mean_hit)
 
 // Shared memory of one SM that the resident CTAs' stacks may take: 227 KB less the static part
 // (steps, thresholds) and the 1 KB the driver reserves per CTA.
+// column slabs (CTAs per unit) of the pass over the subtrees
+uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks)
+{
+	const uint32_t pairs = n_dense * blocks / 2, per_cta = kThreads * (variant == 1 ? 1 : 2);
+	return (pairs + per_cta - 1) / per_cta;
+}
+
 int walk_smem_capacity(int variant)
 {
 	const int ctas = (variant == 1 || variant == 2) ? 3 : 2, pairs = variant == 1 ? 1 : 2;

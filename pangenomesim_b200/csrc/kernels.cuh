@@ -98,6 +98,8 @@ int choose_walk_variant(uint32_t blocks_per_gene, double mean_hit);
 // how many parked rows per thread that kernel can keep in shared memory; deeper levels of a unit's
 // stack go to the global pool
 int walk_smem_capacity(int variant);
+// column slabs (CTAs per unit) that kernel makes of a dense region
+uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks_per_gene);
 // once per device and plan, before the first launch: opt in to the dynamic shared memory the stack needs
 cudaError_t prepare_walk_dense(int variant, int32_t smem_levels);
 void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,

@@ -294,8 +294,16 @@ int plan_walk(Engine &e, SweepPlan &p)
 		std::vector<int64_t> size(N, 1);
 		for (int32_t v : order)
 			if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
-		// units: split the largest subtree until there are enough of them
-		size_t target_units = 80;
+		// units: split the largest subtree until there are enough of them.  Enough = the pass over the
+		// subtrees gets about four waves of CTAs (units x column slabs; 444 CTAs are resident), but no
+		// fewer than 40 units (long serial chains) and no more than 160 (the top of the tree, walked
+		// first by few CTAs, grows with the unit count).  Config 4 on one GPU: 79 slabs -> 40 units;
+		// an eighth of it: 10 slabs -> 160 units.
+		size_t target_units = 0;
+		{
+			const size_t slabs = std::max<size_t>(1, pgs::walk_slabs(e.walk_variant, (uint32_t)D, (uint32_t)e.blocks));
+			target_units = std::min<size_t>(160, std::max<size_t>(40, (1800 + slabs - 1) / slabs));
+		}
 		if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
 		std::vector<int32_t> roots{e.root};
 		std::vector<char> top(N, 0);
