@@ -354,6 +354,9 @@ int plan_walk(Engine &e, SweepPlan &p)
 				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
 					if (top[e.child[c]]) mid_roots.push_back(e.child[c]);
 			}
+			// longest unit first, as in pass C (CTAs are numbered unit-major)
+			std::stable_sort(mid_roots.begin(), mid_roots.end(),
+							 [&](int32_t a, int32_t b) { return top_size[a] > top_size[b]; });
 		}
 		for (int32_t r : mid_roots)
 			if (r != e.root) loc[r] = slot_off(pool_slots++);
