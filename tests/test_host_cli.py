@@ -142,3 +142,22 @@ def test_sharded_cli_is_byte_identical(tmp_path, run, devices):
     assert sorted(p.name for p in (tmp_path / "many").iterdir()) == names
     for name in names:
         assert (tmp_path / "many" / name).read_bytes() == (tmp_path / "one" / name).read_bytes(), name
+
+
+REF_EXE = ROOT / "oracle" / "_ref" / "pangenomesim"
+
+
+@pytest.mark.skipif(not REF_EXE.exists(), reason="oracle/_ref/pangenomesim not built (make -C oracle)")
+@pytest.mark.parametrize("params", [
+    "num-genomes=520,core-size=2,gene-length=20,theta=5,rho=0.5,seed=11",       # n >= 512: threaded distance.mat
+    "num-genomes=97,core-size=3,gene-length=33,theta=40,rho=2,mut-rate=0.2,seed=12",
+    "num-genomes=2,core-size=1,gene-length=5,seed=13",
+])
+def test_host_files_against_the_reference_binary_live(tmp_path, params):
+    """parameter sets outside tests/golden: the unmodified reference (compiled by oracle/Makefile)
+    and the host program run side by side; every host-side file must be byte-identical"""
+    subprocess.run([str(REF_EXE), "-o", str(tmp_path / "ref"), "-p", params], check=True, timeout=600,
+                   capture_output=True)
+    run_cli(tmp_path / "o", params, "--no-sequences", "--rng-compat")
+    for name in HOST_FILES:
+        assert (tmp_path / "o" / name).read_bytes() == (tmp_path / "ref" / name).read_bytes(), name
