@@ -322,7 +322,7 @@ __device__ __forceinline__ void ld_own256_if(U32x8 &v, const U32x8 *p, uint32_t 
 }
 
 #ifndef PGS_WALK_CHUNK
-#define PGS_WALK_CHUNK 16
+#define PGS_WALK_CHUNK 12
 #endif
 constexpr int kWalkChunk = PGS_WALK_CHUNK; // steps a warp stages in shared memory at a time
 
@@ -359,8 +359,6 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	// every warp stages its own copy of the next steps: warps of a CTA drift apart (rare path) and
 	// must not wait for each other at a block barrier
 	__shared__ WalkStep s_steps_all[kThreads / 32][kWalkChunk];
-	__shared__ uint64_t s_tab[kThreads / 32][2][8]; // per warp: H[1..8] of the current step's two branches
-	__shared__ int s_kmax[kThreads / 32][2];
 	// Parked siblings: a thread's own stack, [level][pair][half][thread] (thread-private, so no
 	// synchronisation; consecutive threads hit consecutive 16-byte words: conflict-free).
 	extern __shared__ uint4 s_park[];
@@ -376,7 +374,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
 		WalkStep *const s_steps = s_steps_all[warp];
 		__syncwarp();
-		for (int q = lane; q < 3 * cnt; q += 32)
+		for (int q = lane; q < kWalkStepQuads * cnt; q += 32)
 			reinterpret_cast<uint4 *>(s_steps)[q] = __ldg(reinterpret_cast<const uint4 *>(steps + i0) + q);
 		__syncwarp();
 		for (int k = 0; k < cnt; k++) {
@@ -413,17 +411,6 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 				const uint32_t mj = pair_hits(wa[j], hca) | (pair_hits(wb[j], hcb) << 2);
 				if (active[j]) m |= mj << (4 * j);
 			}
-			if (__any_sync(0xFFFFFFFFu, m != 0)) {
-				// some lane of this warp is on the rare path: lanes 0-17 fetch both branches' first
-				// thresholds and table lengths in one round trip
-				const uint32_t edge_b2 = st.edge_b;
-				__syncwarp();
-				if (lane < 16)
-					s_tab[warp][lane >> 3][lane & 7] = __ldg(t.tab8 + (size_t)(lane < 8 ? edge_a : edge_b2) * 8 + (lane & 7));
-				else if (lane < 18)
-					s_kmax[warp][lane - 16] = __ldg(t.kmax + (lane == 16 ? edge_a : edge_b2));
-				__syncwarp();
-			}
 			uint4 *const park = s_park + (st.slots & 255u) * (PAIRS * 2 * kThreads) + threadIdx.x;
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++) {
@@ -457,11 +444,10 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 							const uint32_t odd = (mf & 1u) ? 0u : 1u;
 							mf &= mf - 1u;
 							const uint32_t edge = first ? edge_b : edge_a;
-							const int kmax = s_kmax[warp][first];
-							const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
-							const uint4 out = mutate_block_slow(odd ? cur[j].hi : cur[j].lo, edge, gid[j], blk[j] + odd,
-																pair_field(first ? wb[j] : wa[j], odd), s_tab[warp][first], tab, kmax,
-																odd ? valid_hi[j] : 64, t.keys);
+							const uint4 out = mutate_block_h12(odd ? cur[j].hi : cur[j].lo, edge, gid[j], blk[j] + odd,
+															   pair_field(first ? wb[j] : wa[j], odd), first ? st.h1b : st.h1a,
+															   first ? st.h2b : st.h2a, t.tab, t.tab_off, t.kmax,
+															   odd ? valid_hi[j] : 64, t.keys);
 							if (odd) y.hi = out; else y.lo = out;
 						}
 						put(first, y);
@@ -473,11 +459,10 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 							const uint32_t odd = (ms & 1u) ? 0u : 1u;
 							ms &= ms - 1u;
 							const uint32_t edge = second ? edge_b : edge_a;
-							const int kmax = s_kmax[warp][second];
-							const uint64_t *tab = kmax > 8 ? t.tab + __ldg(t.tab_off + edge) : nullptr;
-							const uint4 out = mutate_block_slow(odd ? hi0 : lo0, edge, gid[j], blk[j] + odd,
-																pair_field(second ? wb[j] : wa[j], odd), s_tab[warp][second], tab, kmax,
-																odd ? valid_hi[j] : 64, t.keys);
+							const uint4 out = mutate_block_h12(odd ? hi0 : lo0, edge, gid[j], blk[j] + odd,
+															   pair_field(second ? wb[j] : wa[j], odd), second ? st.h1b : st.h1a,
+															   second ? st.h2b : st.h2a, t.tab, t.tab_off, t.kmax,
+															   odd ? valid_hi[j] : 64, t.keys);
 							if (odd) cur[j].hi = out; else cur[j].lo = out;
 						}
 						put(second, cur[j]);
@@ -514,7 +499,7 @@ uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks)
 int walk_smem_capacity(int variant)
 {
 	const int ctas = (variant == 1 || variant == 2) ? 3 : 2, pairs = variant == 1 ? 1 : 2;
-	const int per_cta = (227 * 1024) / ctas - 1024 - (int)(sizeof(WalkStep) * kWalkChunk * (kThreads / 32)) - 1280;
+	const int per_cta = (227 * 1024) / ctas - 1024 - (int)(sizeof(WalkStep) * kWalkChunk * (kThreads / 32)) - 256;
 	int levels = per_cta / (pairs * 2 * 16 * kThreads);
 	if (const char *v = std::getenv("PGS_WALK_SMEM_LEVELS")) levels = std::min(levels, std::max(0, std::atoi(v))); // tuning knob
 	return levels;

@@ -31,8 +31,10 @@ struct __align__(16) WalkStep {
 	uint32_t hca, hcb;            // decision_cmp(H[1]) of the two branches
 	uint32_t flags;               // kWalk* below
 	uint32_t slots;               // bits 0-7: shared-memory level the parked child goes to, bits 8-15: level the input comes from
+	uint64_t h1a, h2a, h1b, h2b;  // H[1], H[2] of the two branches (0 beyond kmax): the rare path needs no table for K <= 1
 };
-static_assert(sizeof(WalkStep) == 48, "WalkStep is staged as three uint4");
+constexpr int kWalkStepQuads = 5;
+static_assert(sizeof(WalkStep) == 16 * kWalkStepQuads, "WalkStep is staged as five uint4");
 constexpr uint32_t kWalkLoad = 1u;     // input comes from memory (else: the value carried in registers)
 constexpr uint32_t kWalkStoreA = 2u;   // write child a's row
 constexpr uint32_t kWalkStoreB = 4u;

@@ -115,18 +115,11 @@ __device__ __forceinline__ uint32_t pair_hits(uint32_t v, uint32_t hc)
 // valid = number of real sites in this block (64 except for the last block of a gene); padding
 // stays zero.
 // tab8 = H[1..8] of the branch (any address space, e.g. a shared-memory copy), tab = H[1..kmax].
-static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
-													   uint32_t D, const uint64_t *tab8, const uint64_t *__restrict__ tab,
-													   int kmax, int valid, const PhiloxKeys &keys)
+// K substitutions in block x: the picks read the branch's stream from word z of stream 1 (= w) on.
+static __device__ __forceinline__ uint4 substitute_sites(uint4 x, uint4 w, int K, uint32_t edge, uint32_t gid,
+														  uint32_t blk, int valid, const PhiloxKeys &keys)
 {
 	uint32_t stream = 1;
-	uint4 w = philox4x32_10(edge, gid, blk, stream, keys);
-	const uint64_t U = ((uint64_t)D << 48) | ((uint64_t)w.x << 16) | (uint64_t)(w.y >> 16);
-	int K = 0;
-	while (K < kmax && K < 8 && U < tab8[K]) K++;
-	if (K == 8)
-		while (K < kmax && U < tab[K]) K++;
-
 	uint64_t taken = 0, mlo = 0, mhi = 0;
 	int have = 2; // unread words of the current call
 	for (int j = 0; j < K; j++) {
@@ -175,6 +168,40 @@ static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge
 	x.z ^= (uint32_t)mhi;
 	x.w ^= (uint32_t)(mhi >> 32);
 	return x;
+}
+
+static __device__ __forceinline__ uint4 mutate_block_slow(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk,
+														   uint32_t D, const uint64_t *tab8, const uint64_t *__restrict__ tab,
+														   int kmax, int valid, const PhiloxKeys &keys)
+{
+	const uint4 w = philox4x32_10(edge, gid, blk, 1u, keys);
+	const uint64_t U = ((uint64_t)D << 48) | ((uint64_t)w.x << 16) | (uint64_t)(w.y >> 16);
+	int K = 0;
+	while (K < kmax && K < 8 && U < tab8[K]) K++;
+	if (K == 8)
+		while (K < kmax && U < tab[K]) K++;
+	return substitute_sites(x, w, K, edge, gid, blk, valid, keys);
+}
+
+// The same with the branch's first two thresholds at hand (h1 = H[1], h2 = H[2], 0 beyond kmax): a
+// block that changes in one site -- nearly all that change -- needs no table access at all; the
+// table (tab_all + tab_off[edge], kmax[edge] entries) is read only when U < H[2].
+static __device__ __forceinline__ uint4 mutate_block_h12(uint4 x, uint32_t edge, uint32_t gid, uint32_t blk, uint32_t D,
+														  uint64_t h1, uint64_t h2, const uint64_t *__restrict__ tab_all,
+														  const int32_t *__restrict__ tab_off, const int32_t *__restrict__ kmax_all,
+														  int valid, const PhiloxKeys &keys)
+{
+	const uint4 w = philox4x32_10(edge, gid, blk, 1u, keys);
+	const uint64_t U = ((uint64_t)D << 48) | ((uint64_t)w.x << 16) | (uint64_t)(w.y >> 16);
+	if (U >= h1) return x;
+	int K = 1;
+	if (U < h2) {
+		const int kmax = __ldg(kmax_all + edge);
+		const uint64_t *tab = tab_all + __ldg(tab_off + edge);
+		K = 2;
+		while (K < kmax && U < __ldg(tab + K)) K++;
+	}
+	return substitute_sites(x, w, K, edge, gid, blk, valid, keys);
 }
 
 // Carry one 64-site block across one edge (generic form used where blocks are handled singly).

@@ -372,6 +372,10 @@ int plan_walk(Engine &e, SweepPlan &p)
 			s.edge_b = (uint32_t)b;
 			s.hca = decision_cmp(e.h1_host[a]);
 			s.hcb = decision_cmp(e.h1_host[b]);
+			s.h1a = e.h1_host[a];
+			s.h1b = e.h1_host[b];
+			s.h2a = e.kmax_host[a] >= 2 ? e.tab_host[e.tab_off_host[a] + 1] : 0;
+			s.h2b = e.kmax_host[b] >= 2 ? e.tab_host[e.tab_off_host[b] + 1] : 0;
 			s.flags = flags;
 			if (flags & pgs::kWalkSmemA) s.slots |= (uint32_t)smem_level[a];
 			if (flags & pgs::kWalkSmemB) s.slots |= (uint32_t)smem_level[b];
