@@ -582,14 +582,19 @@ k1_sweep_sparse(const __grid_constant__ DeviceTables t, const SparseTask *__rest
 		const uint32_t dst = side ? st.dst_right : st.dst_left;
 		if (dst == kNoRow) continue;
 		const uint32_t edge = (uint32_t)(side ? st.edge_right : st.edge_left);
-		const EdgeDecision d = load_edge(t, (int32_t)edge);
-		const uint32_t h16 = (uint32_t)(d.h1 >> 48);
+		const uint32_t h16 = (uint32_t)(__ldg(t.h1 + edge) >> 48); // the fast path needs nothing else of the branch
 		U32x8 y = x;
 		const uint32_t D0 = pick_field(w, side, blk);
-		if (D0 <= h16) y.lo = mutate_block_slow(x.lo, edge, st.gid, blk, D0, d.tab, d.tab, d.kmax, PAIR ? 64 : valid_last, t.keys);
+		if (D0 <= h16) {
+			const EdgeDecision d = load_edge(t, (int32_t)edge);
+			y.lo = mutate_block_slow(x.lo, edge, st.gid, blk, D0, d.tab, d.tab, d.kmax, PAIR ? 64 : valid_last, t.keys);
+		}
 		if (PAIR) {
 			const uint32_t D1 = pick_field(w, side, blk + 1);
-			if (D1 <= h16) y.hi = mutate_block_slow(x.hi, edge, st.gid, blk + 1, D1, d.tab, d.tab, d.kmax, valid_last, t.keys);
+			if (D1 <= h16) {
+				const EdgeDecision d = load_edge(t, (int32_t)edge);
+				y.hi = mutate_block_slow(x.hi, edge, st.gid, blk + 1, D1, d.tab, d.tab, d.kmax, valid_last, t.keys);
+			}
 			st_stream256(reinterpret_cast<U32x8 *>(t.rows + (int64_t)dst * t.blocks + blk), y);
 		} else {
 			st_stream(t.rows + (int64_t)dst * t.blocks + blk, y.lo);
