@@ -325,7 +325,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pangenomesim_b200 import Engine
-    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_MAF, PGS_ALL_GENOMES
+    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_MAF, OUT_PACKED, PGS_ALL_GENOMES
     from pangenomesim_b200.sharding import shard_range
 
     rank = int(os.environ.get("RANK", "0"))
@@ -472,6 +472,31 @@ def main():
                "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) "
                        "into pinned host memory, bytes discarded (no filesystem)"}
 
+    # ---- the same end to end with the optional packed side output instead of the text (genomes.pgs2:
+    # the genomes' 2-bit rows copied straight from the store, an eighth of the bytes)
+    e2e_packed = None
+    if not args.no_e2e:
+        def packed_step():
+            eng.set_tree(parent, rate, leaf)
+            eng.set_genes(gene_id, origin, car_off, car)
+            eng.sweep()
+            return eng.write_outputs(None, OUT_PACKED | OUT_DISCARD, [], [])
+        packed_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rep = packed_step()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        e2e_packed = {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / args.e2e_steps,
+                      "d2h_bytes_per_step": int(rep["bytes"]), "d2h_gb_per_s": rep["bytes"] * args.e2e_steps / wall / 1e9,
+                      "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(PGS_OUT_PACKED: genomes.pgs2, "
+                              "2-bit rows + index) into pinned host memory, bytes discarded; NOT a format of the reference"}
+
     # ---- end to end INTO FILES on a bounded slice of the workload (all 10 000 genomes, the first
     # --files-genes genes: 10 000 genomeNNN.fasta + one alignment.maf), rank 0 of a 1-GPU run only
     files = None
@@ -519,7 +544,7 @@ def main():
                        "sweep": "fused column walk" if st["sweep_mode"] == 1 else "level-synchronous"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
-            "mismatch_allreduce": mm_leg, "strong_scaling": strong, "e2e_files": files,
+            "mismatch_allreduce": mm_leg, "strong_scaling": strong, "e2e_files": files, "e2e_packed": e2e_packed,
         }
         print(json.dumps(line, default=_jsonable), flush=True)
     eng.close()

@@ -145,6 +145,23 @@ int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
 #define PGS_OUT_MAF 16u
 #define PGS_OUT_ALL 31u
 #define PGS_OUT_DISCARD 32u /* produce, copy to pinned host memory, then drop (benchmarking) */
+/* Not a format of the reference (optional): genomes.pgs2, the genomes' sequences
+ * 2-bit packed -- an eighth of the FASTA text's bytes -- behind an index.  Little-endian:
+ *   0  char[8]  "PGS2BIT\0"          8  uint32 version (1)      12  uint32 offset of the row data
+ *  16  int64 n_genomes   24  int64 gene_length   32  int64 blocks (a row = blocks * 16 bytes)
+ *  40  int64 n_records   48  int64 n_dense (genes carried by every genome: their records lead
+ *      every genome's rows, in the same order)
+ *  56  int64 record_off[n_genomes + 1]   rows of genome i: [record_off[i], record_off[i+1]),
+ *                                        n_dense dense records, then the genome's other records
+ *      int64 dense_gene_id[n_dense], dense_key[n_dense]
+ *      int64 other_gene_id[n_other], other_key[n_other]   n_other = n_records - n_genomes * n_dense;
+ *                                        genome i's entries start at record_off[i] - i * n_dense
+ *      (key = the gene's position in gene_ids() order: genomeNNN.fasta lists the genome's records
+ *      by ascending key)
+ *      zero padding up to the row data; then record r's row at data offset + r * blocks * 16:
+ *      site s is bits 2(s%16)..2(s%16)+1 of 32-bit word s/16, A=0 C=1 G=2 T=3, padding sites 0.
+ * Not part of PGS_OUT_ALL; not available with a shard layout.  pangenomesim_b200/packed.py reads it. */
+#define PGS_OUT_PACKED 64u
 
 /* Sharded output: engines that each hold a contiguous slice of the gene table fill disjoint byte
  * ranges of the same genomeNNN.fasta / alignment.maf.  The caller creates (truncates) the files,

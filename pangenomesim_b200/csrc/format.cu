@@ -803,6 +803,11 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		for (auto b : genome_bytes) stage = std::max(stage, b);
 	if (spec->what & PGS_OUT_MAF)
 		for (auto b : maf_bytes) stage = std::max(stage, b + 64);
+	if (spec->what & PGS_OUT_PACKED)
+		for (int32_t i = 0; i < n; i++) {
+			const int32_t v = e.genome_leaf[i];
+			stage = std::max(stage, (D + e.sp_off[v + 1] - e.sp_off[v]) * e.blocks * 16);
+		}
 	{
 		int64_t refs = 0;
 		for (int pass = 0; pass < 2; pass++) {
@@ -904,18 +909,29 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		return w.finish();
 	};
 	// submit: record kernel-done, copy used bytes, mark pending; then drain the OTHER slot
-	auto submit = [&](int s, int64_t bytes, std::vector<FilePiece> &&pieces) -> bool {
-		cudaEventRecord(k1, e.stream);
+	// `direct`: instead of the device staging buffer, these (device pointer, offset in the pinned
+	// buffer, bytes) ranges of the row store are copied (no kernel ran for the chunk)
+	struct Segment {
+		const char *src;
+		int64_t dst_off, bytes;
+	};
+	auto submit = [&](int s, int64_t bytes, std::vector<FilePiece> &&pieces, const std::vector<Segment> *direct = nullptr) -> bool {
+		if (!direct) cudaEventRecord(k1, e.stream);
 		cudaEventRecord(formatted[s], e.stream);
 		cudaStreamWaitEvent(copy_stream, formatted[s], 0);
-		cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream);
+		if (direct) {
+			for (const Segment &sg : *direct)
+				cudaMemcpyAsync(h_stage[s].p + sg.dst_off, sg.src, (size_t)sg.bytes, cudaMemcpyDeviceToHost, copy_stream);
+		} else {
+			cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream);
+		}
 		cudaEventRecord(copied[s], copy_stream);
 		pending[s].live = true;
 		pending[s].pieces = std::move(pieces);
 		pending[s].bytes = bytes;
 		if (!drain(s ^ 1)) return false;
 		// kernel time of this chunk (the stream is idle by the time the next chunk needs the slot)
-		if (cudaEventSynchronize(k1) == cudaSuccess) {
+		if (!direct && cudaEventSynchronize(k1) == cudaSuccess) {
 			float ms = 0;
 			if (cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) device_ms += ms;
 		}
@@ -1050,6 +1066,74 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			slot ^= 1;
 			g = g2;
 			first = false;
+		}
+	}
+
+	// ---- genomes.pgs2 (optional): the genomes' packed 2-bit rows exactly as they
+	// lie in the store, behind an index -- an eighth of the text's bytes over PCIe and to disk.
+	// No kernel: the rows are copied straight from the store.  Layout: include/pgs.h.
+	std::vector<char> packed_head; // must outlive the asynchronous writes
+	if (spec->what & PGS_OUT_PACKED) {
+		if (shard) return fail_out(PGS_ERR_ARG, "pgs_write_outputs: PGS_OUT_PACKED is not available with a shard layout");
+		const int64_t row_bytes = e.blocks * 16;
+		std::vector<int64_t> rec_off((size_t)n + 1, 0);
+		for (int32_t i = 0; i < n; i++) {
+			const int32_t v = e.genome_leaf[i];
+			rec_off[i + 1] = rec_off[i] + D + (e.sp_off[v + 1] - e.sp_off[v]);
+		}
+		const int64_t total = rec_off[n], n_sparse = total - (int64_t)n * D;
+		const int64_t index_bytes = 56 + 8 * ((int64_t)n + 1) + 16 * (D + n_sparse);
+		const int64_t data_off = (index_bytes + 255) & ~(int64_t)255;
+		packed_head.assign((size_t)data_off, 0);
+		{
+			char *h = packed_head.data();
+			std::memcpy(h, "PGS2BIT", 8);
+			const uint32_t version = 1, head32 = (uint32_t)std::min<int64_t>(data_off, 0xFFFFFFFFll);
+			std::memcpy(h + 8, &version, 4);
+			std::memcpy(h + 12, &head32, 4);
+			const int64_t fields[5] = {n, L, e.blocks, total, D};
+			std::memcpy(h + 16, fields, 40);
+			std::memcpy(h + 56, rec_off.data(), 8 * ((size_t)n + 1));
+			// the dense records lead every genome's rows and are the same genes everywhere: listed once
+			int64_t *dense_id = reinterpret_cast<int64_t *>(h + 56 + 8 * ((size_t)n + 1));
+			int64_t *dense_key = dense_id + D, *sparse_id = dense_key + D, *sparse_key = sparse_id + n_sparse;
+			for (int64_t sl = 0; sl < D; sl++) {
+				dense_id[sl] = e.gene_id[e.dense_gene[sl]];
+				dense_key[sl] = e.dense_gene[sl]; // gene table index = position key of genomeNNN.fasta
+			}
+			int64_t r = 0;
+			for (int32_t i = 0; i < n; i++) {
+				const int32_t v = e.genome_leaf[i];
+				for (int64_t j = e.sp_off[v]; j < e.sp_off[v + 1]; j++, r++) {
+					sparse_id[r] = e.gene_id[e.sp_gene[j]];
+					sparse_key[r] = e.sp_gene[j];
+				}
+			}
+		}
+		if (!w.put("genomes.pgs2", 0, packed_head.data(), data_off, false) || !w.finish())
+			return fail_out(PGS_ERR_IO, w.error);
+		const char *store = reinterpret_cast<const char *>(e.tables.rows);
+		int32_t i = 0;
+		while (i < n) {
+			std::vector<Segment> segs;
+			int64_t bytes = 0;
+			int32_t j = i;
+			while (j < n) {
+				const int64_t gb = (rec_off[j + 1] - rec_off[j]) * row_bytes;
+				if (bytes + gb > stage && j > i) break;
+				const char *src = store + e.row_base[e.genome_leaf[j]] * row_bytes;
+				if (!segs.empty() && segs.back().src + segs.back().bytes == src)
+					segs.back().bytes += gb; // neighbours in the store: one copy
+				else if (gb > 0)
+					segs.push_back({src, bytes, gb});
+				bytes += gb;
+				j++;
+			}
+			std::vector<FilePiece> pieces{{"genomes.pgs2", data_off + rec_off[i] * row_bytes, 0, bytes, false}};
+			if (!submit(slot, bytes, std::move(pieces), &segs)) return fail_out(PGS_ERR_IO, w.error);
+			records += rec_off[j] - rec_off[i];
+			slot ^= 1;
+			i = j;
 		}
 	}
 

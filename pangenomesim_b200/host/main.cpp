@@ -58,7 +58,9 @@ static bool verbose = false;
 		"      --rng-fast           Never replay (default for large runs)\n"
 		"      --no-sequences       Host-side files only (no GPU needed)\n"
 		"      --device N           CUDA device ordinal\n"
-		"      --devices N          Shard the genes over N engines (devices 0..N-1, wrapping around)\n\n"
+		"      --devices N          Shard the genes over N engines (devices 0..N-1, wrapping around)\n"
+		"      --packed             Also write genomes.pgs2: all genomes 2-bit packed behind an index\n"
+		"                           (one device only; pangenomesim_b200/packed.py reads it)\n\n"
 		"Simulation Parameters:\n"
 		"  core-size=INT            Minimum size of the core genome\n"
 		"  gene-length=INT          Length of a gene\n"
@@ -179,11 +181,12 @@ int main(int argc, char *argv[])
 		{"verbose", no_argument, nullptr, 'v'},     {"rng-compat", no_argument, nullptr, 0},
 		{"rng-fast", no_argument, nullptr, 0},      {"no-sequences", no_argument, nullptr, 0},
 		{"device", required_argument, nullptr, 0},  {"devices", required_argument, nullptr, 0},
+		{"packed", no_argument, nullptr, 0},
 		{nullptr, 0, nullptr, 0}};
 
 	Model model;
 	std::string out_dir = "./";
-	bool sequences = true;
+	bool sequences = true, packed = false;
 	int device = -1, n_devices = 1;
 
 	for (;;) {
@@ -204,6 +207,7 @@ int main(int argc, char *argv[])
 				if (name == "no-sequences") sequences = false;
 				if (name == "device") device = std::atoi(optarg);
 				if (name == "devices") n_devices = std::atoi(optarg);
+				if (name == "packed") packed = true;
 				break;
 			}
 			case 'o': out_dir = std::string(optarg) + "/"; break;
@@ -295,6 +299,7 @@ int main(int argc, char *argv[])
 		const int available = pgs_device_count();
 		if (available < 1) errx(2, "%s", "no usable CUDA device; this program has no CPU path for sequences");
 		if (n_devices < 1) n_devices = 1;
+		if (packed && n_devices > 1) errx(1, "%s", "--packed needs a single engine (no --devices)");
 
 		// contiguous slices of the gene table, balanced by the rows they occupy
 		std::vector<size_t> cut(n_devices + 1, G);
@@ -370,7 +375,7 @@ int main(int argc, char *argv[])
 			Shard &s = shards[0];
 			pgs_output_spec spec{};
 			spec.out_dir = dir_c.c_str();
-			spec.what = PGS_OUT_ALL;
+			spec.what = PGS_OUT_ALL | (packed ? PGS_OUT_PACKED : 0u);
 			spec.n_ref_core = (int64_t)model.ref_core.size();
 			spec.ref_core = model.ref_core.data();
 			spec.n_ref_acc = (int64_t)model.ref_acc.size();

@@ -190,3 +190,39 @@ def test_sharded_outputs_equal_single_engine(oracle, tmp_path):
         assert eng.copy_origin_ascii(idx) == ref_seq[int(gene_id[g])]
     for e in parts:
         e.close()
+
+
+@pytest.mark.parametrize("n,L,n_core,n_acc,stage_mb", [(14, 77, 4, 30, None), (9, 130, 0, 25, None), (300, 1000, 40, 60, 1),
+                                                      (5, 64, 3, 0, None)])
+def test_packed_side_output_holds_the_fasta_sequences(tmp_path, monkeypatch, n, L, n_core, n_acc, stage_mb):
+    """PGS_OUT_PACKED (genomes.pgs2: rows copied straight from the store behind an index, SURVEY.md
+    §8f-3): unpacked by pangenomesim_b200/packed.py it gives every genomeNNN.fasta byte for byte;
+    with a 1 MB staging buffer the rows arrive in many chunks"""
+    from pangenomesim_b200.capi import OUT_PACKED
+    from pangenomesim_b200.packed import PackedGenomes
+    if stage_mb is not None:
+        monkeypatch.setenv("PGS_STAGE_MB", str(stage_mb))
+    parent, rate, leaf = treegen.coalescent(n, seed=n, mut_rate=0.3)
+    genes = treegen.gene_table(parent, leaf, n_core=n_core, n_acc=n_acc, seed=n + 1)
+    with Engine(99, L) as e:
+        e.set_tree(parent, rate, leaf)
+        e.set_genes(*genes)
+        e.sweep()
+        rep = e.write_outputs(tmp_path, OUT_GENOMES | OUT_PACKED, [], [])
+        pk = PackedGenomes(tmp_path / "genomes.pgs2")
+        assert pk.n_genomes == n and pk.gene_length == L
+        total = 0
+        for g in range(n):
+            text = (tmp_path / (genome_name(g) + ".fasta")).read_bytes()
+            assert pk.fasta(g) == text, g
+            total += len(text)
+        assert rep["files"] == n + 1 and rep["bytes"] == total + (tmp_path / "genomes.pgs2").stat().st_size
+        # the same through a sink, chunks in file order
+        import ctypes
+        got = {}
+
+        def sink(name, offset, data, length):
+            assert len(got.get(name, b"")) == offset
+            got[name] = got.get(name, b"") + ctypes.string_at(data, length)
+        e.write_outputs(None, OUT_PACKED, [], [], sink=sink)
+        assert got["genomes.pgs2"] == (tmp_path / "genomes.pgs2").read_bytes()
