@@ -147,7 +147,8 @@ int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
 #define PGS_OUT_DISCARD 32u /* produce, copy to pinned host memory, then drop (benchmarking) */
 /* Not a format of the reference (optional): genomes.pgs2, the genomes' sequences
  * 2-bit packed -- an eighth of the FASTA text's bytes -- behind an index.  Little-endian:
- *   0  char[8]  "PGS2BIT\0"          8  uint32 version (1)      12  uint32 offset of the row data
+ *   0  char[8]  "PGS2BIT\0"          8  uint32 version (1)      12  uint32 offset of the row data (0 if
+ *      beyond 4 GiB: it is the end of the index below rounded up to a multiple of 256)
  *  16  int64 n_genomes   24  int64 gene_length   32  int64 blocks (a row = blocks * 16 bytes)
  *  40  int64 n_records   48  int64 n_dense (genes carried by every genome: their records lead
  *      every genome's rows, in the same order)

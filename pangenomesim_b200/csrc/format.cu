@@ -1088,7 +1088,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		{
 			char *h = packed_head.data();
 			std::memcpy(h, "PGS2BIT", 8);
-			const uint32_t version = 1, head32 = (uint32_t)std::min<int64_t>(data_off, 0xFFFFFFFFll);
+			const uint32_t version = 1, head32 = data_off <= 0xFFFFFFFFll ? (uint32_t)data_off : 0u; // 0: derive it from the counts
 			std::memcpy(h + 8, &version, 4);
 			std::memcpy(h + 12, &head32, 4);
 			const int64_t fields[5] = {n, L, e.blocks, total, D};

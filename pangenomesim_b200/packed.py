@@ -35,6 +35,10 @@ class PackedGenomes:
         self.other_gene_id = np.frombuffer(self._m, dtype="<i8", count=n_other, offset=at)
         self.other_key = np.frombuffer(self._m, dtype="<i8", count=n_other, offset=at + 8 * n_other)
         self.row_bytes = 16 * self.blocks
+        derived = (at + 16 * n_other + 255) & ~255  # end of the index, rounded up to 256
+        if self.data_offset not in (0, derived):
+            raise ValueError(f"{path}: inconsistent header")
+        self.data_offset = derived
         if int(self.data_offset) + self.n_records * self.row_bytes != self._m.size:
             raise ValueError(f"{path}: truncated ({self._m.size} bytes)")
 
