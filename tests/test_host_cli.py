@@ -161,3 +161,17 @@ def test_host_files_against_the_reference_binary_live(tmp_path, params):
     run_cli(tmp_path / "o", params, "--no-sequences", "--rng-compat")
     for name in HOST_FILES:
         assert (tmp_path / "o" / name).read_bytes() == (tmp_path / "ref" / name).read_bytes(), name
+
+
+@pytest.mark.gpu
+def test_cli_packed_side_output(tmp_path):
+    """--packed: genomes.pgs2 beside the usual files; unpacked it equals every genomeNNN.fasta"""
+    from pangenomesim_b200.packed import PackedGenomes
+    out = tmp_path / "o"
+    run_cli(out, "num-genomes=40,core-size=6,gene-length=130,theta=8,rho=0.5,seed=21", "--packed")
+    pk = PackedGenomes(out / "genomes.pgs2")
+    assert pk.n_genomes == 40 and pk.gene_length == 130 and pk.n_dense >= 6
+    for g in range(40):
+        assert pk.fasta(g) == (out / ("genome%03d.fasta" % (g + 1))).read_bytes(), g
+    r = run_cli(tmp_path / "p", "num-genomes=5,seed=3", "--packed", "--devices", "2", check=False)
+    assert r.returncode == 1 and "--packed needs a single engine" in r.stderr
