@@ -165,7 +165,9 @@ int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
 #define PGS_OUT_PACKED 64u
 
 /* Sharded output: engines that each hold a contiguous slice of the gene table fill disjoint byte
- * ranges of the same genomeNNN.fasta / alignment.maf.  The caller creates (truncates) the files,
+ * ranges of the same genomeNNN.fasta / alignment.maf.  The caller creates (truncates) the files
+ * -- best at their final size (the sum of pgs_output_sizes over the engines): the engines never
+ * resize a shared file, and write a file that is already large enough through a mapping --,
  * asks every engine for its sizes (pgs_output_sizes), prefix-sums them over the engines and
  * passes the resulting offsets.  ref/core/accessory.fasta are then written by the caller from
  * pgs_copy_origin_ascii. */

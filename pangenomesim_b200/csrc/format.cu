@@ -540,8 +540,11 @@ struct Writer {
 		// (MADV_POPULATE_WRITE reports a full disk as an error where a plain store would SIGBUS).
 		char *window = nullptr;
 		if (use_mmap && len > 0) {
+			// (with a shard layout other engines write to the same file: it is never resized here --
+			// an engine with lower offsets would cut off what another one has written; the caller
+			// sizes the file beforehand, else the piece goes through pwrite)
 			bool sized = maf_size >= offset + len;
-			if (!sized && ::ftruncate(maf_fd, (off_t)(offset + len)) == 0) {
+			if (!sized && !spec->shard && ::ftruncate(maf_fd, (off_t)(offset + len)) == 0) {
 				maf_size = offset + len;
 				sized = true;
 			}

@@ -404,8 +404,13 @@ int main(int argc, char *argv[])
 				for (size_t i = 0; i < n; i++) at[i] += shards[d].genome_bytes[i];
 				maf_at += shards[d].maf_bytes;
 			}
-			for (size_t i = 0; i < n; i++) open_out(out_dir + pgshost::genome_name((ssize_t)i) + ".fasta");
-			open_out(out_dir + "alignment.maf");
+			// the files are created at their final size: the engines fill disjoint ranges and never resize them
+			auto create_sized = [&](const std::string &path, int64_t size) {
+				open_out(path);
+				if (::truncate(path.c_str(), (off_t)size) != 0) err(errno, "%s: couldn't set the file size", path.c_str());
+			};
+			for (size_t i = 0; i < n; i++) create_sized(out_dir + pgshost::genome_name((ssize_t)i) + ".fasta", at[i]);
+			create_sized(out_dir + "alignment.maf", maf_at);
 			each([&](int d) {
 				Shard &s = shards[d];
 				pgs_shard_layout lay{};
