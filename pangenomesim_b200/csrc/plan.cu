@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <thread>
 
 namespace pgs {
 
@@ -250,11 +251,23 @@ void plan_edge_tables(Engine &e)
 	e.tab_off_host.assign(N, 0);
 	e.kmax_host.assign(N, 0);
 	e.tab_host.clear();
+	// one table per branch, each a few hundred floating-point operations: computed side by side on a
+	// few host threads for big trees (every table is independent; the results do not depend on it)
+	std::vector<uint64_t> all((size_t)N * 65);
+	auto build = [&](int32_t lo, int32_t hi) {
+		for (int32_t v = lo; v < hi; v++)
+			e.kmax_host[v] = (v == e.root) ? 0 : pgs::build_edge_table(e.rate[v], all.data() + (size_t)v * 65);
+	};
+	unsigned workers = N >= 4096 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	std::vector<std::thread> pool;
+	for (unsigned w = 1; w < workers; w++)
+		pool.emplace_back(build, (int32_t)((int64_t)N * w / workers), (int32_t)((int64_t)N * (w + 1) / workers));
+	build(0, (int32_t)((int64_t)N / workers));
+	for (auto &th : pool) th.join();
 	for (int32_t v = 0; v < N; v++) {
-		uint64_t H[65];
-		const int km = (v == e.root) ? 0 : pgs::build_edge_table(e.rate[v], H);
+		const uint64_t *H = all.data() + (size_t)v * 65;
+		const int km = e.kmax_host[v];
 		e.tab_off_host[v] = (int32_t)e.tab_host.size();
-		e.kmax_host[v] = km;
 		e.h1_host[v] = km > 0 ? H[1] : 0;
 		for (int k = 1; k <= km; k++) e.tab_host.push_back(H[k]);
 	}
