@@ -315,6 +315,8 @@ def main():
     ap.add_argument("--no-files", action="store_true", help="skip the bounded write-to-files leg (N=1 only)")
     ap.add_argument("--files-genes", type=int, default=1000, help="genes of the write-to-files leg (20 MB of text each)")
     ap.add_argument("--small", action="store_true", help="debug: config 2 sized workload")
+    ap.add_argument("--shard-of", type=int, default=0, help="development: on ONE GPU, sweep only rank 0's shard of a SHARD_OF-way split "
+                                                                "of config 4 (what each GPU of a strong-scaling run does)")
     args = ap.parse_args()
     if args.small:
         CFG.update(num_genomes=100, core_size=1000)
@@ -344,6 +346,8 @@ def main():
     root = 2 * n - 2
     # weak scaling: the alignment has G*world genes, rank r owns the contiguous shard [r*G, (r+1)*G)
     g0, g1 = shard_range(G * world, rank, world)
+    if args.shard_of > 1 and world == 1:
+        g0, g1 = shard_range(G, 0, args.shard_of)
     gene_id = np.arange(g0, g1, dtype=np.int64)
     origin = np.full(len(gene_id), root, np.int32)
     car_off = np.arange(len(gene_id) + 1, dtype=np.int64)

@@ -72,7 +72,7 @@ int64_t Engine::device_bytes() const
 {
 	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
 						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch,
-						   &d_tab8, &d_walk_steps, &d_walk_off};
+						   &d_tab8, &d_walk_steps, &d_walk_off, &d_walk_wait, &d_walk_ctl};
 	int64_t s = 0;
 	for (auto b : all) s += (int64_t)b->bytes;
 	return s;
@@ -102,15 +102,10 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 {
 	const DenseTask *dt = d_dense_tasks.as<DenseTask>();
 	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
-	if (walk) { // dense genes: crown, rest of the top, then all subtrees side by side (k1_walk_dense)
-		int64_t first_unit = 0;
-		for (size_t pass = 0; pass < walk_pass_units.size(); pass++) {
-			const int32_t units = walk_pass_units[pass];
-			launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>() + first_unit, units,
-							  walk_smem_levels, walk_variant, pass + 1 < walk_pass_units.size(), s);
-			(*launches)++;
-			first_unit += units;
-		}
+	if (walk) { // dense genes: ONE launch -- origin rows, the top of the tree and every subtree (k1_walk_dense)
+		launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>(), d_walk_wait.as<int32_t>(),
+						  d_walk_ctl.as<uint32_t>(), n_walk_units, walk_smem_levels, walk_variant, s);
+		(*launches)++;
 	}
 	for (int32_t lvl = 1; lvl <= max_level; lvl++) {
 		const int64_t nd = dense_level_off[lvl + 1] - dense_level_off[lvl];

@@ -60,7 +60,8 @@ struct Engine {
 	int64_t n_dense_tasks = 0, n_sparse_tasks = 0, n_root_tasks = 0;
 	// fused column walk of the dense region (default for binary trees)
 	bool walk = false;
-	std::vector<int32_t> walk_pass_units; // units per pass (crown, rest of the top, subtrees)
+	std::vector<int32_t> walk_pass_units; // units by kind (crown, rest of the top, subtrees), in launch order
+	int32_t n_walk_units = 0;
 	int walk_variant = 2;                 // kernel of the pass over the subtrees (choose_walk_variant)
 	int32_t walk_smem_levels = 0;         // deepest shared-memory stack level used by any step, plus one
 	int64_t rows_parked_smem = 0;         // rows per sweep parked in shared memory instead of the global pool
@@ -72,7 +73,7 @@ struct Engine {
 
 	// ---- device
 	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
-	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off;
+	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off, d_walk_wait, d_walk_ctl;
 	DevBuf d_stage[2];          // K3 staging, kept between pgs_write_outputs calls
 	char *h_stage[2] = {nullptr, nullptr}; // pinned
 	int64_t stage_bytes = 0;

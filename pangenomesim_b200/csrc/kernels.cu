@@ -309,16 +309,29 @@ __device__ __forceinline__ void st_park256(U32x8 *p, const U32x8 &v)
 
 // Predicated re-load of a parked row straight into the registers that carry the running value
 // (read-write operands, two 128-bit loads: a 256-bit load wants an 8-aligned register octet, which
-// made ptxas keep a second copy of the value and shuffle 16 registers per step).
+// made ptxas keep a second copy of the value and shuffle 16 registers per step).  The row may have
+// been written by another SM earlier in the same launch (a unit's root): L2 only (.cg), never L1.
 __device__ __forceinline__ void ld_own256_if(U32x8 &v, const U32x8 *p, uint32_t pred)
 {
 	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-				 "@q ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%8];\n\t"
-				 "@q ld.global.L1::no_allocate.v4.u32 {%4,%5,%6,%7}, [%8+16];\n\t}"
+				 "@q ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%8];\n\t"
+				 "@q ld.global.cg.v4.u32 {%4,%5,%6,%7}, [%8+16];\n\t}"
 				 : "+r"(v.lo.x), "+r"(v.lo.y), "+r"(v.lo.z), "+r"(v.lo.w), "+r"(v.hi.x), "+r"(v.hi.y), "+r"(v.hi.z),
 				   "+r"(v.hi.w)
 				 : "l"(p), "r"(pred)
 				 : "memory");
+}
+
+// Ready flags of the fused launch (see kWalkCtl*): written with release, polled with acquire.
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
 }
 
 #ifndef PGS_WALK_CHUNK
@@ -331,14 +344,28 @@ constexpr int kWalkChunk = PGS_WALK_CHUNK; // steps a warp stages in shared memo
 template <int MINB, int PAIRS, bool QUAD, bool HINTS = true>
 __global__ void __launch_bounds__(kThreads, MINB)
 k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
-			  const int64_t *__restrict__ unit_off, uint32_t n_units, uint32_t pairs_per_node)
+			  const int64_t *__restrict__ unit_off, const int32_t *__restrict__ unit_wait, uint32_t *__restrict__ ctl,
+			  uint32_t n_units, uint32_t pairs_per_node)
 {
 	static_assert(!QUAD || PAIRS % 2 == 0, "a quad is two pairs");
-	// Units are sorted by decreasing length and CTAs start in index order: unit-major numbering
-	// (all slabs of the longest unit first, the shortest units last) keeps the tail of the launch short.
-	// (config 4: 2.28 -> 2.11 ms against slab-major numbering; 625 genes: 0.49 -> 0.36 ms)
-	const uint32_t n_slabs = gridDim.x / n_units;
-	const uint32_t unit = blockIdx.x / n_slabs, slab = blockIdx.x - unit * n_slabs;
+	// ONE launch holds the whole sweep: the units over the top of the tree come first, then the
+	// subtree units by decreasing length.  A unit whose root row is produced by another unit waits
+	// for that row's ready flag; the row's producer always holds a LOWER ticket.  Tickets are handed
+	// out in the order CTAs actually start, so whoever a resident CTA waits for is resident or done:
+	// no deadlock whatever the hardware's dispatch order.  Unit-major numbering (all slabs of a unit
+	// in a row, the shortest units last) keeps the tail of the launch short.
+	__shared__ uint32_t s_ctl[3]; // epoch of this launch, this CTA's first ready flag, flags per unit root
+	__shared__ uint32_t s_unit;
+	if (threadIdx.x == 0) {
+		const uint32_t ticket = atomicAdd(ctl + kWalkCtlTicket, 1u);
+		const uint32_t n_slabs = gridDim.x / n_units, u = ticket / n_slabs;
+		s_unit = u;
+		s_ctl[0] = *reinterpret_cast<volatile uint32_t *>(ctl + kWalkCtlEpoch) + 1u; // advanced by the last CTA of a launch
+		s_ctl[1] = (ticket - u * n_slabs) * (kThreads / 32);
+		s_ctl[2] = n_slabs * (kThreads / 32);
+	}
+	__syncthreads();
+	const uint32_t unit = s_unit, slab = s_ctl[1] / (kThreads / 32);
 	// this thread's PAIRS columns (block pairs) inside any node's dense region
 	uint32_t p[PAIRS], gid[PAIRS], blk[PAIRS];
 	bool active[PAIRS];
@@ -363,6 +390,9 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	// synchronisation; consecutive threads hit consecutive 16-byte words: conflict-free).
 	extern __shared__ uint4 s_park[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	// ready flags: one per (unit root, slab, warp) -- the warp of the consumer CTA reads exactly the
+	// columns the same warp of the producer CTA wrote, so warps hand over without a block barrier
+	auto ready_flag = [&](uint32_t sig) { return ctl + kWalkCtlFlags + ((size_t)sig * s_ctl[2] + s_ctl[1] + (uint32_t)warp); };
 	U32x8 cur[PAIRS]; // the values carried from step to step
 #pragma unroll
 	for (int j = 0; j < PAIRS; j++) {
@@ -370,6 +400,29 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 		cur[j].hi = cur[j].lo;
 	}
 	const int64_t begin = unit_off[unit], end = unit_off[unit + 1];
+	{
+		const int32_t wait_sig = __ldg(unit_wait + unit);
+		if (wait_sig == kWalkWaitGenRoot) {
+			// the unit starts at the tree's root: draw the origin rows (what K0 does for other genes),
+			// keep them in memory (the outputs read them) and carry them into the first step
+			const int64_t root_off = __ldg(&steps[begin].in_off);
+#pragma unroll
+			for (int j = 0; j < PAIRS; j++) {
+				if (!active[j]) continue;
+				cur[j].lo = root_block(gid[j], blk[j], 64, t.keys);
+				cur[j].hi = root_block(gid[j], blk[j] + 1u, valid_hi[j], t.keys);
+				st_stream256(reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + root_off), cur[j]);
+			}
+		} else if (wait_sig >= 0) {
+			// the unit's root row comes from another unit: wait until this warp's columns of it are there
+			if (lane == 0) {
+				const uint32_t *const flag = ready_flag((uint32_t)wait_sig);
+				const uint32_t epoch = s_ctl[0];
+				while (ld_acquire_gpu(flag) != epoch) __nanosleep(40);
+			}
+			__syncwarp();
+		}
+	}
 	for (int64_t i0 = begin; i0 < end; i0 += kWalkChunk) {
 		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
 		WalkStep *const s_steps = s_steps_all[warp];
@@ -394,7 +447,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 					ld_own256_if(cur[j], reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off),
 								 (f & kWalkLoad) && active[j] ? 1u : 0u);
 			}
-			const uint32_t edge_a = st.edge_a, hca = st.hca, hcb = st.hcb;
+			const uint32_t edge_a = st.edge_a, hca = decision_cmp(st.h1a), hcb = decision_cmp(st.h1b);
 			uint32_t wa[PAIRS], wb[PAIRS]; // the pair words of branch a and branch b
 			uint32_t m = 0;
 #pragma unroll
@@ -469,6 +522,23 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 					}
 				}
 			}
+			if (f & (kWalkSignalA | kWalkSignalB)) { // a stored child is another unit's root: this warp's columns of it are ready
+				__syncwarp();
+				if (lane == 0) {
+					if (f & kWalkSignalA) st_release_gpu(ready_flag(st.sig_a), s_ctl[0]);
+					if (f & kWalkSignalB) st_release_gpu(ready_flag(st.sig_b), s_ctl[0]);
+				}
+			}
+		}
+	}
+	// the last CTA to finish makes the control block ready for the next launch
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(ctl + kWalkCtlDone, 1u) == gridDim.x - 1u) {
+			ctl[kWalkCtlTicket] = 0u;
+			ctl[kWalkCtlDone] = 0u;
+			ctl[kWalkCtlEpoch] = s_ctl[0];
 		}
 	}
 }
@@ -487,65 +557,73 @@ int choose_walk_variant(uint32_t blocks, double mean_hit)
 	return mean_hit > 0.003 ? 0 : 2;
 }
 
-// Shared memory of one SM that the resident CTAs' stacks may take: 227 KB less the static part
-// (steps, thresholds) and the 1 KB the driver reserves per CTA.
-// column slabs (CTAs per unit) of the pass over the subtrees
+// column slabs (CTAs per unit)
 uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks)
 {
 	const uint32_t pairs = n_dense * blocks / 2, per_cta = kThreads * (variant == 1 ? 1 : 2);
 	return (pairs + per_cta - 1) / per_cta;
 }
 
-int walk_smem_capacity(int variant)
+size_t walk_ctl_words(int variant, uint32_t n_dense, uint32_t blocks, int32_t n_signals)
+{
+	return (size_t)kWalkCtlFlags + (size_t)n_signals * walk_slabs(variant, n_dense, blocks) * (kThreads / 32);
+}
+
+// Shared memory of one SM that the resident CTAs' stacks may take: 227 KB less the static part
+// (steps, control words) and the 1 KB the driver reserves per CTA.
+static int walk_smem_hw_levels(int variant)
 {
 	const int ctas = (variant == 1 || variant == 2) ? 3 : 2, pairs = variant == 1 ? 1 : 2;
 	const int per_cta = (227 * 1024) / ctas - 1024 - (int)(sizeof(WalkStep) * kWalkChunk * (kThreads / 32)) - 256;
-	int levels = per_cta / (pairs * 2 * 16 * kThreads);
+	return per_cta / (pairs * 2 * 16 * kThreads);
+}
+
+int walk_smem_capacity(int variant)
+{
+	int levels = walk_smem_hw_levels(variant);
 	if (const char *v = std::getenv("PGS_WALK_SMEM_LEVELS")) levels = std::min(levels, std::max(0, std::atoi(v))); // tuning knob
 	return levels;
 }
 
 template <int MINB, int PAIRS, bool QUAD, bool HINTS>
-static void launch_walk_variant(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-								int32_t smem_levels, cudaStream_t s)
+static void launch_walk_variant(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, const int32_t *unit_wait,
+								uint32_t *ctl, int32_t n_units, int32_t smem_levels, cudaStream_t s)
 {
 	const uint32_t pairs = t.n_dense * t.blocks / 2;
 	const uint32_t per_cta = kThreads * PAIRS;
 	const unsigned grid = (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
 	const size_t dyn = (size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads; // allowed by prepare_walk_dense
-	k1_walk_dense<MINB, PAIRS, QUAD, HINTS><<<grid, kThreads, dyn, s>>>(t, steps, unit_off, (uint32_t)n_units, pairs);
+	k1_walk_dense<MINB, PAIRS, QUAD, HINTS><<<grid, kThreads, dyn, s>>>(t, steps, unit_off, unit_wait, ctl, (uint32_t)n_units, pairs);
 }
 
 template <int MINB, int PAIRS, bool QUAD, bool HINTS>
-static cudaError_t allow_walk_smem(int32_t smem_levels)
+static cudaError_t allow_walk_smem(int variant)
 {
 	return cudaFuncSetAttribute(k1_walk_dense<MINB, PAIRS, QUAD, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-								(int)((size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads));
+								(int)((size_t)walk_smem_hw_levels(variant) * PAIRS * 2 * sizeof(uint4) * kThreads));
 }
 
-cudaError_t prepare_walk_dense(int variant, int32_t smem_levels)
+// The attribute belongs to the function on the current device, not to an engine: every engine sets
+// the same value (the most any plan can ask for), so engines that share a device cannot lower it
+// under each other's feet.
+cudaError_t prepare_walk_dense()
 {
-	const cudaError_t ce = allow_walk_smem<3, 1, false, true>(smem_levels); // the passes over the top of the tree
-	if (ce != cudaSuccess) return ce;
-	switch (variant) {
-		case 0: return allow_walk_smem<2, 2, true, true>(smem_levels);
-		case 2: return allow_walk_smem<3, 2, true, true>(smem_levels);
-		case 3: return allow_walk_smem<2, 2, true, false>(smem_levels);
-		default: return allow_walk_smem<3, 1, false, true>(smem_levels);
-	}
+	cudaError_t ce = allow_walk_smem<2, 2, true, true>(0);
+	if (ce == cudaSuccess) ce = allow_walk_smem<3, 1, false, true>(1);
+	if (ce == cudaSuccess) ce = allow_walk_smem<3, 2, true, true>(2);
+	if (ce == cudaSuccess) ce = allow_walk_smem<2, 2, true, false>(3);
+	return ce;
 }
 
-void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-					   int32_t smem_levels, int variant, bool top_pass, cudaStream_t s)
+void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, const int32_t *unit_wait,
+					   uint32_t *ctl, int32_t n_units, int32_t smem_levels, int variant, cudaStream_t s)
 {
 	if (n_units == 0 || t.n_dense == 0) return;
-	// The passes over the top of the tree are short serial chains on long branches (most blocks
-	// take the rare path): the finest split of the columns gives them the most threads.
-	switch (top_pass ? 1 : variant) {
-		case 0: launch_walk_variant<2, 2, true, true>(t, steps, unit_off, n_units, smem_levels, s); break;
-		case 2: launch_walk_variant<3, 2, true, true>(t, steps, unit_off, n_units, smem_levels, s); break;
-		case 3: launch_walk_variant<2, 2, true, false>(t, steps, unit_off, n_units, smem_levels, s); break;
-		default: launch_walk_variant<3, 1, false, true>(t, steps, unit_off, n_units, smem_levels, s); break;
+	switch (variant) {
+		case 0: launch_walk_variant<2, 2, true, true>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
+		case 2: launch_walk_variant<3, 2, true, true>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
+		case 3: launch_walk_variant<2, 2, true, false>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
+		default: launch_walk_variant<3, 1, false, true>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
 	}
 }
 

@@ -28,7 +28,7 @@ struct RootTask {
 struct __align__(16) WalkStep {
 	int64_t in_off, a_off, b_off; // dense regions of the node and of its children a (pair leader) and b
 	uint32_t edge_a, edge_b;      // child node indices = RNG edge ids (edge_a < edge_b)
-	uint32_t hca, hcb;            // decision_cmp(H[1]) of the two branches
+	uint32_t sig_a, sig_b;        // kWalkSignalA/B: index of the ready flag of the unit rooted at child a / b
 	uint32_t flags;               // kWalk* below
 	uint32_t slots;               // bits 0-7: shared-memory level the parked child goes to, bits 8-15: level the input comes from
 	uint64_t h1a, h2a, h1b, h2b;  // H[1], H[2] of the two branches (0 beyond kmax): the rare path needs no table for K <= 1
@@ -45,6 +45,15 @@ constexpr uint32_t kWalkParkB = 128u;
 constexpr uint32_t kWalkSmemA = 256u;  // child a is parked in the thread's shared-memory stack (no global store)
 constexpr uint32_t kWalkSmemB = 512u;
 constexpr uint32_t kWalkLoadSmem = 1024u; // input comes from the shared-memory stack
+constexpr uint32_t kWalkSignalA = 2048u;  // the stored child a is the root of another unit: raise its ready flag
+constexpr uint32_t kWalkSignalB = 4096u;
+constexpr int32_t kWalkWaitGenRoot = -2;  // unit_wait value of the unit that starts at the tree's root: it draws the origin rows
+
+// Control block of the fused walk launch (device memory, uint32 words): a ticket counter that
+// numbers the CTAs in the order they start, a count of finished CTAs, the epoch of the last
+// completed sweep, then one ready flag per (unit root, column slab, warp) holding the epoch in
+// which it was last raised.  The last CTA of a launch resets the counters and advances the epoch.
+constexpr int kWalkCtlTicket = 0, kWalkCtlDone = 1, kWalkCtlEpoch = 2, kWalkCtlFlags = 4;
 
 // Unsigned division by a launch constant: q = umulhi(x, mul) >> shift (x < 2^31).
 struct FastDiv {
@@ -92,20 +101,23 @@ extern int g_walk_variant;
 void launch_rootgen(const DeviceTables &t, const RootTask *tasks, int64_t n_tasks, cudaStream_t s);
 void launch_sweep_dense(const DeviceTables &t, const DenseTask *tasks, int32_t n_tasks, cudaStream_t s);
 void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t n_tasks, cudaStream_t s);
-// Fused dense sweep: unit u executes steps[unit_off[u] .. unit_off[u+1]) for every column slab.
-// variant = choose_walk_variant(...); smem_levels = deepest shared-memory stack level any step
-// uses, plus one; top_pass = one of the short passes over the top of the tree that precede the
-// pass over all subtrees.
+// Fused dense sweep.  variant = choose_walk_variant(...); smem_levels = deepest shared-memory stack
+// level any step uses, plus one.
 int choose_walk_variant(uint32_t blocks_per_gene, double mean_hit);
 // how many parked rows per thread that kernel can keep in shared memory; deeper levels of a unit's
 // stack go to the global pool
 int walk_smem_capacity(int variant);
 // column slabs (CTAs per unit) that kernel makes of a dense region
 uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks_per_gene);
-// once per device and plan, before the first launch: opt in to the dynamic shared memory the stack needs
-cudaError_t prepare_walk_dense(int variant, int32_t smem_levels);
-void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, int32_t n_units,
-					   int32_t smem_levels, int variant, bool top_pass, cudaStream_t s);
+// before the first launch on a device: opt in to the largest dynamic shared memory any plan may ask
+// for (the attribute is per function and device, not per engine: it is only ever set to this value)
+cudaError_t prepare_walk_dense();
+// One launch sweeps every unit: unit u executes steps[unit_off[u] .. unit_off[u+1]) for every column
+// slab; unit_wait[u] = index of the ready flag its first load waits for (-1: none); ctl = control block.
+void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, const int32_t *unit_wait,
+					   uint32_t *ctl, int32_t n_units, int32_t smem_levels, int variant, cudaStream_t s);
+// words of the control block for n_signals ready flags
+size_t walk_ctl_words(int variant, uint32_t n_dense, uint32_t blocks_per_gene, int32_t n_signals);
 
 // K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
 // i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).

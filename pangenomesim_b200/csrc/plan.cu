@@ -22,6 +22,8 @@ struct SweepPlan {
 	std::vector<RootTask> root_tasks;
 	std::vector<WalkStep> walk_steps;
 	std::vector<int64_t> walk_off;
+	std::vector<int32_t> walk_wait; // per unit: ready flag its first load waits for, -1 = none
+	int32_t n_signals = 0;
 };
 
 int64_t dense_rows(const Engine &e, const SweepPlan &p, int32_t v)
@@ -228,7 +230,9 @@ void plan_level_tasks(Engine &e, SweepPlan &plan)
 	e.n_sparse_tasks = (int64_t)sparse_tasks.size();
 
 	root_tasks.reserve(n_genes);
-	for (int64_t s = 0; s < D; s++) root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[e.root] + s), e.dense_gid[s]});
+	// (the fused column walk draws the dense genes' origin rows itself: no K0 work for them)
+	for (int64_t s = 0; s < D && !plan.walk_mode; s++)
+		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[e.root] + s), e.dense_gid[s]});
 	for (int64_t g = 0; g < n_genes; g++) {
 		if (e.dense_slot[g] >= 0) continue;
 		const int32_t v = e.origin[g];
@@ -238,7 +242,7 @@ void plan_level_tasks(Engine &e, SweepPlan &plan)
 		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + dr(v) + (it - b)), (uint32_t)e.gene_id[g]});
 	}
 	e.n_root_tasks = (int64_t)root_tasks.size();
-	e.rows_origin = e.n_root_tasks;
+	e.rows_origin = e.n_root_tasks + (plan.walk_mode ? D : 0);
 }
 
 // Per-branch decision tables (edge_table.cpp) in the layouts the kernels read.
@@ -371,10 +375,19 @@ int plan_walk(Engine &e, SweepPlan &p)
 			std::stable_sort(mid_roots.begin(), mid_roots.end(),
 							 [&](int32_t a, int32_t b) { return top_size[a] > top_size[b]; });
 		}
+		// a unit root other than the tree's root lives in a pool slot: written (and its ready flag
+		// raised) by the unit above, read by its own unit
+		std::vector<int32_t> sig_of(N, -1);
 		for (int32_t r : mid_roots)
-			if (r != e.root) loc[r] = slot_off(pool_slots++);
+			if (r != e.root) {
+				loc[r] = slot_off(pool_slots++);
+				sig_of[r] = p.n_signals++;
+			}
 		for (size_t u = 0; u < roots.size(); u++)
-			if (roots[u] != e.root) loc[roots[u]] = slot_off(pool_slots++);
+			if (roots[u] != e.root) {
+				loc[roots[u]] = slot_off(pool_slots++);
+				sig_of[roots[u]] = p.n_signals++;
+			}
 		auto make_step = [&](int32_t v, uint32_t flags) {
 			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
 			pgs::WalkStep s{};
@@ -383,8 +396,8 @@ int plan_walk(Engine &e, SweepPlan &p)
 			s.b_off = loc[b] >= 0 ? loc[b] : 0;
 			s.edge_a = (uint32_t)a;
 			s.edge_b = (uint32_t)b;
-			s.hca = decision_cmp(e.h1_host[a]);
-			s.hcb = decision_cmp(e.h1_host[b]);
+			s.sig_a = (flags & pgs::kWalkSignalA) ? (uint32_t)sig_of[a] : 0u;
+			s.sig_b = (flags & pgs::kWalkSignalB) ? (uint32_t)sig_of[b] : 0u;
 			s.h1a = e.h1_host[a];
 			s.h1b = e.h1_host[b];
 			s.h2a = e.kmax_host[a] >= 2 ? e.tab_host[e.tab_off_host[a] + 1] : 0;
@@ -410,7 +423,9 @@ int plan_walk(Engine &e, SweepPlan &p)
 				const bool ia = internal(a), ib = internal(b);
 				const bool da = ia && descend(a), db = ib && descend(b);
 				uint32_t f = 0;
-				if (!in_reg && smem_level[v] >= 0) {
+				if (!in_reg && v == e.root) {
+					e.rows_stored += D; // the origin rows are drawn by the unit itself (kWalkWaitGenRoot) and stored: the outputs read them
+				} else if (!in_reg && smem_level[v] >= 0) {
 					f |= pgs::kWalkLoadSmem;
 				} else if (!in_reg) {
 					f |= pgs::kWalkLoad;
@@ -418,8 +433,8 @@ int plan_walk(Engine &e, SweepPlan &p)
 				}
 				if (!ia) f |= pgs::kWalkStoreA;                       // a genome's row
 				if (!ib) f |= pgs::kWalkStoreB;
-				if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA; // root of another unit
-				if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB;
+				if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA | pgs::kWalkSignalA; // root of another unit
+				if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB | pgs::kWalkSignalB;
 				int32_t carry = -1;
 				if (da && db) {
 					const bool a_first = size[a] <= size[b];
@@ -469,20 +484,24 @@ int plan_walk(Engine &e, SweepPlan &p)
 		if (crown[e.root]) {
 			emit_walk(e.root, [&](int32_t c) { return crown[c] != 0; });
 			walk_off.push_back((int64_t)walk_steps.size());
+			p.walk_wait.push_back(pgs::kWalkWaitGenRoot);
 			e.walk_pass_units.push_back(1);
 		}
 		if (!mid_roots.empty()) {
 			for (int32_t r : mid_roots) {
 				emit_walk(r, [&](int32_t c) { return top[c] != 0; });
 				walk_off.push_back((int64_t)walk_steps.size());
+				p.walk_wait.push_back(r == e.root ? pgs::kWalkWaitGenRoot : sig_of[r]);
 			}
 			e.walk_pass_units.push_back((int32_t)mid_roots.size());
 		}
 		for (int32_t r : roots) {
 			emit_walk(r, [](int32_t) { return true; });
 			walk_off.push_back((int64_t)walk_steps.size());
+			p.walk_wait.push_back(r == e.root ? pgs::kWalkWaitGenRoot : sig_of[r]);
 		}
 		e.walk_pass_units.push_back((int32_t)roots.size());
+		e.n_walk_units = (int32_t)p.walk_wait.size();
 		e.walk = true;
 	}
 	rows += pool_slots * D;
@@ -505,8 +524,17 @@ int upload_plan(Engine &e, SweepPlan &p)
 	int rc = 0;
 	if ((rc = e.upload(e.d_walk_steps, p.walk_steps.data(), sizeof(WalkStep) * p.walk_steps.size(), "walk steps"))) return rc;
 	if ((rc = e.upload(e.d_walk_off, p.walk_off.data(), sizeof(int64_t) * p.walk_off.size(), "walk units"))) return rc;
-	if (e.walk && pgs::prepare_walk_dense(e.walk_variant, e.walk_smem_levels) != cudaSuccess)
-		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the walk kernel's shared-memory stack does not fit this device");
+	if ((rc = e.upload(e.d_walk_wait, p.walk_wait.data(), sizeof(int32_t) * p.walk_wait.size(), "walk unit waits"))) return rc;
+	if (e.walk) {
+		if (pgs::prepare_walk_dense() != cudaSuccess)
+			return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the walk kernel's shared-memory stack does not fit this device");
+		// control block of the fused launch: counters and ready flags start at zero (epoch 0 = "never raised")
+		const size_t words = pgs::walk_ctl_words(e.walk_variant, (uint32_t)D, (uint32_t)e.blocks, p.n_signals);
+		if ((rc = e.alloc(e.d_walk_ctl, words * sizeof(uint32_t), "walk control block"))) return rc;
+		cudaError_t ce = cudaMemsetAsync(e.d_walk_ctl.p, 0, words * sizeof(uint32_t), e.stream);
+		if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
+		if (ce != cudaSuccess) return e.cuda_fail(ce, "walk control block");
+	}
 
 	// ---- device
 	const size_t row_bytes = (size_t)e.blocks * 16;
