@@ -57,7 +57,7 @@ typedef struct pgs_config {
 
 #define PGS_FLAG_NO_GRAPH 1u /* launch the level sweep kernel by kernel instead of one CUDA graph */
 /* Keep the row of every internal node in memory (level-synchronous sweep).  Without this flag
- * the dense genes are swept by the fused column walk, which only materialises what the outputs
+ * the genes are swept by the fused walks (binary trees), which only materialise what the outputs
  * need: the rows of the genomes (leaves) and of the origins; pgs_copy_packed / pgs_copy_dense on
  * any other node then fail with PGS_ERR_STATE. */
 #define PGS_FLAG_KEEP_INTERNAL 2u
@@ -116,7 +116,7 @@ typedef struct pgs_stats {
 	int64_t leaf_nucleotides;    /* sum over genomes of carried genes * gene_length */
 	int64_t site_edges;          /* rows_written * gene_length */
 	int64_t levels;              /* tree levels below the root */
-	int64_t kernel_launches;     /* kernels launched by the last pgs_sweep */
+	int64_t kernel_launches;     /* kernels launched by the last pgs_sweep (fused walks: masks + walk for the dense genes, one for the sparse genes) */
 	int64_t device_bytes;        /* bytes of HBM held by the engine */
 	int64_t sweep_mode;          /* 0 = level-synchronous, 1 = fused column walk (dense genes) */
 	int64_t rows_stored;         /* rows K1 actually writes to memory */
@@ -214,7 +214,9 @@ int pgs_genome_name(int64_t genome_index, char *dst, size_t cap);
 /* ---- test hooks ----------------------------------------------------------------------- */
 
 /* Copy the packed row of (node, gene table index) to dst (blocks_per_gene*16 bytes).
- * Returns 1 if the row does not exist (gene absent at node). */
+ * Returns 1 if the row does not exist (gene absent at node), PGS_ERR_STATE if the gene is present
+ * at the node but the sweep does not keep that row (an internal node other than the gene's origin,
+ * without PGS_FLAG_KEEP_INTERNAL). */
 int pgs_copy_packed(pgs_engine *h, int32_t node, int64_t gene_index, void *dst);
 /* Copy the dense-gene region of a node: n_dense_genes rows in ascending gene_id order. */
 int pgs_copy_dense(pgs_engine *h, int32_t node, void *dst);

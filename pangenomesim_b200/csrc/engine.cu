@@ -72,7 +72,7 @@ int64_t Engine::device_bytes() const
 {
 	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
 						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch,
-						   &d_tab8, &d_walk_steps, &d_walk_off, &d_walk_wait, &d_walk_ctl};
+						   &d_tab8, &d_walk_steps, &d_walk_off, &d_unit_path_off, &d_unit_path, &d_unit_store, &d_top_tasks, &d_sp_genes, &d_sp_steps};
 	int64_t s = 0;
 	for (auto b : all) s += (int64_t)b->bytes;
 	return s;
@@ -96,16 +96,38 @@ int64_t Engine::row_index(int32_t node, int64_t g) const
 	return row_base[node] + (materialised[node] ? (int64_t)dense_gid.size() : 0) + (it - b);
 }
 
+// Does the sweep leave a valid row for (node, gene) in memory?  The fused walks keep only what the
+// outputs read: genomes' rows and origin rows.  (True also where the gene is absent: row_index says so.)
+bool Engine::row_kept(int32_t node, int64_t g) const
+{
+	if (dense_slot[g] >= 0) return materialised[node] != 0;
+	if (!sparse_walk) return true;
+	return child_off[node + 1] == child_off[node] || node == origin[g] || row_index(node, g) < 0;
+}
+
 // K1 for every level below the root: dense region, then sparse region.  Levels are separated by
 // stream order (each launch reads rows written by the previous level's launches).
 void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 {
 	const DenseTask *dt = d_dense_tasks.as<DenseTask>();
 	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
-	if (walk) { // dense genes: ONE launch -- origin rows, the top of the tree and every subtree (k1_walk_dense)
-		launch_walk_dense(tables, d_walk_steps.as<WalkStep>(), d_walk_off.as<int64_t>(), d_walk_wait.as<int32_t>(),
-						  d_walk_ctl.as<uint32_t>(), n_walk_units, walk_smem_levels, walk_variant, s);
+	if (walk) { // dense genes: origin rows and the masks of the top branches, then ONE launch for every unit of the tree
+		launch_top_masks(tables, d_top_tasks.as<TopMaskTask>(), n_top_tasks, s);
 		(*launches)++;
+		WalkUnits u{};
+		u.steps = d_walk_steps.as<WalkStep>();
+		u.unit_off = d_walk_off.as<int64_t>();
+		u.unit_path_off = d_unit_path_off.as<int32_t>();
+		u.unit_path = d_unit_path.as<int64_t>();
+		u.unit_store = d_unit_store.as<int64_t>();
+		u.root_off = row_base[root] * blocks;
+		u.n_units = n_walk_units;
+		launch_walk_dense(tables, u, walk_smem_levels, walk_variant, s);
+		(*launches)++;
+	}
+	if (sparse_walk) { // sparse genes: origin rows and every branch in one launch
+		launch_walk_sparse(tables, d_sp_genes.as<SparseGene>(), d_sp_steps.as<SparseStep>(), n_sp_genes, s);
+		if (n_sp_genes > 0) (*launches)++;
 	}
 	for (int32_t lvl = 1; lvl <= max_level; lvl++) {
 		const int64_t nd = dense_level_off[lvl + 1] - dense_level_off[lvl];
@@ -114,7 +136,7 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 			(*launches)++;
 		}
 		const int64_t ns = sparse_level_off[lvl + 1] - sparse_level_off[lvl];
-		if (ns > 0) {
+		if (ns > 0 && !sparse_walk) {
 			launch_sweep_sparse(tables, st + sparse_level_off[lvl], ns, s);
 			(*launches)++;
 		}
@@ -503,10 +525,10 @@ int pgs_copy_packed(pgs_engine *h, int32_t node, int64_t gene_index, void *dst)
 	if (!dst) return e.fail(PGS_ERR_ARG, "pgs_copy_packed: null dst");
 	if (node < 0 || node >= e.n_nodes || gene_index < 0 || gene_index >= e.n_genes)
 		return e.fail(PGS_ERR_ARG, "pgs_copy_packed: index out of range");
+	if (!e.row_kept(node, gene_index))
+		return e.fail(PGS_ERR_STATE, "pgs_copy_packed: this internal row is not kept (create the engine with PGS_FLAG_KEEP_INTERNAL)");
 	const int64_t row = e.row_index(node, gene_index);
 	if (row < 0) return 1;
-	if (e.dense_slot[gene_index] >= 0 && !e.materialised[node])
-		return e.fail(PGS_ERR_STATE, "pgs_copy_packed: this internal row is not kept (create the engine with PGS_FLAG_KEEP_INTERNAL)");
 	cudaError_t ce = cudaStreamSynchronize(e.stream);
 	if (ce == cudaSuccess)
 		ce = cudaMemcpy(dst, e.tables.rows + row * e.blocks, (size_t)e.blocks * 16, cudaMemcpyDeviceToHost);

@@ -61,7 +61,9 @@ struct Engine {
 	// fused column walk of the dense region (default for binary trees)
 	bool walk = false;
 	std::vector<int32_t> walk_pass_units; // units by kind (crown, rest of the top, subtrees), in launch order
-	int32_t n_walk_units = 0;
+	int32_t n_walk_units = 0, n_top_tasks = 0;
+	bool sparse_walk = false;             // sparse genes: fused walk (k1_walk_sparse); internal sparse rows are not kept
+	int64_t n_sp_genes = 0, sparse_rows_written = 0, sparse_rows_read = 0; // (W and R of the sparse region)
 	int walk_variant = 2;                 // kernel of the pass over the subtrees (choose_walk_variant)
 	int32_t walk_smem_levels = 0;         // deepest shared-memory stack level used by any step, plus one
 	int64_t rows_parked_smem = 0;         // rows per sweep parked in shared memory instead of the global pool
@@ -73,7 +75,7 @@ struct Engine {
 
 	// ---- device
 	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
-	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off, d_walk_wait, d_walk_ctl;
+	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off, d_unit_path_off, d_unit_path, d_unit_store, d_top_tasks, d_sp_genes, d_sp_steps;
 	DevBuf d_stage[2];          // K3 staging, kept between pgs_write_outputs calls
 	char *h_stage[2] = {nullptr, nullptr}; // pinned
 	int64_t stage_bytes = 0;
@@ -90,6 +92,7 @@ struct Engine {
 	int upload(DevBuf &b, const void *src, size_t bytes, const char *what);
 	int64_t device_bytes() const;
 	int64_t row_index(int32_t node, int64_t gene_index) const;
+	bool row_kept(int32_t node, int64_t gene_index) const;
 	void drop_graph();
 	void enqueue_levels(cudaStream_t s, int64_t *launches);
 };

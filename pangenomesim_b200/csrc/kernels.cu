@@ -309,29 +309,24 @@ __device__ __forceinline__ void st_park256(U32x8 *p, const U32x8 &v)
 
 // Predicated re-load of a parked row straight into the registers that carry the running value
 // (read-write operands, two 128-bit loads: a 256-bit load wants an 8-aligned register octet, which
-// made ptxas keep a second copy of the value and shuffle 16 registers per step).  The row may have
-// been written by another SM earlier in the same launch (a unit's root): L2 only (.cg), never L1.
+// made ptxas keep a second copy of the value and shuffle 16 registers per step).
 __device__ __forceinline__ void ld_own256_if(U32x8 &v, const U32x8 *p, uint32_t pred)
 {
 	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-				 "@q ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%8];\n\t"
-				 "@q ld.global.cg.v4.u32 {%4,%5,%6,%7}, [%8+16];\n\t}"
+				 "@q ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%8];\n\t"
+				 "@q ld.global.L1::no_allocate.v4.u32 {%4,%5,%6,%7}, [%8+16];\n\t}"
 				 : "+r"(v.lo.x), "+r"(v.lo.y), "+r"(v.lo.z), "+r"(v.lo.w), "+r"(v.hi.x), "+r"(v.hi.y), "+r"(v.hi.z),
 				   "+r"(v.hi.w)
 				 : "l"(p), "r"(pred)
 				 : "memory");
 }
 
-// Ready flags of the fused launch (see kWalkCtl*): written with release, polled with acquire.
-__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v)
+__device__ __forceinline__ U32x8 operator^(const U32x8 &a, const U32x8 &b)
 {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
-{
-	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
+	U32x8 r;
+	r.lo = make_uint4(a.lo.x ^ b.lo.x, a.lo.y ^ b.lo.y, a.lo.z ^ b.lo.z, a.lo.w ^ b.lo.w);
+	r.hi = make_uint4(a.hi.x ^ b.hi.x, a.hi.y ^ b.hi.y, a.hi.z ^ b.hi.z, a.hi.w ^ b.hi.w);
+	return r;
 }
 
 #ifndef PGS_WALK_CHUNK
@@ -343,29 +338,15 @@ constexpr int kWalkChunk = PGS_WALK_CHUNK; // steps a warp stages in shared memo
 // quad of blocks -- 64 contiguous bytes, one Philox call per step for the eight decisions.
 template <int MINB, int PAIRS, bool QUAD, bool HINTS = true>
 __global__ void __launch_bounds__(kThreads, MINB)
-k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict__ steps,
-			  const int64_t *__restrict__ unit_off, const int32_t *__restrict__ unit_wait, uint32_t *__restrict__ ctl,
-			  uint32_t n_units, uint32_t pairs_per_node)
+k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ WalkUnits u, uint32_t pairs_per_node)
 {
 	static_assert(!QUAD || PAIRS % 2 == 0, "a quad is two pairs");
-	// ONE launch holds the whole sweep: the units over the top of the tree come first, then the
-	// subtree units by decreasing length.  A unit whose root row is produced by another unit waits
-	// for that row's ready flag; the row's producer always holds a LOWER ticket.  Tickets are handed
-	// out in the order CTAs actually start, so whoever a resident CTA waits for is resident or done:
-	// no deadlock whatever the hardware's dispatch order.  Unit-major numbering (all slabs of a unit
-	// in a row, the shortest units last) keeps the tail of the launch short.
-	__shared__ uint32_t s_ctl[3]; // epoch of this launch, this CTA's first ready flag, flags per unit root
-	__shared__ uint32_t s_unit;
-	if (threadIdx.x == 0) {
-		const uint32_t ticket = atomicAdd(ctl + kWalkCtlTicket, 1u);
-		const uint32_t n_slabs = gridDim.x / n_units, u = ticket / n_slabs;
-		s_unit = u;
-		s_ctl[0] = *reinterpret_cast<volatile uint32_t *>(ctl + kWalkCtlEpoch) + 1u; // advanced by the last CTA of a launch
-		s_ctl[1] = (ticket - u * n_slabs) * (kThreads / 32);
-		s_ctl[2] = n_slabs * (kThreads / 32);
-	}
-	__syncthreads();
-	const uint32_t unit = s_unit, slab = s_ctl[1] / (kThreads / 32);
+	// Units are sorted by decreasing length and CTAs start in index order: unit-major numbering
+	// (all slabs of the longest unit first, the shortest units last) keeps the tail of the launch short.
+	// (config 4: 2.28 -> 2.11 ms against slab-major numbering; 625 genes: 0.49 -> 0.36 ms)
+	const WalkStep *__restrict__ const steps = u.steps;
+	const uint32_t n_slabs = gridDim.x / (uint32_t)u.n_units;
+	const uint32_t unit = blockIdx.x / n_slabs, slab = blockIdx.x - unit * n_slabs;
 	// this thread's PAIRS columns (block pairs) inside any node's dense region
 	uint32_t p[PAIRS], gid[PAIRS], blk[PAIRS];
 	bool active[PAIRS];
@@ -390,39 +371,34 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 	// synchronisation; consecutive threads hit consecutive 16-byte words: conflict-free).
 	extern __shared__ uint4 s_park[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	// ready flags: one per (unit root, slab, warp) -- the warp of the consumer CTA reads exactly the
-	// columns the same warp of the producer CTA wrote, so warps hand over without a block barrier
-	auto ready_flag = [&](uint32_t sig) { return ctl + kWalkCtlFlags + ((size_t)sig * s_ctl[2] + s_ctl[1] + (uint32_t)warp); };
 	U32x8 cur[PAIRS]; // the values carried from step to step
 #pragma unroll
 	for (int j = 0; j < PAIRS; j++) {
 		cur[j].lo = make_uint4(0u, 0u, 0u, 0u);
 		cur[j].hi = cur[j].lo;
 	}
-	const int64_t begin = unit_off[unit], end = unit_off[unit + 1];
 	{
-		const int32_t wait_sig = __ldg(unit_wait + unit);
-		if (wait_sig == kWalkWaitGenRoot) {
-			// the unit starts at the tree's root: draw the origin rows (what K0 does for other genes),
-			// keep them in memory (the outputs read them) and carry them into the first step
-			const int64_t root_off = __ldg(&steps[begin].in_off);
+		// The unit's root value: the origin row XORed with the masks of the branches on the path from
+		// the tree's root (k1_top_masks wrote both; every load is independent of the others).
+		const uint4 *const base = reinterpret_cast<const uint4 *>(t.rows);
 #pragma unroll
-			for (int j = 0; j < PAIRS; j++) {
-				if (!active[j]) continue;
-				cur[j].lo = root_block(gid[j], blk[j], 64, t.keys);
-				cur[j].hi = root_block(gid[j], blk[j] + 1u, valid_hi[j], t.keys);
-				st_stream256(reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(column[j]) + root_off), cur[j]);
-			}
-		} else if (wait_sig >= 0) {
-			// the unit's root row comes from another unit: wait until this warp's columns of it are there
-			if (lane == 0) {
-				const uint32_t *const flag = ready_flag((uint32_t)wait_sig);
-				const uint32_t epoch = s_ctl[0];
-				while (ld_acquire_gpu(flag) != epoch) __nanosleep(40);
-			}
-			__syncwarp();
+		for (int j = 0; j < PAIRS; j++)
+			if (active[j]) cur[j] = ld_stream256(reinterpret_cast<const U32x8 *>(base + u.root_off) + p[j]);
+		const int32_t pe = __ldg(u.unit_path_off + unit + 1);
+		for (int32_t k = __ldg(u.unit_path_off + unit); k < pe; k++) {
+			const int64_t off = __ldg(u.unit_path + k);
+#pragma unroll
+			for (int j = 0; j < PAIRS; j++)
+				if (active[j]) cur[j] = cur[j] ^ ld_stream256(reinterpret_cast<const U32x8 *>(base + off) + p[j]);
+		}
+		const int64_t store = __ldg(u.unit_store + unit);
+		if (store >= 0) { // the unit's root is a genome directly below a top node
+#pragma unroll
+			for (int j = 0; j < PAIRS; j++)
+				if (active[j]) st_leaf256(reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(t.rows) + store) + p[j], cur[j]);
 		}
 	}
+	const int64_t begin = __ldg(u.unit_off + unit), end = __ldg(u.unit_off + unit + 1);
 	for (int64_t i0 = begin; i0 < end; i0 += kWalkChunk) {
 		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
 		WalkStep *const s_steps = s_steps_all[warp];
@@ -447,7 +423,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 					ld_own256_if(cur[j], reinterpret_cast<const U32x8 *>(reinterpret_cast<const uint4 *>(column[j]) + st.in_off),
 								 (f & kWalkLoad) && active[j] ? 1u : 0u);
 			}
-			const uint32_t edge_a = st.edge_a, hca = decision_cmp(st.h1a), hcb = decision_cmp(st.h1b);
+			const uint32_t edge_a = st.edge_a, hca = st.hca, hcb = st.hcb;
 			uint32_t wa[PAIRS], wb[PAIRS]; // the pair words of branch a and branch b
 			uint32_t m = 0;
 #pragma unroll
@@ -522,25 +498,71 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const WalkStep *__restrict
 					}
 				}
 			}
-			if (f & (kWalkSignalA | kWalkSignalB)) { // a stored child is another unit's root: this warp's columns of it are ready
-				__syncwarp();
-				if (lane == 0) {
-					if (f & kWalkSignalA) st_release_gpu(ready_flag(st.sig_a), s_ctl[0]);
-					if (f & kWalkSignalB) st_release_gpu(ready_flag(st.sig_b), s_ctl[0]);
-				}
-			}
 		}
 	}
-	// the last CTA to finish makes the control block ready for the next launch
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		if (atomicAdd(ctl + kWalkCtlDone, 1u) == gridDim.x - 1u) {
-			ctl[kWalkCtlTicket] = 0u;
-			ctl[kWalkCtlDone] = 0u;
-			ctl[kWalkCtlEpoch] = s_ctl[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, masks of the branches below the top nodes.  A substitution XORs a non-zero delta into a
+// base, and which sites change (and by which delta) depends only on (seed, edge, gene, block) --
+// never on the sequence.  So the effect of a branch on a block is an XOR mask that can be drawn
+// before the parent's value exists.  The top of the tree -- long branches, where most blocks take the
+// rare path, walked by few threads one node after the other -- is therefore split in two: all
+// masks are drawn here, side by side over (top node, block pair), and the walk's steps over the
+// top reduce to "load two masks, XOR, store" (kWalkMask).  Thread = one pair of blocks of one
+// top node's two branches: 1 Philox call for the four decisions, then the flagged blocks' rare paths.
+__global__ void __launch_bounds__(kThreads)
+k1_top_masks(const __grid_constant__ DeviceTables t, const TopMaskTask *__restrict__ tasks, uint32_t slabs_per_task,
+			 uint32_t pairs_per_node)
+{
+	const uint32_t task = blockIdx.x / slabs_per_task, slab = blockIdx.x - task * slabs_per_task;
+	const uint32_t p = slab * kThreads + threadIdx.x;
+	if (p >= pairs_per_node) return;
+	const TopMaskTask &tk = tasks[task];
+	const uint32_t idx = 2u * p;
+	const uint32_t slot = fastdiv(idx, t.div_blocks);
+	const uint32_t blk = idx - slot * t.blocks; // the pair's even block
+	const uint32_t gid = __ldg(t.dense_gid + slot);
+	const int valid_hi = (blk + 2 == t.blocks) ? t.last_valid : 64;
+	const uint32_t edge_a = tk.edge_a, edge_b = tk.edge_b;
+	if (edge_a == kRootEdge) { // the dense genes' origin rows: what gene::gene(len, -1, id) draws (gene.cxx:13-25)
+		U32x8 r;
+		r.lo = root_block(gid, blk, 64, t.keys);
+		r.hi = root_block(gid, blk + 1u, valid_hi, t.keys);
+		st_park256(reinterpret_cast<U32x8 *>(t.rows + tk.ma_off) + p, r);
+		return;
+	}
+	const uint64_t h1a = tk.h1a, h1b = tk.h1b;
+	const uint4 w = quad_words(edge_a, gid, blk, t.keys);
+	const uint32_t wa = pick_pair_word(w, 0u, blk), wb = pick_pair_word(w, 1u, blk);
+	uint32_t hits = pair_hits(wa, decision_cmp(h1a)) | (pair_hits(wb, decision_cmp(h1b)) << 2);
+	const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+	U32x8 ma, mb;
+	ma.lo = ma.hi = mb.lo = mb.hi = zero;
+	while (hits) { // every lane works through its own flagged blocks
+		const uint32_t b = (uint32_t)__ffs((int)hits) - 1u;
+		hits &= hits - 1u;
+		const uint32_t side = b >> 1, odd = b & 1u;
+		const uint4 out = mutate_block_h12(zero, side ? edge_b : edge_a, gid, blk + odd, pair_field(side ? wb : wa, odd),
+										   side ? h1b : h1a, side ? tk.h2b : tk.h2a, t.tab, t.tab_off, t.kmax,
+										   odd ? valid_hi : 64, t.keys);
+		if (side) {
+			if (odd) mb.hi = out; else mb.lo = out;
+		} else {
+			if (odd) ma.hi = out; else ma.lo = out;
 		}
 	}
+	// read again by the walk within microseconds: keep them in L2
+	st_park256(reinterpret_cast<U32x8 *>(t.rows + tk.ma_off) + p, ma);
+	st_park256(reinterpret_cast<U32x8 *>(t.rows + tk.mb_off) + p, mb);
+}
+
+void launch_top_masks(const DeviceTables &t, const TopMaskTask *tasks, int32_t n_tasks, cudaStream_t s)
+{
+	if (n_tasks == 0 || t.n_dense == 0) return;
+	const uint32_t pairs = t.n_dense * t.blocks / 2;
+	const uint32_t slabs = (pairs + kThreads - 1) / kThreads;
+	k1_top_masks<<<(unsigned)((uint64_t)slabs * (uint32_t)n_tasks), kThreads, 0, s>>>(t, tasks, slabs, pairs);
 }
 
 int g_walk_variant = -1; // development knob (PGS_WALK_VARIANT): force a kernel, see choose_walk_variant
@@ -564,11 +586,6 @@ uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks)
 	return (pairs + per_cta - 1) / per_cta;
 }
 
-size_t walk_ctl_words(int variant, uint32_t n_dense, uint32_t blocks, int32_t n_signals)
-{
-	return (size_t)kWalkCtlFlags + (size_t)n_signals * walk_slabs(variant, n_dense, blocks) * (kThreads / 32);
-}
-
 // Shared memory of one SM that the resident CTAs' stacks may take: 227 KB less the static part
 // (steps, control words) and the 1 KB the driver reserves per CTA.
 static int walk_smem_hw_levels(int variant)
@@ -586,14 +603,13 @@ int walk_smem_capacity(int variant)
 }
 
 template <int MINB, int PAIRS, bool QUAD, bool HINTS>
-static void launch_walk_variant(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, const int32_t *unit_wait,
-								uint32_t *ctl, int32_t n_units, int32_t smem_levels, cudaStream_t s)
+static void launch_walk_variant(const DeviceTables &t, const WalkUnits &u, int32_t smem_levels, cudaStream_t s)
 {
 	const uint32_t pairs = t.n_dense * t.blocks / 2;
 	const uint32_t per_cta = kThreads * PAIRS;
-	const unsigned grid = (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)n_units);
+	const unsigned grid = (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)u.n_units);
 	const size_t dyn = (size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads; // allowed by prepare_walk_dense
-	k1_walk_dense<MINB, PAIRS, QUAD, HINTS><<<grid, kThreads, dyn, s>>>(t, steps, unit_off, unit_wait, ctl, (uint32_t)n_units, pairs);
+	k1_walk_dense<MINB, PAIRS, QUAD, HINTS><<<grid, kThreads, dyn, s>>>(t, u, pairs);
 }
 
 template <int MINB, int PAIRS, bool QUAD, bool HINTS>
@@ -615,15 +631,14 @@ cudaError_t prepare_walk_dense()
 	return ce;
 }
 
-void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, const int32_t *unit_wait,
-					   uint32_t *ctl, int32_t n_units, int32_t smem_levels, int variant, cudaStream_t s)
+void launch_walk_dense(const DeviceTables &t, const WalkUnits &u, int32_t smem_levels, int variant, cudaStream_t s)
 {
-	if (n_units == 0 || t.n_dense == 0) return;
+	if (u.n_units == 0 || t.n_dense == 0) return;
 	switch (variant) {
-		case 0: launch_walk_variant<2, 2, true, true>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
-		case 2: launch_walk_variant<3, 2, true, true>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
-		case 3: launch_walk_variant<2, 2, true, false>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
-		default: launch_walk_variant<3, 1, false, true>(t, steps, unit_off, unit_wait, ctl, n_units, smem_levels, s); break;
+		case 0: launch_walk_variant<2, 2, true, true>(t, u, smem_levels, s); break;
+		case 2: launch_walk_variant<3, 2, true, true>(t, u, smem_levels, s); break;
+		case 3: launch_walk_variant<2, 2, true, false>(t, u, smem_levels, s); break;
+		default: launch_walk_variant<3, 1, false, true>(t, u, smem_levels, s); break;
 	}
 }
 
@@ -690,6 +705,139 @@ void launch_sweep_sparse(const DeviceTables &t, const SparseTask *tasks, int64_t
 		k1_sweep_sparse<true><<<(unsigned)grid, kThreads, 0, s>>>(t, tasks, items);
 	else
 		k1_sweep_sparse<false><<<(unsigned)grid, kThreads, 0, s>>>(t, tasks, items);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, fused walk of the sparse region (default for binary trees).  The level-synchronous kernel
+// above needs one launch per tree level with a handful of CTAs each: launch-bound.  Here ONE launch
+// does everything for the accessory genes: a thread owns one quad of blocks (64 B, 256 sites) of one
+// gene, draws the gene's origin row itself (K0's work), and carries the quad depth-first down the
+// gene's presence subtree -- the child it descends into stays in registers, a sibling that is
+// visited later is parked in the thread's shared-memory stack (deeper levels: in the sibling's own
+// row), and only genomes' rows and origin rows are written.  The lanes of a warp walk different
+// genes with their own step lists (32-byte steps, read through L1); genes are sorted by the number
+// of steps so that the lanes of a warp finish together.
+// Replaces gene::bulk_mutate over the per-node gene map, reference gene.h:26-40 (img.cxx:285-286),
+// and the gained gene's fresh sequence, img.cxx:302.
+
+constexpr int kSpStackLevels = 4; // shared-memory stack levels per thread (64 B each)
+
+__device__ __forceinline__ uint4 ld_cg(const uint4 *p)
+{
+	uint4 r;
+	asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+	return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+k1_walk_sparse(const __grid_constant__ DeviceTables t, const SparseGene *__restrict__ genes,
+			   const SparseStep *__restrict__ steps, uint32_t n_items, uint32_t quads_per_gene)
+{
+	extern __shared__ uint4 s_stack[]; // [level][block of the quad][thread]
+	const uint32_t item = blockIdx.x * kThreads + threadIdx.x;
+	if (item >= n_items) return;
+	const uint32_t rank = item / quads_per_gene;
+	const uint32_t blk0 = (item - rank * quads_per_gene) * 4u;
+	const uint32_t nb = min(4u, t.blocks - blk0); // blocks of this quad that exist
+	const uint4 gene = __ldg(reinterpret_cast<const uint4 *>(genes) + rank);
+	const uint32_t gid = gene.x, n_steps = gene.w;
+	const uint32_t live = (1u << nb) - 1u;
+	auto valid_of = [&](uint32_t i) { return (blk0 + i + 1u == t.blocks) ? t.last_valid : 64; };
+	auto row_ptr = [&](uint32_t row) { return t.rows + (int64_t)row * t.blocks + blk0; };
+
+	uint4 cur[4];
+	{ // origin row: what gene::gene(len, -1, id) draws (gene.cxx:13-25)
+		uint4 *const dst = row_ptr(gene.y);
+#pragma unroll
+		for (uint32_t i = 0; i < 4; i++) {
+			cur[i] = make_uint4(0u, 0u, 0u, 0u);
+			if (i < nb) {
+				cur[i] = root_block(gid, blk0 + i, valid_of(i), t.keys);
+				st_stream(dst + i, cur[i]);
+			}
+		}
+	}
+	const uint4 *sp = reinterpret_cast<const uint4 *>(steps + gene.z);
+	for (uint32_t k = 0; k < n_steps; k++, sp += 2) {
+		const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+		const uint32_t f = s1.y;
+		if (f & kSpLoadSmem) {
+			const uint4 *const src = s_stack + ((s1.w >> 8) & 255u) * (4 * kThreads) + threadIdx.x;
+#pragma unroll
+			for (int i = 0; i < 4; i++) cur[i] = src[i * kThreads];
+		} else if (f & kSpLoadRow) {
+			const uint4 *const src = row_ptr(s1.z);
+#pragma unroll
+			for (uint32_t i = 0; i < 4; i++)
+				if (i < nb) cur[i] = ld_cg(src + i); // written by this thread a few steps ago
+		}
+		// one Philox call: the eight decisions {a, b} x {four blocks}
+		const uint4 w = quad_words(s0.z, gid, blk0, t.keys);
+		const uint32_t hca = (s1.x << 16) | 0xFFFFu, hcb = (s1.x & 0xFFFF0000u) | 0xFFFFu;
+		uint32_t hits_a = (f & kSpHasA) ? ((pair_hits(w.x, hca) | (pair_hits(w.y, hca) << 2)) & live) : 0u;
+		uint32_t hits_b = (f & kSpHasB) ? ((pair_hits(w.z, hcb) | (pair_hits(w.w, hcb) << 2)) & live) : 0u;
+		// rare path of block i on one side; `from` is the parent's value of the block
+		auto rare = [&](uint32_t side, uint32_t i, const uint4 &from) {
+			const uint32_t edge = side ? s0.w : s0.z;
+			const uint32_t word = side ? ((i & 2u) ? w.w : w.z) : ((i & 2u) ? w.y : w.x);
+			const uint64_t h1 = __ldg(t.tab8 + (size_t)edge * 8), h2 = __ldg(t.tab8 + (size_t)edge * 8 + 1);
+			return mutate_block_h12(from, edge, gid, blk0 + i, pair_field(word, i & 1u), h1, h2, t.tab, t.tab_off, t.kmax,
+									valid_of(i), t.keys);
+		};
+		auto emit = [&](uint32_t side, const uint4 (&v)[4]) {
+			const uint32_t dst = side ? s0.y : s0.x;
+			if (dst != kNoRow) {
+				uint4 *const d = row_ptr(dst);
+#pragma unroll
+				for (uint32_t i = 0; i < 4; i++)
+					if (i < nb) st_stream(d + i, v[i]);
+			}
+			if (f & (side ? kSpParkB : kSpParkA)) {
+				uint4 *const d = s_stack + (s1.w & 255u) * (4 * kThreads) + threadIdx.x;
+#pragma unroll
+				for (int i = 0; i < 4; i++) d[i * kThreads] = v[i];
+			}
+		};
+		// The child that is NOT carried on goes first; the carried child's value replaces the running one.
+		const uint32_t second = (f & kSpCarryA) ? 0u : 1u;
+#pragma unroll 1
+		for (uint32_t pass = 0; pass < 2; pass++) {
+			const uint32_t side = pass ? second : (second ^ 1u);
+			if (!(f & (side ? kSpHasB : kSpHasA))) continue;
+			uint4 y[4] = {cur[0], cur[1], cur[2], cur[3]};
+			const uint32_t h = side ? hits_b : hits_a;
+			if (h) { // rare: some block of this child may change (static indices: the values stay in registers)
+#pragma unroll
+				for (uint32_t i = 0; i < 4; i++)
+					if (h & (1u << i)) y[i] = rare(side, i, cur[i]);
+			}
+			emit(side, y);
+			if (pass) {
+#pragma unroll
+				for (int i = 0; i < 4; i++) cur[i] = y[i];
+			}
+		}
+	}
+}
+
+int sparse_walk_smem_levels()
+{
+	return kSpStackLevels;
+}
+
+cudaError_t prepare_walk_sparse()
+{
+	return cudaFuncSetAttribute(k1_walk_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+								kSpStackLevels * 4 * (int)sizeof(uint4) * kThreads);
+}
+
+void launch_walk_sparse(const DeviceTables &t, const SparseGene *genes, const SparseStep *steps, int64_t n_genes, cudaStream_t s)
+{
+	if (n_genes == 0) return;
+	const uint32_t quads = (t.blocks + 3u) / 4u;
+	const int64_t items = n_genes * quads;
+	const size_t dyn = (size_t)kSpStackLevels * 4 * sizeof(uint4) * kThreads;
+	k1_walk_sparse<<<(unsigned)((items + kThreads - 1) / kThreads), kThreads, dyn, s>>>(t, genes, steps, (uint32_t)items, quads);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -28,11 +28,12 @@ struct RootTask {
 struct __align__(16) WalkStep {
 	int64_t in_off, a_off, b_off; // dense regions of the node and of its children a (pair leader) and b
 	uint32_t edge_a, edge_b;      // child node indices = RNG edge ids (edge_a < edge_b)
-	uint32_t sig_a, sig_b;        // kWalkSignalA/B: index of the ready flag of the unit rooted at child a / b
+	uint32_t hca, hcb;            // decision_cmp(H[1]) of the two branches
 	uint32_t flags;               // kWalk* below
 	uint32_t slots;               // bits 0-7: shared-memory level the parked child goes to, bits 8-15: level the input comes from
 	uint64_t h1a, h2a, h1b, h2b;  // H[1], H[2] of the two branches (0 beyond kmax): the rare path needs no table for K <= 1
 };
+
 constexpr int kWalkStepQuads = 5;
 static_assert(sizeof(WalkStep) == 16 * kWalkStepQuads, "WalkStep is staged as five uint4");
 constexpr uint32_t kWalkLoad = 1u;     // input comes from memory (else: the value carried in registers)
@@ -45,15 +46,38 @@ constexpr uint32_t kWalkParkB = 128u;
 constexpr uint32_t kWalkSmemA = 256u;  // child a is parked in the thread's shared-memory stack (no global store)
 constexpr uint32_t kWalkSmemB = 512u;
 constexpr uint32_t kWalkLoadSmem = 1024u; // input comes from the shared-memory stack
-constexpr uint32_t kWalkSignalA = 2048u;  // the stored child a is the root of another unit: raise its ready flag
-constexpr uint32_t kWalkSignalB = 4096u;
-constexpr int32_t kWalkWaitGenRoot = -2;  // unit_wait value of the unit that starts at the tree's root: it draws the origin rows
 
-// Control block of the fused walk launch (device memory, uint32 words): a ticket counter that
-// numbers the CTAs in the order they start, a count of finished CTAs, the epoch of the last
-// completed sweep, then one ready flag per (unit root, column slab, warp) holding the epoch in
-// which it was last raised.  The last CTA of a launch resets the counters and advances the epoch.
-constexpr int kWalkCtlTicket = 0, kWalkCtlDone = 1, kWalkCtlEpoch = 2, kWalkCtlFlags = 4;
+// One task of k1_top_masks: the two branches below a node of the top of the tree (or, with
+// edge_a == kRootEdge, the origin rows of the dense genes, written to ma_off).
+struct TopMaskTask {
+	int64_t ma_off, mb_off;       // where the masks of branch a / b go (uint4 units from the start of the row store)
+	uint32_t edge_a, edge_b;      // child node indices (edge_a leads the sibling pair)
+	uint32_t pad0, pad1;
+	uint64_t h1a, h2a, h1b, h2b;  // H[1], H[2] of the two branches
+};
+
+// Fused walk of the sparse (accessory) genes, k1_walk_sparse: a thread carries one quad of blocks
+// of ONE gene from the gene's origin down the gene's own presence subtree (the nodes on the paths
+// from the origin to the genomes that carry it).
+struct SparseGene {
+	uint32_t gid;        // gene_id (Philox counter word 1)
+	uint32_t origin_row; // the origin row is drawn by the kernel itself and stored here
+	uint32_t step_begin; // first of the gene's steps
+	uint32_t n_steps;
+};
+struct __align__(16) SparseStep {
+	uint32_t dst_a, dst_b;   // rows the two children's values are stored to (kNoRow: not stored)
+	uint32_t edge_a, edge_b; // child node indices; edge_a leads the sibling pair (RNG key) even if child a lacks the gene
+	uint32_t h16;            // decision thresholds H[1] >> 48 of branch a (low half) and branch b (high half)
+	uint32_t flags;          // kSp* below
+	uint32_t in_row;         // kSpLoadRow: the row the input is read from (a sibling parked in its own row)
+	uint32_t levels;         // bits 0-7: stack level the parked child goes to, bits 8-15: level the input comes from
+};
+static_assert(sizeof(SparseStep) == 32, "SparseStep is read as two uint4");
+constexpr uint32_t kSpHasA = 1u, kSpHasB = 2u;       // the child carries the gene
+constexpr uint32_t kSpCarryA = 4u, kSpCarryB = 8u;   // the child's value is the next step's input
+constexpr uint32_t kSpParkA = 16u, kSpParkB = 32u;   // the child is parked in the thread's shared-memory stack
+constexpr uint32_t kSpLoadSmem = 64u, kSpLoadRow = 128u; // where the input comes from (neither: carried in registers)
 
 // Unsigned division by a launch constant: q = umulhi(x, mul) >> shift (x < 2^31).
 struct FastDiv {
@@ -112,12 +136,28 @@ uint32_t walk_slabs(int variant, uint32_t n_dense, uint32_t blocks_per_gene);
 // before the first launch on a device: opt in to the largest dynamic shared memory any plan may ask
 // for (the attribute is per function and device, not per engine: it is only ever set to this value)
 cudaError_t prepare_walk_dense();
-// One launch sweeps every unit: unit u executes steps[unit_off[u] .. unit_off[u+1]) for every column
-// slab; unit_wait[u] = index of the ready flag its first load waits for (-1: none); ctl = control block.
-void launch_walk_dense(const DeviceTables &t, const WalkStep *steps, const int64_t *unit_off, const int32_t *unit_wait,
-					   uint32_t *ctl, int32_t n_units, int32_t smem_levels, int variant, cudaStream_t s);
-// words of the control block for n_signals ready flags
-size_t walk_ctl_words(int variant, uint32_t n_dense, uint32_t blocks_per_gene, int32_t n_signals);
+// Origin rows of the dense genes and the substitution masks of the branches below the top nodes
+// (fully parallel: no node waits for its parent).
+void launch_top_masks(const DeviceTables &t, const TopMaskTask *tasks, int32_t n_tasks, cudaStream_t s);
+// One launch walks every unit: unit u starts from  origin row ^ masks on its path
+// (unit_path[unit_path_off[u] .. unit_path_off[u+1])), stores that value at unit_store[u] if >= 0
+// (a genome directly below a top node), then executes steps[unit_off[u] .. unit_off[u+1]) -- for
+// every column slab.  root_off = the origin rows (all offsets in uint4 units from the row store).
+struct WalkUnits {
+	const WalkStep *steps;
+	const int64_t *unit_off;
+	const int32_t *unit_path_off;
+	const int64_t *unit_path;
+	const int64_t *unit_store;
+	int64_t root_off;
+	int32_t n_units;
+};
+void launch_walk_dense(const DeviceTables &t, const WalkUnits &u, int32_t smem_levels, int variant, cudaStream_t s);
+
+// Fused sparse sweep: origin rows and every branch of every sparse gene in one launch.
+int sparse_walk_smem_levels();
+cudaError_t prepare_walk_sparse();
+void launch_walk_sparse(const DeviceTables &t, const SparseGene *genes, const SparseStep *steps, int64_t n_genes, cudaStream_t s);
 
 // K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
 // i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).

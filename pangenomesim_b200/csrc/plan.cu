@@ -22,8 +22,17 @@ struct SweepPlan {
 	std::vector<RootTask> root_tasks;
 	std::vector<WalkStep> walk_steps;
 	std::vector<int64_t> walk_off;
-	std::vector<int32_t> walk_wait; // per unit: ready flag its first load waits for, -1 = none
-	int32_t n_signals = 0;
+	std::vector<TopMaskTask> top_tasks; // k1_top_masks: origin rows, then the branches below the top nodes
+	std::vector<int32_t> unit_path_off; // per unit: its entries of unit_path
+	std::vector<int64_t> unit_path;     // offsets of the mask regions on the path from the tree's root to the unit's root
+	std::vector<int64_t> unit_store;    // per unit: where the root value is stored (a genome below a top node), -1 = nowhere
+	bool binary = false;       // every internal node has exactly two children
+	bool sparse_walk = false;  // fused walk for the sparse region
+	// per sparse gene: the nodes that hold a row of it and the row's rank inside the node's sparse list
+	std::vector<int64_t> gn_off;
+	std::vector<int32_t> gn_node, gn_rank;
+	std::vector<SparseGene> sp_genes;
+	std::vector<SparseStep> sp_steps;
 };
 
 int64_t dense_rows(const Engine &e, const SweepPlan &p, int32_t v)
@@ -81,8 +90,10 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 	std::vector<std::vector<int64_t>> at_node(N);
 	std::vector<int64_t> stamp(N, -1);
 	e.genome_gene_count.assign(n, D);
+	p.gn_off.assign(n_genes + 1, 0);
 	for (int64_t g = 0; g < n_genes; g++) {
 		e.carrier_off[g] = (int64_t)e.carrier_genome.size();
+		p.gn_off[g + 1] = p.gn_off[g];
 		if (e.dense_slot[g] >= 0) continue;
 		const int64_t b = carrier_off[g], c = carrier_off[g + 1];
 		const int32_t org = origin_node[g];
@@ -106,12 +117,15 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 			e.genome_gene_count[e.carrier_genome[k]]++;
 			while (stamp[v] != g) {
 				stamp[v] = g;
+				p.gn_node.push_back(v);
+				p.gn_rank.push_back((int32_t)at_node[v].size());
 				at_node[v].push_back(g);
 				if (v == org) break;
 				v = e.parent[v];
 				if (v < 0) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier is not below the gene's origin");
 			}
 		}
+		p.gn_off[g + 1] = (int64_t)p.gn_node.size();
 	}
 	e.carrier_off[n_genes] = (int64_t)e.carrier_genome.size();
 	{ // gene ids must be unique across the whole table
@@ -139,11 +153,17 @@ int plan_layout(Engine &e, SweepPlan &p)
 	// ---- sweep mode.  The fused column walk (k1_walk_dense) needs a binary tree and an even number
 	// of blocks per gene; it keeps dense rows only where an output reads them (genomes and the root).
 	bool &walk_mode = p.walk_mode;
-	walk_mode = N > 1 && D > 0 && (e.blocks % 2) == 0 && !(e.cfg.flags & PGS_FLAG_KEEP_INTERNAL);
-	for (int32_t v = 0; v < N && walk_mode; v++) {
+	p.binary = true;
+	for (int32_t v = 0; v < N && p.binary; v++) {
 		const int32_t nc = e.child_off[v + 1] - e.child_off[v];
-		if (nc != 0 && nc != 2) walk_mode = false;
+		if (nc != 0 && nc != 2) p.binary = false;
 	}
+	const bool keep = (e.cfg.flags & PGS_FLAG_KEEP_INTERNAL) != 0;
+	walk_mode = N > 1 && D > 0 && (e.blocks % 2) == 0 && !keep && p.binary;
+	// the sparse region has its own fused walk (any number of blocks); internal sparse rows are then
+	// not kept either (PGS_SPARSE_WALK=0, development knob: level by level as with KEEP_INTERNAL)
+	p.sparse_walk = N > 1 && !keep && p.binary && !e.sp_gene.empty();
+	if (const char *v = std::getenv("PGS_SPARSE_WALK")) p.sparse_walk = p.sparse_walk && std::atoi(v) != 0;
 	e.materialised.assign(N, 1);
 	if (walk_mode)
 		for (int32_t v = 0; v < N; v++) e.materialised[v] = (e.child_off[v + 1] == e.child_off[v] || v == e.root) ? 1 : 0;
@@ -177,6 +197,7 @@ void plan_level_tasks(Engine &e, SweepPlan &plan)
 	std::vector<std::vector<pgs::DenseTask>> dl(ML + 2);
 	std::vector<std::vector<pgs::SparseTask>> sl(ML + 2);
 	e.rows_written = e.rows_read = 0;
+	e.sparse_rows_written = e.sparse_rows_read = 0;
 	for (int32_t p = 0; p < N; p++) {
 		const int32_t nc = e.child_off[p + 1] - e.child_off[p];
 		if (nc == 0) continue;
@@ -203,16 +224,20 @@ void plan_level_tasks(Engine &e, SweepPlan &plan)
 				while (ir < nr && rg[ir] < g) ir++;
 				const bool hl = il < nl && lg[il] == g, hr = ir < nr && rg[ir] == g;
 				if (!hl && !hr) continue;
-				pgs::SparseTask t;
-				t.src = (uint32_t)(e.row_base[p] + dr(p) + ip);
-				t.dst_left = hl ? (uint32_t)(e.row_base[l] + dr(l) + il) : pgs::kNoRow;
-				t.dst_right = hr ? (uint32_t)(e.row_base[r] + dr(r) + ir) : pgs::kNoRow;
-				t.gid = (uint32_t)e.gene_id[g];
-				t.edge_left = l;
-				t.edge_right = r;
-				sl[lvl].push_back(t);
+				if (!plan.sparse_walk) {
+					pgs::SparseTask t;
+					t.src = (uint32_t)(e.row_base[p] + dr(p) + ip);
+					t.dst_left = hl ? (uint32_t)(e.row_base[l] + dr(l) + il) : pgs::kNoRow;
+					t.dst_right = hr ? (uint32_t)(e.row_base[r] + dr(r) + ir) : pgs::kNoRow;
+					t.gid = (uint32_t)e.gene_id[g];
+					t.edge_left = l;
+					t.edge_right = r;
+					sl[lvl].push_back(t);
+				}
 				e.rows_read += 1;
 				e.rows_written += (hl ? 1 : 0) + (hr ? 1 : 0);
+				e.sparse_rows_read += 1;
+				e.sparse_rows_written += (hl ? 1 : 0) + (hr ? 1 : 0);
 			}
 		}
 	}
@@ -233,16 +258,19 @@ void plan_level_tasks(Engine &e, SweepPlan &plan)
 	// (the fused column walk draws the dense genes' origin rows itself: no K0 work for them)
 	for (int64_t s = 0; s < D && !plan.walk_mode; s++)
 		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[e.root] + s), e.dense_gid[s]});
+	int64_t sparse_origins = 0;
 	for (int64_t g = 0; g < n_genes; g++) {
 		if (e.dense_slot[g] >= 0) continue;
 		const int32_t v = e.origin[g];
 		const int64_t *b = e.sp_gene.data() + e.sp_off[v], *en = e.sp_gene.data() + e.sp_off[v + 1];
 		const int64_t *it = std::lower_bound(b, en, g);
 		if (it == en || *it != g) continue; // gene carried by no genome: no rows at all
-		root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + dr(v) + (it - b)), (uint32_t)e.gene_id[g]});
+		sparse_origins++;
+		if (!plan.sparse_walk) // (the fused sparse walk draws the origin rows itself)
+			root_tasks.push_back(pgs::RootTask{(uint32_t)(e.row_base[v] + dr(v) + (it - b)), (uint32_t)e.gene_id[g]});
 	}
 	e.n_root_tasks = (int64_t)root_tasks.size();
-	e.rows_origin = e.n_root_tasks + (plan.walk_mode ? D : 0);
+	e.rows_origin = D + sparse_origins;
 }
 
 // Per-branch decision tables (edge_table.cpp) in the layouts the kernels read.
@@ -277,7 +305,16 @@ void plan_edge_tables(Engine &e)
 	}
 }
 
-// Fused column walk of the dense region: units, depth-first step lists, pool of transient rows.
+// Fused column walk of the dense region: top of the tree, units, depth-first step lists, pool of
+// transient rows.
+//
+// A substitution XORs a value-independent mask into the sequence (philox.cuh), so the value at any
+// node is  origin row ^ XOR of the masks of the branches on the path from the root.  The tree is
+// cut into a small TOP (the nodes whose subtrees were split) and the UNITS hanging below it.
+// k1_top_masks draws the origin rows and the masks of all branches below top nodes side by side (no
+// node waits for its parent); k1_walk_dense then walks every unit on its own: a unit's root value is
+// the origin row XORed with the few masks on its path (at most ~16 for 160 units of a 10 000-leaf
+// coalescent).  No pass waits for another one.
 int plan_walk(Engine &e, SweepPlan &p)
 {
 	const int32_t N = e.n_nodes;
@@ -287,8 +324,6 @@ int plan_walk(Engine &e, SweepPlan &p)
 	std::vector<WalkStep> &walk_steps = p.walk_steps;
 	std::vector<int64_t> &walk_off = p.walk_off;
 
-	// ---- fused column walk of the dense region (see k1_walk_dense): cut the tree into units,
-	// order every unit depth-first with the smaller subtree first
 	e.walk = false;
 	e.walk_pass_units.clear();
 	e.rows_stored = e.rows_written;
@@ -296,6 +331,7 @@ int plan_walk(Engine &e, SweepPlan &p)
 	int64_t pool_slots = 0; // transient dense regions (D rows each) behind the node regions
 	e.walk_smem_levels = 0;
 	e.rows_parked_smem = 0;
+	e.n_walk_units = 0;
 	if (walk_mode) {
 		// a thread's parked siblings go to its shared-memory stack; levels beyond what fits go to the pool
 		double mean_hit = 0.0; // mean over the branches of P(a block changes) = H[1] / 2^64
@@ -311,11 +347,11 @@ int plan_walk(Engine &e, SweepPlan &p)
 		std::vector<int64_t> size(N, 1);
 		for (int32_t v : order)
 			if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
-		// units: split the largest subtree until there are enough of them.  Enough = the pass over the
-		// subtrees gets about four waves of CTAs (units x column slabs; 444 CTAs are resident), but no
-		// fewer than 40 units (long serial chains) and no more than 160 (the top of the tree, walked
-		// first by few CTAs, grows with the unit count).  Config 4 on one GPU: 79 slabs -> 40 units;
-		// an eighth of it: 10 slabs -> 160 units.
+		// units: split the largest subtree until there are enough of them.  Enough = the walk gets
+		// about four waves of CTAs (units x column slabs; 444 CTAs are resident), but no fewer than 40
+		// units and no more than 160 (every split adds a top node, whose branches are the long ones:
+		// the work of k1_top_masks grows with the unit count).  Config 4 on one GPU: 79 slabs -> 40
+		// units; an eighth of it: 10 slabs -> 160 units.
 		size_t target_units = 0;
 		{
 			const size_t slabs = std::max<size_t>(1, pgs::walk_slabs(e.walk_variant, (uint32_t)D, (uint32_t)e.blocks));
@@ -337,57 +373,42 @@ int plan_walk(Engine &e, SweepPlan &p)
 			for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
 				if (internal(e.child[c])) roots.push_back(e.child[c]);
 		}
+		// longest unit first (CTAs are numbered unit-major: the shortest units fill the tail of the launch)
 		std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+		// genomes hanging directly below a top node: units without steps (root value = the genome's row)
+		for (int32_t v = 0; v < N; v++)
+			if (top[v])
+				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
+					if (!internal(e.child[c])) roots.push_back(e.child[c]);
 		const int64_t B = e.blocks;
 		// where a node's dense region lives (uint4 units): its own region for genomes and the root,
-		// a pool slot for unit roots (written by pass 1, read by pass 2) and parked siblings
+		// a pool slot for the deeper levels of a unit's stack of parked siblings
 		std::vector<int64_t> loc(N, -1);
 		for (int32_t v = 0; v < N; v++)
 			if (e.materialised[v]) loc[v] = e.row_base[v] * B;
 		auto slot_off = [&](int64_t slot) { return (rows + slot * D) * B; };
-		// The top part is cut once more: its own top ("crown", pass A: one unit) and the subtrees of
-		// top nodes below it (pass B), so that the serial chain before the big pass C is ~2 sqrt(n_top)
-		// steps instead of n_top.
-		std::vector<char> crown(N, 0);
-		std::vector<int32_t> mid_roots; // roots of the pass-B units (top nodes)
+		// k1_top_masks: task 0 draws the origin rows, then one task per top node (both branches below it)
+		std::vector<int64_t> mask_off(N, -1); // per child of a top node: where its branch's mask region lives
 		{
-			std::vector<int64_t> top_size(N, 0); // top nodes in the subtree
-			for (int32_t v : order) {
-				if (top[v]) top_size[v] += 1;
-				if (e.parent[v] >= 0) top_size[e.parent[v]] += top_size[v];
-			}
-			if (top[e.root]) mid_roots.push_back(e.root);
-			size_t want = 1;
-			while (want * want < n_top) want++;
-			if (n_top < 24) want = 1; // a small top is walked in one go
-			while (!mid_roots.empty() && mid_roots.size() < want) {
-				size_t best = 0;
-				for (size_t i = 1; i < mid_roots.size(); i++)
-					if (top_size[mid_roots[i]] > top_size[mid_roots[best]]) best = i;
-				const int32_t v = mid_roots[best];
-				if (top_size[v] < 4) break;
-				crown[v] = 1;
-				mid_roots.erase(mid_roots.begin() + best);
-				for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
-					if (top[e.child[c]]) mid_roots.push_back(e.child[c]);
-			}
-			// longest unit first, as in pass C (CTAs are numbered unit-major)
-			std::stable_sort(mid_roots.begin(), mid_roots.end(),
-							 [&](int32_t a, int32_t b) { return top_size[a] > top_size[b]; });
+			pgs::TopMaskTask tk{};
+			tk.ma_off = loc[e.root];
+			tk.edge_a = pgs::kRootEdge;
+			p.top_tasks.push_back(tk);
 		}
-		// a unit root other than the tree's root lives in a pool slot: written (and its ready flag
-		// raised) by the unit above, read by its own unit
-		std::vector<int32_t> sig_of(N, -1);
-		for (int32_t r : mid_roots)
-			if (r != e.root) {
-				loc[r] = slot_off(pool_slots++);
-				sig_of[r] = p.n_signals++;
-			}
-		for (size_t u = 0; u < roots.size(); u++)
-			if (roots[u] != e.root) {
-				loc[roots[u]] = slot_off(pool_slots++);
-				sig_of[roots[u]] = p.n_signals++;
-			}
+		for (int32_t v = 0; v < N; v++) {
+			if (!top[v]) continue;
+			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
+			pgs::TopMaskTask tk{};
+			tk.ma_off = mask_off[a] = slot_off(pool_slots++);
+			tk.mb_off = mask_off[b] = slot_off(pool_slots++);
+			tk.edge_a = (uint32_t)a;
+			tk.edge_b = (uint32_t)b;
+			tk.h1a = e.h1_host[a];
+			tk.h1b = e.h1_host[b];
+			tk.h2a = e.kmax_host[a] >= 2 ? e.tab_host[e.tab_off_host[a] + 1] : 0;
+			tk.h2b = e.kmax_host[b] >= 2 ? e.tab_host[e.tab_off_host[b] + 1] : 0;
+			p.top_tasks.push_back(tk);
+		}
 		auto make_step = [&](int32_t v, uint32_t flags) {
 			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
 			pgs::WalkStep s{};
@@ -396,8 +417,8 @@ int plan_walk(Engine &e, SweepPlan &p)
 			s.b_off = loc[b] >= 0 ? loc[b] : 0;
 			s.edge_a = (uint32_t)a;
 			s.edge_b = (uint32_t)b;
-			s.sig_a = (flags & pgs::kWalkSignalA) ? (uint32_t)sig_of[a] : 0u;
-			s.sig_b = (flags & pgs::kWalkSignalB) ? (uint32_t)sig_of[b] : 0u;
+			s.hca = decision_cmp(e.h1_host[a]);
+			s.hcb = decision_cmp(e.h1_host[b]);
 			s.h1a = e.h1_host[a];
 			s.h1b = e.h1_host[b];
 			s.h2a = e.kmax_host[a] >= 2 ? e.tab_host[e.tab_off_host[a] + 1] : 0;
@@ -408,35 +429,32 @@ int plan_walk(Engine &e, SweepPlan &p)
 			if (flags & pgs::kWalkLoadSmem) s.slots |= (uint32_t)smem_level[v] << 8;
 			return s;
 		};
-		e.rows_stored = e.rows_loaded = 0;
-		// Depth-first step list of the subtree below `start`, smaller child first.  `descend(c)`
-		// says whether an internal child belongs to this walk; an internal child that does not
-		// (the root of another unit) is written to its pool slot and picked up by its own unit.
-		auto emit_walk = [&](int32_t start, auto descend) {
-			const int64_t stack_base = pool_slots; // this walk's parked rows: slots stack_base + depth
+		// rows K1 really moves: the sparse region's as before (plan_sparse_walk corrects them if it
+		// walks too), the dense region's counted below
+		e.rows_stored = e.sparse_rows_written + D * (int64_t)(1 + 2 * n_top); // k1_top_masks: origin rows and masks
+		e.rows_loaded = e.sparse_rows_read;
+		// Depth-first step list of the subtree below `start`, smaller child first.  The unit's root
+		// value is in registers when the first step begins (unit prologue of k1_walk_dense).
+		auto emit_walk = [&](int32_t start) {
+			const int64_t stack_base = pool_slots; // this walk's deep parked rows: slots stack_base + depth - smem_cap
 			int64_t deepest = 0;
 			std::vector<int32_t> parked;
 			int32_t v = start;
-			bool in_reg = false, have = true;
+			bool in_reg = true, have = internal(start);
 			while (have) {
 				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
 				const bool ia = internal(a), ib = internal(b);
-				const bool da = ia && descend(a), db = ib && descend(b);
 				uint32_t f = 0;
-				if (!in_reg && v == e.root) {
-					e.rows_stored += D; // the origin rows are drawn by the unit itself (kWalkWaitGenRoot) and stored: the outputs read them
-				} else if (!in_reg && smem_level[v] >= 0) {
+				if (!in_reg && smem_level[v] >= 0) {
 					f |= pgs::kWalkLoadSmem;
 				} else if (!in_reg) {
 					f |= pgs::kWalkLoad;
 					e.rows_loaded += D;
 				}
-				if (!ia) f |= pgs::kWalkStoreA;                       // a genome's row
+				if (!ia) f |= pgs::kWalkStoreA; // a genome's row
 				if (!ib) f |= pgs::kWalkStoreB;
-				if (ia && !da) f |= pgs::kWalkStoreA | pgs::kWalkParkA | pgs::kWalkSignalA; // root of another unit
-				if (ib && !db) f |= pgs::kWalkStoreB | pgs::kWalkParkB | pgs::kWalkSignalB;
 				int32_t carry = -1;
-				if (da && db) {
+				if (ia && ib) {
 					const bool a_first = size[a] <= size[b];
 					carry = a_first ? a : b;
 					const int32_t later = a_first ? b : a;
@@ -453,10 +471,10 @@ int plan_walk(Engine &e, SweepPlan &p)
 						deepest = std::max(deepest, depth - smem_cap + 1);
 					}
 					parked.push_back(later);
-				} else if (da) {
+				} else if (ia) {
 					carry = a;
 					f |= pgs::kWalkCarryA;
-				} else if (db) {
+				} else if (ib) {
 					carry = b;
 					f |= pgs::kWalkCarryB;
 				}
@@ -476,38 +494,137 @@ int plan_walk(Engine &e, SweepPlan &p)
 			}
 			pool_slots += deepest;
 		};
-		// pass A (one unit): the crown; pass B: the rest of the top, one unit per subtree below the
-		// crown; pass C: every final unit loads its root row and walks its own subtree.  A pass only
-		// reads rows written by earlier passes (stream order).
 		walk_off.push_back(0);
-		e.walk_pass_units.clear();
-		if (crown[e.root]) {
-			emit_walk(e.root, [&](int32_t c) { return crown[c] != 0; });
-			walk_off.push_back((int64_t)walk_steps.size());
-			p.walk_wait.push_back(pgs::kWalkWaitGenRoot);
-			e.walk_pass_units.push_back(1);
-		}
-		if (!mid_roots.empty()) {
-			for (int32_t r : mid_roots) {
-				emit_walk(r, [&](int32_t c) { return top[c] != 0; });
-				walk_off.push_back((int64_t)walk_steps.size());
-				p.walk_wait.push_back(r == e.root ? pgs::kWalkWaitGenRoot : sig_of[r]);
-			}
-			e.walk_pass_units.push_back((int32_t)mid_roots.size());
-		}
+		p.unit_path_off.push_back(0);
 		for (int32_t r : roots) {
-			emit_walk(r, [](int32_t) { return true; });
+			// the masks on the path root -> r, and where the value goes if r is a genome
+			for (int32_t v = r; v != e.root; v = e.parent[v]) p.unit_path.push_back(mask_off[v]);
+			p.unit_path_off.push_back((int32_t)p.unit_path.size());
+			e.rows_loaded += D * (1 + (p.unit_path_off.back() - p.unit_path_off[p.unit_path_off.size() - 2]));
+			const bool genome = !internal(r);
+			p.unit_store.push_back(genome ? loc[r] : -1);
+			if (genome) e.rows_stored += D;
+			emit_walk(r);
 			walk_off.push_back((int64_t)walk_steps.size());
-			p.walk_wait.push_back(r == e.root ? pgs::kWalkWaitGenRoot : sig_of[r]);
 		}
 		e.walk_pass_units.push_back((int32_t)roots.size());
-		e.n_walk_units = (int32_t)p.walk_wait.size();
+		e.n_walk_units = (int32_t)roots.size();
 		e.walk = true;
 	}
 	rows += pool_slots * D;
 	if (rows >= (int64_t)pgs::kNoRow) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32-2 rows on one engine; shard the genes");
 	e.rows_total = rows;
 
+	return PGS_OK;
+}
+
+// Fused walk of the sparse region (k1_walk_sparse): per gene a depth-first step list over the
+// gene's presence subtree, smaller subtree first (a thread's stack of parked siblings stays
+// shallow: at most log2(carriers) levels).
+int plan_sparse_walk(Engine &e, SweepPlan &p)
+{
+	e.sparse_walk = p.sparse_walk;
+	e.n_sp_genes = 0;
+	if (!p.sparse_walk) return PGS_OK;
+	const int32_t N = e.n_nodes;
+	const int64_t D = p.D;
+	const int smem_cap = pgs::sparse_walk_smem_levels();
+	std::vector<int64_t> stamp(N, -1);
+	std::vector<int32_t> rank_at(N, 0), sub(N, 0);
+	std::vector<int32_t> order, parked;
+	int64_t stored = 0, loaded = 0; // rows the sparse walk writes to / reads from memory
+	auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
+	auto row_of = [&](int32_t v) { return (uint32_t)(e.row_base[v] + dense_rows(e, p, v) + rank_at[v]); };
+	for (int64_t g = 0; g < e.n_genes; g++) {
+		const int64_t nb = p.gn_off[g], ne = p.gn_off[g + 1];
+		if (nb == ne) continue;
+		order.assign(p.gn_node.begin() + nb, p.gn_node.begin() + ne);
+		for (int64_t k = nb; k < ne; k++) {
+			stamp[p.gn_node[k]] = g;
+			rank_at[p.gn_node[k]] = p.gn_rank[k];
+			sub[p.gn_node[k]] = 1;
+		}
+		// sizes of the gene's subtrees: children before parents
+		std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
+		const int32_t org = e.origin[g];
+		for (int32_t v : order)
+			if (v != org) sub[e.parent[v]] += sub[v];
+		pgs::SparseGene sg{};
+		sg.gid = (uint32_t)e.gene_id[g];
+		sg.origin_row = row_of(org);
+		if (p.sp_steps.size() >= 0xFFFFFFFFull) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse walk steps; shard the genes");
+		sg.step_begin = (uint32_t)p.sp_steps.size();
+		stored++;
+		parked.clear();
+		int32_t v = org;
+		uint32_t load = 0, load_level = 0, load_row = 0; // how the next step gets its input (0: carried in registers)
+		bool have = internal(org);
+		while (have) {
+			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
+			const bool ha = stamp[a] == g, hb = stamp[b] == g;
+			const bool da = ha && internal(a), db = hb && internal(b);
+			pgs::SparseStep st{};
+			st.dst_a = (ha && !da) ? row_of(a) : pgs::kNoRow; // a genome's row
+			st.dst_b = (hb && !db) ? row_of(b) : pgs::kNoRow;
+			st.edge_a = (uint32_t)a;
+			st.edge_b = (uint32_t)b;
+			st.h16 = (uint32_t)(e.h1_host[a] >> 48) | ((uint32_t)(e.h1_host[b] >> 48) << 16);
+			st.flags = (ha ? pgs::kSpHasA : 0u) | (hb ? pgs::kSpHasB : 0u) | load;
+			st.in_row = load_row;
+			st.levels = load_level << 8;
+			if (load == pgs::kSpLoadRow) loaded++;
+			int32_t carry = -1;
+			if (da && db) {
+				const bool a_first = sub[a] <= sub[b];
+				carry = a_first ? a : b;
+				const int32_t later = a_first ? b : a;
+				const int depth = (int)parked.size();
+				st.flags |= a_first ? pgs::kSpCarryA : pgs::kSpCarryB;
+				if (depth < smem_cap) {
+					st.flags |= a_first ? pgs::kSpParkB : pgs::kSpParkA;
+					st.levels |= (uint32_t)depth;
+				} else { // deeper than the shared-memory stack: parked in its own row
+					(a_first ? st.dst_b : st.dst_a) = row_of(later);
+				}
+				parked.push_back(later);
+			} else if (da) {
+				carry = a;
+				st.flags |= pgs::kSpCarryA;
+			} else if (db) {
+				carry = b;
+				st.flags |= pgs::kSpCarryB;
+			}
+			stored += (st.dst_a != pgs::kNoRow) + (st.dst_b != pgs::kNoRow);
+			p.sp_steps.push_back(st);
+			if (carry >= 0) {
+				v = carry;
+				load = 0;
+			} else if (!parked.empty()) {
+				v = parked.back();
+				parked.pop_back();
+				const int depth = (int)parked.size();
+				if (depth < smem_cap) {
+					load = pgs::kSpLoadSmem;
+					load_level = (uint32_t)depth;
+				} else {
+					load = pgs::kSpLoadRow;
+					load_row = row_of(v);
+				}
+			} else {
+				have = false;
+			}
+		}
+		sg.n_steps = (uint32_t)(p.sp_steps.size() - sg.step_begin);
+		p.sp_genes.push_back(sg);
+	}
+	// lanes of a warp walk different genes: sort by length so that they finish together, longest first
+	std::stable_sort(p.sp_genes.begin(), p.sp_genes.end(),
+					 [](const pgs::SparseGene &a, const pgs::SparseGene &b) { return a.n_steps > b.n_steps; });
+	e.n_sp_genes = (int64_t)p.sp_genes.size();
+	(void)D;
+	// rows K1 really moves: these instead of every sparse row written and every sparse parent row read
+	e.rows_stored += stored - e.sparse_rows_written;
+	e.rows_loaded += loaded - e.sparse_rows_read;
 	return PGS_OK;
 }
 
@@ -524,17 +641,17 @@ int upload_plan(Engine &e, SweepPlan &p)
 	int rc = 0;
 	if ((rc = e.upload(e.d_walk_steps, p.walk_steps.data(), sizeof(WalkStep) * p.walk_steps.size(), "walk steps"))) return rc;
 	if ((rc = e.upload(e.d_walk_off, p.walk_off.data(), sizeof(int64_t) * p.walk_off.size(), "walk units"))) return rc;
-	if ((rc = e.upload(e.d_walk_wait, p.walk_wait.data(), sizeof(int32_t) * p.walk_wait.size(), "walk unit waits"))) return rc;
-	if (e.walk) {
-		if (pgs::prepare_walk_dense() != cudaSuccess)
-			return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the walk kernel's shared-memory stack does not fit this device");
-		// control block of the fused launch: counters and ready flags start at zero (epoch 0 = "never raised")
-		const size_t words = pgs::walk_ctl_words(e.walk_variant, (uint32_t)D, (uint32_t)e.blocks, p.n_signals);
-		if ((rc = e.alloc(e.d_walk_ctl, words * sizeof(uint32_t), "walk control block"))) return rc;
-		cudaError_t ce = cudaMemsetAsync(e.d_walk_ctl.p, 0, words * sizeof(uint32_t), e.stream);
-		if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
-		if (ce != cudaSuccess) return e.cuda_fail(ce, "walk control block");
-	}
+	if ((rc = e.upload(e.d_sp_genes, p.sp_genes.data(), sizeof(SparseGene) * p.sp_genes.size(), "sparse walk genes"))) return rc;
+	if ((rc = e.upload(e.d_sp_steps, p.sp_steps.data(), sizeof(SparseStep) * p.sp_steps.size(), "sparse walk steps"))) return rc;
+	if (e.sparse_walk && pgs::prepare_walk_sparse() != cudaSuccess)
+		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the sparse walk kernel's shared-memory stack does not fit this device");
+	if ((rc = e.upload(e.d_top_tasks, p.top_tasks.data(), sizeof(TopMaskTask) * p.top_tasks.size(), "top mask tasks"))) return rc;
+	e.n_top_tasks = (int32_t)p.top_tasks.size();
+	if ((rc = e.upload(e.d_unit_path_off, p.unit_path_off.data(), sizeof(int32_t) * p.unit_path_off.size(), "walk unit paths"))) return rc;
+	if ((rc = e.upload(e.d_unit_path, p.unit_path.data(), sizeof(int64_t) * p.unit_path.size(), "walk unit path masks"))) return rc;
+	if ((rc = e.upload(e.d_unit_store, p.unit_store.data(), sizeof(int64_t) * p.unit_store.size(), "walk unit stores"))) return rc;
+	if (e.walk && pgs::prepare_walk_dense() != cudaSuccess)
+		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the walk kernel's shared-memory stack does not fit this device");
 
 	// ---- device
 	const size_t row_bytes = (size_t)e.blocks * 16;
@@ -591,6 +708,7 @@ int plan_genes(Engine &e, int64_t n_genes, const int64_t *gene_id, const int32_t
 	plan_level_tasks(e, p);
 	plan_edge_tables(e);
 	if ((rc = plan_walk(e, p))) return rc;
+	if ((rc = plan_sparse_walk(e, p))) return rc;
 	return upload_plan(e, p);
 }
 

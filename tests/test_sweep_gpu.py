@@ -274,12 +274,24 @@ def test_fused_walk_equals_level_sweep_and_oracle(oracle, n, L, mut_rate):
         if n > 2:
             with pytest.raises(PgsError):
                 walk.copy_dense(n, 9)  # an internal node other than the root is not kept
-        # sparse genes still go level by level in both modes
+        # sparse genes have their own fused walk: genomes' rows and origin rows are kept, nothing else
+        is_leaf = np.ones(len(parent), bool)
+        is_leaf[parent[parent >= 0]] = False
         for gi in range(len(gene_id)):
             if gene_id[gi] >= 9:
                 for v in range(len(parent)):
-                    a, b = walk.copy_packed(v, gi), keep.copy_packed(v, gi)
-                    assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))
+                    b = keep.copy_packed(v, gi)
+                    if b is None or is_leaf[v] or v == origin[gi]:
+                        a = walk.copy_packed(v, gi)
+                        assert (a is None) == (b is None) and (a is None or np.array_equal(a, b)), (gi, v)
+                    else:
+                        with pytest.raises(PgsError) as ex:
+                            walk.copy_packed(v, gi)
+                        assert ex.value.code == -2  # PGS_ERR_STATE, as include/pgs.h documents
+        if n > 2:
+            with pytest.raises(PgsError) as ex:
+                walk.copy_packed(n, dense[0])  # internal dense row: not kept either
+            assert ex.value.code == -2
         mw, _ = walk.mismatch()
         mk, _ = keep.mismatch()
         assert np.array_equal(mw, mk)
@@ -382,3 +394,52 @@ def test_fused_walk_kernel_variants_and_stack_placement(oracle, monkeypatch, var
                     walk.sync()
                 got = np.stack([walk.copy_dense(v, G) for v in list(range(n)) + [root]])
                 assert np.array_equal(got, want), (L, rep)
+
+
+def _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L):
+    gene_id, origin, off, car = genes
+    genome_leaf = {int(g): v for v, g in enumerate(leaf) if g >= 0}
+    checked = 0
+    for gi in range(len(gene_id)):
+        c = car[off[gi]:off[gi + 1]]
+        if len(c) == 1 and c[0] == -1:
+            continue  # dense gene
+        want = oracle.gene_all_nodes(seed, parent, rate, int(origin[gi]), int(gene_id[gi]), L)
+        for v in [genome_leaf[int(g)] for g in c] + [int(origin[gi])]:
+            got = e.copy_packed(v, gi)
+            assert got is not None and np.array_equal(got, want[v]), f"gene {gene_id[gi]} node {v}"
+            checked += 1
+        absent = set(genome_leaf.values()) - {genome_leaf[int(g)] for g in c}
+        for v in list(absent)[:5]:
+            assert e.copy_packed(v, gi) is None
+    return checked
+
+
+@pytest.mark.parametrize("L", [1, 64, 65, 100, 130, 1000, 1500])
+def test_sparse_walk_rows_match_oracle(oracle, L):
+    """fused walk of the accessory genes (k1_walk_sparse): origin rows drawn in the kernel, every genome's
+    row equal to the host replay; block counts 1, 2, 3 (odd), 16, 24"""
+    n, seed = 60, 4000 + L
+    parent, rate, leaf = treegen.coalescent(n, seed=17, mut_rate=0.3)
+    genes = treegen.gene_table(parent, leaf, n_core=3, n_acc=80, seed=L)
+    with build(seed, L, parent, rate, leaf, genes, flags=0) as e:
+        st = e.stats()
+        assert st["n_dense_genes"] == 3
+        # one launch for the sparse genes, two (masks, walk) for the dense ones where the dense walk applies
+        assert st["kernel_launches"] <= 3 or ((L + 63) // 64) % 2 == 1
+        assert _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L) > 80
+        e.sweep()
+        e.sync()
+        assert _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L) > 80
+
+
+@pytest.mark.parametrize("sparse_walk", ["1", "0"])
+def test_sparse_walk_deep_stacks_and_rates(oracle, monkeypatch, sparse_walk):
+    """genes carried by hundreds of genomes: the stack of parked siblings outgrows the shared-memory
+    levels (the deeper ones go to the siblings' own rows); high rate: most blocks take the rare path"""
+    monkeypatch.setenv("PGS_SPARSE_WALK", sparse_walk)
+    n, L, seed = 700, 256, 606
+    parent, rate, leaf = treegen.coalescent(n, seed=23, mut_rate=1.0)
+    genes = treegen.gene_table(parent, leaf, n_core=2, n_acc=24, seed=9)
+    with build(seed, L, parent, rate, leaf, genes, flags=0) as e:
+        assert _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L) > 1000
