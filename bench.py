@@ -1,22 +1,25 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the pangenomesim sequence path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
-    python bench.py --impl reference [--steps K] [--warmup W]     # the reference's CPU code
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 4|3|5]   # this repo's CUDA engine
+    python bench.py --impl reference [--steps K] [--warmup W]               # the reference's CPU code
 
-Metric (BASELINE.json): simulated leaf nucleotides per second.  Workload at N=1: BASELINE config 4
-(num-genomes=10000, core-size=5000, gene-length=1000, default mut-rate) -- 25.6 GB of 2-bit rows,
-far larger than L2, so no flush is needed between steps.  One step = one pgs_sweep (kernel K0 root
-rows + kernel K1 level sweep over every branch of the coalescent) with tree and tables resident.
-With N > 1 (torchrun, one rank per GPU) every rank sweeps its own 5000-gene shard of a 5000*N
-gene alignment (weak scaling; genes are independent, no collective in the sweep).
+Metric (BASELINE.json): simulated leaf nucleotides per second.  Workload: BASELINE config 4
+(num-genomes=10000, core-size=5000, gene-length=1000, default mut-rate) -- 12.9 GB of 2-bit rows
+rewritten every step, far larger than L2, so no flush is needed between steps.  One step = one
+pgs_sweep (origin rows + every branch of the coalescent: k1_top_masks + k1_walk_dense, and
+k1_walk_sparse for accessory genes) with tree and tables resident.
+With N > 1 (torchrun, one rank per GPU) config 4 is taken AS WRITTEN: its 5000 genes are sharded N
+ways ("scaling": "strong"; genes are independent, no collective in the sweep); the weak-scaling
+leg (5000 genes per rank) is reported beside it.  --config 3 / 5 run the other BASELINE configs
+(3: large accessory genome through the host model; 5: 50000 genomes at a high mutation rate).
 
 Besides the contract keys the line carries
   roofline      K1's achieved algorithmic HBM GB/s against MEASURED_PEAKS.json
   cpu_baseline  the unmodified reference code (oracle/_ref/ref_seqpath) on one host core, bounded sample
   e2e           the same metric through the C ABI from host tables to host text: pgs_set_tree +
-                pgs_set_genes (H2D) + pgs_sweep + pgs_write_outputs (K3 formatter, D2H of every
-                genomeNNN.fasta and alignment.maf byte into pinned host memory)
+                pgs_set_genes (H2D) + pgs_sweep + pgs_write_outputs (every genomeNNN.fasta and
+                alignment.maf byte delivered in host memory)
 """
 from __future__ import annotations
 
@@ -48,10 +51,24 @@ def _jsonable(x):
     return str(x)
 
 
-def workload_name(n_gpus):
-    return (f"config4: num-genomes={CFG['num_genomes']} core-size={CFG['core_size']}"
-            f"{'x%d (one shard per GPU)' % n_gpus if n_gpus > 1 else ''} gene-length={CFG['gene_length']}"
-            f" mut-rate={CFG['mut_rate']} seed={CFG['seed']}")
+CONFIGS = {
+    # BASELINE.json configs[3]: the headline
+    4: {"num_genomes": 10000, "core_size": 5000, "gene_length": 1000, "mut_rate": 0.01, "seed": 1},
+    # configs[2]: theta / rho raised for a large accessory genome (SURVEY.md §8d suggests theta=2000, rho=1)
+    3: {"num_genomes": 1000, "core_size": 3000, "gene_length": 1500, "mut_rate": 0.01, "seed": 1, "theta": 2000, "rho": 1},
+    # configs[4]: memory pressure and a high mutation rate
+    5: {"num_genomes": 50000, "core_size": 2000, "gene_length": 2000, "mut_rate": 0.5, "seed": 3},
+}
+
+
+def workload_name(n_gpus, weak=False, config=4):
+    c = CONFIGS[config] if config != 4 else CFG
+    extra = "".join(f" {k}={c[k]}" for k in ("theta", "rho") if k in c)
+    shard = ""
+    if n_gpus > 1:
+        shard = (f" x{n_gpus} (weak: one such gene set per GPU)" if weak else f" (its genes sharded {n_gpus}-way, one shard per GPU)")
+    return (f"config{config}: num-genomes={c['num_genomes']} core-size={c['core_size']}{shard} gene-length={c['gene_length']}"
+            f" mut-rate={c['mut_rate']}{extra} seed={c['seed']}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -300,12 +317,50 @@ def files_leg(eng, parent, rate, leaf, genes, root, n, L):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def make_workload(config, rank, world, weak=False, shard_of=0):
+    """Tree and gene table of one rank.  Config 4 / 5: the reference's coalescent and dense core genes,
+    sharded by contiguous gene ranges (strong) or one full gene set per rank (weak).  Config 3: the
+    retained host model (coalescent + IMG gain/loss), its gene table cut into contiguous ranges."""
+    from pangenomesim_b200.capi import PGS_ALL_GENOMES, HostModel
+    from pangenomesim_b200.sharding import shard_range
+    c = CFG if config == 4 else CONFIGS[config]
+    n, L, G = c["num_genomes"], c["gene_length"], c["core_size"]
+    w = {"n": n, "L": L, "seed": c["seed"], "config": config}
+    if config == 3:
+        m = HostModel("fast", num_genomes=n, core_size=G, gene_length=L, theta=c["theta"], rho=c["rho"], seed=c["seed"],
+                      mut_rate=c["mut_rate"])
+        g0, g1 = shard_range(m.n_genes, rank, world)
+        off = m.carrier_off[g0:g1 + 1]
+        w.update(parent=m.parent, rate=m.rate, leaf=m.leaf_genome, all_order=m.all_order,
+                 genes=(m.gene_id[g0:g1], m.origin[g0:g1], off - off[0], m.carriers[off[0]:off[-1]], m.all_order),
+                 n_genes_total=m.n_genes, leaf_nt_total=float(m.genome_gene_count.sum()) * L,
+                 ref=np.arange(g1 - g0, dtype=np.int64))
+        m.close()
+        return w
+    parent, rate, leaf = coalescent(n, c["seed"], c["mut_rate"])
+    root = 2 * n - 2
+    if weak:
+        g0, g1 = shard_range(G * world, rank, world)
+    else:
+        g0, g1 = shard_range(G, rank, world)
+        if shard_of > 1 and world == 1:
+            g0, g1 = shard_range(G, 0, shard_of)
+    k = g1 - g0
+    w.update(parent=parent, rate=rate, leaf=leaf, all_order=None,
+             genes=(np.arange(g0, g1, dtype=np.int64), np.full(k, root, np.int32), np.arange(k + 1, dtype=np.int64),
+                    np.full(k, PGS_ALL_GENOMES, np.int32), None),
+             n_genes_total=G * (world if weak else 1), leaf_nt_total=float(n) * L * G * (world if weak else 1),
+             ref=np.arange(k, dtype=np.int64))
+    return w
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5], help="BASELINE.json config (4 = headline)")
     ap.add_argument("--e2e-steps", type=int, default=2, help="end-to-end steps (each moves ~100 GB over PCIe)")
     ap.add_argument("--cpu-genes", type=int, default=60, help="gene sample of the cpu_baseline leg (~0.2 s per gene)")
     ap.add_argument("--ref-genes", type=int, default=8, help="genes per process per step of --impl reference")
@@ -313,6 +368,7 @@ def main():
     ap.add_argument("--level-sync", action="store_true", help="sweep level by level and keep all internal rows (PGS_FLAG_KEEP_INTERNAL)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the bounded write-to-files leg (N=1 only)")
+    ap.add_argument("--no-mismatch", action="store_true", help="skip the K2 legs")
     ap.add_argument("--files-genes", type=int, default=1000, help="genes of the write-to-files leg (20 MB of text each)")
     ap.add_argument("--small", action="store_true", help="debug: config 2 sized workload")
     ap.add_argument("--shard-of", type=int, default=0, help="development: on ONE GPU, sweep only rank 0's shard of a SHARD_OF-way split "
@@ -327,8 +383,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pangenomesim_b200 import Engine
-    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_MAF, OUT_PACKED, PGS_ALL_GENOMES
-    from pangenomesim_b200.sharding import shard_range
+    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_MAF, OUT_PACKED
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -341,51 +396,55 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n, L, G = CFG["num_genomes"], CFG["gene_length"], CFG["core_size"]
-    parent, rate, leaf = coalescent(n, CFG["seed"], CFG["mut_rate"])
-    root = 2 * n - 2
-    # weak scaling: the alignment has G*world genes, rank r owns the contiguous shard [r*G, (r+1)*G)
-    g0, g1 = shard_range(G * world, rank, world)
-    if args.shard_of > 1 and world == 1:
-        g0, g1 = shard_range(G, 0, args.shard_of)
-    gene_id = np.arange(g0, g1, dtype=np.int64)
-    origin = np.full(len(gene_id), root, np.int32)
-    car_off = np.arange(len(gene_id) + 1, dtype=np.int64)
-    car = np.full(len(gene_id), PGS_ALL_GENOMES, np.int32)
+    # the headline: the config as written, its genes sharded over the ranks (strong scaling)
+    w = make_workload(args.config, rank, world, weak=False, shard_of=args.shard_of)
+    n, L = w["n"], w["L"]
+    parent, rate, leaf = w["parent"], w["rate"], w["leaf"]
 
     stream = torch.cuda.Stream()
     flags = 1 if os.environ.get("PGS_NO_GRAPH") else 0  # PGS_FLAG_NO_GRAPH: plain launches (profiling)
     if args.level_sync:
         flags |= 2  # PGS_FLAG_KEEP_INTERNAL: level-synchronous sweep, every internal row kept in HBM
-    eng = Engine(CFG["seed"], L, device=local, flags=flags)
+    eng = Engine(w["seed"], L, device=local, flags=flags)
     eng.set_stream(stream.cuda_stream)
     eng.set_tree(parent, rate, leaf)
-    eng.set_genes(gene_id, origin, car_off, car)
+    eng.set_genes(*w["genes"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_sweeps():
+        for _ in range(args.warmup):
+            eng.sweep()
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            eng.sweep()
+        ev1.record(stream)
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
     # ---- kernel-resident steps
-    for _ in range(args.warmup):
-        eng.sweep()
-    barrier()
+    # the first sweep of a plan is launched kernel by kernel with an event between the dense and the
+    # sparse genes: K1's split (later sweeps replay one CUDA graph)
+    eng.sweep()
+    split = eng.stats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1_ms = []
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        eng.sweep()
-    ev1.record(stream)
-    barrier()
-    total_ms = ev0.elapsed_time(ev1)
-    # per-kernel split (CUDA events recorded by the library around K0 and around the K1 level graph)
-    k0_ms = []
+    total_ms = timed_sweeps()
+    k1_ms, k0_ms = [], []
     for _ in range(3):
         eng.sweep()
         st = eng.stats()
@@ -395,11 +454,7 @@ def main():
         time.sleep(0.15)
         clocks = sampler.stop()
     st = eng.stats()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    leaf_nt_all = float(st["leaf_nucleotides"]) * world
+    leaf_nt_all = w["leaf_nt_total"]
     value = leaf_nt_all * args.steps / (total_ms * 1e-3)
 
     peaks = {}
@@ -407,9 +462,9 @@ def main():
     if pk.exists():
         peaks = json.loads(pk.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # Algorithmic HBM bytes of one sweep.  Level-synchronous definition: every row
-    # written once + every parent row read once, L/4 bytes each (0.375 B per site-edge).  The fused
-    # column walk keeps internal nodes on chip, so -- as §8d prescribes for that case -- the bound
+    # Algorithmic HBM bytes of one sweep on this rank.  Level-synchronous definition:
+    # every row written once + every parent row read once, L/4 bytes each (0.375 B per site-edge).
+    # The fused walks keep internal nodes on chip, so -- as §8d prescribes for that case -- the bound
     # switches to "every leaf row written once": 0.25 B per leaf nucleotide.
     level_bytes = (st["rows_written"] + st["rows_read"]) * L / 4.0
     leaf_bytes = st["leaf_nucleotides"] / 4.0
@@ -422,59 +477,65 @@ def main():
     achieved = alg_bytes / (k1 * 1e-3) / 1e9
     traffic = None
     tr = ROOT / "profiles" / "k1_traffic.json"
-    if tr.exists():
+    if tr.exists() and args.config == 4 and world == 1 and not args.shard_of:
         try:
             traffic = json.loads(tr.read_text()).get("dram_bytes_per_sweep_walk" if walk else "dram_bytes_per_sweep")
         except ValueError:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k1_walk_dense" if walk else "k1_sweep_dense", "achieved": achieved, "peak": peak,
+    row_bytes = st["blocks_per_gene"] * 16
+    roofline = {"bound": "hbm", "kernel": "k1_top_masks + k1_walk_dense (+ k1_walk_sparse)" if walk else "k1_sweep_dense / k1_sweep_sparse",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_sweep": alg_bytes, "k1_ms_per_sweep": k1, "k1_ms_single_sweep": k1_single,
-                "launches_per_sweep": st["kernel_launches"] - 1,
-                "definition": ("leaf-write-only bound, 0.25 B per leaf nucleotide (internal nodes stay on chip: fused column walk)"
+                "launches_per_sweep": st["kernel_launches"],
+                "definition": ("leaf-write-only bound, 0.25 B per leaf nucleotide (internal nodes stay on chip: fused walks), this rank's shard"
                                if walk else "level-synchronous bound, 0.375 B per site-edge"),
                 "level_synchronous_definition": {"algorithmic_bytes_per_sweep": level_bytes,
                                                  "achieved": level_bytes / (k1 * 1e-3) / 1e9,
                                                  "frac": level_bytes / (k1 * 1e-3) / 1e9 / peak},
-                "rows_stored_per_sweep": st["rows_stored"], "rows_loaded_per_sweep": st["rows_loaded"]}
+                "rows_stored_per_sweep": st["rows_stored"], "rows_loaded_per_sweep": st["rows_loaded"],
+                "stored_bytes_per_sweep": st["rows_stored"] * row_bytes}
+    if split["sparse_ms"] > 0 or split["dense_ms"] > 0:
+        # K1 split (one plain sweep): the sparse genes against THEIR level-synchronous byte count
+        # (every sparse row written + every sparse parent row read, L/4 B each)
+        dense_rows = st["n_dense_genes"] * (st["n_nodes"] - 1)
+        sp_bytes = (st["rows_written"] + st["rows_read"] - dense_rows - st["n_dense_genes"] * (st["n_genomes"] - 1)) * row_bytes
+        roofline["split"] = {"dense_ms": split["dense_ms"], "sparse_ms": split["sparse_ms"],
+                             "sparse_level_synchronous_bytes": sp_bytes,
+                             "sparse_frac_of_peak": (sp_bytes / (split["sparse_ms"] * 1e-3) / 1e9 / peak) if split["sparse_ms"] > 0 else None,
+                             "what": "first sweep of the plan, launched kernel by kernel; sparse bytes = rows written + parent rows read (padded rows)"}
 
     # ---- end to end through the C ABI with host tables in, host text out
     e2e = None
     if not args.no_e2e:
         what = OUT_GENOMES | OUT_MAF | OUT_DISCARD
-        ref_core = np.arange(len(gene_id), dtype=np.int64)
-        h2d = parent.nbytes + rate.nbytes + leaf.nbytes + gene_id.nbytes + origin.nbytes + car_off.nbytes + car.nbytes
-
+        h2d = sum(a.nbytes for a in (parent, rate, leaf) + tuple(x for x in w["genes"] if x is not None))
         plan_s = []
 
         def e2e_step():
             t_plan = time.perf_counter()
             eng.set_tree(parent, rate, leaf)
-            eng.set_genes(gene_id, origin, car_off, car)
+            eng.set_genes(*w["genes"])
             plan_s.append(time.perf_counter() - t_plan)
             eng.sweep()
-            return eng.write_outputs(None, what, ref_core, [])
-        e2e_step()  # warm-up (allocations, pinned buffers, graph capture)
+            return eng.write_outputs(None, what, w["ref"], [])
+        e2e_step()  # warm-up (allocations, pinned buffers)
         barrier()
         t0 = time.perf_counter()
-        ev0.record(stream)
         rep = None
         for _ in range(args.e2e_steps):
             rep = e2e_step()
-        ev1.record(stream)
         barrier()
-        wall = time.perf_counter() - t0
-        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall = float(t.item())
+        wall = max_over_ranks(time.perf_counter() - t0)
+        bytes_all = max_over_ranks(float(rep["bytes"])) if world == 1 else None
         e2e = {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(rep["bytes"]), "steps": args.e2e_steps, "ms_per_step": 1e3 * wall / args.e2e_steps,
                "k3_device_ms_per_step": rep["device_ms"], "files_per_step": int(rep["files"]),
                "plan_ms_per_step": 1e3 * float(np.mean(plan_s[1:])), "d2h_gb_per_s": rep["bytes"] * args.e2e_steps / wall / 1e9,
                "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) "
-                       "into pinned host memory, bytes discarded (no filesystem)"}
+                       "into pinned host memory, bytes discarded (no filesystem); per-rank bytes"}
+        del bytes_all
 
     # ---- the same end to end with the optional packed side output instead of the text (genomes.pgs2:
     # the genomes' 2-bit rows copied straight from the store, an eighth of the bytes)
@@ -482,7 +543,7 @@ def main():
     if not args.no_e2e:
         def packed_step():
             eng.set_tree(parent, rate, leaf)
-            eng.set_genes(gene_id, origin, car_off, car)
+            eng.set_genes(*w["genes"])
             eng.sweep()
             return eng.write_outputs(None, OUT_PACKED | OUT_DISCARD, [], [])
         packed_step()
@@ -491,11 +552,7 @@ def main():
         for _ in range(args.e2e_steps):
             rep = packed_step()
         barrier()
-        wall = time.perf_counter() - t0
-        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall = float(t.item())
+        wall = max_over_ranks(time.perf_counter() - t0)
         e2e_packed = {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / args.e2e_steps,
                       "d2h_bytes_per_step": int(rep["bytes"]), "d2h_gb_per_s": rep["bytes"] * args.e2e_steps / wall / 1e9,
                       "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(PGS_OUT_PACKED: genomes.pgs2, "
@@ -504,51 +561,45 @@ def main():
     # ---- end to end INTO FILES on a bounded slice of the workload (all 10 000 genomes, the first
     # --files-genes genes: 10 000 genomeNNN.fasta + one alignment.maf), rank 0 of a 1-GPU run only
     files = None
-    if world == 1 and not args.no_e2e and not args.no_files:
-        files = files_leg(eng, parent, rate, leaf, min(args.files_genes, G), root, n, L)
+    if world == 1 and args.config == 4 and not args.no_e2e and not args.no_files:
+        files = files_leg(eng, parent, rate, leaf, min(args.files_genes, CFG["core_size"]), 2 * n - 2, n, L)
 
-    # ---- strong-scaling leg (BASELINE config 4 as written: its 5000 genes sharded over the GPUs)
-    strong = None
-    if world > 1:
-        s0, s1 = shard_range(G, rank, world)
-        eng.set_genes(np.arange(s0, s1, dtype=np.int64), np.full(s1 - s0, root, np.int32),
-                      np.arange(s1 - s0 + 1, dtype=np.int64), np.full(s1 - s0, PGS_ALL_GENOMES, np.int32))
-        for _ in range(args.warmup):
-            eng.sweep()
-        barrier()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            eng.sweep()
-        ev1.record(stream)
-        barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item()) / args.steps
-        strong = {"value": float(n) * G * L / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                  "what": f"the same {G} genes sharded {world}-way ({s1 - s0} genes on rank 0), no collective"}
+    # ---- weak-scaling leg (N > 1): every rank sweeps a full gene set of the config
+    weak = None
+    if world > 1 and args.config != 3:
+        ww = make_workload(args.config, rank, world, weak=True)
+        eng.set_tree(parent, rate, leaf)
+        eng.set_genes(*ww["genes"])
+        ms = timed_sweeps() / args.steps
+        weak = {"value": ww["leaf_nt_total"] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "scaling": "weak",
+                "what": workload_name(world, weak=True, config=args.config) + ", no collective"}
 
     # ---- the path's only collective: all-reduce of the per-rank partial mismatch counts (K2),
     # untimed verification leg on a reduced problem (2000 genomes, 250 genes per rank)
     mm_leg = None
-    if world > 1:
+    if world > 1 and not args.no_mismatch:
         mm_leg = mismatch_allreduce_leg(torch, dist, Engine, rank, world, local)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.config == 4:
         cpu = cpu_baseline(args.cpu_genes if not args.small else 200)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(world), "l2": f"inputs_larger_than_l2 ({st['device_bytes'] / 1e9:.1f} GB of rows per GPU, rewritten every step)",
-                       "rng": "Philox4x32-10 keyed (seed, edge, gene, 64-site block); 16-bit decision fields, one call per sibling pair and 4 blocks", "rows_per_gpu": st["rows_total"],
-                       "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"],
-                       "sweep": "fused column walk" if st["sweep_mode"] == 1 else "level-synchronous"},
+            "config": {"workload": workload_name(world, config=args.config),
+                       "l2": f"inputs_larger_than_l2 ({st['device_bytes'] / 1e9:.1f} GB of rows per GPU, rewritten every step)"
+                             if st["device_bytes"] > 400e6 else
+                             f"{st['device_bytes'] / 1e6:.0f} MB of rows per GPU, rewritten every step (not larger than L2)",
+                       "rng": "Philox4x32-10 keyed (seed, edge, gene, 64-site block); 16-bit decision fields, one call per sibling pair and 4 blocks",
+                       "genes_total": w["n_genes_total"], "genes_this_rank": st["n_genes"], "dense_genes_this_rank": st["n_dense_genes"],
+                       "rows_per_gpu": st["rows_total"], "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"],
+                       "sweep": "fused walks (k1_top_masks + k1_walk_dense, k1_walk_sparse)" if st["sweep_mode"] == 1 else "level-synchronous"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
-            "mismatch_allreduce": mm_leg, "strong_scaling": strong, "e2e_files": files, "e2e_packed": e2e_packed,
+            "mismatch_allreduce": mm_leg, "weak_scaling": weak, "e2e_files": files, "e2e_packed": e2e_packed,
         }
         print(json.dumps(line, default=_jsonable), flush=True)
     eng.close()

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PGS_ABI_VERSION 1
+#define PGS_ABI_VERSION 2
 
 typedef struct pgs_engine pgs_engine;
 
@@ -123,6 +123,9 @@ typedef struct pgs_stats {
 	int64_t rows_loaded;         /* rows K1 actually reads from memory */
 	double sweep_ms, rootgen_ms; /* device time of the last completed pgs_sweep (CUDA events) */
 	double mismatch_ms, format_ms;
+	/* K1 split into the dense (core) and the sparse (accessory) genes; measured by sweeps that are
+	 * launched kernel by kernel (the first sweep of a plan, or PGS_FLAG_NO_GRAPH) */
+	double dense_ms, sparse_ms;
 } pgs_stats;
 int pgs_get_stats(pgs_engine *h, pgs_stats *out); /* synchronises */
 

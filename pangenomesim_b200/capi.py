@@ -37,7 +37,7 @@ class Stats(C.Structure):
         "n_nodes", "n_genomes", "n_genes", "n_dense_genes", "blocks_per_gene", "rows_total",
         "rows_written", "rows_read", "rows_origin", "leaf_nucleotides", "site_edges", "levels",
         "kernel_launches", "device_bytes", "sweep_mode", "rows_stored", "rows_loaded")] + [(k, C.c_double) for k in (
-        "sweep_ms", "rootgen_ms", "mismatch_ms", "format_ms")]
+        "sweep_ms", "rootgen_ms", "mismatch_ms", "format_ms", "dense_ms", "sparse_ms")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -313,3 +313,73 @@ def host_coalescent(n: int, seed: int, mut_rate: float = 0.01, return_time: bool
     if return_time:
         return parent, time, leaf
     return parent, time * float(np.float32(mut_rate)), leaf
+
+
+class HostModel:
+    """The host program's model (pangenomesim_b200/host/model.cpp: coalescent + IMG gain/loss, the
+    reference's img_model without nucleotides) for Python callers: parameters as on the command line,
+    results as the arrays pgs_set_tree / pgs_set_genes / pgs_write_outputs take."""
+
+    def __init__(self, rng_mode: str = "auto", **params):
+        path = _HERE / "lib" / "libpgshost.so"
+        if not path.exists():
+            raise PgsError(-6, f"{path} is missing: build it with `make cli`")
+        lib = C.CDLL(str(path))
+        lib.pgsh_model_create.restype = C.c_void_p
+        lib.pgsh_model_destroy.argtypes = [C.c_void_p]
+        lib.pgsh_model_error.restype = C.c_char_p
+        lib.pgsh_model_error.argtypes = [C.c_void_p]
+        lib.pgsh_model_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        lib.pgsh_model_simulate.argtypes = [C.c_void_p, C.c_int]
+        lib.pgsh_model_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pgsh_model_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+        lib.pgsh_model_distance_row.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        self._lib = lib
+        self._h = lib.pgsh_model_create()
+        try:
+            for k, v in params.items():
+                if lib.pgsh_model_param(self._h, k.replace("_", "-").encode(), str(v).encode()) != 0:
+                    raise PgsError(-1, lib.pgsh_model_error(self._h).decode())
+            if lib.pgsh_model_simulate(self._h, {"auto": 0, "compat": 1, "fast": 2}[rng_mode]) != 0:
+                raise PgsError(-1, lib.pgsh_model_error(self._h).decode())
+            sz = np.zeros(7, dtype=np.int64)
+            lib.pgsh_model_sizes(self._h, _ptr(sz))
+            N, n, G, nc, nrc, nra, compat = (int(x) for x in sz)
+            self.n_nodes, self.n_genomes, self.n_genes, self.used_compat = N, n, G, bool(compat)
+            self.parent = np.zeros(N, np.int32)
+            self.rate = np.zeros(N, np.float64)
+            self.leaf_genome = np.zeros(N, np.int32)
+            self.gene_id = np.zeros(G, np.int64)
+            self.origin = np.zeros(G, np.int32)
+            self.carrier_off = np.zeros(G + 1, np.int64)
+            self.carriers = np.zeros(nc, np.int32)
+            self.all_order = np.zeros(n, np.int32)
+            self.ref_core = np.zeros(nrc, np.int64)
+            self.ref_acc = np.zeros(nra, np.int64)
+            self.genome_gene_count = np.zeros(n, np.int64)
+            lib.pgsh_model_tables(self._h, _ptr(self.parent), _ptr(self.rate), _ptr(self.leaf_genome), _ptr(self.gene_id),
+                                  _ptr(self.origin), _ptr(self.carrier_off), _ptr(self.carriers), _ptr(self.all_order),
+                                  _ptr(self.ref_core), _ptr(self.ref_acc), _ptr(self.genome_gene_count))
+        except Exception:
+            self.close()
+            raise
+
+    @property
+    def root(self) -> int:
+        return self.n_nodes - 1
+
+    def gene_table(self):
+        """arguments of Engine.set_genes"""
+        return self.gene_id, self.origin, self.carrier_off, self.carriers, self.all_order
+
+    def distance_row(self, i: int):
+        row = np.zeros(self.n_genomes, np.float64)
+        self._lib.pgsh_model_distance_row(self._h, i, _ptr(row))
+        return row
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgsh_model_destroy(self._h)
+            self._h = None
+
+    __del__ = close

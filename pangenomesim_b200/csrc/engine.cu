@@ -107,7 +107,7 @@ bool Engine::row_kept(int32_t node, int64_t g) const
 
 // K1 for every level below the root: dense region, then sparse region.  Levels are separated by
 // stream order (each launch reads rows written by the previous level's launches).
-void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
+void Engine::enqueue_levels(cudaStream_t s, int64_t *launches, cudaEvent_t after_dense)
 {
 	const DenseTask *dt = d_dense_tasks.as<DenseTask>();
 	const SparseTask *st = d_sparse_tasks.as<SparseTask>();
@@ -125,6 +125,7 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches)
 		launch_walk_dense(tables, u, walk_smem_levels, walk_variant, s);
 		(*launches)++;
 	}
+	if (after_dense && (walk || tables.n_dense == 0)) cudaEventRecord(after_dense, s); // (plain launches only: splits K1's time)
 	if (sparse_walk) { // sparse genes: origin rows and every branch in one launch
 		launch_walk_sparse(tables, d_sp_genes.as<SparseGene>(), d_sp_steps.as<SparseStep>(), n_sp_genes, s);
 		if (n_sp_genes > 0) (*launches)++;
@@ -216,7 +217,7 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 	e.device = dev;
 	ce = cudaSetDevice(dev);
 	if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking);
-	for (int i = 0; i < 6 && ce == cudaSuccess; i++) ce = cudaEventCreate(&e.ev[i]);
+	for (int i = 0; i < 7 && ce == cudaSuccess; i++) ce = cudaEventCreate(&e.ev[i]);
 	if (ce != cudaSuccess) {
 		pgs::g_create_error = std::string("pgs_create: ") + cudaGetErrorString(ce);
 		delete h;
@@ -370,15 +371,17 @@ int pgs_sweep(pgs_engine *h)
 	// costs more than it saves for a single sweep, e.g. the CLI); repeated sweeps replay a graph.
 	const bool plain = (e.cfg.flags & PGS_FLAG_NO_GRAPH) || e.sweeps_done == 0;
 	e.sweeps_done++;
+	e.phase_split = false;
 	if (plain) {
-		e.enqueue_levels(e.stream, &launches);
+		e.enqueue_levels(e.stream, &launches, e.ev[6]);
+		e.phase_split = e.walk || e.tables.n_dense == 0;
 	} else {
 		if (!e.graph_exec) {
 			// capture the level launches once; replays cost one graph launch per sweep
 			int64_t captured = 0;
 			ce = cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal);
 			if (ce != cudaSuccess) return e.cuda_fail(ce, "cudaStreamBeginCapture");
-			e.enqueue_levels(e.stream, &captured);
+			e.enqueue_levels(e.stream, &captured, nullptr);
 			ce = cudaStreamEndCapture(e.stream, &e.graph);
 			if (ce != cudaSuccess) return e.cuda_fail(ce, "cudaStreamEndCapture");
 			ce = cudaGraphInstantiate(&e.graph_exec, e.graph, 0);
@@ -430,10 +433,17 @@ int pgs_get_stats(pgs_engine *h, pgs_stats *out)
 		float a = 0, b = 0;
 		if (cudaEventElapsedTime(&a, e.ev[0], e.ev[1]) == cudaSuccess) out->rootgen_ms = a;
 		if (cudaEventElapsedTime(&b, e.ev[1], e.ev[2]) == cudaSuccess) out->sweep_ms = b;
+		if (e.phase_split) {
+			float c = 0, d = 0;
+			if (cudaEventElapsedTime(&c, e.ev[1], e.ev[6]) == cudaSuccess) e.dense_ms = c;
+			if (cudaEventElapsedTime(&d, e.ev[6], e.ev[2]) == cudaSuccess) e.sparse_ms = d;
+		}
 		cudaGetLastError();
 	}
 	out->mismatch_ms = e.mismatch_ms;
 	out->format_ms = e.format_ms;
+	out->dense_ms = e.dense_ms;
+	out->sparse_ms = e.sparse_ms;
 	return PGS_OK;
 }
 

@@ -25,7 +25,7 @@ struct Engine {
 	pgs_config cfg{};
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
-	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // 0-2 sweep, 3-4 mismatch, 5 format
+	cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // 0-2 sweep, 3-4 mismatch, 5 format, 6 between the dense and the sparse genes
 	std::string err;
 
 	// ---- tree (pgs_set_tree)
@@ -83,7 +83,8 @@ struct Engine {
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t graph_exec = nullptr;
 	int64_t launches_last_sweep = 0, sweeps_done = 0;
-	double mismatch_ms = 0.0, format_ms = 0.0;
+	double mismatch_ms = 0.0, format_ms = 0.0, dense_ms = 0.0, sparse_ms = 0.0;
+	bool phase_split = false; // the last sweep recorded ev[6]
 
 	~Engine();
 	int fail(int code, const std::string &msg);
@@ -94,7 +95,7 @@ struct Engine {
 	int64_t row_index(int32_t node, int64_t gene_index) const;
 	bool row_kept(int32_t node, int64_t gene_index) const;
 	void drop_graph();
-	void enqueue_levels(cudaStream_t s, int64_t *launches);
+	void enqueue_levels(cudaStream_t s, int64_t *launches, cudaEvent_t after_dense);
 };
 
 // plan.cu: everything behind pgs_set_genes (validation, layout, tasks, tables, uploads)

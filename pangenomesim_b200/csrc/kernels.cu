@@ -385,7 +385,18 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 		for (int j = 0; j < PAIRS; j++)
 			if (active[j]) cur[j] = ld_stream256(reinterpret_cast<const U32x8 *>(base + u.root_off) + p[j]);
 		const int32_t pe = __ldg(u.unit_path_off + unit + 1);
-		for (int32_t k = __ldg(u.unit_path_off + unit); k < pe; k++) {
+		int32_t k = __ldg(u.unit_path_off + unit);
+		for (; k + 2 <= pe; k += 2) { // two masks in flight per pair
+			const int64_t off0 = __ldg(u.unit_path + k), off1 = __ldg(u.unit_path + k + 1);
+#pragma unroll
+			for (int j = 0; j < PAIRS; j++) {
+				if (!active[j]) continue;
+				const U32x8 m0 = ld_stream256(reinterpret_cast<const U32x8 *>(base + off0) + p[j]);
+				const U32x8 m1 = ld_stream256(reinterpret_cast<const U32x8 *>(base + off1) + p[j]);
+				cur[j] = cur[j] ^ m0 ^ m1;
+			}
+		}
+		if (k < pe) {
 			const int64_t off = __ldg(u.unit_path + k);
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++)

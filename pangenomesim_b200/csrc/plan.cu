@@ -349,13 +349,13 @@ int plan_walk(Engine &e, SweepPlan &p)
 			if (e.parent[v] >= 0) size[e.parent[v]] += size[v];
 		// units: split the largest subtree until there are enough of them.  Enough = the walk gets
 		// about four waves of CTAs (units x column slabs; 444 CTAs are resident), but no fewer than 40
-		// units and no more than 160 (every split adds a top node, whose branches are the long ones:
+		// units and no more than 120 (every split adds a top node, whose branches are the long ones:
 		// the work of k1_top_masks grows with the unit count).  Config 4 on one GPU: 79 slabs -> 40
-		// units; an eighth of it: 10 slabs -> 160 units.
+		// units; an eighth of it: 10 slabs -> 120 units (0.288 ms against 0.296 with 160, 0.313 with 80).
 		size_t target_units = 0;
 		{
 			const size_t slabs = std::max<size_t>(1, pgs::walk_slabs(e.walk_variant, (uint32_t)D, (uint32_t)e.blocks));
-			target_units = std::min<size_t>(160, std::max<size_t>(40, (1800 + slabs - 1) / slabs));
+			target_units = std::min<size_t>(120, std::max<size_t>(40, (1800 + slabs - 1) / slabs));
 		}
 		if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
 		std::vector<int32_t> roots{e.root};

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = load_library()
     for name in declared_functions():
         assert hasattr(lib, name), f"libpgs.so does not export {name}"
-    assert lib.pgs_abi_version() == 1
+    assert lib.pgs_abi_version() == 2
 
 
 def test_signatures_are_plain_c():

@@ -440,6 +440,14 @@ def test_sparse_walk_deep_stacks_and_rates(oracle, monkeypatch, sparse_walk):
     monkeypatch.setenv("PGS_SPARSE_WALK", sparse_walk)
     n, L, seed = 700, 256, 606
     parent, rate, leaf = treegen.coalescent(n, seed=23, mut_rate=1.0)
-    genes = treegen.gene_table(parent, leaf, n_core=2, n_acc=24, seed=9)
+    gene_id, origin, off, car = treegen.gene_table(parent, leaf, n_core=2, n_acc=24, seed=9)
+    # plus four genes that appeared at the root and are carried by 300 .. 699 of the 700 genomes
+    rng = np.random.default_rng(1)
+    extra = [sorted(rng.choice(n, size=k, replace=False)) for k in (300, 450, 600, 699)]
+    gene_id = np.concatenate([gene_id, np.arange(100, 104)])
+    origin = np.concatenate([origin, np.full(4, len(parent) - 1, np.int32)])
+    off = np.concatenate([off, off[-1] + np.cumsum([len(x) for x in extra])])
+    car = np.concatenate([car] + [np.array(x, np.int32) for x in extra])
+    genes = (gene_id, origin, off, car)
     with build(seed, L, parent, rate, leaf, genes, flags=0) as e:
-        assert _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L) > 1000
+        assert _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L) > 2000
