@@ -11,9 +11,9 @@ LIBDIR   := pangenomesim_b200/lib
 BINDIR   := pangenomesim_b200/bin
 OBJDIR   := build/obj
 
-LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/plan.cu $(CSRC)/kernels.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp
+LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/plan.cu $(CSRC)/kernels.cu $(CSRC)/mismatch.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp
 LIB_HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/pgs.h
-LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/plan.o $(OBJDIR)/kernels.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o
+LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/plan.o $(OBJDIR)/kernels.o $(OBJDIR)/mismatch.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o
 
 all: lib cli oracle
 
@@ -33,7 +33,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(LIB_HDRS)
 
 $(LIBDIR)/libpgs.so: $(LIB_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart shared -Xlinker -rpath,/usr/local/cuda/lib64
+	$(NVCC) $(ARCH) -shared -o $@ $(LIB_OBJS) -cudart shared -Xlinker -rpath,/usr/local/cuda/lib64 -ldl
 
 HOST_HDRS := $(wildcard $(HOST)/*.h) include/pgs.h
 $(BINDIR)/pangenomesim-b200: $(HOST)/main.cpp $(HOST)/model.cpp $(HOST_HDRS) $(LIBDIR)/libpgs.so

@@ -280,6 +280,56 @@ def mismatch_allreduce_leg(torch, dist, Engine, rank, world, local):
             "bytes": int(part.numel() * 4), "pair01_observed": obs, "pair01_jc_expected": float(p)}
 
 
+def k2_leg(torch, dist, eng, stats, rank, world, peaks):
+    """K2 (pairwise mismatch, north_star part 3) on this rank's genes at the config's FULL size, and
+    -- N > 1 -- the path's only collective at its real size: the NCCL all-reduce of the packed
+    upper-triangular counts (pgs_mismatch_allreduce).  ALU-bound: per genome pair and 32 sites the
+    kernel issues XOR + LOP3 + POPC on the ALU pipe (the add rides the FMA pipe as an IMAD):
+    3 ALU instructions per 32 site pairs; the pipe takes 64 lanes per clock per SM."""
+    from pangenomesim_b200.capi import comm_unique_id
+    n, L = stats["n_genomes"], eng.gene_length
+    out = {}
+    if world > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        eng.comm_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
+        eng.mismatch_allreduce(want_matrix=False)  # warm-up: NCCL sets up its channels for this size
+        _, sites, ar_ms = eng.mismatch_allreduce(want_matrix=False)
+        t = torch.tensor([ar_ms, eng.stats()["mismatch_ms"], float(sites)], dtype=torch.float64, device="cuda")
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ar_ms, k2_ms, sites_all = float(tm[0]), float(tm[1]), float(t[2])
+        words = 4096 * ((n + 63) // 64) * ((n + 63) // 64 + 1) // 2
+        out["allreduce"] = {"ms": ar_ms, "bytes": words * 4, "algbw_gb_per_s": words * 4 / (ar_ms * 1e-3) / 1e9,
+                            "busbw_gb_per_s": words * 4 / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+                            "what": "ncclAllReduce(sum, uint32) of every rank's packed upper-triangular mismatch counts, in place, "
+                                    "max over ranks of the CUDA-event time"}
+    else:
+        eng.mismatch_tiles_device()
+        eng.mismatch_tiles_device()
+        k2_ms, sites_all = eng.stats()["mismatch_ms"], float(stats["n_dense_genes"]) * L
+    pairs = n * (n - 1) / 2.0
+    # tiles of the upper triangle are computed whole (64 x 64, diagonal tiles in full): the kernel's own work
+    T = (n + 63) // 64
+    tile_pairs = T * (T + 1) / 2.0 * 4096
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    alu_peak = 148 * 64 * sm_mhz * 1e6 / 3.0 * 32  # site pairs per second at 3 ALU instructions per 32 site pairs
+    site_pairs_rank = pairs * (sites_all / world)
+    out.update({"k2_ms": k2_ms, "site_pairs_total": pairs * sites_all,
+                "site_pairs_per_s": pairs * sites_all / (k2_ms * 1e-3),
+                "roofline": {"bound": "alu", "achieved": site_pairs_rank / (k2_ms * 1e-3), "peak": alu_peak, "unit": "site-pairs/s per GPU",
+                             "frac": site_pairs_rank / (k2_ms * 1e-3) / alu_peak,
+                             "frac_counting_whole_tiles": tile_pairs * (sites_all / world) / (k2_ms * 1e-3) / alu_peak,
+                             "definition": f"148 SMs x 64 ALU lanes per clock x {sm_mhz:.0f} MHz (max clock) / 3 ALU instructions "
+                                           "(XOR, LOP3, POPC) per 32 site pairs"},
+                "what": f"k2_split_planes + k2_mismatch_tiles over {n} genomes x this rank's dense genes, max over ranks; "
+                        "counts kept as packed upper-triangular tiles on the device"})
+    return out
+
+
 def files_leg(eng, parent, rate, leaf, genes, root, n, L):
     """host tables -> sweep -> genomeNNN.fasta + alignment.maf written as FILES (pwrite / mapped
     writes by the library's writer threads) into a scratch directory that is removed afterwards.
@@ -564,6 +614,14 @@ def main():
     if world == 1 and args.config == 4 and not args.no_e2e and not args.no_files:
         files = files_leg(eng, parent, rate, leaf, min(args.files_genes, CFG["core_size"]), 2 * n - 2, n, L)
 
+    # ---- K2 at full size on this rank's shard (+ the all-reduce of the partial counts for N > 1)
+    k2 = None
+    if not args.no_mismatch and args.config != 3:
+        eng.set_tree(parent, rate, leaf)
+        eng.set_genes(*w["genes"])
+        eng.sweep()
+        k2 = k2_leg(torch, dist, eng, eng.stats(), rank, world, peaks)
+
     # ---- weak-scaling leg (N > 1): every rank sweeps a full gene set of the config
     weak = None
     if world > 1 and args.config != 3:
@@ -599,7 +657,7 @@ def main():
                        "sweep": "fused walks (k1_top_masks + k1_walk_dense, k1_walk_sparse)" if st["sweep_mode"] == 1 else "level-synchronous"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
-            "mismatch_allreduce": mm_leg, "weak_scaling": weak, "e2e_files": files, "e2e_packed": e2e_packed,
+            "mismatch": k2, "mismatch_allreduce_check": mm_leg, "weak_scaling": weak, "e2e_files": files, "e2e_packed": e2e_packed,
         }
         print(json.dumps(line, default=_jsonable), flush=True)
     eng.close()

@@ -129,12 +129,33 @@ typedef struct pgs_stats {
 } pgs_stats;
 int pgs_get_stats(pgs_engine *h, pgs_stats *out); /* synchronises */
 
-/* Replaces nothing in the reference (its distance.mat is the EXPECTED distance, img.cxx:121-165):
- * observed pairwise mismatch counts over the dense (all-genome, root-origin) genes, kernel K2.
- * out is n_genomes x n_genomes uint32, symmetric, zero diagonal.  *sites_out = sites compared. */
+/* Replaces nothing in the reference (its distance.mat is the EXPECTED distance, img.cxx:121-165,
+ * printed at pangenomesim.cxx:214-234): OBSERVED pairwise mismatch counts over the dense
+ * (all-genome, root-origin) genes, kernel K2 -- what that matrix is checked against.
+ * out is n_genomes x n_genomes uint32, symmetric, zero diagonal.  *sites_out = sites compared.
+ * On the device the counts are kept as packed upper-triangular 64 x 64 tiles (never the square);
+ * the result reaches the host through pinned buffers in pieces. */
 int pgs_mismatch(pgs_engine *h, uint32_t *out_host, int64_t *sites_out);
-/* Same, result left in caller-provided DEVICE memory (for an NCCL all-reduce across engines). */
+/* Same, full square left in caller-provided DEVICE memory (n_genomes^2 uint32). */
 int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out);
+/* The packed form: tile (ti <= tj) number ti*T - ti(ti-1)/2 + (tj - ti), T = ceil(n/64), holds
+ * counts[r][c] of genomes (64 ti + r, 64 tj + c) for 64 ti + r < 64 tj + c, zero elsewhere.
+ * *tiles_device_u32 = the engine's own buffer (pgs_mismatch_tile_words(n) uint32, valid until the
+ * next mismatch call on h): one contiguous range to all-reduce across engines. */
+int64_t pgs_mismatch_tile_words(int32_t n_genomes);
+int pgs_mismatch_tiles_device(pgs_engine *h, void **tiles_device_u32, int64_t *sites_out);
+
+/* The path's only collective: genes shard across engines with no communication during the sweep;
+ * every engine's partial counts are summed with an NCCL all-reduce (NVLink / NVSwitch).  NCCL is
+ * loaded at run time (libnccl.so.2); without it these calls fail with PGS_ERR_STATE.
+ *  - engines of ONE process, one per device (the CLI's --devices N): */
+int pgs_mismatch_multi(pgs_engine *const *engines, int n_engines, uint32_t *out_host, int64_t *sites_out);
+/*  - one engine per PROCESS (one rank per GPU, MPI-style launchers): rank 0 draws an id (128 bytes), the caller hands it
+ *    to every rank, every rank joins; then every rank calls pgs_mismatch_allreduce together.
+ *    out_host may be NULL on ranks that do not need the matrix.  *sites_out = THIS rank's sites. */
+int pgs_comm_unique_id(void *id128);
+int pgs_comm_init(pgs_engine *h, const void *id128, int rank, int world);
+int pgs_mismatch_allreduce(pgs_engine *h, uint32_t *out_host, int64_t *sites_out, double *allreduce_ms);
 
 /* ---- outputs -------------------------------------------------------------------------- */
 

@@ -94,6 +94,13 @@ def load_library():
     lib.pgs_get_stats.argtypes = [C.c_void_p, P(Stats)]
     lib.pgs_mismatch.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
     lib.pgs_mismatch_device.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
+    lib.pgs_mismatch_tile_words.argtypes = [C.c_int32]
+    lib.pgs_mismatch_tile_words.restype = C.c_int64
+    lib.pgs_mismatch_tiles_device.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_int64)]
+    lib.pgs_mismatch_multi.argtypes = [P(C.c_void_p), C.c_int, C.c_void_p, P(C.c_int64)]
+    lib.pgs_comm_unique_id.argtypes = [C.c_void_p]
+    lib.pgs_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.pgs_mismatch_allreduce.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64), P(C.c_double)]
     lib.pgs_write_outputs.argtypes = [C.c_void_p, P(OutputSpec), P(OutputReport)]
     lib.pgs_output_sizes.argtypes = [C.c_void_p, P(OutputSpec), C.c_void_p, P(C.c_int64)]
     lib.pgs_copy_origin_ascii.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]
@@ -201,6 +208,25 @@ class Engine:
         self._check(self._lib.pgs_mismatch_device(self._h, device_ptr, C.byref(sites)))
         return sites.value
 
+    def mismatch_tiles_device(self):
+        """(device pointer of the packed upper-triangular tiles, number of uint32 words, sites)"""
+        ptr, sites = C.c_void_p(), C.c_int64()
+        self._check(self._lib.pgs_mismatch_tiles_device(self._h, C.byref(ptr), C.byref(sites)))
+        return ptr.value, self._lib.pgs_mismatch_tile_words(self.n_genomes), sites.value
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """join the NCCL communicator of a multi-process run (one engine per process)"""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.pgs_comm_init(self._h, buf, rank, world))
+
+    def mismatch_allreduce(self, want_matrix: bool = True):
+        """K2 on this rank's genes, NCCL all-reduce of the partial counts; returns (matrix or None,
+        this rank's sites, all-reduce milliseconds)"""
+        out = np.zeros((self.n_genomes, self.n_genomes), dtype=np.uint32) if want_matrix else None
+        sites, ms = C.c_int64(), C.c_double()
+        self._check(self._lib.pgs_mismatch_allreduce(self._h, _ptr(out), C.byref(sites), C.byref(ms)))
+        return out, sites.value, ms.value
+
     def blocks_per_gene(self) -> int:
         return (self.gene_length + 63) // 64
 
@@ -293,6 +319,28 @@ class Engine:
         rep = OutputReport()
         self._check(self._lib.pgs_write_outputs(self._h, C.byref(spec), C.byref(rep)))
         return rep.as_dict()
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id (128 bytes) for Engine.comm_init: draw it on one rank, hand it to all"""
+    buf = C.create_string_buffer(128)
+    rc = load_library().pgs_comm_unique_id(buf)
+    if rc != 0:
+        raise PgsError(rc, "pgs_comm_unique_id: NCCL is not available")
+    return buf.raw
+
+
+def mismatch_multi(engines):
+    """engines of this process, one per device: (summed n x n matrix, sites)"""
+    lib = load_library()
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    n = engines[0].n_genomes
+    out = np.zeros((n, n), dtype=np.uint32)
+    sites = C.c_int64()
+    rc = lib.pgs_mismatch_multi(arr, len(engines), _ptr(out), C.byref(sites))
+    if rc < 0:
+        raise PgsError(rc, lib.pgs_last_error(engines[0]._h).decode())
+    return out, sites.value
 
 
 def host_coalescent(n: int, seed: int, mut_rate: float = 0.01, return_time: bool = False):

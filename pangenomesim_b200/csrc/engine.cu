@@ -23,7 +23,10 @@ void DevBuf::release()
 Engine::~Engine()
 {
 	drop_graph();
+	drop_comm();
 	for (auto &p : h_stage)
+		if (p) cudaFreeHost(p);
+	for (auto &p : h_mm_stage)
 		if (p) cudaFreeHost(p);
 	for (auto &x : ev)
 		if (x) cudaEventDestroy(x);
@@ -71,8 +74,8 @@ int Engine::upload(DevBuf &b, const void *src, size_t bytes, const char *what)
 int64_t Engine::device_bytes() const
 {
 	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
-						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words, &d_mismatch,
-						   &d_tab8, &d_walk_steps, &d_walk_off, &d_unit_path_off, &d_unit_path, &d_unit_store, &d_top_tasks, &d_sp_genes, &d_sp_steps};
+						   &d_dense_tasks, &d_sparse_tasks, &d_root_tasks, &d_leaf_base_words,
+						   &d_tab8, &d_walk_steps, &d_walk_off, &d_unit_path_off, &d_unit_path, &d_unit_store, &d_top_tasks, &d_sp_units, &d_sp_steps, &d_sp_paths, &d_planes, &d_tiles};
 	int64_t s = 0;
 	for (auto b : all) s += (int64_t)b->bytes;
 	return s;
@@ -127,8 +130,8 @@ void Engine::enqueue_levels(cudaStream_t s, int64_t *launches, cudaEvent_t after
 	}
 	if (after_dense && (walk || tables.n_dense == 0)) cudaEventRecord(after_dense, s); // (plain launches only: splits K1's time)
 	if (sparse_walk) { // sparse genes: origin rows and every branch in one launch
-		launch_walk_sparse(tables, d_sp_genes.as<SparseGene>(), d_sp_steps.as<SparseStep>(), n_sp_genes, s);
-		if (n_sp_genes > 0) (*launches)++;
+		launch_walk_sparse(tables, d_sp_units.as<SparseUnit>(), d_sp_steps.as<SparseStep>(), d_sp_paths.as<SparsePathEdge>(), n_sp_units, s);
+		if (n_sp_units > 0) (*launches)++;
 	}
 	for (int32_t lvl = 1; lvl <= max_level; lvl++) {
 		const int64_t nd = dense_level_off[lvl + 1] - dense_level_off[lvl];
@@ -447,24 +450,32 @@ int pgs_get_stats(pgs_engine *h, pgs_stats *out)
 	return PGS_OK;
 }
 
+// K2 on the engine's stream, timed; the packed tiles stay in e.d_tiles
+static int run_mismatch(Engine &e, int64_t *sites_out)
+{
+	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_mismatch: call pgs_sweep first");
+	cudaEventRecord(e.ev[3], e.stream);
+	const int rc = pgs::mismatch_tiles(e, sites_out);
+	if (rc) return rc;
+	cudaEventRecord(e.ev[4], e.stream);
+	cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce == cudaSuccess) ce = cudaGetLastError();
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch");
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e.ev[3], e.ev[4]);
+	e.mismatch_ms = ms;
+	return PGS_OK;
+}
+
 int pgs_mismatch_device(pgs_engine *h, void *out_device_u32, int64_t *sites_out)
 {
 	ENGINE_OR_RETURN(h);
-	if (!e.swept) return e.fail(PGS_ERR_STATE, "pgs_mismatch: call pgs_sweep first");
 	if (!out_device_u32) return e.fail(PGS_ERR_ARG, "pgs_mismatch: null output");
-	const int64_t D = (int64_t)e.dense_gid.size();
-	cudaEvent_t t0 = e.ev[3], t1 = e.ev[4];
-	cudaEventRecord(t0, e.stream);
-	pgs::launch_mismatch(e.tables.rows, e.d_leaf_base_words.as<int64_t>(), e.n_genomes, D * e.blocks * 4,
-						 static_cast<uint32_t *>(out_device_u32), e.stream);
-	cudaEventRecord(t1, e.stream);
-	cudaError_t ce = cudaStreamSynchronize(e.stream);
-	if (ce == cudaSuccess) ce = cudaGetLastError();
-	float ms = 0;
-	if (ce == cudaSuccess) cudaEventElapsedTime(&ms, t0, t1);
+	int rc = run_mismatch(e, sites_out);
+	if (rc) return rc;
+	if ((rc = pgs::mismatch_square_device(e, static_cast<uint32_t *>(out_device_u32)))) return rc;
+	const cudaError_t ce = cudaStreamSynchronize(e.stream);
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch");
-	e.mismatch_ms = ms;
-	if (sites_out) *sites_out = D * e.cfg.gene_length;
 	return PGS_OK;
 }
 
@@ -472,16 +483,64 @@ int pgs_mismatch(pgs_engine *h, uint32_t *out_host, int64_t *sites_out)
 {
 	ENGINE_OR_RETURN(h);
 	if (!out_host) return e.fail(PGS_ERR_ARG, "pgs_mismatch: null output");
-	const size_t bytes = sizeof(uint32_t) * (size_t)e.n_genomes * (size_t)e.n_genomes;
-	if (e.d_mismatch.bytes < bytes) {
-		int rc = e.alloc(e.d_mismatch, bytes, "mismatch matrix");
-		if (rc) return rc;
-	}
-	int rc = pgs_mismatch_device(h, e.d_mismatch.p, sites_out);
+	const int rc = run_mismatch(e, sites_out);
 	if (rc) return rc;
-	cudaError_t ce = cudaMemcpy(out_host, e.d_mismatch.p, bytes, cudaMemcpyDeviceToHost);
-	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch copy");
+	return pgs::mismatch_tiles_to_host(e, out_host);
+}
+
+int64_t pgs_mismatch_tile_words(int32_t n_genomes)
+{
+	return n_genomes < 0 ? 0 : pgs::mismatch_tile_words(n_genomes);
+}
+
+int pgs_mismatch_tiles_device(pgs_engine *h, void **tiles_device_u32, int64_t *sites_out)
+{
+	ENGINE_OR_RETURN(h);
+	const int rc = run_mismatch(e, sites_out);
+	if (rc) return rc;
+	if (tiles_device_u32) *tiles_device_u32 = e.d_tiles.p;
 	return PGS_OK;
+}
+
+int pgs_comm_unique_id(void *id128)
+{
+	return pgs::comm_unique_id(id128);
+}
+
+int pgs_comm_init(pgs_engine *h, const void *id128, int rank, int world)
+{
+	ENGINE_OR_RETURN(h);
+	return pgs::comm_init(e, id128, rank, world);
+}
+
+int pgs_mismatch_allreduce(pgs_engine *h, uint32_t *out_host, int64_t *sites_out, double *allreduce_ms)
+{
+	ENGINE_OR_RETURN(h);
+	int64_t sites = 0;
+	int rc = run_mismatch(e, &sites);
+	if (rc) return rc;
+	cudaEventRecord(e.ev[3], e.stream);
+	if ((rc = pgs::allreduce_tiles(e))) return rc;
+	cudaEventRecord(e.ev[4], e.stream);
+	const cudaError_t ce = cudaStreamSynchronize(e.stream);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch_allreduce");
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e.ev[3], e.ev[4]);
+	if (allreduce_ms) *allreduce_ms = ms;
+	if (sites_out) *sites_out = sites; // this rank's sites: the caller sums them (it knows how the genes were split)
+	return out_host ? pgs::mismatch_tiles_to_host(e, out_host) : PGS_OK;
+}
+
+int pgs_mismatch_multi(pgs_engine *const *engines, int n_engines, uint32_t *out_host, int64_t *sites_out)
+{
+	if (!engines || n_engines < 1 || !engines[0]) return PGS_ERR_ARG;
+	std::vector<Engine *> es(n_engines);
+	for (int d = 0; d < n_engines; d++) {
+		if (!engines[d]) return PGS_ERR_ARG;
+		es[d] = &engines[d]->e;
+		if (!es[d]->swept) return es[0]->fail(PGS_ERR_STATE, "pgs_mismatch_multi: call pgs_sweep on every engine first");
+	}
+	return pgs::mismatch_multi(es.data(), n_engines, out_host, sites_out);
 }
 
 int pgs_write_outputs(pgs_engine *h, const pgs_output_spec *spec, pgs_output_report *report)

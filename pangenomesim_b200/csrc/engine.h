@@ -63,7 +63,7 @@ struct Engine {
 	std::vector<int32_t> walk_pass_units; // units by kind (crown, rest of the top, subtrees), in launch order
 	int32_t n_walk_units = 0, n_top_tasks = 0;
 	bool sparse_walk = false;             // sparse genes: fused walk (k1_walk_sparse); internal sparse rows are not kept
-	int64_t n_sp_genes = 0, sparse_rows_written = 0, sparse_rows_read = 0; // (W and R of the sparse region)
+	int64_t n_sp_units = 0, sparse_rows_written = 0, sparse_rows_read = 0; // (W and R of the sparse region)
 	int walk_variant = 2;                 // kernel of the pass over the subtrees (choose_walk_variant)
 	int32_t walk_smem_levels = 0;         // deepest shared-memory stack level used by any step, plus one
 	int64_t rows_parked_smem = 0;         // rows per sweep parked in shared memory instead of the global pool
@@ -75,7 +75,11 @@ struct Engine {
 
 	// ---- device
 	DevBuf d_rows, d_row_base, d_h1, d_tab, d_tab_off, d_kmax, d_dense_gid;
-	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off, d_unit_path_off, d_unit_path, d_unit_store, d_top_tasks, d_sp_genes, d_sp_steps;
+	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off, d_unit_path_off, d_unit_path, d_unit_store, d_top_tasks, d_sp_units, d_sp_steps, d_sp_paths, d_planes, d_tiles;
+	char *h_mm_stage[2] = {nullptr, nullptr}; // pinned staging of pgs_mismatch's result
+	size_t mm_stage_bytes = 0;
+	void *comm = nullptr;       // ncclComm_t of pgs_comm_init (one engine per process), else nullptr
+	int comm_world = 1, comm_rank = 0;
 	DevBuf d_stage[2];          // K3 staging, kept between pgs_write_outputs calls
 	char *h_stage[2] = {nullptr, nullptr}; // pinned
 	int64_t stage_bytes = 0;
@@ -95,12 +99,23 @@ struct Engine {
 	int64_t row_index(int32_t node, int64_t gene_index) const;
 	bool row_kept(int32_t node, int64_t gene_index) const;
 	void drop_graph();
+	void drop_comm();
 	void enqueue_levels(cudaStream_t s, int64_t *launches, cudaEvent_t after_dense);
 };
 
 // plan.cu: everything behind pgs_set_genes (validation, layout, tasks, tables, uploads)
 int plan_genes(Engine &e, int64_t n_genes, const int64_t *gene_id, const int32_t *origin_node,
 			   const int64_t *carrier_off, const int32_t *carrier_genome, const int32_t *all_order);
+
+// mismatch.cu: K2 and the all-reduce of its partial results
+int64_t mismatch_tile_words(int32_t n);
+int mismatch_tiles(Engine &e, int64_t *sites_out);
+int mismatch_square_device(Engine &e, uint32_t *out_device);
+int mismatch_tiles_to_host(Engine &e, uint32_t *out_host);
+int comm_unique_id(void *id128);
+int comm_init(Engine &e, const void *id128, int rank, int world);
+int allreduce_tiles(Engine &e);
+int mismatch_multi(Engine *const *engines, int n_engines, uint32_t *out_host, int64_t *sites_out);
 
 // format.cu
 int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report);

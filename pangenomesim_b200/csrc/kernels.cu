@@ -1,5 +1,5 @@
-// kernels.cu -- K0 (origin rows), K1 (level-synchronous tree sweep), K2 (pairwise mismatch).
-// Hand-written for sm_100a; integer / byte work bounded by HBM (K0, K1) or the integer pipes (K2),
+// kernels.cu -- K0 (origin rows) and K1 (tree sweep: fused walks and the level-synchronous kernels).
+// Hand-written for sm_100a; integer / byte work bounded by HBM,
 // so no tensor cores: coalesced 16-byte accesses, several loads in flight per thread, grids that
 // are whole multiples of what the 148 SMs hold.
 #include "kernels.cuh"
@@ -741,8 +741,9 @@ __device__ __forceinline__ uint4 ld_cg(const uint4 *p)
 }
 
 __global__ void __launch_bounds__(kThreads, 3)
-k1_walk_sparse(const __grid_constant__ DeviceTables t, const SparseGene *__restrict__ genes,
-			   const SparseStep *__restrict__ steps, uint32_t n_items, uint32_t quads_per_gene)
+k1_walk_sparse(const __grid_constant__ DeviceTables t, const SparseUnit *__restrict__ units,
+			   const SparseStep *__restrict__ steps, const SparsePathEdge *__restrict__ paths, uint32_t n_items,
+			   uint32_t quads_per_gene)
 {
 	extern __shared__ uint4 s_stack[]; // [level][block of the quad][thread]
 	const uint32_t item = blockIdx.x * kThreads + threadIdx.x;
@@ -750,26 +751,51 @@ k1_walk_sparse(const __grid_constant__ DeviceTables t, const SparseGene *__restr
 	const uint32_t rank = item / quads_per_gene;
 	const uint32_t blk0 = (item - rank * quads_per_gene) * 4u;
 	const uint32_t nb = min(4u, t.blocks - blk0); // blocks of this quad that exist
-	const uint4 gene = __ldg(reinterpret_cast<const uint4 *>(genes) + rank);
-	const uint32_t gid = gene.x, n_steps = gene.w;
+	const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(units + rank)), u1 = __ldg(reinterpret_cast<const uint4 *>(units + rank) + 1);
+	const uint32_t gid = u0.x, n_steps = u0.w;
 	const uint32_t live = (1u << nb) - 1u;
 	auto valid_of = [&](uint32_t i) { return (blk0 + i + 1u == t.blocks) ? t.last_valid : 64; };
 	auto row_ptr = [&](uint32_t row) { return t.rows + (int64_t)row * t.blocks + blk0; };
+	// rare path of block i on the branch `edge`; `from` is the value of the block above the branch
+	auto rare = [&](uint32_t edge, uint32_t word, uint32_t i, const uint4 &from) {
+		const uint64_t h1 = __ldg(t.tab8 + (size_t)edge * 8), h2 = __ldg(t.tab8 + (size_t)edge * 8 + 1);
+		return mutate_block_h12(from, edge, gid, blk0 + i, pair_field(word, i & 1u), h1, h2, t.tab, t.tab_off, t.kmax, valid_of(i),
+								t.keys);
+	};
 
 	uint4 cur[4];
-	{ // origin row: what gene::gene(len, -1, id) draws (gene.cxx:13-25)
-		uint4 *const dst = row_ptr(gene.y);
+	// origin row: what gene::gene(len, -1, id) draws (gene.cxx:13-25); the gene's origin unit keeps it
 #pragma unroll
-		for (uint32_t i = 0; i < 4; i++) {
-			cur[i] = make_uint4(0u, 0u, 0u, 0u);
-			if (i < nb) {
-				cur[i] = root_block(gid, blk0 + i, valid_of(i), t.keys);
-				st_stream(dst + i, cur[i]);
-			}
+	for (uint32_t i = 0; i < 4; i++) {
+		cur[i] = make_uint4(0u, 0u, 0u, 0u);
+		if (i < nb) cur[i] = root_block(gid, blk0 + i, valid_of(i), t.keys);
+	}
+	if (u0.y != kNoRow) {
+		uint4 *const dst = row_ptr(u0.y);
+#pragma unroll
+		for (uint32_t i = 0; i < 4; i++)
+			if (i < nb) st_stream(dst + i, cur[i]);
+	}
+	// a unit below the origin: carry the value across the branches of its path (no memory involved)
+	for (uint32_t k = 0; k < u1.y; k++) {
+		const uint4 pe = __ldg(reinterpret_cast<const uint4 *>(paths + u1.x + k));
+		const uint4 w = quad_words(pe.x, gid, blk0, t.keys);
+		const bool second = (pe.z >> 31) != 0;
+		const uint32_t hc = (pe.z << 16) | 0xFFFFu;
+		const uint32_t w01 = second ? w.z : w.x, w23 = second ? w.w : w.y;
+		const uint32_t h = (pair_hits(w01, hc) | (pair_hits(w23, hc) << 2)) & live;
+		if (h) {
+#pragma unroll
+			for (uint32_t i = 0; i < 4; i++)
+				if (h & (1u << i)) cur[i] = rare(pe.y, (i & 2u) ? w23 : w01, i, cur[i]);
 		}
 	}
-	const uint4 *sp = reinterpret_cast<const uint4 *>(steps + gene.z);
+
+	const uint4 *sp = reinterpret_cast<const uint4 *>(steps + u0.z);
 	for (uint32_t k = 0; k < n_steps; k++, sp += 2) {
+		// the descriptors two and three steps ahead are pulled into L1 while this one is worked on (a
+		// prefetch holds no register; reading a little past the unit's last step is harmless)
+		asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + 4));
 		const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
 		const uint32_t f = s1.y;
 		if (f & kSpLoadSmem) {
@@ -785,16 +811,8 @@ k1_walk_sparse(const __grid_constant__ DeviceTables t, const SparseGene *__restr
 		// one Philox call: the eight decisions {a, b} x {four blocks}
 		const uint4 w = quad_words(s0.z, gid, blk0, t.keys);
 		const uint32_t hca = (s1.x << 16) | 0xFFFFu, hcb = (s1.x & 0xFFFF0000u) | 0xFFFFu;
-		uint32_t hits_a = (f & kSpHasA) ? ((pair_hits(w.x, hca) | (pair_hits(w.y, hca) << 2)) & live) : 0u;
-		uint32_t hits_b = (f & kSpHasB) ? ((pair_hits(w.z, hcb) | (pair_hits(w.w, hcb) << 2)) & live) : 0u;
-		// rare path of block i on one side; `from` is the parent's value of the block
-		auto rare = [&](uint32_t side, uint32_t i, const uint4 &from) {
-			const uint32_t edge = side ? s0.w : s0.z;
-			const uint32_t word = side ? ((i & 2u) ? w.w : w.z) : ((i & 2u) ? w.y : w.x);
-			const uint64_t h1 = __ldg(t.tab8 + (size_t)edge * 8), h2 = __ldg(t.tab8 + (size_t)edge * 8 + 1);
-			return mutate_block_h12(from, edge, gid, blk0 + i, pair_field(word, i & 1u), h1, h2, t.tab, t.tab_off, t.kmax,
-									valid_of(i), t.keys);
-		};
+		const uint32_t hits_a = (f & kSpHasA) ? ((pair_hits(w.x, hca) | (pair_hits(w.y, hca) << 2)) & live) : 0u;
+		const uint32_t hits_b = (f & kSpHasB) ? ((pair_hits(w.z, hcb) | (pair_hits(w.w, hcb) << 2)) & live) : 0u;
 		auto emit = [&](uint32_t side, const uint4 (&v)[4]) {
 			const uint32_t dst = side ? s0.y : s0.x;
 			if (dst != kNoRow) {
@@ -818,9 +836,10 @@ k1_walk_sparse(const __grid_constant__ DeviceTables t, const SparseGene *__restr
 			uint4 y[4] = {cur[0], cur[1], cur[2], cur[3]};
 			const uint32_t h = side ? hits_b : hits_a;
 			if (h) { // rare: some block of this child may change (static indices: the values stay in registers)
+				const uint32_t edge = side ? s0.w : s0.z;
 #pragma unroll
 				for (uint32_t i = 0; i < 4; i++)
-					if (h & (1u << i)) y[i] = rare(side, i, cur[i]);
+					if (h & (1u << i)) y[i] = rare(edge, side ? ((i & 2u) ? w.w : w.z) : ((i & 2u) ? w.y : w.x), i, cur[i]);
 			}
 			emit(side, y);
 			if (pass) {
@@ -842,144 +861,14 @@ cudaError_t prepare_walk_sparse()
 								kSpStackLevels * 4 * (int)sizeof(uint4) * kThreads);
 }
 
-void launch_walk_sparse(const DeviceTables &t, const SparseGene *genes, const SparseStep *steps, int64_t n_genes, cudaStream_t s)
+void launch_walk_sparse(const DeviceTables &t, const SparseUnit *units, const SparseStep *steps, const SparsePathEdge *paths,
+						int64_t n_units, cudaStream_t s)
 {
-	if (n_genes == 0) return;
+	if (n_units == 0) return;
 	const uint32_t quads = (t.blocks + 3u) / 4u;
-	const int64_t items = n_genes * quads;
+	const int64_t items = n_units * quads;
 	const size_t dyn = (size_t)kSpStackLevels * 4 * sizeof(uint4) * kThreads;
-	k1_walk_sparse<<<(unsigned)((items + kThreads - 1) / kThreads), kThreads, dyn, s>>>(t, genes, steps, (uint32_t)items, quads);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2: observed pairwise mismatch counts over the dense regions of the leaves.  A CTA owns a
-// 64 x 64 tile of genome pairs and a slice of the columns.  While a chunk of 512 sites is staged
-// into shared memory each row is split into its two BIT PLANES (low bit / high bit of every
-// 2-bit base, 32 sites per word), so that the inner loop per pair and 32 sites is
-//     mismatch mask = (lo_i ^ lo_j) | (hi_i ^ hi_j)      -> XOR + LOP3
-//     count        += popc(mask) [+ popc(next mask)]      -> POPC + half an IADD3
-// i.e. 3.5 instructions per 32 site pairs instead of 5 per 16 on the packed form.  Each thread
-// keeps a 4 x 4 sub-tile in registers and fetches two groups per shared-memory load.  Bound by the integer pipes (n^2 S / 2 site pairs), not by HBM.
-
-constexpr int kMmTile = 64;    // genomes per tile side
-constexpr int kMmGroups = 16;  // 32-site groups per staged chunk (= 32 packed words per row)
-
-// even bits of x -> low 16 bits
-__device__ __forceinline__ uint32_t even_bits(uint32_t x)
-{
-	x &= 0x55555555u;
-	x = (x | (x >> 1)) & 0x33333333u;
-	x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-	x = (x | (x >> 4)) & 0x00FF00FFu;
-	x = (x | (x >> 8)) & 0x0000FFFFu;
-	return x;
-}
-
-__global__ void __launch_bounds__(256)
-k2_mismatch(const uint32_t *__restrict__ words, const int64_t *__restrict__ leaf_base_words, int32_t n,
-			int64_t words_per_leaf, int64_t words_per_split, uint32_t *__restrict__ out)
-{
-	// tile coordinates in the upper triangle: blockIdx.x enumerates (ti <= tj)
-	const int tiles = (n + kMmTile - 1) / kMmTile;
-	int ti = 0, rem = blockIdx.x;
-	while (rem >= tiles - ti) {
-		rem -= tiles - ti;
-		ti++;
-	}
-	const int tj = ti + rem;
-
-	// [side a/b][plane lo/hi][row][group], row stride 18 words: the inner loop reads two groups at a
-	// time (LDS.64); 16 consecutive rows at a stride of 18 words start in 16 different even banks
-	__shared__ __align__(8) uint32_t sm[2][2][kMmTile][kMmGroups + 2];
-
-	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // pairs (ty + 16 i, tx + 16 j)
-	uint32_t acc[4][4];
-#pragma unroll
-	for (int i = 0; i < 4; i++)
-#pragma unroll
-		for (int j = 0; j < 4; j++) acc[i][j] = 0;
-
-	const int64_t w_begin = (int64_t)blockIdx.y * words_per_split;
-	int64_t w_end = w_begin + words_per_split;
-	if (w_end > words_per_leaf) w_end = words_per_leaf;
-
-	for (int64_t w0 = w_begin; w0 < w_end; w0 += 2 * kMmGroups) {
-		// stage: 2 sides x 64 rows x 16 groups = 2048 (row, group) items, 8 per thread; a group is two
-		// packed words (8 bytes, aligned: rows start at multiples of 4 words and w0 is even)
-		for (int e = threadIdx.x; e < 2 * kMmTile * kMmGroups; e += 256) {
-			const int side = e / (kMmTile * kMmGroups);
-			const int row = (e / kMmGroups) % kMmTile, grp = e % kMmGroups;
-			const int g = (side ? tj : ti) * kMmTile + row;
-			const int64_t w = w0 + 2 * grp;
-			uint2 v = make_uint2(0u, 0u);
-			if (g < n && w < w_end) v = __ldg(reinterpret_cast<const uint2 *>(words + leaf_base_words[g] + w));
-			sm[side][0][row][grp] = even_bits(v.x) | (even_bits(v.y) << 16);
-			sm[side][1][row][grp] = even_bits(v.x >> 1) | (even_bits(v.y >> 1) << 16);
-		}
-		__syncthreads();
-#pragma unroll 2
-		for (int k = 0; k < kMmGroups; k += 2) {
-			uint2 alo[4], ahi[4], blo[4], bhi[4];
-#pragma unroll
-			for (int i = 0; i < 4; i++) {
-				alo[i] = *reinterpret_cast<const uint2 *>(&sm[0][0][ty + 16 * i][k]);
-				ahi[i] = *reinterpret_cast<const uint2 *>(&sm[0][1][ty + 16 * i][k]);
-				blo[i] = *reinterpret_cast<const uint2 *>(&sm[1][0][tx + 16 * i][k]);
-				bhi[i] = *reinterpret_cast<const uint2 *>(&sm[1][1][tx + 16 * i][k]);
-			}
-#pragma unroll
-			for (int i = 0; i < 4; i++)
-#pragma unroll
-				for (int j = 0; j < 4; j++) // one three-input add per two groups.  (XOR, LOP3, POPC and the add all
-											// issue on the ALU pipe, which is the bound -- 73 % busy; a carry-save
-											// adder tree that trades POPCs for LOP3s was measured 17 % slower)
-					acc[i][j] += __popc((alo[i].x ^ blo[j].x) | (ahi[i].x ^ bhi[j].x)) +
-								 __popc((alo[i].y ^ blo[j].y) | (ahi[i].y ^ bhi[j].y));
-		}
-		__syncthreads();
-	}
-
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const int gi = ti * kMmTile + ty + 16 * i, gj = tj * kMmTile + tx + 16 * j;
-			if (gi < n && gj < n && gi < gj && acc[i][j]) {
-				atomicAdd(out + (int64_t)gi * n + gj, acc[i][j]);
-			}
-		}
-	}
-}
-
-__global__ void k2_mirror(uint32_t *__restrict__ out, int32_t n)
-{
-	const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= (int64_t)n * n) return;
-	const int32_t i = (int32_t)(idx / n), j = (int32_t)(idx % n);
-	if (i > j) out[idx] = out[(int64_t)j * n + i];
-}
-
-void launch_mismatch(const uint4 *rows, const int64_t *leaf_base_words, int32_t n, int64_t words_per_leaf,
-					 uint32_t *out, cudaStream_t s)
-{
-	cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n * (size_t)n, s);
-	if (n < 2 || words_per_leaf == 0) return;
-	const int tiles = (n + kMmTile - 1) / kMmTile;
-	const int64_t tri = (int64_t)tiles * (tiles + 1) / 2;
-	// split the columns so that small n still fills the 148 SMs (4 CTAs each)
-	int64_t splits = (148 * 4 + tri - 1) / tri;
-	constexpr int kMmChunk = 2 * kMmGroups; // packed words per staged chunk
-	const int64_t chunks = (words_per_leaf + kMmChunk - 1) / kMmChunk;
-	if (splits > chunks) splits = chunks;
-	if (splits > 65535) splits = 65535;
-	if (splits < 1) splits = 1;
-	const int64_t words_per_split = ((chunks + splits - 1) / splits) * kMmChunk;
-	const int64_t used = (words_per_leaf + words_per_split - 1) / words_per_split;
-	dim3 grid((unsigned)tri, (unsigned)used);
-	k2_mismatch<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t *>(rows), leaf_base_words, n,
-									  words_per_leaf, words_per_split, out);
-	const int64_t cells = (int64_t)n * n;
-	k2_mirror<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(out, n);
+	k1_walk_sparse<<<(unsigned)((items + kThreads - 1) / kThreads), kThreads, dyn, s>>>(t, units, steps, paths, (uint32_t)items, quads);
 }
 
 } // namespace pgs

@@ -1,5 +1,5 @@
 // kernels.cuh -- device tables and launchers of the sm_100a kernels (K0 root rows, K1 level
-// sweep, K2 pairwise mismatch, K3 text formatter).  See DESIGN.md §4 for the roofline of each.
+// sweep; K2 pairwise mismatch lives in mismatch.cu, the K3 text formatter in format.cu).  See DESIGN.md §4 for the roofline of each.
 #pragma once
 #include "philox.cuh"
 #include <cstdint>
@@ -57,13 +57,26 @@ struct TopMaskTask {
 };
 
 // Fused walk of the sparse (accessory) genes, k1_walk_sparse: a thread carries one quad of blocks
-// of ONE gene from the gene's origin down the gene's own presence subtree (the nodes on the paths
-// from the origin to the genomes that carry it).
-struct SparseGene {
+// of ONE gene down the gene's own presence subtree (the nodes on the paths from the gene's origin
+// to the genomes that carry it).  A widespread gene's subtree is cut into UNITS of bounded length;
+// a unit below the origin starts from the origin row (drawn again, 4 Philox calls) carried across
+// the branches on its path -- one Philox call per branch, the substitution masks being independent
+// of the sequence -- so no unit waits for another one.
+struct __align__(16) SparseUnit {
 	uint32_t gid;        // gene_id (Philox counter word 1)
-	uint32_t origin_row; // the origin row is drawn by the kernel itself and stored here
-	uint32_t step_begin; // first of the gene's steps
+	uint32_t origin_row; // the gene's origin unit stores the origin row here; kNoRow for the other units
+	uint32_t step_begin; // first of the unit's steps
 	uint32_t n_steps;
+	uint32_t path_begin; // branches from the origin down to the unit's root (SparsePathEdge)
+	uint32_t path_len;
+	uint32_t pad0, pad1;
+};
+static_assert(sizeof(SparseUnit) == 32, "SparseUnit is read as two uint4");
+struct __align__(16) SparsePathEdge {
+	uint32_t leader;   // first child of the branch's parent node (RNG key of the decision fields)
+	uint32_t edge;     // child node index of the branch
+	uint32_t side_h16; // bit 31: the branch is the second of its sibling pair; low 16 bits: H[1] >> 48
+	uint32_t pad;
 };
 struct __align__(16) SparseStep {
 	uint32_t dst_a, dst_b;   // rows the two children's values are stored to (kNoRow: not stored)
@@ -157,11 +170,7 @@ void launch_walk_dense(const DeviceTables &t, const WalkUnits &u, int32_t smem_l
 // Fused sparse sweep: origin rows and every branch of every sparse gene in one launch.
 int sparse_walk_smem_levels();
 cudaError_t prepare_walk_sparse();
-void launch_walk_sparse(const DeviceTables &t, const SparseGene *genes, const SparseStep *steps, int64_t n_genes, cudaStream_t s);
-
-// K2: mismatch counts between the dense regions of n leaves.  leaf_base[i] = first row of genome
-// i's leaf.  out is n x n uint32 (zeroed by the launcher, upper triangle filled then mirrored).
-void launch_mismatch(const uint4 *rows, const int64_t *leaf_base, int32_t n, int64_t words_per_leaf,
-					 uint32_t *out, cudaStream_t s);
+void launch_walk_sparse(const DeviceTables &t, const SparseUnit *units, const SparseStep *steps, const SparsePathEdge *paths,
+						int64_t n_units, cudaStream_t s);
 
 } // namespace pgs

@@ -31,8 +31,9 @@ struct SweepPlan {
 	// per sparse gene: the nodes that hold a row of it and the row's rank inside the node's sparse list
 	std::vector<int64_t> gn_off;
 	std::vector<int32_t> gn_node, gn_rank;
-	std::vector<SparseGene> sp_genes;
+	std::vector<SparseUnit> sp_units;
 	std::vector<SparseStep> sp_steps;
+	std::vector<SparsePathEdge> sp_paths;
 };
 
 int64_t dense_rows(const Engine &e, const SweepPlan &p, int32_t v)
@@ -518,20 +519,24 @@ int plan_walk(Engine &e, SweepPlan &p)
 	return PGS_OK;
 }
 
-// Fused walk of the sparse region (k1_walk_sparse): per gene a depth-first step list over the
-// gene's presence subtree, smaller subtree first (a thread's stack of parked siblings stays
-// shallow: at most log2(carriers) levels).
+// Fused walk of the sparse region (k1_walk_sparse).  A gene's presence subtree is cut into units of
+// at most ~kSpUnitSteps steps (a widespread gene would otherwise be one serial chain of up to 2n
+// steps); every unit gets a depth-first step list, smaller subtree first (a thread's stack of
+// parked siblings stays shallow: at most log2(carriers) levels), and the list of branches from the
+// gene's origin down to its root.
 int plan_sparse_walk(Engine &e, SweepPlan &p)
 {
 	e.sparse_walk = p.sparse_walk;
-	e.n_sp_genes = 0;
+	e.n_sp_units = 0;
 	if (!p.sparse_walk) return PGS_OK;
 	const int32_t N = e.n_nodes;
-	const int64_t D = p.D;
 	const int smem_cap = pgs::sparse_walk_smem_levels();
+	int32_t unit_steps = 96; // steps per unit (a unit below the origin pays 4 + depth Philox calls to start)
+	if (const char *v = std::getenv("PGS_SPARSE_UNIT_STEPS")) unit_steps = std::max(1, std::atoi(v)); // tuning knob
 	std::vector<int64_t> stamp(N, -1);
-	std::vector<int32_t> rank_at(N, 0), sub(N, 0);
-	std::vector<int32_t> order, parked;
+	std::vector<int32_t> rank_at(N, 0), sub(N, 0), acc(N, 0);
+	std::vector<char> cut(N, 0);
+	std::vector<int32_t> order, parked, unit_roots;
 	int64_t stored = 0, loaded = 0; // rows the sparse walk writes to / reads from memory
 	auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
 	auto row_of = [&](int32_t v) { return (uint32_t)(e.row_base[v] + dense_rows(e, p, v) + rank_at[v]); };
@@ -540,88 +545,118 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 		if (nb == ne) continue;
 		order.assign(p.gn_node.begin() + nb, p.gn_node.begin() + ne);
 		for (int64_t k = nb; k < ne; k++) {
-			stamp[p.gn_node[k]] = g;
-			rank_at[p.gn_node[k]] = p.gn_rank[k];
-			sub[p.gn_node[k]] = 1;
+			const int32_t v = p.gn_node[k];
+			stamp[v] = g;
+			rank_at[v] = p.gn_rank[k];
+			sub[v] = 1;
+			acc[v] = internal(v) ? 1 : 0; // steps (internal nodes) of the piece of the subtree that is not cut off yet
+			cut[v] = 0;
 		}
-		// sizes of the gene's subtrees: children before parents
+		// children before parents: subtree sizes, and a cut wherever a piece has grown to a unit
 		std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
 		const int32_t org = e.origin[g];
-		for (int32_t v : order)
-			if (v != org) sub[e.parent[v]] += sub[v];
-		pgs::SparseGene sg{};
-		sg.gid = (uint32_t)e.gene_id[g];
-		sg.origin_row = row_of(org);
-		if (p.sp_steps.size() >= 0xFFFFFFFFull) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse walk steps; shard the genes");
-		sg.step_begin = (uint32_t)p.sp_steps.size();
-		stored++;
-		parked.clear();
-		int32_t v = org;
-		uint32_t load = 0, load_level = 0, load_row = 0; // how the next step gets its input (0: carried in registers)
-		bool have = internal(org);
-		while (have) {
-			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
-			const bool ha = stamp[a] == g, hb = stamp[b] == g;
-			const bool da = ha && internal(a), db = hb && internal(b);
-			pgs::SparseStep st{};
-			st.dst_a = (ha && !da) ? row_of(a) : pgs::kNoRow; // a genome's row
-			st.dst_b = (hb && !db) ? row_of(b) : pgs::kNoRow;
-			st.edge_a = (uint32_t)a;
-			st.edge_b = (uint32_t)b;
-			st.h16 = (uint32_t)(e.h1_host[a] >> 48) | ((uint32_t)(e.h1_host[b] >> 48) << 16);
-			st.flags = (ha ? pgs::kSpHasA : 0u) | (hb ? pgs::kSpHasB : 0u) | load;
-			st.in_row = load_row;
-			st.levels = load_level << 8;
-			if (load == pgs::kSpLoadRow) loaded++;
-			int32_t carry = -1;
-			if (da && db) {
-				const bool a_first = sub[a] <= sub[b];
-				carry = a_first ? a : b;
-				const int32_t later = a_first ? b : a;
-				const int depth = (int)parked.size();
-				st.flags |= a_first ? pgs::kSpCarryA : pgs::kSpCarryB;
-				if (depth < smem_cap) {
-					st.flags |= a_first ? pgs::kSpParkB : pgs::kSpParkA;
-					st.levels |= (uint32_t)depth;
-				} else { // deeper than the shared-memory stack: parked in its own row
-					(a_first ? st.dst_b : st.dst_a) = row_of(later);
-				}
-				parked.push_back(later);
-			} else if (da) {
-				carry = a;
-				st.flags |= pgs::kSpCarryA;
-			} else if (db) {
-				carry = b;
-				st.flags |= pgs::kSpCarryB;
-			}
-			stored += (st.dst_a != pgs::kNoRow) + (st.dst_b != pgs::kNoRow);
-			p.sp_steps.push_back(st);
-			if (carry >= 0) {
-				v = carry;
-				load = 0;
-			} else if (!parked.empty()) {
-				v = parked.back();
-				parked.pop_back();
-				const int depth = (int)parked.size();
-				if (depth < smem_cap) {
-					load = pgs::kSpLoadSmem;
-					load_level = (uint32_t)depth;
-				} else {
-					load = pgs::kSpLoadRow;
-					load_row = row_of(v);
-				}
+		unit_roots.assign(1, org);
+		for (int32_t v : order) {
+			if (v == org) continue;
+			sub[e.parent[v]] += sub[v];
+			if (acc[v] >= unit_steps) {
+				cut[v] = 1;
+				unit_roots.push_back(v);
 			} else {
-				have = false;
+				acc[e.parent[v]] += acc[v];
 			}
 		}
-		sg.n_steps = (uint32_t)(p.sp_steps.size() - sg.step_begin);
-		p.sp_genes.push_back(sg);
+		if (p.sp_steps.size() + (size_t)(ne - nb) >= 0xFFFFFFFFull || p.sp_paths.size() >= 0xF0000000ull)
+			return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse walk steps; shard the genes");
+		for (int32_t ur : unit_roots) {
+			pgs::SparseUnit su{};
+			su.gid = (uint32_t)e.gene_id[g];
+			su.origin_row = ur == org ? row_of(org) : pgs::kNoRow;
+			su.step_begin = (uint32_t)p.sp_steps.size();
+			su.path_begin = (uint32_t)p.sp_paths.size();
+			if (ur == org) stored++;
+			{ // branches origin -> unit root, top down
+				const size_t first = p.sp_paths.size();
+				for (int32_t v = ur; v != org; v = e.parent[v]) {
+					const int32_t par = e.parent[v], leader = e.child[e.child_off[par]];
+					pgs::SparsePathEdge pe{};
+					pe.leader = (uint32_t)leader;
+					pe.edge = (uint32_t)v;
+					pe.side_h16 = (uint32_t)(e.h1_host[v] >> 48) | (v == leader ? 0u : 0x80000000u);
+					p.sp_paths.push_back(pe);
+				}
+				std::reverse(p.sp_paths.begin() + first, p.sp_paths.end());
+				su.path_len = (uint32_t)(p.sp_paths.size() - first);
+			}
+			parked.clear();
+			int32_t v = ur;
+			uint32_t load = 0, load_level = 0, load_row = 0; // how the next step gets its input (0: carried in registers)
+			bool have = internal(ur);
+			while (have) {
+				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
+				// a child that roots another unit is none of this unit's business
+				const bool ha = stamp[a] == g && !cut[a], hb = stamp[b] == g && !cut[b];
+				const bool da = ha && internal(a), db = hb && internal(b);
+				pgs::SparseStep st{};
+				st.dst_a = (ha && !da) ? row_of(a) : pgs::kNoRow; // a genome's row
+				st.dst_b = (hb && !db) ? row_of(b) : pgs::kNoRow;
+				st.edge_a = (uint32_t)a;
+				st.edge_b = (uint32_t)b;
+				st.h16 = (uint32_t)(e.h1_host[a] >> 48) | ((uint32_t)(e.h1_host[b] >> 48) << 16);
+				st.flags = (ha ? pgs::kSpHasA : 0u) | (hb ? pgs::kSpHasB : 0u) | load;
+				st.in_row = load_row;
+				st.levels = load_level << 8;
+				if (load == pgs::kSpLoadRow) loaded++;
+				int32_t carry = -1;
+				if (da && db) {
+					const bool a_first = sub[a] <= sub[b];
+					carry = a_first ? a : b;
+					const int32_t later = a_first ? b : a;
+					const int depth = (int)parked.size();
+					st.flags |= a_first ? pgs::kSpCarryA : pgs::kSpCarryB;
+					if (depth < smem_cap) {
+						st.flags |= a_first ? pgs::kSpParkB : pgs::kSpParkA;
+						st.levels |= (uint32_t)depth;
+					} else { // deeper than the shared-memory stack: parked in its own row
+						(a_first ? st.dst_b : st.dst_a) = row_of(later);
+					}
+					parked.push_back(later);
+				} else if (da) {
+					carry = a;
+					st.flags |= pgs::kSpCarryA;
+				} else if (db) {
+					carry = b;
+					st.flags |= pgs::kSpCarryB;
+				}
+				stored += (st.dst_a != pgs::kNoRow) + (st.dst_b != pgs::kNoRow);
+				if (ha || hb) p.sp_steps.push_back(st); // (both children cut off: nothing to do here)
+				if (carry >= 0) {
+					v = carry;
+					load = 0;
+				} else if (!parked.empty()) {
+					v = parked.back();
+					parked.pop_back();
+					const int depth = (int)parked.size();
+					if (depth < smem_cap) {
+						load = pgs::kSpLoadSmem;
+						load_level = (uint32_t)depth;
+					} else {
+						load = pgs::kSpLoadRow;
+						load_row = row_of(v);
+					}
+				} else {
+					have = false;
+				}
+			}
+			su.n_steps = (uint32_t)(p.sp_steps.size() - su.step_begin);
+			p.sp_units.push_back(su);
+		}
 	}
-	// lanes of a warp walk different genes: sort by length so that they finish together, longest first
-	std::stable_sort(p.sp_genes.begin(), p.sp_genes.end(),
-					 [](const pgs::SparseGene &a, const pgs::SparseGene &b) { return a.n_steps > b.n_steps; });
-	e.n_sp_genes = (int64_t)p.sp_genes.size();
-	(void)D;
+	for (int k = 0; k < 4; k++) p.sp_steps.push_back(pgs::SparseStep{}); // the kernel prefetches a few steps past a unit's end
+	// lanes of a warp walk different units: sort by length so that they finish together, longest first
+	std::stable_sort(p.sp_units.begin(), p.sp_units.end(),
+					 [](const pgs::SparseUnit &a, const pgs::SparseUnit &b) { return a.n_steps + a.path_len > b.n_steps + b.path_len; });
+	e.n_sp_units = (int64_t)p.sp_units.size();
 	// rows K1 really moves: these instead of every sparse row written and every sparse parent row read
 	e.rows_stored += stored - e.sparse_rows_written;
 	e.rows_loaded += loaded - e.sparse_rows_read;
@@ -641,8 +676,9 @@ int upload_plan(Engine &e, SweepPlan &p)
 	int rc = 0;
 	if ((rc = e.upload(e.d_walk_steps, p.walk_steps.data(), sizeof(WalkStep) * p.walk_steps.size(), "walk steps"))) return rc;
 	if ((rc = e.upload(e.d_walk_off, p.walk_off.data(), sizeof(int64_t) * p.walk_off.size(), "walk units"))) return rc;
-	if ((rc = e.upload(e.d_sp_genes, p.sp_genes.data(), sizeof(SparseGene) * p.sp_genes.size(), "sparse walk genes"))) return rc;
+	if ((rc = e.upload(e.d_sp_units, p.sp_units.data(), sizeof(SparseUnit) * p.sp_units.size(), "sparse walk units"))) return rc;
 	if ((rc = e.upload(e.d_sp_steps, p.sp_steps.data(), sizeof(SparseStep) * p.sp_steps.size(), "sparse walk steps"))) return rc;
+	if ((rc = e.upload(e.d_sp_paths, p.sp_paths.data(), sizeof(SparsePathEdge) * p.sp_paths.size(), "sparse walk paths"))) return rc;
 	if (e.sparse_walk && pgs::prepare_walk_sparse() != cudaSuccess)
 		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the sparse walk kernel's shared-memory stack does not fit this device");
 	if ((rc = e.upload(e.d_top_tasks, p.top_tasks.data(), sizeof(TopMaskTask) * p.top_tasks.size(), "top mask tasks"))) return rc;
@@ -670,7 +706,6 @@ int upload_plan(Engine &e, SweepPlan &p)
 	std::vector<int64_t> leaf_words(n);
 	for (int32_t g = 0; g < n; g++) leaf_words[g] = e.row_base[e.genome_leaf[g]] * e.blocks * 4;
 	if ((rc = e.upload(e.d_leaf_base_words, leaf_words.data(), sizeof(int64_t) * n, "leaf bases"))) return rc;
-	e.d_mismatch.release();
 	{ // first eight thresholds of every branch at a fixed stride, for the kernels' shared-memory copy
 		std::vector<uint64_t> tab8((size_t)N * 8, 0);
 		for (int32_t v = 0; v < N; v++)

@@ -451,3 +451,49 @@ def test_sparse_walk_deep_stacks_and_rates(oracle, monkeypatch, sparse_walk):
     genes = (gene_id, origin, off, car)
     with build(seed, L, parent, rate, leaf, genes, flags=0) as e:
         assert _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L) > 2000
+
+
+@pytest.mark.parametrize("n,L,G,planes_mb", [(70, 130, 33, None), (200, 1000, 9, "1"), (129, 64, 3, None), (2, 100, 5, None),
+                                              (333, 448, 21, "1")])
+def test_mismatch_tiles_chunks_and_edges(oracle, monkeypatch, n, L, G, planes_mb):
+    """K2 (bit planes + 64 x 64 tiles of the upper triangle): genome counts off the tile size, column
+    chunks (a 1 MB plane budget forces several), packed tiles against the square, all against numpy"""
+    if planes_mb:
+        monkeypatch.setenv("PGS_K2_PLANES_MB", planes_mb)
+    seed = 50 + n
+    parent, rate, leaf = treegen.coalescent(n, seed=n, mut_rate=0.5)
+    root = len(parent) - 1
+    with build(seed, L, parent, rate, leaf, core_table(G, root), flags=0) as e:
+        mm, sites = e.mismatch()
+        assert sites == G * L
+        codes = np.stack([oracle.unpack_codes(e.copy_dense(v, G), L).reshape(-1) for v in range(n)])
+        want = np.zeros((n, n), np.uint32)
+        for i in range(n):
+            want[i] = (codes != codes[i]).sum(-1)
+        assert np.array_equal(mm, want)
+        # the same through the device-side square and the packed tiles
+        import torch
+        sq = torch.zeros((n, n), dtype=torch.int32, device="cuda")
+        assert e.mismatch_device(sq.data_ptr()) == sites
+        assert np.array_equal(sq.cpu().numpy().astype(np.uint32), want)
+        ptr, words, _ = e.mismatch_tiles_device()
+        T = (n + 63) // 64
+        assert words == T * (T + 1) // 2 * 4096
+        tiles = np.zeros(words, np.uint32)
+        torch.cuda.synchronize()
+        import ctypes
+        from pangenomesim_b200.capi import load_library
+        cudart = ctypes.CDLL("libcudart.so")
+        assert cudart.cudaMemcpy(tiles.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(ptr), ctypes.c_size_t(words * 4), 2) == 0
+        tiles = tiles.reshape(-1, 64, 64)
+        k = 0
+        for ti in range(T):
+            for tj in range(ti, T):
+                blockw = np.zeros((64, 64), np.uint32)
+                r, c = want[64 * ti:64 * ti + 64, 64 * tj:64 * tj + 64].shape
+                blockw[:r, :c] = want[64 * ti:64 * ti + 64, 64 * tj:64 * tj + 64]
+                if ti == tj:
+                    blockw = np.triu(blockw, 1)
+                assert np.array_equal(tiles[k], blockw), (ti, tj)
+                k += 1
+        del load_library
