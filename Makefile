@@ -11,9 +11,9 @@ LIBDIR   := pangenomesim_b200/lib
 BINDIR   := pangenomesim_b200/bin
 OBJDIR   := build/obj
 
-LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/plan.cu $(CSRC)/kernels.cu $(CSRC)/mismatch.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp
+LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/plan.cu $(CSRC)/kernels.cu $(CSRC)/mismatch.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp $(CSRC)/expand.cpp
 LIB_HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/pgs.h
-LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/plan.o $(OBJDIR)/kernels.o $(OBJDIR)/mismatch.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o
+LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/plan.o $(OBJDIR)/kernels.o $(OBJDIR)/mismatch.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o $(OBJDIR)/expand.o
 
 all: lib cli oracle
 
@@ -30,6 +30,11 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(LIB_HDRS)
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(LIB_HDRS)
 	@mkdir -p $(OBJDIR)
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off -c $< -o $@
+
+# the host-side base expander is a plain byte loop with SIMD variants: optimise it fully
+$(OBJDIR)/expand.o: $(CSRC)/expand.cpp $(CSRC)/expand.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@
 
 $(LIBDIR)/libpgs.so: $(LIB_OBJS)
 	@mkdir -p $(LIBDIR)

@@ -187,6 +187,12 @@ int pgs_mismatch_allreduce(pgs_engine *h, uint32_t *out_host, int64_t *sites_out
  *      site s is bits 2(s%16)..2(s%16)+1 of 32-bit word s/16, A=0 C=1 G=2 T=3, padding sites 0.
  * Not part of PGS_OUT_ALL; not available with a shard layout.  pangenomesim_b200/packed.py reads it. */
 #define PGS_OUT_PACKED 64u
+/* genomeNNN.fasta and alignment.maf from PACKED rows: the rows cross PCIe 2-bit packed (a quarter
+ * of the text's bytes) and the host's cores write the text -- headers and bases -- where it has to
+ * end up (threaded, SIMD; PGS_EXPAND_THREADS overrides the thread count).  Same bytes as without
+ * the flag.  With a sink: genomeNNN.fasta arrives whole in one call per file, from worker threads
+ * (one call at a time, in no particular order across files); alignment.maf in consecutive pieces. */
+#define PGS_OUT_HOST_EXPAND 128u
 
 /* Sharded output: engines that each hold a contiguous slice of the gene table fill disjoint byte
  * ranges of the same genomeNNN.fasta / alignment.maf.  The caller creates (truncates) the files

@@ -71,6 +71,21 @@ int Engine::upload(DevBuf &b, const void *src, size_t bytes, const char *what)
 	return PGS_OK;
 }
 
+// The buffer is only replaced when it is too small; the copy is queued on the engine's stream (the
+// source is pageable: the runtime has taken its copy when the call returns).
+int Engine::upload_keep(DevBuf &b, const void *src, size_t bytes, const char *what)
+{
+	if (b.bytes < bytes || !b.p) {
+		const int rc = alloc(b, bytes, what);
+		if (rc) return rc;
+	}
+	if (bytes) {
+		const cudaError_t e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream);
+		if (e != cudaSuccess) return cuda_fail(e, what);
+	}
+	return PGS_OK;
+}
+
 int64_t Engine::device_bytes() const
 {
 	const DevBuf *all[] = {&d_rows, &d_row_base, &d_h1, &d_tab, &d_tab_off, &d_kmax, &d_dense_gid,
@@ -353,6 +368,8 @@ int pgs_set_genes(pgs_engine *h, int64_t n_genes, const int64_t *gene_id, const 
 		return e.fail(PGS_ERR_ARG, "pgs_set_genes: null table");
 	e.have_genes = e.swept = false;
 	e.sweeps_done = 0;
+	e.plan_serial++;
+	e.fmt_key = 0;
 	e.drop_graph();
 	const int rc = pgs::plan_genes(e, n_genes, gene_id, origin_node, carrier_off, carrier_genome, all_order); // plan.cu
 	if (rc) return rc;

@@ -80,6 +80,11 @@ struct Engine {
 	size_t mm_stage_bytes = 0;
 	void *comm = nullptr;       // ncclComm_t of pgs_comm_init (one engine per process), else nullptr
 	int comm_world = 1, comm_rank = 0;
+	// K3's tables and per-chunk index buffers: kept between pgs_write_outputs calls (they change with
+	// pgs_set_genes and with the caller's totals only), so that a call allocates nothing after the first
+	DevBuf d_fmt[16], d_fmt_aux_a[2], d_fmt_aux_b[2];
+	uint64_t fmt_key = 0;       // what d_fmt holds: plan serial + the spec's totals (0: nothing)
+	uint64_t plan_serial = 0;   // bumped by every pgs_set_genes
 	DevBuf d_stage[2];          // K3 staging, kept between pgs_write_outputs calls
 	char *h_stage[2] = {nullptr, nullptr}; // pinned
 	int64_t stage_bytes = 0;
@@ -95,6 +100,7 @@ struct Engine {
 	int cuda_fail(cudaError_t e, const char *what);
 	int alloc(DevBuf &b, size_t bytes, const char *what);
 	int upload(DevBuf &b, const void *src, size_t bytes, const char *what);
+	int upload_keep(DevBuf &b, const void *src, size_t bytes, const char *what); // grow-only, no synchronisation
 	int64_t device_bytes() const;
 	int64_t row_index(int32_t node, int64_t gene_index) const;
 	bool row_kept(int32_t node, int64_t gene_index) const;

@@ -11,8 +11,10 @@
 // gene ids before it, and both terms come from two small prefix tables; a MAF block is laid out
 // the same way from a per-gene block offset and a per-carrier prefix.
 #include "engine.h"
+#include "expand.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
@@ -68,7 +70,7 @@ __host__ __device__ inline int genome_name_len(int64_t genome)
 	return 6 + (d < 3 ? 3 : d);
 }
 
-__device__ inline char *put_uint(char *p, uint64_t x, int min_digits)
+__host__ __device__ inline char *put_uint(char *p, uint64_t x, int min_digits)
 {
 	int d = dec_digits(x);
 	if (d < min_digits) d = min_digits;
@@ -86,13 +88,13 @@ __device__ inline char *put_uint(char *p, uint64_t x, int min_digits)
 	return p + d;
 }
 
-__device__ inline char *put_str(char *p, const char *s)
+__host__ __device__ inline char *put_str(char *p, const char *s)
 {
 	while (*s) *p++ = *s++;
 	return p;
 }
 
-__device__ inline char *put_genome_name(char *p, int64_t genome)
+__host__ __device__ inline char *put_genome_name(char *p, int64_t genome)
 {
 	p = put_str(p, "genome");
 	if (genome < 0) return put_str(p, "ref");
@@ -164,7 +166,7 @@ struct FormatTables {
 	int64_t n_dense, blocks, L;
 };
 
-__device__ inline int64_t sparse_rank(const FormatTables &t, int32_t node, int64_t g)
+__host__ __device__ inline int64_t sparse_rank(const FormatTables &t, int32_t node, int64_t g)
 {
 	const int64_t *b = t.sp_gene + t.sp_off[node];
 	int64_t lo = 0, hi = t.sp_off[node + 1] - t.sp_off[node];
@@ -188,6 +190,43 @@ struct Record {
 	int plen, tail;      // header bytes, trailing newlines
 };
 
+// Where a record goes and what it holds, the same on the device (K3) and on the host
+// (PGS_OUT_HOST_EXPAND): offset inside its file / MAF block, the row of the store, header text.
+struct RecordInfo {
+	int64_t off; // start of the record inside genomeNNN.fasta / inside the gene's MAF block
+	int64_t row; // row of the store that holds the sequence
+	int plen, tail; // header bytes, trailing newlines
+};
+
+// record `slot` of a genome's leaf region (dense rows first, then the leaf's sparse rows); the
+// header ">genomeNNN.<gene id>\n" is written to text
+__host__ __device__ inline RecordInfo fasta_record(const FormatTables &t, int32_t genome, int64_t slot, char *text)
+{
+	const int32_t leaf = t.genome_leaf[genome];
+	int64_t g, srank;
+	if (slot < t.n_dense) {
+		g = t.dense_gene[slot];
+		srank = sparse_rank(t, leaf, g);
+	} else {
+		srank = slot - t.n_dense;
+		g = t.sp_gene[t.sp_off[leaf] + srank];
+	}
+	const int64_t k = t.dense_before[g] + srank;
+	const int name_len = genome_name_len(genome);
+	char *p = text;
+	*p++ = '>';
+	p = put_genome_name(p, genome);
+	*p++ = '.';
+	p = put_uint(p, (uint64_t)t.gene_id[g], 1);
+	*p++ = '\n';
+	RecordInfo r;
+	r.off = k * (name_len + t.L + 4) + t.dense_digits_before[g] + t.sp_digits[t.sp_off[leaf] + leaf + srank];
+	r.row = t.row_base[leaf] + slot;
+	r.plen = (int)(p - text);
+	r.tail = 1;
+	return r;
+}
+
 // ---- genomeNNN.fasta.  rows_prefix[i] = number of leaf rows of the chunk's genomes before genome
 // first_genome + i; file_off[i] = offset of that genome's file in the staging buffer.
 __device__ Record genome_fasta_record(const FormatTables &t, char *out, int32_t first_genome, int32_t n_chunk_genomes,
@@ -202,32 +241,12 @@ __device__ Record genome_fasta_record(const FormatTables &t, char *out, int32_t 
 		else
 			hi = mid - 1;
 	}
-	const int32_t genome = first_genome + lo;
-	const int64_t slot = item - rows_prefix[lo];
-	const int32_t leaf = t.genome_leaf[genome];
-	int64_t g, srank;
-	if (slot < t.n_dense) {
-		g = t.dense_gene[slot];
-		srank = sparse_rank(t, leaf, g);
-	} else {
-		srank = slot - t.n_dense;
-		g = t.sp_gene[t.sp_off[leaf] + srank];
-	}
-	const int64_t k = t.dense_before[g] + srank;
-	const int name_len = genome_name_len(genome);
-	const int64_t off = k * (name_len + t.L + 4) + t.dense_digits_before[g] +
-						t.sp_digits[t.sp_off[leaf] + leaf + srank];
-	char *p = text;
-	*p++ = '>';
-	p = put_genome_name(p, genome);
-	*p++ = '.';
-	p = put_uint(p, (uint64_t)t.gene_id[g], 1);
-	*p++ = '\n';
+	const RecordInfo ri = fasta_record(t, first_genome + lo, item - rows_prefix[lo], text);
 	Record r;
-	r.dst = out + file_off[lo] + off;
-	r.row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
-	r.plen = (int)(p - text);
-	r.tail = 1;
+	r.dst = out + file_off[lo] + ri.off;
+	r.row = reinterpret_cast<const uint32_t *>(t.rows + ri.row * t.blocks);
+	r.plen = ri.plen;
+	r.tail = ri.tail;
 	return r;
 }
 
@@ -287,32 +306,20 @@ struct MafTables {
 	int32_t n_genomes;
 };
 
-__device__ Record maf_record(const FormatTables &t, const MafTables &m, char *out, int64_t first_gene, int32_t n_chunk_genes,
-							 const int64_t *__restrict__ lines_prefix, const int64_t *__restrict__ block_off, int64_t item,
-							 char *text)
+// line j of gene g's block (0 = the reference line, which also carries the "a\n"; 1.. = carriers)
+__host__ __device__ inline RecordInfo maf_line(const FormatTables &t, const MafTables &m, int64_t g, int64_t j, int64_t lines, char *text)
 {
-	int lo = 0, hi = n_chunk_genes - 1;
-	while (lo < hi) {
-		const int mid = (lo + hi + 1) >> 1;
-		if (lines_prefix[mid] <= item)
-			lo = mid;
-		else
-			hi = mid - 1;
-	}
-	const int64_t g = first_gene + lo;
-	const int64_t j = item - lines_prefix[lo]; // 0 = reference line, 1.. = carriers
-	const int64_t lines = lines_prefix[lo + 1] - lines_prefix[lo];
 	const uint64_t gid = (uint64_t)t.gene_id[g];
 	const bool dense = t.dense_slot[g] >= 0;
 	const int idd = dec_digits(gid), ld = dec_digits((uint64_t)t.L);
 	const int64_t ref_len = 2 + 9 + 1 + idd + 3 + ld + 3 + dec_digits((uint64_t)m.ref_size) + 1 + t.L + 1;
 
-	Record r;
-	int64_t off, genome = -1, size;
+	RecordInfo r;
+	int64_t genome = -1, size;
 	if (j == 0) {
-		off = 0; // "a\n" is part of this line's prefix
+		r.off = 0; // "a\n" is part of this line's prefix
 		size = m.ref_size;
-		r.row = reinterpret_cast<const uint32_t *>(t.rows + (int64_t)t.origin_row[g] * t.blocks);
+		r.row = (int64_t)t.origin_row[g];
 	} else {
 		const int64_t c = j - 1;
 		int64_t pre;
@@ -323,11 +330,11 @@ __device__ Record maf_record(const FormatTables &t, const MafTables &m, char *ou
 			genome = m.carrier_genome[m.carrier_off[g] + c];
 			pre = m.carrier_prefix[m.carrier_off[g] + g + c];
 		}
-		off = 2 + ref_len + c * (idd + ld + t.L + 11) + pre;
+		r.off = 2 + ref_len + c * (idd + ld + t.L + 11) + pre;
 		size = t.genome_count[genome] * t.L;
 		const int32_t leaf = t.genome_leaf[genome];
 		const int64_t slot = dense ? t.dense_slot[g] : t.n_dense + sparse_rank(t, leaf, g);
-		r.row = reinterpret_cast<const uint32_t *>(t.rows + (t.row_base[leaf] + slot) * t.blocks);
+		r.row = t.row_base[leaf] + slot;
 	}
 	char *p = text;
 	if (j == 0) p = put_str(p, "a\n");
@@ -340,11 +347,63 @@ __device__ Record maf_record(const FormatTables &t, const MafTables &m, char *ou
 	p = put_str(p, " + ");
 	p = put_uint(p, (uint64_t)size, 1);
 	*p++ = ' ';
-	r.dst = out + block_off[lo] + off;
 	r.plen = (int)(p - text);
 	// the last line of a block is followed by the blank line (std::endl at pangenomesim.cxx:289)
 	r.tail = (j == lines - 1) ? 2 : 1;
 	return r;
+}
+
+// item -> (gene of the chunk, line of its block)
+__device__ inline int maf_item_gene(const int64_t *__restrict__ lines_prefix, int32_t n_chunk_genes, int64_t item)
+{
+	int lo = 0, hi = n_chunk_genes - 1;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (lines_prefix[mid] <= item)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	return lo;
+}
+
+__device__ Record maf_record(const FormatTables &t, const MafTables &m, char *out, int64_t first_gene, int32_t n_chunk_genes,
+							 const int64_t *__restrict__ lines_prefix, const int64_t *__restrict__ block_off, int64_t item,
+							 char *text)
+{
+	const int lo = maf_item_gene(lines_prefix, n_chunk_genes, item);
+	const RecordInfo ri = maf_line(t, m, first_gene + lo, item - lines_prefix[lo], lines_prefix[lo + 1] - lines_prefix[lo], text);
+	Record r;
+	r.dst = out + block_off[lo] + ri.off;
+	r.row = reinterpret_cast<const uint32_t *>(t.rows + ri.row * t.blocks);
+	r.plen = ri.plen;
+	r.tail = ri.tail;
+	return r;
+}
+
+// PGS_OUT_HOST_EXPAND: the rows of a MAF chunk's lines, gathered in line order (one warp per row);
+// the host writes the headers and expands the bases.
+__global__ void __launch_bounds__(kFmtWarps * 32)
+k3_gather_maf_rows(const __grid_constant__ FormatTables t, const __grid_constant__ MafTables m, uint4 *__restrict__ out,
+				   int64_t first_gene, int32_t n_chunk_genes, const int64_t *__restrict__ lines_prefix)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t item = (int64_t)blockIdx.x * kFmtWarps + warp, total = lines_prefix[n_chunk_genes];
+	if (item >= total) return;
+	const int lo = maf_item_gene(lines_prefix, n_chunk_genes, item);
+	const int64_t g = first_gene + lo, j = item - lines_prefix[lo];
+	int64_t row;
+	if (j == 0) {
+		row = (int64_t)t.origin_row[g];
+	} else {
+		const bool dense = t.dense_slot[g] >= 0;
+		const int64_t genome = dense ? m.all_order[j - 1] : m.carrier_genome[m.carrier_off[g] + j - 1];
+		const int32_t leaf = t.genome_leaf[genome];
+		row = t.row_base[leaf] + (dense ? t.dense_slot[g] : t.n_dense + sparse_rank(t, leaf, g));
+	}
+	const uint4 *src = t.rows + row * t.blocks;
+	uint4 *dst = out + item * t.blocks;
+	for (int64_t b = lane; b < t.blocks; b += 32) dst[b] = __ldg(src + b);
 }
 
 __global__ void __launch_bounds__(kFmtWarps * 32, 8)
@@ -563,16 +622,23 @@ struct Writer {
 			const int64_t now = std::min(kSlice, len - at);
 			const int fd = maf_fd;
 			if (window) {
-				pool->submit([this, path, window, data, at, now] {
+				pool->submit([this, fd, path, window, data, at, now, offset] {
+					// Storing into a page the file system cannot back raises SIGBUS: the pages are
+					// populated first (an error instead of a signal); where that is not possible --
+					// no MADV_POPULATE_WRITE, or it fails for any reason -- the slice goes through pwrite.
+					bool populated = false;
 #ifdef MADV_POPULATE_WRITE
 					const uintptr_t page = (uintptr_t)::sysconf(_SC_PAGESIZE);
 					const uintptr_t b = (uintptr_t)(window + at) & ~(page - 1);
 					const uintptr_t en = ((uintptr_t)(window + at + now) + page - 1) & ~(page - 1);
-					if (::madvise(reinterpret_cast<void *>(b), (size_t)(en - b), MADV_POPULATE_WRITE) != 0 &&
-						(errno == EFAULT || errno == ENOMEM))
-						return fail(path + ": cannot allocate file pages (file system full?)");
+					populated = ::madvise(reinterpret_cast<void *>(b), (size_t)(en - b), MADV_POPULATE_WRITE) == 0;
 #endif
-					std::memcpy(window + at, data + at, (size_t)now);
+					if (populated) {
+						std::memcpy(window + at, data + at, (size_t)now);
+						return;
+					}
+					std::string msg;
+					if (!write_range(fd, data + at, now, offset + at, msg)) fail(path + ": " + msg);
 				});
 				continue;
 			}
@@ -751,28 +817,46 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	auto &maf_bytes = plan.maf_bytes;
 	const int64_t ref_size = plan.ref_size;
 
-	DevBuf d_genome_leaf, d_genome_count, d_sp_off, d_sp_gene, d_sp_digits, d_dense_slot, d_dense_gene,
-		d_dense_before, d_dense_digits_before, d_gene_id, d_origin_row, d_carrier_off, d_carrier_genome,
-		d_carrier_prefix, d_all_order, d_all_prefix;
+	// the tables live in the engine between calls: uploaded again only when the plan or the caller's
+	// totals (shard layout, number of reference genes) have changed
+	DevBuf &d_genome_leaf = e.d_fmt[0], &d_genome_count = e.d_fmt[1], &d_sp_off = e.d_fmt[2], &d_sp_gene = e.d_fmt[3],
+		   &d_sp_digits = e.d_fmt[4], &d_dense_slot = e.d_fmt[5], &d_dense_gene = e.d_fmt[6], &d_dense_before = e.d_fmt[7],
+		   &d_dense_digits_before = e.d_fmt[8], &d_gene_id = e.d_fmt[9], &d_origin_row = e.d_fmt[10], &d_carrier_off = e.d_fmt[11],
+		   &d_carrier_genome = e.d_fmt[12], &d_carrier_prefix = e.d_fmt[13], &d_all_order = e.d_fmt[14], &d_all_prefix = e.d_fmt[15];
+	uint64_t key = 1469598103934665603ull; // FNV-1a over what the tables depend on besides the plan
+	auto mix = [&](uint64_t v) {
+		for (int i = 0; i < 8; i++) {
+			key ^= (v >> (8 * i)) & 0xFF;
+			key *= 1099511628211ull;
+		}
+	};
+	mix(e.plan_serial);
+	mix((uint64_t)plan.ref_size);
+	for (int64_t c : plan.genome_count) mix((uint64_t)c);
+	if (key == 0) key = 1;
+	if (e.fmt_key != key) {
+		e.fmt_key = 0;
 #define UP(buf, vec) \
-	if ((rc = e.upload(buf, (vec).data(), sizeof((vec)[0]) * (vec).size(), #vec))) return rc
-	UP(d_genome_leaf, e.genome_leaf);
-	UP(d_genome_count, plan.genome_count);
-	UP(d_sp_off, e.sp_off);
-	UP(d_sp_gene, e.sp_gene);
-	UP(d_sp_digits, sp_digits);
-	UP(d_dense_slot, e.dense_slot);
-	UP(d_dense_gene, e.dense_gene);
-	UP(d_dense_before, dense_before);
-	UP(d_dense_digits_before, dense_digits_before);
-	UP(d_gene_id, e.gene_id);
-	UP(d_origin_row, origin_row);
-	UP(d_carrier_off, e.carrier_off);
-	UP(d_carrier_genome, e.carrier_genome);
-	UP(d_carrier_prefix, carrier_prefix);
-	UP(d_all_order, e.all_order);
-	UP(d_all_prefix, all_prefix);
+	if ((rc = e.upload_keep(buf, (vec).data(), sizeof((vec)[0]) * (vec).size(), #vec))) return rc
+		UP(d_genome_leaf, e.genome_leaf);
+		UP(d_genome_count, plan.genome_count);
+		UP(d_sp_off, e.sp_off);
+		UP(d_sp_gene, e.sp_gene);
+		UP(d_sp_digits, sp_digits);
+		UP(d_dense_slot, e.dense_slot);
+		UP(d_dense_gene, e.dense_gene);
+		UP(d_dense_before, dense_before);
+		UP(d_dense_digits_before, dense_digits_before);
+		UP(d_gene_id, e.gene_id);
+		UP(d_origin_row, origin_row);
+		UP(d_carrier_off, e.carrier_off);
+		UP(d_carrier_genome, e.carrier_genome);
+		UP(d_carrier_prefix, carrier_prefix);
+		UP(d_all_order, e.all_order);
+		UP(d_all_prefix, all_prefix);
 #undef UP
+		e.fmt_key = key;
+	}
 	FormatTables t{};
 	t.rows = e.tables.rows;
 	t.row_base = e.d_row_base.as<int64_t>();
@@ -823,7 +907,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	stage = (stage + 255) & ~(int64_t)255;
 	// staging buffers (2 device + 2 pinned) are kept by the engine between calls: cudaHostAlloc of
 	// tens of megabytes costs milliseconds each time
-	DevBuf d_aux_a[2], d_aux_b[2];
+	DevBuf *const d_aux_a = e.d_fmt_aux_a, *const d_aux_b = e.d_fmt_aux_b;
 	DevBuf *d_stage = e.d_stage;
 	struct HostView {
 		char *p;
@@ -875,8 +959,8 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	// would synchronise the device, inside the pipeline)
 	const size_t aux_entries = (size_t)std::max<int64_t>(65537, spec->n_ref_core + spec->n_ref_acc + 1);
 	for (int i = 0; i < 2; i++) {
-		if ((rc = e.alloc(d_aux_a[i], aux_entries * sizeof(int64_t), "format aux")) ||
-			(rc = e.alloc(d_aux_b[i], aux_entries * sizeof(int64_t), "format aux"))) {
+		if ((d_aux_a[i].bytes < aux_entries * sizeof(int64_t) && (rc = e.alloc(d_aux_a[i], aux_entries * sizeof(int64_t), "format aux"))) ||
+			(d_aux_b[i].bytes < aux_entries * sizeof(int64_t) && (rc = e.alloc(d_aux_b[i], aux_entries * sizeof(int64_t), "format aux")))) {
 			cleanup();
 			return rc;
 		}
@@ -918,17 +1002,29 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		const char *src;
 		int64_t dst_off, bytes;
 	};
+	// every CUDA call of the pipeline is checked: the first failure ends the call with its message
+	cudaError_t pipe_err = cudaSuccess;
+	auto ck = [&](cudaError_t c) {
+		if (c != cudaSuccess && pipe_err == cudaSuccess) pipe_err = c;
+	};
+	auto pipe_ok = [&]() -> bool {
+		if (pipe_err == cudaSuccess) return true;
+		if (w.error.empty()) w.error = std::string("output pipeline: ") + cudaGetErrorName(pipe_err) + " (" + cudaGetErrorString(pipe_err) + ")";
+		return false;
+	};
 	auto submit = [&](int s, int64_t bytes, std::vector<FilePiece> &&pieces, const std::vector<Segment> *direct = nullptr) -> bool {
-		if (!direct) cudaEventRecord(k1, e.stream);
-		cudaEventRecord(formatted[s], e.stream);
-		cudaStreamWaitEvent(copy_stream, formatted[s], 0);
+		if (!direct) ck(cudaEventRecord(k1, e.stream));
+		ck(cudaGetLastError()); // the chunk's kernel launches
+		ck(cudaEventRecord(formatted[s], e.stream));
+		ck(cudaStreamWaitEvent(copy_stream, formatted[s], 0));
 		if (direct) {
 			for (const Segment &sg : *direct)
-				cudaMemcpyAsync(h_stage[s].p + sg.dst_off, sg.src, (size_t)sg.bytes, cudaMemcpyDeviceToHost, copy_stream);
+				ck(cudaMemcpyAsync(h_stage[s].p + sg.dst_off, sg.src, (size_t)sg.bytes, cudaMemcpyDeviceToHost, copy_stream));
 		} else {
-			cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream);
+			ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream));
 		}
-		cudaEventRecord(copied[s], copy_stream);
+		ck(cudaEventRecord(copied[s], copy_stream));
+		if (!pipe_ok()) return false;
 		pending[s].live = true;
 		pending[s].pieces = std::move(pieces);
 		pending[s].bytes = bytes;
@@ -942,7 +1038,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	};
 	auto begin_chunk = [&](int s) {
 		// the staging buffer of slot s is free once its previous copy finished
-		cudaStreamWaitEvent(e.stream, copied[s], 0);
+		ck(cudaStreamWaitEvent(e.stream, copied[s], 0));
 	};
 	auto fail_out = [&](int code, const std::string &msg) {
 		cudaStreamSynchronize(e.stream);
@@ -951,7 +1047,71 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		return e.fail(code, msg);
 	};
 	// make cudaStreamWaitEvent on never-recorded events harmless
-	for (int i = 0; i < 2; i++) cudaEventRecord(copied[i], copy_stream);
+	for (int i = 0; i < 2; i++) ck(cudaEventRecord(copied[i], copy_stream));
+
+	// ---- PGS_OUT_HOST_EXPAND: genomeNNN.fasta / alignment.maf from PACKED rows shipped over PCIe
+	// (a quarter of the text's bytes) and expanded by the host's cores -- same bytes as K3's.
+	const bool host_expand = (spec->what & PGS_OUT_HOST_EXPAND) != 0;
+	FormatTables ht = t; // the same tables with host pointers: the record layout code is shared
+	MafTables hm = mt;
+	ht.rows = nullptr;
+	ht.row_base = e.row_base.data();
+	ht.genome_leaf = e.genome_leaf.data();
+	ht.genome_count = plan.genome_count.data();
+	ht.sp_off = e.sp_off.data();
+	ht.sp_gene = e.sp_gene.data();
+	ht.sp_digits = sp_digits.data();
+	ht.dense_slot = e.dense_slot.data();
+	ht.dense_gene = e.dense_gene.data();
+	ht.dense_before = dense_before.data();
+	ht.dense_digits_before = dense_digits_before.data();
+	ht.gene_id = e.gene_id.data();
+	ht.origin_row = origin_row.data();
+	hm.carrier_off = e.carrier_off.data();
+	hm.carrier_genome = e.carrier_genome.data();
+	hm.carrier_prefix = carrier_prefix.data();
+	hm.all_order = e.all_order.data();
+	hm.all_prefix = all_prefix.data();
+	std::unique_ptr<WritePool> xpool;
+	std::atomic<int64_t> hx_files{0}, hx_bytes{0};
+	std::mutex hx_sink_mutex;
+	const int64_t row_bytes = e.blocks * 16;
+	if (host_expand) {
+		unsigned nthreads = std::max(2u, std::thread::hardware_concurrency());
+		if (const char *v = std::getenv("PGS_EXPAND_THREADS")) nthreads = (unsigned)std::max(1, std::atoi(v)); // tuning knob
+		xpool.reset(new WritePool(std::min(nthreads, 128u)));
+	}
+	// a finished piece of a file, from a worker thread
+	auto hx_deliver = [&](const std::string &name, int64_t offset, const char *data, int64_t len, bool first_piece) {
+		if (first_piece) hx_files++;
+		hx_bytes += len;
+		if (spec->what & PGS_OUT_DISCARD) return;
+		if (spec->sink) {
+			std::lock_guard<std::mutex> l(hx_sink_mutex);
+			if (spec->sink(spec->sink_user, name.c_str(), offset, data, len) != 0) w.fail("sink aborted at " + name);
+			return;
+		}
+		const std::string path = std::string(spec->out_dir) + "/" + name;
+		const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | ((offset == 0 && !shard) ? O_TRUNC : 0), 0644);
+		if (fd < 0) return w.fail(path + ": " + std::strerror(errno));
+		std::string msg;
+		if (!Writer::write_range(fd, data, len, offset, msg)) w.fail(path + ": " + msg);
+		::close(fd);
+	};
+	// a worker thread's own buffer, kept between tasks (no zero-filling, no reallocation per file)
+	auto thread_buffer = [](size_t bytes) -> char * {
+		thread_local std::unique_ptr<char[]> buf;
+		thread_local size_t cap = 0;
+		if (cap < bytes) {
+			buf.reset(new char[bytes + bytes / 8]);
+			cap = bytes + bytes / 8;
+		}
+		return buf.get();
+	};
+	if (host_expand) { // the copies wait for the sweep (and whatever else is queued on the engine's stream)
+		ck(cudaEventRecord(formatted[0], e.stream));
+		ck(cudaStreamWaitEvent(copy_stream, formatted[0], 0));
+	}
 
 	// ---- ref.fasta, core.fasta, accessory.fasta
 	struct RefFile {
@@ -973,14 +1133,14 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			total += 9 + id_digits[rf.genes[i]] + L + 4;
 		}
 		begin_chunk(slot);
-		cudaEventRecord(k0, e.stream);
+		ck(cudaEventRecord(k0, e.stream));
 		if (!rf.genes.empty()) {
 			if ((rc = h2d(d_aux_a[slot], rf.genes)) || (rc = h2d(d_aux_b[slot], offs))) {
 				cleanup();
 				return rc;
 			}
 			const int64_t nrec = (int64_t)rf.genes.size();
-			cudaEventRecord(k0, e.stream);
+			ck(cudaEventRecord(k0, e.stream));
 			k3_ref_fasta<<<(unsigned)((nrec + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
 				t, d_stage[slot].as<char>(), d_aux_a[slot].as<int64_t>(), d_aux_b[slot].as<int64_t>(), nrec);
 			records += nrec;
@@ -990,8 +1150,90 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		slot ^= 1;
 	}
 
+	// ---- genomeNNN.fasta, host-expanded: a genome's rows lie together in the store (its leaf's
+	// region), so a chunk is a handful of plain copies; one task per genome writes the whole file
+	if ((spec->what & PGS_OUT_GENOMES) && host_expand) {
+		struct Chunk {
+			int32_t i = 0, j = 0;
+			int slot = 0;
+			std::vector<int64_t> region_off;
+		};
+		const char *store = reinterpret_cast<const char *>(e.tables.rows);
+		auto issue = [&](int32_t i, int s) {
+			Chunk c;
+			c.i = i;
+			c.slot = s;
+			int64_t bytes = 0;
+			int32_t j = i;
+			const char *run_src = nullptr;
+			int64_t run_dst = 0, run_len = 0;
+			auto flush = [&]() {
+				if (run_len) ck(cudaMemcpyAsync(h_stage[s].p + run_dst, run_src, (size_t)run_len, cudaMemcpyDeviceToHost, copy_stream));
+				run_len = 0;
+			};
+			while (j < n) {
+				const int64_t gb = genome_rows[j] * row_bytes;
+				if (bytes + gb > stage && j > i) break;
+				const char *src = store + e.row_base[e.genome_leaf[j]] * row_bytes;
+				c.region_off.push_back(bytes);
+				if (run_len && run_src + run_len == src) {
+					run_len += gb; // neighbours in the store: one copy
+				} else {
+					flush();
+					run_src = src;
+					run_dst = bytes;
+					run_len = gb;
+				}
+				bytes += gb;
+				j++;
+			}
+			flush();
+			ck(cudaEventRecord(copied[s], copy_stream));
+			c.j = j;
+			return c;
+		};
+		Chunk cur = issue(0, slot);
+		while (cur.i < n) {
+			Chunk next;
+			next.i = n;
+			if (cur.j < n) {
+				xpool->wait_all(); // the tasks that read the other pinned buffer are done
+				next = issue(cur.j, cur.slot ^ 1);
+			}
+			ck(cudaEventSynchronize(copied[cur.slot]));
+			if (!pipe_ok()) return fail_out(PGS_ERR_CUDA, w.error);
+			for (int32_t g = cur.i; g < cur.j; g++) {
+				const char *region = h_stage[cur.slot].p + cur.region_off[g - cur.i];
+				xpool->submit([&, g, region] {
+					const int64_t bytes = genome_bytes[g], nrows = genome_rows[g], L = ht.L;
+					char *buf = thread_buffer((size_t)bytes);
+					char text[64];
+					for (int64_t sl = 0; sl < nrows; sl++) {
+						const RecordInfo ri = fasta_record(ht, g, sl, text);
+						char *d = buf + ri.off;
+						std::memcpy(d, text, (size_t)ri.plen);
+						expand_bases(region + sl * row_bytes, L, d + ri.plen);
+						d[ri.plen + L] = '\n';
+					}
+					char name[64];
+					const int nl = format_genome_name(g, name, sizeof name);
+					const int64_t at = shard ? shard->genome_offset[g] : 0;
+					hx_deliver(std::string(name, (size_t)nl) + ".fasta", at, buf, bytes, at == 0);
+				});
+			}
+			for (int32_t g = cur.i; g < cur.j; g++) records += genome_rows[g];
+			cur = std::move(next);
+		}
+		xpool->wait_all();
+		slot = 0;
+		{
+			std::lock_guard<std::mutex> l(w.err_mutex);
+			if (!w.error.empty()) return fail_out(PGS_ERR_IO, w.error);
+		}
+	}
+
 	// ---- genomeNNN.fasta
-	if (spec->what & PGS_OUT_GENOMES) {
+	if ((spec->what & PGS_OUT_GENOMES) && !host_expand) {
 		int32_t i = 0;
 		while (i < n) {
 			int32_t j = i;
@@ -1013,7 +1255,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				return rc;
 			}
 			const int64_t items = rows_prefix.back();
-			cudaEventRecord(k0, e.stream);
+			ck(cudaEventRecord(k0, e.stream));
 			if (items > 0)
 				k3_genome_fasta<<<(unsigned)((items + kRecPerCta - 1) / kRecPerCta), kFmtWarps * 32, 0, e.stream>>>(
 					t, d_stage[slot].as<char>(), i, j - i, d_aux_a[slot].as<int64_t>(), d_aux_b[slot].as<int64_t>());
@@ -1024,8 +1266,211 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		}
 	}
 
+	// ---- alignment.maf, host-expanded: a kernel gathers the rows of a chunk's lines in line order,
+	// the host writes the headers and expands the bases -- into the mapped file, into a buffer handed
+	// to the sink, or (PGS_OUT_DISCARD) block by block into the workers' own buffers
+	if ((spec->what & PGS_OUT_MAF) && host_expand) {
+		const bool with_header = !shard || shard->maf_offset == 0;
+		const int64_t hlen = with_header ? (int64_t)sizeof(kMafHeader) - 1 : 0;
+		const int64_t file_begin = shard ? shard->maf_offset : 0;
+		int64_t maf_total = hlen;
+		for (auto b : maf_bytes) maf_total += b;
+		const bool to_file = !(spec->what & PGS_OUT_DISCARD) && !spec->sink;
+		const bool to_sink = !(spec->what & PGS_OUT_DISCARD) && spec->sink;
+		int fd = -1;
+		const std::string path = to_file ? std::string(spec->out_dir) + "/alignment.maf" : std::string();
+		if (to_file) {
+			fd = ::open(path.c_str(), O_RDWR | O_CREAT | (shard ? 0 : O_TRUNC), 0644);
+			if (fd < 0) return fail_out(PGS_ERR_IO, path + ": " + std::strerror(errno));
+			// one engine: the file gets its final size here; several: the caller has sized it
+			if (!shard && ::ftruncate(fd, (off_t)maf_total) != 0) {
+				const std::string msg = path + ": " + std::strerror(errno);
+				::close(fd);
+				return fail_out(PGS_ERR_IO, msg);
+			}
+		}
+		// a file that is not large enough yet (several engines, not sized by the caller) is never
+		// resized here -- another engine may be writing to it -- and never mapped: pwrite extends it
+		bool can_map = to_file;
+		if (to_file && shard) {
+			struct stat sb;
+			can_map = ::fstat(fd, &sb) == 0 && (int64_t)sb.st_size >= file_begin + maf_total;
+		}
+		if (const char *v = std::getenv("PGS_WRITE_MMAP")) can_map = can_map && std::atoi(v) != 0; // tuning knob
+		int64_t packed_cap = std::min<int64_t>(stage, (int64_t)64 << 20); // 64 MB of rows = ~260 MB of text per chunk
+		for (int64_t g = 0; g < G; g++) packed_cap = std::max(packed_cap, maf_lines[g] * row_bytes);
+		if (packed_cap > stage) {
+			if (fd >= 0) ::close(fd);
+			return fail_out(PGS_ERR_NOMEM, "pgs_write_outputs: a gene's rows do not fit the staging buffer");
+		}
+		struct Chunk {
+			int64_t g = 0, g2 = 0, bytes = 0, file_pos = 0;
+			int slot = 0;
+			bool first = false;
+			std::vector<int64_t> lines_prefix, block_off;
+			char *window = nullptr; // where the chunk's text goes (mapped file / sink buffer), nullptr: workers' own buffers
+			void *map = nullptr;
+			size_t map_len = 0;
+		};
+		std::vector<char> sink_buf[2];
+		auto issue = [&](int64_t g, int s, bool first, int64_t file_pos) {
+			std::unique_ptr<Chunk> cp(new Chunk()); // on the heap: the chunk's tasks keep a pointer to it
+			Chunk &c = *cp;
+			c.g = g;
+			c.slot = s;
+			c.first = first;
+			c.file_pos = file_pos;
+			c.bytes = first ? hlen : 0;
+			c.lines_prefix.push_back(0);
+			int64_t g2 = g, packed = 0;
+			while (g2 < G && packed + maf_lines[g2] * row_bytes <= packed_cap && (g2 - g) < 65536) {
+				c.block_off.push_back(c.bytes);
+				c.bytes += maf_bytes[g2];
+				packed += maf_lines[g2] * row_bytes;
+				c.lines_prefix.push_back(c.lines_prefix.back() + maf_lines[g2]);
+				g2++;
+			}
+			c.g2 = g2;
+			const int64_t items = c.lines_prefix.back();
+			begin_chunk(s);
+			if (items > 0) {
+				if (h2d(d_aux_a[s], c.lines_prefix)) ck(cudaErrorUnknown);
+				ck(cudaEventRecord(k0, e.stream));
+				k3_gather_maf_rows<<<(unsigned)((items + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
+					t, mt, d_stage[s].as<uint4>(), g, (int32_t)(g2 - g), d_aux_a[s].as<int64_t>());
+				ck(cudaGetLastError());
+				ck(cudaEventRecord(k1, e.stream));
+			}
+			ck(cudaEventRecord(formatted[s], e.stream));
+			ck(cudaStreamWaitEvent(copy_stream, formatted[s], 0));
+			if (items > 0) ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)(items * row_bytes), cudaMemcpyDeviceToHost, copy_stream));
+			ck(cudaEventRecord(copied[s], copy_stream));
+			return cp;
+		};
+		auto finish_chunk = [&](Chunk &c) { // all of the chunk's tasks are done
+			if (c.map) ::munmap(c.map, c.map_len);
+			c.map = nullptr;
+			if (c.first && with_header) hx_files++;
+			if (to_sink && c.bytes > 0) {
+				if (spec->sink(spec->sink_user, "alignment.maf", c.file_pos, c.window, c.bytes) != 0) w.fail("sink aborted at alignment.maf");
+				hx_bytes += c.bytes;
+			}
+		};
+		std::unique_ptr<Chunk> cur = issue(0, slot, true, file_begin), prev;
+		for (;;) {
+			std::unique_ptr<Chunk> next;
+			const bool more = cur->g2 < G;
+			if (more || prev) xpool->wait_all(); // the tasks that read the other pinned buffer are done
+			if (prev) finish_chunk(*prev);
+			prev.reset();
+			if (more) next = issue(cur->g2, cur->slot ^ 1, false, cur->file_pos + cur->bytes);
+			ck(cudaEventSynchronize(copied[cur->slot]));
+			if (cur->lines_prefix.back() > 0 && !more && cudaEventSynchronize(k1) == cudaSuccess) {
+				float ms = 0; // (the gather kernels are a few microseconds each: the last one stands for the call's K3 time)
+				if (cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) device_ms += ms;
+			}
+			if (!pipe_ok()) {
+				if (fd >= 0) ::close(fd);
+				return fail_out(PGS_ERR_CUDA, w.error);
+			}
+			// where the text goes
+			if (can_map && cur->bytes > 0) {
+				const int64_t page = (int64_t)::sysconf(_SC_PAGESIZE);
+				const int64_t map_start = cur->file_pos & ~(page - 1);
+				cur->map_len = (size_t)(cur->file_pos + cur->bytes - map_start);
+				cur->map = ::mmap(nullptr, cur->map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_start);
+				if (cur->map == MAP_FAILED) {
+					const std::string msg = path + ": mmap: " + std::strerror(errno);
+					cur->map = nullptr;
+					::close(fd);
+					xpool->wait_all();
+					return fail_out(PGS_ERR_IO, msg);
+				}
+				cur->window = static_cast<char *>(cur->map) + (cur->file_pos - map_start);
+			} else if (to_sink) {
+				sink_buf[cur->slot].resize((size_t)cur->bytes);
+				cur->window = sink_buf[cur->slot].data();
+			}
+			if (cur->first && hlen > 0) {
+				if (cur->window) {
+					std::memcpy(cur->window, kMafHeader, (size_t)hlen);
+				} else if (to_file) {
+					std::string msg;
+					if (!Writer::write_range(fd, kMafHeader, hlen, cur->file_pos, msg)) w.fail(path + ": " + msg);
+				}
+				if (!to_sink) hx_bytes += hlen;
+			}
+			// tasks: runs of at most 256 lines of one gene's block
+			const Chunk *cp = cur.get();
+			for (int64_t k = 0; k < cur->g2 - cur->g; k++) {
+				const int64_t lines = cur->lines_prefix[k + 1] - cur->lines_prefix[k];
+				for (int64_t j0 = 0; j0 < lines; j0 += 256) {
+					const int64_t j1 = std::min(lines, j0 + 256);
+					xpool->submit([&, cp, k, lines, j0, j1] {
+						const int64_t g = cp->g + k, L = ht.L;
+						const char *rows_in = h_stage[cp->slot].p + (cp->lines_prefix[k] + j0) * row_bytes;
+						char text[96];
+						// line offsets grow with j: the run [j0, j1) is one contiguous range of the block
+						const int64_t run_begin = maf_line(ht, hm, g, j0, lines, text).off;
+						int64_t run_end;
+						{
+							const RecordInfo last = maf_line(ht, hm, g, j1 - 1, lines, text);
+							run_end = last.off + last.plen + L + last.tail;
+						}
+						// dst of block offset x = base + (x - base_off)
+						char *base = cp->window ? cp->window + cp->block_off[k] : nullptr;
+						int64_t base_off = 0;
+						bool spill = to_file && !cp->map; // the run is built in the worker's own buffer and written with pwrite
+						if (cp->map) { // pages of a mapped file are populated before they are stored to (full disk: an error, not SIGBUS)
+							bool populated = false;
+#ifdef MADV_POPULATE_WRITE
+							const uintptr_t page = (uintptr_t)::sysconf(_SC_PAGESIZE);
+							const uintptr_t b = (uintptr_t)(base + run_begin) & ~(page - 1);
+							const uintptr_t en = ((uintptr_t)(base + run_end) + page - 1) & ~(page - 1);
+							populated = ::madvise(reinterpret_cast<void *>(b), (size_t)(en - b), MADV_POPULATE_WRITE) == 0;
+#endif
+							spill = !populated;
+						}
+						if (!base || spill) {
+							base = thread_buffer((size_t)(run_end - run_begin));
+							base_off = run_begin;
+						}
+						for (int64_t j = j0; j < j1; j++) {
+							const RecordInfo ri = maf_line(ht, hm, g, j, lines, text);
+							char *d = base + (ri.off - base_off);
+							std::memcpy(d, text, (size_t)ri.plen);
+							expand_bases(rows_in + (j - j0) * row_bytes, L, d + ri.plen);
+							d[ri.plen + L] = '\n';
+							if (ri.tail == 2) d[ri.plen + L + 1] = '\n';
+						}
+						if (!to_sink) hx_bytes += run_end - run_begin;
+						if (spill) {
+							std::string msg;
+							if (!Writer::write_range(fd, base, run_end - run_begin, cp->file_pos + cp->block_off[k] + run_begin, msg))
+								w.fail(path + ": " + msg);
+						}
+					});
+				}
+			}
+			records += cur->lines_prefix.back();
+			if (!more) {
+				xpool->wait_all();
+				finish_chunk(*cur);
+				break;
+			}
+			prev = std::move(cur);
+			cur = std::move(next);
+		}
+		if (fd >= 0) ::close(fd);
+		slot = 0;
+		{
+			std::lock_guard<std::mutex> l(w.err_mutex);
+			if (!w.error.empty()) return fail_out(PGS_ERR_IO, w.error);
+		}
+	}
+
 	// ---- alignment.maf
-	if (spec->what & PGS_OUT_MAF) {
+	if ((spec->what & PGS_OUT_MAF) && !host_expand) {
 		const char *header = kMafHeader;
 		const bool with_header = !shard || shard->maf_offset == 0;
 		const int64_t hlen = with_header ? (int64_t)sizeof(kMafHeader) - 1 : 0;
@@ -1051,13 +1496,13 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				}
 			}
 			const int64_t items = lines_prefix.back();
-			cudaEventRecord(k0, e.stream);
+			ck(cudaEventRecord(k0, e.stream));
 			if (items > 0) {
 				if ((rc = h2d(d_aux_a[slot], lines_prefix)) || (rc = h2d(d_aux_b[slot], block_off))) {
 					cleanup();
 					return rc;
 				}
-				cudaEventRecord(k0, e.stream);
+				ck(cudaEventRecord(k0, e.stream));
 				k3_maf<<<(unsigned)((items + kRecPerCta - 1) / kRecPerCta), kFmtWarps * 32, 0, e.stream>>>(
 					t, mt, d_stage[slot].as<char>(), g, (int32_t)(g2 - g), d_aux_a[slot].as<int64_t>(),
 					d_aux_b[slot].as<int64_t>());
@@ -1148,6 +1593,8 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	w.close_file();
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_write_outputs");
 	e.format_ms = device_ms;
+	w.rep.files += hx_files.load();
+	w.rep.bytes += hx_bytes.load();
 	if (report) {
 		*report = w.rep;
 		report->records = records;

@@ -11,8 +11,9 @@
 //                     sites per word, interleaved (lo, hi) per 32-site group.  Done once per column
 //                     chunk, so the pair kernel's staging is a plain asynchronous copy.
 //   k2_mismatch_tiles CTA = 64 x 64 tile of genome pairs (upper triangle only), 4 x 4 pairs per
-//                     thread; chunks of 512 sites staged with cp.async, double buffered; per pair
-//                     and 32 sites  mask = (lo_i ^ lo_j) | (hi_i ^ hi_j);  count += popc(mask).
+//                     thread; chunks of 384 sites staged with cp.async, double buffered; per pair
+//                     and 32 sites  mask = (lo_i ^ lo_j) | (hi_i ^ hi_j), three masks through a
+//                     carry-save adder, count += popc(sum) + 2 popc(carry).
 //   output            upper-triangular 64 x 64 tiles, packed: n = 50 000 needs 5 GB instead of the
 //                     10 GB square, and a partial result is ONE contiguous buffer for the all-reduce.
 #include "engine.h"
@@ -28,10 +29,10 @@
 namespace pgs {
 
 constexpr int kMmTile = 64;     // genomes per tile side
-constexpr int kMmGroups = 16;   // 32-site groups per staged chunk
-constexpr int kMmRowWords = 36; // shared-memory row stride in words: 16 groups x (lo, hi) + 4 of padding
-                                // (16-byte aligned rows; 16 rows at this stride start in banks 0, 4, 8 ...:
-                                // a warp's 128-bit reads take the minimum of two wavefronts)
+constexpr int kMmGroups = 12;   // 32-site groups per staged chunk (a multiple of three: see the adder below)
+constexpr int kMmRowWords = 28; // shared-memory row stride in words: 12 groups x (lo, hi) + 4 of padding
+                                // (16-byte aligned rows; 8 consecutive rows start in banks 0, 28, 24, ... 4:
+                                // the 16 rows a warp reads 64 bits of take the minimum number of wavefronts)
 
 // even bits of x -> low 16 bits
 __device__ __forceinline__ uint32_t even_bits(uint32_t x)
@@ -85,8 +86,12 @@ __host__ __device__ inline int64_t tri_row_start(int64_t tiles, int64_t ti)
 	return ti * tiles - ti * (ti - 1) / 2;
 }
 
-// `one` is 1: the adds are written as multiply-adds so that they issue on the FMA pipe (IMAD) and
-// leave the ALU pipe -- the bound of this kernel -- to XOR / LOP3 / POPC.
+// Where the time goes (ncu, B200): POPC issues on the XU pipe at 16 lanes per clock per SM, a
+// quarter of the ALU pipe's 64 -- one POPC per mask made XU the bound (88 % busy, ALU 47 %).  So
+// three masks go through a carry-save adder first (sum = a ^ b ^ c, carry = majority: two LOP3) and
+// only sum and carry are counted: per three masks 8 ALU instructions (16 pipe cycles per warp) and
+// 2 POPC (16 XU cycles) -- the two pipes are level; a deeper adder tree would only load ALU more.
+// `one` is 1: the adds are written as multiply-adds so that they issue on the FMA pipe (IMAD).
 __global__ void __launch_bounds__(256, 2)
 k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_groups, int64_t groups_per_split,
 				  uint32_t *__restrict__ tiles_out, uint32_t one)
@@ -113,13 +118,13 @@ k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_gro
 	const int64_t g_end = min(g_begin + groups_per_split, chunk_groups);
 	const int64_t n_stages = (g_end - g_begin + kMmGroups - 1) / kMmGroups;
 
-	// stage s: 2 sides x 64 rows x 128 bytes = 1024 pieces of 16 bytes (two groups), 4 per thread
+	// stage s: 2 sides x 64 rows x 96 bytes = 768 pieces of 16 bytes (two groups), 3 per thread
 	auto issue = [&](int64_t s, int buf) {
 		const int64_t g0 = g_begin + s * kMmGroups;
 #pragma unroll
-		for (int q = 0; q < 4; q++) {
+		for (int q = 0; q < 3; q++) {
 			const int e = threadIdx.x + 256 * q;
-			const int side = e >> 9, row = (e >> 3) & 63, piece = e & 7;
+			const int side = e / 384, row = (e % 384) / 6, piece = e % 6;
 			const int genome = (side ? tj : ti) * kMmTile + row;
 			const int64_t grp = g0 + 2 * piece;
 			const bool valid = genome < n && grp < g_end; // (chunk_groups is even: a piece never straddles the end)
@@ -139,22 +144,27 @@ k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_gro
 			cp_async_wait<0>();
 		}
 		__syncthreads();
-#pragma unroll 2
-		for (int k = 0; k < kMmGroups; k += 2) {
-			uint4 a[4], b[4]; // two groups each: lo0, hi0, lo1, hi1
+		const uint32_t two = one + one;
+#pragma unroll 1
+		for (int k = 0; k < kMmGroups; k += 3) {
+			uint2 a[4][3], b[4][3]; // three groups each: (lo, hi)
 #pragma unroll
-			for (int i = 0; i < 4; i++) {
-				a[i] = *reinterpret_cast<const uint4 *>(&sm[buf][0][ty + 16 * i][2 * k]);
-				b[i] = *reinterpret_cast<const uint4 *>(&sm[buf][1][tx + 16 * i][2 * k]);
-			}
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int g = 0; g < 3; g++) {
+					a[i][g] = *reinterpret_cast<const uint2 *>(&sm[buf][0][ty + 16 * i][2 * (k + g)]);
+					b[i][g] = *reinterpret_cast<const uint2 *>(&sm[buf][1][tx + 16 * i][2 * (k + g)]);
+				}
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
-					const uint32_t m0 = (a[i].x ^ b[j].x) | (a[i].y ^ b[j].y);
-					const uint32_t m1 = (a[i].z ^ b[j].z) | (a[i].w ^ b[j].w);
-					acc[i][j] = __popc(m0) * one + acc[i][j];
-					acc[i][j] = __popc(m1) * one + acc[i][j];
+					const uint32_t m0 = (a[i][0].x ^ b[j][0].x) | (a[i][0].y ^ b[j][0].y);
+					const uint32_t m1 = (a[i][1].x ^ b[j][1].x) | (a[i][1].y ^ b[j][1].y);
+					const uint32_t m2 = (a[i][2].x ^ b[j][2].x) | (a[i][2].y ^ b[j][2].y);
+					const uint32_t sum = m0 ^ m1 ^ m2, carry = (m0 & m1) | (m2 & (m0 | m1));
+					acc[i][j] = __popc(sum) * one + acc[i][j];
+					acc[i][j] = __popc(carry) * two + acc[i][j];
 				}
 		}
 		__syncthreads(); // everyone is done with `buf` before the copy of stage s + 2 lands in it
@@ -215,6 +225,7 @@ int mismatch_tiles(Engine &e, int64_t *sites_out)
 	// column chunks: the bit planes of a chunk take n * chunk_groups * 8 bytes (default: at most 2 GB)
 	int64_t budget = (int64_t)2048 << 20;
 	if (const char *v = std::getenv("PGS_K2_PLANES_MB")) budget = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
+	static_assert(kMmGroups % 6 == 0, "a stage is whole 64-site blocks and whole adder steps");
 	int64_t chunk_blocks = std::max<int64_t>(kMmGroups / 2, budget / ((int64_t)n * 16));
 	chunk_blocks = std::min(chunk_blocks, blocks_total);
 	chunk_blocks = (chunk_blocks + kMmGroups / 2 - 1) / (kMmGroups / 2) * (kMmGroups / 2); // whole stages

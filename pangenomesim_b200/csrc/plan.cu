@@ -356,7 +356,10 @@ int plan_walk(Engine &e, SweepPlan &p)
 		size_t target_units = 0;
 		{
 			const size_t slabs = std::max<size_t>(1, pgs::walk_slabs(e.walk_variant, (uint32_t)D, (uint32_t)e.blocks));
-			target_units = std::min<size_t>(120, std::max<size_t>(40, (1800 + slabs - 1) / slabs));
+			// (a small tree has few steps to hand out: units of at least ~64 steps, so that a CTA's
+			// fixed cost -- prologue, step staging -- stays small beside its walk)
+			const size_t lo = std::min<size_t>(40, std::max<size_t>(8, (size_t)N / 128));
+			target_units = std::min<size_t>(120, std::max<size_t>(lo, (1800 + slabs - 1) / slabs));
 		}
 		if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
 		std::vector<int32_t> roots{e.root};
@@ -531,7 +534,9 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 	if (!p.sparse_walk) return PGS_OK;
 	const int32_t N = e.n_nodes;
 	const int smem_cap = pgs::sparse_walk_smem_levels();
-	int32_t unit_steps = 96; // steps per unit (a unit below the origin pays 4 + depth Philox calls to start)
+	// steps per unit (a unit below the origin pays 4 + depth Philox calls to start).  Config 3's
+	// accessory genes: 0.37 ms with 48, 0.41 with 96, 0.62 with 192, 1.26 uncut.
+	int32_t unit_steps = 48;
 	if (const char *v = std::getenv("PGS_SPARSE_UNIT_STEPS")) unit_steps = std::max(1, std::atoi(v)); // tuning knob
 	std::vector<int64_t> stamp(N, -1);
 	std::vector<int32_t> rank_at(N, 0), sub(N, 0), acc(N, 0);

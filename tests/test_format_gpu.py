@@ -5,7 +5,7 @@ import pytest
 
 import treegen
 from pangenomesim_b200 import Engine
-from pangenomesim_b200.capi import genome_name, OUT_ALL, OUT_GENOMES, OUT_MAF
+from pangenomesim_b200.capi import genome_name, OUT_ALL, OUT_DISCARD, OUT_GENOMES, OUT_HOST_EXPAND, OUT_MAF
 
 pytestmark = pytest.mark.gpu
 
@@ -50,7 +50,7 @@ def expected_files(oracle, seed, L, parent, rate, leaf, genes, ref_core, ref_acc
     return files
 
 
-def run_case(oracle, tmp_path, n, L, n_core, n_acc, seed, all_order=None, use_sink=False):
+def run_case(oracle, tmp_path, n, L, n_core, n_acc, seed, all_order=None, use_sink=False, what=OUT_ALL):
     parent, rate, leaf = treegen.coalescent(n, seed=seed, mut_rate=0.3)
     genes = treegen.gene_table(parent, leaf, n_core=n_core, n_acc=n_acc, seed=seed + 1)
     gene_id = genes[0]
@@ -69,15 +69,18 @@ def run_case(oracle, tmp_path, n, L, n_core, n_acc, seed, all_order=None, use_si
             buf = ctypes.string_at(data, length)
             assert len(got.get(name, b"")) == offset, "chunks must arrive in file order"
             got[name] = got.get(name, b"") + buf
-        rep = e.write_outputs(None, OUT_ALL, ref_core, ref_acc, sink=sink)
+        rep = e.write_outputs(None, what, ref_core, ref_acc, sink=sink)
         got = {k: v.decode() for k, v in got.items()}
     else:
-        rep = e.write_outputs(tmp_path, OUT_ALL, ref_core, ref_acc)
+        rep = e.write_outputs(tmp_path, what, ref_core, ref_acc)
         got = {p.name: p.read_text() for p in tmp_path.iterdir()}
     assert set(got) == set(want)
     for name in want:
         assert got[name] == want[name], name
     assert rep["files"] == len(want) and rep["bytes"] == sum(len(v) for v in want.values())
+    if what & OUT_HOST_EXPAND:  # and the same totals when the text is produced and dropped
+        rep2 = e.write_outputs(None, what | OUT_DISCARD, ref_core, ref_acc)
+        assert rep2["files"] == rep["files"] and rep2["bytes"] == rep["bytes"] and rep2["records"] == rep["records"]
     e.close()
 
 
@@ -139,7 +142,9 @@ def test_more_than_999_genomes_and_many_chunks(oracle):
     e.close()
 
 
-def test_sharded_outputs_equal_single_engine(oracle, tmp_path):
+@pytest.mark.parametrize("presize", [False, True])
+@pytest.mark.parametrize("extra", [0, OUT_HOST_EXPAND])
+def test_sharded_outputs_equal_single_engine(oracle, tmp_path, extra, presize):
     """two engines that each hold a slice of the gene table fill disjoint byte ranges of the same
     files (pgs_shard_layout); the result is byte-identical to one engine holding everything"""
     n, L, seed = 13, 90, 21
@@ -153,7 +158,7 @@ def test_sharded_outputs_equal_single_engine(oracle, tmp_path):
         for x in (below[int(origin[g])] if list(c) == [-1] else c):
             total[int(x)] += 1
     order = np.random.default_rng(3).permutation(n).astype(np.int32)
-    what = OUT_GENOMES | OUT_MAF
+    what = OUT_GENOMES | OUT_MAF | extra
 
     single = tmp_path / "single"
     single.mkdir()
@@ -161,7 +166,7 @@ def test_sharded_outputs_equal_single_engine(oracle, tmp_path):
         e.set_tree(parent, rate, leaf)
         e.set_genes(gene_id, origin, off, car, all_order=order)
         e.sweep()
-        e.write_outputs(single, what, list(range(G)), [])
+        e.write_outputs(single, OUT_GENOMES | OUT_MAF, list(range(G)), [])
         ref_seq = {int(gene_id[g]): e.copy_origin_ascii(g) for g in range(G)}
 
     cut = 11
@@ -177,8 +182,9 @@ def test_sharded_outputs_equal_single_engine(oracle, tmp_path):
     gb1, mb1 = parts[1].output_sizes(shard=dict(shard0, maf_offset=mb0))
     sharded = tmp_path / "sharded"
     sharded.mkdir()
-    for name in [genome_name(i) + ".fasta" for i in range(n)] + ["alignment.maf"]:
-        (sharded / name).write_bytes(b"")
+    for i, name in enumerate([genome_name(i) + ".fasta" for i in range(n)] + ["alignment.maf"]):
+        # created empty, or (as the host program does) at the final size: the engines never resize a shared file
+        (sharded / name).write_bytes(b"\0" * int((gb0[i] + gb1[i]) if i < n else (mb0 + mb1)) if presize else b"")
     parts[1].write_outputs(sharded, what, [], [], shard=dict(shard0, genome_offset=gb0, maf_offset=mb0))
     parts[0].write_outputs(sharded, what, [], [], shard=dict(shard0, genome_offset=np.zeros(n, np.int64)))
     for p in sorted(single.iterdir()):
@@ -226,3 +232,24 @@ def test_packed_side_output_holds_the_fasta_sequences(tmp_path, monkeypatch, n, 
             got[name] = got.get(name, b"") + ctypes.string_at(data, length)
         e.write_outputs(None, OUT_PACKED, [], [], sink=sink)
         assert got["genomes.pgs2"] == (tmp_path / "genomes.pgs2").read_bytes()
+
+
+# ---- PGS_OUT_HOST_EXPAND: packed rows over PCIe, text written by the host's cores; same bytes
+
+@pytest.mark.parametrize("L", [1, 16, 63, 64, 65, 100, 128, 1000, 1500])
+def test_host_expand_equals_reference_layout(oracle, tmp_path, L):
+    run_case(oracle, tmp_path, n=7, L=L, n_core=6, n_acc=9, seed=30 + L, what=OUT_ALL | OUT_HOST_EXPAND)
+
+
+def test_host_expand_sink_and_order(oracle, tmp_path):
+    order = np.random.default_rng(5).permutation(13).astype(np.int32)
+    run_case(oracle, tmp_path, n=13, L=130, n_core=3, n_acc=25, seed=8, all_order=order, use_sink=True, what=OUT_ALL | OUT_HOST_EXPAND)
+
+
+@pytest.mark.parametrize("use_sink", [False, True])
+def test_host_expand_many_chunks(oracle, tmp_path, monkeypatch, use_sink):
+    """1 MB staging: the genomes and the MAF lines take several chunks each (double buffering,
+    mapped windows of the MAF file at unaligned offsets)"""
+    monkeypatch.setenv("PGS_STAGE_MB", "1")
+    monkeypatch.setenv("PGS_EXPAND_THREADS", "5")
+    run_case(oracle, tmp_path, n=150, L=1000, n_core=30, n_acc=40, seed=12, use_sink=use_sink, what=OUT_ALL | OUT_HOST_EXPAND)
