@@ -433,7 +433,7 @@ def main():
     import torch
     import torch.distributed as dist
     from pangenomesim_b200 import Engine
-    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_MAF, OUT_PACKED
+    from pangenomesim_b200.capi import OUT_DISCARD, OUT_GENOMES, OUT_HOST_EXPAND, OUT_MAF, OUT_PACKED
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -556,36 +556,51 @@ def main():
                              "sparse_frac_of_peak": (sp_bytes / (split["sparse_ms"] * 1e-3) / 1e9 / peak) if split["sparse_ms"] > 0 else None,
                              "what": "first sweep of the plan, launched kernel by kernel; sparse bytes = rows written + parent rows read (padded rows)"}
 
-    # ---- end to end through the C ABI with host tables in, host text out
-    e2e = None
+    # ---- end to end through the C ABI with host tables in, host text out.  Two ways to the same
+    # bytes: K3 formats on the GPU and the text crosses PCIe (4.1 x the packed rows), or
+    # (PGS_OUT_HOST_EXPAND) the packed rows cross PCIe and the host's cores write the text.
+    e2e = e2e_device = e2e_host = None
     if not args.no_e2e:
-        what = OUT_GENOMES | OUT_MAF | OUT_DISCARD
         h2d = sum(a.nbytes for a in (parent, rate, leaf) + tuple(x for x in w["genes"] if x is not None))
-        plan_s = []
+        threads = max(2, (os.cpu_count() or 2) // world)
+        os.environ.setdefault("PGS_EXPAND_THREADS", str(threads))
+        row_bytes_packed = st["blocks_per_gene"] * 16
 
-        def e2e_step():
-            t_plan = time.perf_counter()
-            eng.set_tree(parent, rate, leaf)
-            eng.set_genes(*w["genes"])
-            plan_s.append(time.perf_counter() - t_plan)
-            eng.sweep()
-            return eng.write_outputs(None, what, w["ref"], [])
-        e2e_step()  # warm-up (allocations, pinned buffers)
-        barrier()
-        t0 = time.perf_counter()
-        rep = None
-        for _ in range(args.e2e_steps):
-            rep = e2e_step()
-        barrier()
-        wall = max_over_ranks(time.perf_counter() - t0)
-        bytes_all = max_over_ranks(float(rep["bytes"])) if world == 1 else None
-        e2e = {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(rep["bytes"]), "steps": args.e2e_steps, "ms_per_step": 1e3 * wall / args.e2e_steps,
-               "k3_device_ms_per_step": rep["device_ms"], "files_per_step": int(rep["files"]),
-               "plan_ms_per_step": 1e3 * float(np.mean(plan_s[1:])), "d2h_gb_per_s": rep["bytes"] * args.e2e_steps / wall / 1e9,
-               "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) "
-                       "into pinned host memory, bytes discarded (no filesystem); per-rank bytes"}
-        del bytes_all
+        def e2e_run(what, describe):
+            plan_s = []
+
+            def e2e_step():
+                t_plan = time.perf_counter()
+                eng.set_tree(parent, rate, leaf)
+                eng.set_genes(*w["genes"])
+                plan_s.append(time.perf_counter() - t_plan)
+                eng.sweep()
+                return eng.write_outputs(None, what, w["ref"], [])
+            e2e_step()  # warm-up (allocations, pinned buffers)
+            barrier()
+            t0 = time.perf_counter()
+            rep = None
+            for _ in range(args.e2e_steps):
+                rep = e2e_step()
+            barrier()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            host = bool(what & OUT_HOST_EXPAND)
+            # bytes that cross PCIe per step: the text itself, or the packed rows of every record / MAF line
+            d2h = int(rep["records"]) * row_bytes_packed if host else int(rep["bytes"])
+            return {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": d2h, "text_bytes_per_step": int(rep["bytes"]), "steps": args.e2e_steps,
+                    "ms_per_step": 1e3 * wall / args.e2e_steps, "k3_device_ms_per_step": rep["device_ms"],
+                    "files_per_step": int(rep["files"]), "plan_ms_per_step": 1e3 * float(np.mean(plan_s[1:])),
+                    "text_gb_per_s": rep["bytes"] * args.e2e_steps / wall / 1e9, "d2h_gb_per_s": d2h * args.e2e_steps / wall / 1e9,
+                    "what": "pgs_set_tree + pgs_set_genes + pgs_sweep + pgs_write_outputs(genomeNNN.fasta + alignment.maf) " + describe
+                            + "; no filesystem; per-rank bytes"}
+        e2e_device = e2e_run(OUT_GENOMES | OUT_MAF | OUT_DISCARD,
+                             "formatted by K3 on the GPU, the text copied into pinned host memory and dropped")
+        e2e_host = e2e_run(OUT_GENOMES | OUT_MAF | OUT_DISCARD | OUT_HOST_EXPAND,
+                           f"PGS_OUT_HOST_EXPAND: packed rows copied into pinned host memory, every genomeNNN.fasta and every run of "
+                           f"256 MAF lines written in full (headers + bases, AVX2) into a worker thread's buffer by {threads} host threads, then dropped")
+        e2e = dict(e2e_host if e2e_host["value"] >= e2e_device["value"] else e2e_device)
+        e2e["mode"] = "host_expand" if e2e is not None and e2e_host["value"] >= e2e_device["value"] else "device_formatter"
 
     # ---- the same end to end with the optional packed side output instead of the text (genomes.pgs2:
     # the genomes' 2-bit rows copied straight from the store, an eighth of the bytes)
@@ -657,6 +672,7 @@ def main():
                        "sweep": "fused walks (k1_top_masks + k1_walk_dense, k1_walk_sparse)" if st["sweep_mode"] == 1 else "level-synchronous"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
+            "e2e_device_formatter": e2e_device, "e2e_host_expand": e2e_host,
             "mismatch": k2, "mismatch_allreduce_check": mm_leg, "weak_scaling": weak, "e2e_files": files, "e2e_packed": e2e_packed,
         }
         print(json.dumps(line, default=_jsonable), flush=True)

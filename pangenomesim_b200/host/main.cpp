@@ -15,6 +15,7 @@
 
 #include <atomic>
 #include <charconv>
+#include <cmath>
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
@@ -60,7 +61,12 @@ static bool verbose = false;
 		"      --device N           CUDA device ordinal\n"
 		"      --devices N          Shard the genes over N engines (devices 0..N-1, wrapping around)\n"
 		"      --packed             Also write genomes.pgs2: all genomes 2-bit packed behind an index\n"
-		"                           (one device only; pangenomesim_b200/packed.py reads it)\n\n"
+		"                           (one device only; pangenomesim_b200/packed.py reads it)\n"
+		"      --gpu-format         Format the text on the GPU (kernel K3) instead of shipping packed rows\n"
+		"                           and expanding them on the host's cores; same bytes either way\n"
+		"      --check-distances    Count the observed pairwise differences over the core genes on the GPU(s)\n"
+		"                           (partial counts summed with NCCL), write distance.observed.mat (Jukes-Cantor\n"
+		"                           corrected) and check every pair against distance.mat's expectation (99 %% band)\n\n"
 		"Simulation Parameters:\n"
 		"  core-size=INT            Minimum size of the core genome\n"
 		"  gene-length=INT          Length of a gene\n"
@@ -85,11 +91,28 @@ static void make_path(const std::string &path)
 	if (::mkdir(path.c_str(), 0755) != 0 && errno != EEXIST) err(errno, "%s", path.c_str());
 }
 
+// A fatal error after threads have been started: thrown to main, which joins the threads before it
+// exits (exit() while another thread is still writing is undefined behaviour and leaves partial files).
+struct Fatal {
+	int code;
+	std::string msg;
+};
+[[noreturn]] static void fatal(int code, const std::string &msg)
+{
+	throw Fatal{code, msg};
+}
+
 static std::ofstream open_out(const std::string &name)
 {
 	std::ofstream f(name);
-	if (!f.good()) err(errno, "%s: couldn't write to file", name.c_str());
+	if (!f.good()) fatal(errno ? errno : 1, name + ": couldn't write to file: " + std::strerror(errno)); // reference: check_io, util.cxx:66-70
 	return f;
+}
+
+static void check_out(std::ostream &f, const std::string &name)
+{
+	f.flush();
+	if (!f.good()) fatal(errno ? errno : 1, name + ": couldn't write to file: " + std::strerror(errno));
 }
 
 static void write_newick(const Model &m, std::ostream &out)
@@ -170,10 +193,10 @@ static void write_distance_matrix(const Model &m, const std::string &name)
 		});
 	}
 	if (writing.valid()) writing.get();
-	if (!out.good()) err(errno, "%s: couldn't write to file", name.c_str());
+	check_out(out, name);
 }
 
-int main(int argc, char *argv[])
+static int run(int argc, char *argv[], std::thread &matrices, std::string &matrices_error)
 {
 	static const struct option long_options[] = {
 		{"version", no_argument, nullptr, 0},      {"help", no_argument, nullptr, 0},
@@ -181,12 +204,13 @@ int main(int argc, char *argv[])
 		{"verbose", no_argument, nullptr, 'v'},     {"rng-compat", no_argument, nullptr, 0},
 		{"rng-fast", no_argument, nullptr, 0},      {"no-sequences", no_argument, nullptr, 0},
 		{"device", required_argument, nullptr, 0},  {"devices", required_argument, nullptr, 0},
-		{"packed", no_argument, nullptr, 0},
+		{"packed", no_argument, nullptr, 0},        {"gpu-format", no_argument, nullptr, 0},
+		{"check-distances", no_argument, nullptr, 0},
 		{nullptr, 0, nullptr, 0}};
 
 	Model model;
 	std::string out_dir = "./";
-	bool sequences = true, packed = false;
+	bool sequences = true, packed = false, gpu_format = false, check_distances = false;
 	int device = -1, n_devices = 1;
 
 	for (;;) {
@@ -208,6 +232,8 @@ int main(int argc, char *argv[])
 				if (name == "device") device = std::atoi(optarg);
 				if (name == "devices") n_devices = std::atoi(optarg);
 				if (name == "packed") packed = true;
+				if (name == "gpu-format") gpu_format = true;
+				if (name == "check-distances") check_distances = true;
 				break;
 			}
 			case 'o': out_dir = std::string(optarg) + "/"; break;
@@ -218,7 +244,11 @@ int main(int argc, char *argv[])
 				std::smatch m;
 				while (std::regex_search(rest, m, item)) {
 					const std::string key = m[1], value = m.size() == 3 ? std::string(m[2]) : std::string();
-					if (!model.parse_param(key, value)) errx(1, "unkown key %s.", key.c_str());
+					try {
+						if (!model.parse_param(key, value)) errx(1, "unkown key %s.", key.c_str());
+					} catch (const std::exception &) { // the reference dies of an uncaught std::invalid_argument here
+						errx(1, "invalid value '%s' for parameter %s", value.c_str(), key.c_str());
+					}
 					rest = m.suffix();
 				}
 				if (!rest.empty()) errx(1, "invalid parameter %s", optarg);
@@ -229,6 +259,7 @@ int main(int argc, char *argv[])
 		}
 	}
 
+	if (model.num_genomes < 1) errx(1, "num-genomes must be at least 1");
 	make_path(out_dir);
 	const auto t0 = std::chrono::steady_clock::now();
 	model.simulate();
@@ -280,9 +311,14 @@ int main(int argc, char *argv[])
 			}
 		}
 	};
-	std::thread matrices;
 	if (sequences)
-		matrices = std::thread(write_matrices);
+		matrices = std::thread([&] {
+			try {
+				write_matrices();
+			} catch (const Fatal &f) {
+				matrices_error = f.msg;
+			}
+		});
 	else
 		write_matrices();
 	const auto t2 = std::chrono::steady_clock::now();
@@ -297,9 +333,9 @@ int main(int argc, char *argv[])
 			if (v < n) leaf_genome[v] = (int32_t)v;
 		}
 		const int available = pgs_device_count();
-		if (available < 1) errx(2, "%s", "no usable CUDA device; this program has no CPU path for sequences");
+		if (available < 1) fatal(2, "no usable CUDA device; this program has no CPU path for sequences");
 		if (n_devices < 1) n_devices = 1;
-		if (packed && n_devices > 1) errx(1, "%s", "--packed needs a single engine (no --devices)");
+		if (packed && n_devices > 1) fatal(1, "--packed needs a single engine (no --devices)");
 
 		// contiguous slices of the gene table, balanced by the rows they occupy
 		std::vector<size_t> cut(n_devices + 1, G);
@@ -328,7 +364,7 @@ int main(int argc, char *argv[])
 			for (int d = 0; d < n_devices; d++) pool.emplace_back([&, d] { fn(d); });
 			for (auto &th : pool) th.join();
 			for (int d = 0; d < n_devices; d++)
-				if (!shards[d].error.empty()) errx(2, "device %d: %s", d, shards[d].error.c_str());
+				if (!shards[d].error.empty()) fatal(2, "device " + std::to_string(d) + ": " + shards[d].error);
 		};
 		std::unordered_map<int64_t, std::pair<int, int64_t>> where; // gene table index -> (shard, local index)
 		each([&](int d) {
@@ -375,12 +411,12 @@ int main(int argc, char *argv[])
 			Shard &s = shards[0];
 			pgs_output_spec spec{};
 			spec.out_dir = dir_c.c_str();
-			spec.what = PGS_OUT_ALL | (packed ? PGS_OUT_PACKED : 0u);
+			spec.what = PGS_OUT_ALL | (packed ? PGS_OUT_PACKED : 0u) | (gpu_format ? 0u : PGS_OUT_HOST_EXPAND);
 			spec.n_ref_core = (int64_t)model.ref_core.size();
 			spec.ref_core = model.ref_core.data();
 			spec.n_ref_acc = (int64_t)model.ref_acc.size();
 			spec.ref_acc = model.ref_acc.data();
-			if (pgs_write_outputs(s.h, &spec, &s.rep) < 0) errx(2, "%s", pgs_last_error(s.h));
+			if (pgs_write_outputs(s.h, &spec, &s.rep) < 0) fatal(2, pgs_last_error(s.h));
 		} else {
 			// several engines fill disjoint byte ranges of the same files
 			const int64_t n_ref_total = (int64_t)(model.ref_core.size() + model.ref_acc.size());
@@ -407,7 +443,7 @@ int main(int argc, char *argv[])
 			// the files are created at their final size: the engines fill disjoint ranges and never resize them
 			auto create_sized = [&](const std::string &path, int64_t size) {
 				open_out(path);
-				if (::truncate(path.c_str(), (off_t)size) != 0) err(errno, "%s: couldn't set the file size", path.c_str());
+				if (::truncate(path.c_str(), (off_t)size) != 0) fatal(errno, path + ": couldn't set the file size: " + std::strerror(errno));
 			};
 			for (size_t i = 0; i < n; i++) create_sized(out_dir + pgshost::genome_name((ssize_t)i) + ".fasta", at[i]);
 			create_sized(out_dir + "alignment.maf", maf_at);
@@ -420,7 +456,7 @@ int main(int argc, char *argv[])
 				lay.n_ref_total = n_ref_total;
 				pgs_output_spec spec{};
 				spec.out_dir = dir_c.c_str();
-				spec.what = PGS_OUT_GENOMES | PGS_OUT_MAF;
+				spec.what = PGS_OUT_GENOMES | PGS_OUT_MAF | (gpu_format ? 0u : PGS_OUT_HOST_EXPAND);
 				spec.shard = &lay;
 				if (pgs_write_outputs(s.h, &spec, &s.rep) < 0) s.error = pgs_last_error(s.h);
 			});
@@ -428,7 +464,7 @@ int main(int argc, char *argv[])
 			std::string seq(model.gene_length, 'N');
 			auto record = [&](int64_t k) {
 				const auto w = where.at(k);
-				if (pgs_copy_origin_ascii(shards[w.first].h, w.second, &seq[0]) < 0) errx(2, "%s", pgs_last_error(shards[w.first].h));
+				if (pgs_copy_origin_ascii(shards[w.first].h, w.second, &seq[0]) < 0) fatal(2, pgs_last_error(shards[w.first].h));
 				return ">genomeref." + std::to_string(model.genes[k].id) + "\n" + seq + "\n";
 			};
 			std::ofstream ref = open_out(out_dir + "ref.fasta"), cor = open_out(out_dir + "core.fasta"),
@@ -443,6 +479,73 @@ int main(int argc, char *argv[])
 				ref << r;
 				acc << r;
 			}
+			check_out(ref, out_dir + "ref.fasta"); // the reference checks every file it has written (check_io)
+			check_out(cor, out_dir + "core.fasta");
+			check_out(acc, out_dir + "accessory.fasta");
+		}
+		if (check_distances) {
+			// Observed pairwise differences over the core genes (kernel K2 on every engine's genes, the
+			// partial counts summed with NCCL over NVLink) against what distance.mat promises: a pair at
+			// expected distance d differs in p = 3/4 (1 - exp(-4d/3)) of its sites (Jukes-Cantor), and the
+			// observed fraction must lie within the 99 % band of a Binomial(S, p), Bonferroni over all pairs.
+			std::vector<uint32_t> mm(n * n);
+			int64_t sites = 0;
+			std::vector<pgs_engine *> hs;
+			for (auto &sh : shards) hs.push_back(sh.h);
+			if (n_devices == 1) {
+				if (pgs_mismatch(hs[0], mm.data(), &sites) < 0) fatal(2, pgs_last_error(hs[0]));
+			} else if (n_devices <= available) {
+				if (pgs_mismatch_multi(hs.data(), n_devices, mm.data(), &sites) < 0) fatal(2, pgs_last_error(hs[0]));
+			} else { // engines share a device: no NCCL rank per device, the partial matrices are summed here
+				std::vector<uint32_t> part(n * n);
+				for (auto h : hs) {
+					int64_t ps = 0;
+					if (pgs_mismatch(h, part.data(), &ps) < 0) fatal(2, pgs_last_error(h));
+					for (size_t i = 0; i < n * n; i++) mm[i] += part[i];
+					sites += ps;
+				}
+			}
+			const double pairs = (double)n * (double)(n - 1) / 2.0;
+			double zc = 0.0; // two-sided critical value at 0.01 / pairs
+			if (pairs >= 1) {
+				double lo = 0.0, hi = 40.0;
+				for (int it = 0; it < 200; it++) {
+					zc = 0.5 * (lo + hi);
+					(std::erfc(zc / std::sqrt(2.0)) > 0.01 / pairs ? lo : hi) = zc;
+				}
+			}
+			std::ofstream out = open_out(out_dir + "distance.observed.mat");
+			out << n << "\n";
+			std::vector<double> row;
+			size_t outside = 0;
+			double worst = 0.0;
+			std::string line;
+			char buf[64];
+			for (size_t i = 0; i < n; i++) {
+				model.distance_row(i, row);
+				line = pgshost::genome_name((ssize_t)i);
+				for (size_t j = 0; j < n; j++) {
+					const double ph = sites > 0 ? (double)mm[i * n + j] / (double)sites : 0.0;
+					const double dh = ph < 0.75 ? -0.75 * std::log1p(-4.0 * ph / 3.0) : INFINITY; // Jukes-Cantor correction
+					const std::to_chars_result r = std::to_chars(buf, buf + sizeof buf, dh, std::chars_format::general, 4);
+					const size_t len = (size_t)(r.ptr - buf);
+					line.append(len < 8 ? 10 - len : 2, ' ');
+					line.append(buf, len);
+					if (j > i && sites > 0) {
+						const double pe = 0.75 * (1.0 - std::exp(-4.0 * row[j] / 3.0));
+						const double sd = std::sqrt(std::max(pe * (1.0 - pe), 0.0) / (double)sites);
+						const double z = sd > 0 ? std::fabs(ph - pe) / sd : (ph == pe ? 0.0 : INFINITY);
+						worst = std::max(worst, z);
+						if (std::fabs(ph - pe) > zc * sd + 1e-12) outside++;
+					}
+				}
+				line += "\n";
+				out << line;
+			}
+			check_out(out, out_dir + "distance.observed.mat");
+			std::fprintf(stderr, "check-distances: %lld sites, %.0f pairs, largest |z| %.2f (99 %% band: %.2f), %zu pairs outside\n",
+						 (long long)sites, pairs, worst, zc, outside);
+			if (outside > 0) fatal(3, "observed distances disagree with distance.mat");
 		}
 		for (int d = 0; d < n_devices; d++) {
 			Shard &s = shards[d];
@@ -459,6 +562,7 @@ int main(int argc, char *argv[])
 		}
 	}
 	if (matrices.joinable()) matrices.join();
+	if (!matrices_error.empty()) fatal(2, matrices_error);
 	if (verbose) {
 		const auto t3 = std::chrono::steady_clock::now();
 		auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -466,4 +570,21 @@ int main(int argc, char *argv[])
 					 model.used_compat ? "rng-compat" : "rng-fast", ms(t1, t2), ms(t2, t3));
 	}
 	return 0;
+}
+
+int main(int argc, char *argv[])
+{
+	std::thread matrices; // distance.mat and panmatrix.tsv are written beside the GPU work
+	std::string matrices_error;
+	int rc = 0;
+	Fatal failure{0, ""};
+	try {
+		rc = run(argc, argv, matrices, matrices_error);
+	} catch (const Fatal &f) {
+		failure = f;
+		if (failure.code == 0) failure.code = 1;
+	}
+	if (matrices.joinable()) matrices.join(); // never exit under a running thread
+	if (failure.code) errx(failure.code, "%s", failure.msg.c_str());
+	return rc;
 }

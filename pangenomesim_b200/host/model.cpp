@@ -178,6 +178,13 @@ void Model::simulate()
 		rng = std::default_random_engine(seed);
 	}
 	const size_t n = num_genomes;
+	genes.clear(); // a second simulate() on the same Model starts from scratch
+	ref_core.clear();
+	ref_acc.clear();
+	ref_core_ids.clear();
+	ref_acc_ids.clear();
+	all_order.clear();
+	genome_gene_count.clear();
 	create_coalescent(); // first consumer of the engine: coalescent.newick is bit-exact in every mode
 	const Tree &t = tree;
 

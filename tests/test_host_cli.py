@@ -61,6 +61,10 @@ def test_cli_error_behaviour(tmp_path):
     assert r.returncode == 0 and "--param KEY=VALUE" in r.stdout
     r = run_cli(tmp_path / "deep" / "er" / "dir", "seed=3", "--no-sequences")
     assert (tmp_path / "deep" / "er" / "dir" / "coalescent.newick").exists()
+    r = run_cli(tmp_path / "o", "num-genomes=0", "--no-sequences", check=False)
+    assert r.returncode == 1 and "num-genomes must be at least 1" in r.stderr  # (the reference dies of an uncaught exception)
+    r = run_cli(tmp_path / "o", "seed", "--no-sequences", check=False)
+    assert r.returncode == 1 and "invalid value" in r.stderr
 
 
 def test_more_than_999_genomes_host_side(tmp_path):
@@ -136,12 +140,33 @@ def test_sharded_cli_is_byte_identical(tmp_path, run, devices):
     """--devices N shards the gene table over N engines (wrapping around the available GPUs);
     every output file must equal the single-engine run byte for byte"""
     params, _ = param_string(run)
-    run_cli(tmp_path / "one", params)
+    run_cli(tmp_path / "one", params, "--gpu-format")
     run_cli(tmp_path / "many", params, "--devices", str(devices))
+    run_cli(tmp_path / "many_gpu", params, "--devices", str(devices), "--gpu-format")
+    run_cli(tmp_path / "one_host", params)
     names = sorted(p.name for p in (tmp_path / "one").iterdir())
-    assert sorted(p.name for p in (tmp_path / "many").iterdir()) == names
-    for name in names:
-        assert (tmp_path / "many" / name).read_bytes() == (tmp_path / "one" / name).read_bytes(), name
+    for other in ("many", "many_gpu", "one_host"):  # host-expanded (default) and GPU-formatted text, one and several engines
+        assert sorted(p.name for p in (tmp_path / other).iterdir()) == names
+        for name in names:
+            assert (tmp_path / other / name).read_bytes() == (tmp_path / "one" / name).read_bytes(), (other, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", [1, 2, 3])
+def test_cli_check_distances(tmp_path, devices):
+    """--check-distances: K2 on every engine, partial counts summed (NCCL where every engine has its own
+    GPU, on the host where engines share one), observed distances within the 99 % band of distance.mat"""
+    import torch
+    params = "num-genomes=40,core-size=300,gene-length=1000,mut-rate=0.05,seed=5"
+    r = run_cli(tmp_path / "o", params, "--check-distances", "--devices", str(devices))
+    assert "check-distances: 300000 sites, 780 pairs" in r.stderr and " 0 pairs outside" in r.stderr, r.stderr
+    exp = (tmp_path / "o" / "distance.mat").read_text().split("\n")
+    obs = (tmp_path / "o" / "distance.observed.mat").read_text().split("\n")
+    assert exp[0] == obs[0] == "40" and len(exp) == len(obs)
+    e = np.array([[float(x) for x in line.split()[1:]] for line in exp[1:41]])
+    o = np.array([[float(x) for x in line.split()[1:]] for line in obs[1:41]])
+    assert np.allclose(o, o.T) and (np.diag(o) == 0).all()
+    assert np.abs(o - e).max() < 0.01 and np.abs(o - e).max() > 0  # sampling noise, not a copy
 
 
 REF_EXE = ROOT / "oracle" / "_ref" / "pangenomesim"
