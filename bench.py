@@ -330,6 +330,45 @@ def k2_leg(torch, dist, eng, stats, rank, world, peaks):
     return out
 
 
+def cli_multi_device_leg(world):
+    """The product CLI on real devices (rank 0 only, the other ranks' engines are closed and they wait
+    on the CPU): pangenomesim-b200 --devices N on N distinct GPUs against --devices 1, every output
+    file compared byte for byte; --check-distances sums the engines' K2 counts with NCCL."""
+    import filecmp
+    import shutil
+    import tempfile
+    exe = ROOT / "pangenomesim_b200" / "bin" / "pangenomesim-b200"
+    if not exe.exists():
+        return {"skipped": "pangenomesim_b200/bin/pangenomesim-b200 not built"}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="pgs_cli_", dir=base)
+    params = "num-genomes=1000,core-size=256,gene-length=1000,theta=30,rho=0.5,mut-rate=0.02,seed=7"
+    out = {"params": params, "devices": world}
+    try:
+        for name, extra in (("one", ["--devices", "1"]), ("many", ["--devices", str(world), "--check-distances"])):
+            t0 = time.perf_counter()
+            r = subprocess.run([str(exe), "-o", f"{tmp}/{name}", "-p", params, "--rng-fast", "-v", *extra],
+                               capture_output=True, text=True, timeout=600)
+            out[f"seconds_{name}"] = time.perf_counter() - t0
+            if r.returncode != 0:
+                out["ok"] = False
+                out["error"] = r.stderr[-400:]
+                return out
+            if name == "many":
+                out["check_distances"] = next((ln for ln in r.stderr.splitlines() if ln.startswith("check-distances")), None)
+                out["device_lines"] = [ln for ln in r.stderr.splitlines() if ln.startswith("device ")][:8]
+        names = sorted(os.listdir(f"{tmp}/one"))
+        extra_files = sorted(set(os.listdir(f"{tmp}/many")) - set(names))
+        differ = [nm for nm in names if not filecmp.cmp(f"{tmp}/one/{nm}", f"{tmp}/many/{nm}", shallow=False)]
+        out.update(ok=(not differ and extra_files == ["distance.observed.mat"]), files_compared=len(names), differing=differ[:5],
+                   bytes=sum(os.path.getsize(f"{tmp}/one/{nm}") for nm in names))
+    except (subprocess.SubprocessError, OSError) as ex:
+        out.update(ok=False, error=f"{type(ex).__name__}: {ex}")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def files_leg(eng, parent, rate, leaf, genes, root, n, L):
     """host tables -> sweep -> genomeNNN.fasta + alignment.maf written as FILES (pwrite / mapped
     writes by the library's writer threads) into a scratch directory that is removed afterwards.
@@ -657,6 +696,18 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu and args.config == 4:
         cpu = cpu_baseline(args.cpu_genes if not args.small else 200)
 
+    # ---- the product CLI with one engine per GPU (N > 1): rank 0 drives it, everybody else has let go
+    # of its GPU and waits on the CPU (a gloo barrier: no kernel spins beside the CLI's own work)
+    cli = None
+    eng.close()
+    if world > 1 and not args.no_e2e:
+        torch.cuda.synchronize()
+        cpu_group = dist.new_group(backend="gloo")
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            cli = cli_multi_device_leg(world)
+        dist.barrier(group=cpu_group)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -673,10 +724,9 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
             "e2e_device_formatter": e2e_device, "e2e_host_expand": e2e_host,
-            "mismatch": k2, "mismatch_allreduce_check": mm_leg, "weak_scaling": weak, "e2e_files": files, "e2e_packed": e2e_packed,
+            "mismatch": k2, "mismatch_allreduce_check": mm_leg, "weak_scaling": weak, "cli_multi_device": cli, "e2e_files": files, "e2e_packed": e2e_packed,
         }
         print(json.dumps(line, default=_jsonable), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -195,6 +195,12 @@ void Model::simulate()
 	}
 	used_compat = compat;
 
+	if (!compat) { // nothing to keep in lock step with: flat arrays instead of the reference's hash maps
+		simulate_flat();
+		build_distance_graph();
+		return;
+	}
+
 	using id_map = std::unordered_map<ssize_t, char>; // stands for unordered_map<ssize_t, gene>
 	std::unordered_set<ssize_t> gene_id_list;          // img.h:32
 	std::unordered_map<ssize_t, id_map> store;         // img.h:34-35, accessory genes only
@@ -318,7 +324,95 @@ void Model::simulate()
 	for (ssize_t id : ref_core_ids) ref_core.push_back(index_of.at(id));
 	for (ssize_t id : ref_acc_ids) ref_acc.push_back(index_of.at(id));
 
+	build_distance_graph();
+}
+
+// The IMG gain/loss process (img.cxx:257-333) on flat arrays, for runs where the reference's draws are
+// not replayed (rng-fast): the same process -- Poisson(theta/rho) start set, competing exponential
+// clocks for gain (theta) and loss (rho per gene) along every branch, a uniformly chosen victim --
+// drawn from the same engine, but with vectors instead of unordered_map copies per node (config 3:
+// 2.5 s -> 0.1 s of host time).  Orders are this program's own: genes by ascending id, carriers by
+// ascending genome (the reference's orders are hash-table iteration orders, which only rng-compat
+// runs reproduce).
+void Model::simulate_flat()
+{
+	const Tree &t = tree;
+	const size_t n = num_genomes;
+	std::vector<int32_t> origin_of;               // per accessory gene (id - core_size)
+	std::vector<std::vector<int32_t>> carriers;   // per accessory gene: genomes, ascending after the sort below
+	auto new_gene = [&](int32_t node) {
+		origin_of.push_back(node);
+		carriers.emplace_back();
+		return (ssize_t)(core_size + origin_of.size() - 1);
+	};
+	std::vector<ssize_t> start;
+	const size_t start_size = draw_poisson(rng, theta / rho);
+	for (size_t k = 0; k < start_size; k++) start.push_back(new_gene(t.root()));
+	std::vector<std::vector<ssize_t>> stack;
+	stack.push_back(std::move(start));
+	traverse(
+		t,
+		[&](int32_t v) {
+			if (t.parent[v] < 0) return;
+			const double branch = t.time[v];
+			std::vector<ssize_t> neu = stack.back();
+			double time = 0.0;
+			while (time < branch) {
+				const double to_go = branch - time;
+				const double gain = draw_exp(rng, theta);
+				const double loss = draw_exp(rng, rho * neu.size());
+				if (gain > to_go && loss > to_go) break;
+				if (gain < loss || neu.empty()) {
+					neu.push_back(new_gene(v));
+					time += gain;
+				} else {
+					const size_t loser = draw_int(rng, 0, neu.size());
+					neu[loser] = neu.back();
+					neu.pop_back();
+					time += loss;
+				}
+			}
+			stack.push_back(std::move(neu));
+		},
+		[&](int32_t v) {
+			if (t.left[v] >= 0) return;
+			for (ssize_t id : stack.back()) carriers[(size_t)id - core_size].push_back(v);
+		},
+		[&](int32_t) { stack.pop_back(); });
+
+	all_order.resize(n);
+	for (size_t i = 0; i < n; i++) all_order[i] = (int32_t)i;
+	genome_gene_count.assign(n, (int64_t)core_size);
+	for (size_t g = 0; g < core_size; g++) {
+		GeneRecord r;
+		r.id = (ssize_t)g;
+		r.origin = t.root();
+		r.all = true;
+		ref_core.push_back((int64_t)genes.size());
+		ref_core_ids.push_back(r.id);
+		genes.push_back(std::move(r));
+	}
+	std::vector<int64_t> acc_index;
+	for (size_t a = 0; a < carriers.size(); a++) {
+		if (carriers[a].empty()) continue; // lost everywhere (img.cxx:355-358)
+		GeneRecord r;
+		r.id = (ssize_t)(core_size + a);
+		r.origin = origin_of[a];
+		std::sort(carriers[a].begin(), carriers[a].end());
+		for (int32_t g : carriers[a]) genome_gene_count[g]++;
+		const bool everywhere = carriers[a].size() == n;
+		r.carriers = std::move(carriers[a]);
+		// an accessory gene that no genome has lost joins the core reference (img.cxx:361-368)
+		(everywhere ? ref_core : ref_acc).push_back((int64_t)genes.size());
+		(everywhere ? ref_core_ids : ref_acc_ids).push_back(r.id);
+		genes.push_back(std::move(r));
+	}
+}
+
+void Model::build_distance_graph()
+{
 	// undirected adjacency (CSR) with edge weight time * mut_rate (img.cxx:142) for distance rows
+	const Tree &t = tree;
 	const size_t N = t.nodes();
 	adj_off.assign(N + 1, 0);
 	for (size_t v = 0; v + 1 < N; v++) {

@@ -75,6 +75,8 @@ class Model {
 
   private:
 	void create_coalescent();
+	void simulate_flat();        // rng-fast: the gain/loss process on flat arrays
+	void build_distance_graph();
 	void replay_root_draws();
 	void replay_mutate(double rate);
 	void build_children_lists();
