@@ -1150,6 +1150,10 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		slot ^= 1;
 	}
 
+	// the host-expanded outputs use the pinned buffers themselves: what the reference files left in
+	// them is delivered first
+	if (host_expand && (!drain(0) || !drain(1))) return fail_out(PGS_ERR_IO, w.error);
+
 	// ---- genomeNNN.fasta, host-expanded: a genome's rows lie together in the store (its leaf's
 	// region), so a chunk is a handful of plain copies; one task per genome writes the whole file
 	if ((spec->what & PGS_OUT_GENOMES) && host_expand) {

@@ -5,6 +5,8 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 
@@ -743,13 +745,29 @@ int plan_genes(Engine &e, int64_t n_genes, const int64_t *gene_id, const int32_t
 {
 	SweepPlan p;
 	int rc;
+	const bool timing = std::getenv("PGS_PLAN_TIMING") != nullptr; // development knob: phase times on stderr
+	auto t0 = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!timing) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "plan: %-14s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	};
 	if ((rc = plan_gene_table(e, p, n_genes, gene_id, origin_node, carrier_off, carrier_genome, all_order))) return rc;
+	lap("gene table");
 	if ((rc = plan_layout(e, p))) return rc;
+	lap("layout");
 	plan_level_tasks(e, p);
+	lap("level tasks");
 	plan_edge_tables(e);
+	lap("edge tables");
 	if ((rc = plan_walk(e, p))) return rc;
+	lap("dense walk");
 	if ((rc = plan_sparse_walk(e, p))) return rc;
-	return upload_plan(e, p);
+	lap("sparse walk");
+	rc = upload_plan(e, p);
+	lap("upload");
+	return rc;
 }
 
 } // namespace pgs
