@@ -11,7 +11,7 @@
 //                     sites per word, interleaved (lo, hi) per 32-site group.  Done once per column
 //                     chunk, so the pair kernel's staging is a plain asynchronous copy.
 //   k2_mismatch_tiles CTA = 64 x 64 tile of genome pairs (upper triangle only), 4 x 4 pairs per
-//                     thread; chunks of 384 sites staged with cp.async, double buffered; per pair
+//                     thread; chunks of 576 sites staged with cp.async, double buffered; per pair
 //                     and 32 sites  mask = (lo_i ^ lo_j) | (hi_i ^ hi_j), three masks through a
 //                     carry-save adder, count += popc(sum) + 2 popc(carry).
 //   output            upper-triangular 64 x 64 tiles, packed: n = 50 000 needs 5 GB instead of the
@@ -29,10 +29,15 @@
 namespace pgs {
 
 constexpr int kMmTile = 64;     // genomes per tile side
-constexpr int kMmGroups = 12;   // 32-site groups per staged chunk (a multiple of three: see the adder below)
-constexpr int kMmRowWords = 28; // shared-memory row stride in words: 12 groups x (lo, hi) + 4 of padding
-                                // (16-byte aligned rows; 8 consecutive rows start in banks 0, 28, 24, ... 4:
-                                // the 16 rows a warp reads 64 bits of take the minimum number of wavefronts)
+constexpr int kMmGroups = 18;   // 32-site groups per staged chunk (a multiple of three: see the adder below)
+constexpr int kMmRowWords = 44; // shared-memory row stride in words: 18 groups x (lo, hi), one group of skew, padding.
+                                // Rows 8..15 of every 16 are skewed by one group (8 bytes): the 16 rows a warp reads 64 bits
+                                // of then start in banks 0, 12, 24, 4, ... (rows 0-7) and 2, 14, 26, ... (rows 8-15) -- all 32
+                                // banks once, no conflict (unskewed, rows r and r + 8 collide: 53 % of the LSU's wavefronts).
+__device__ __forceinline__ int mm_skew(int row)
+{
+	return (row >> 3) & 1; // in groups
+}
 
 // even bits of x -> low 16 bits
 __device__ __forceinline__ uint32_t even_bits(uint32_t x)
@@ -65,12 +70,6 @@ k2_split_planes(const uint4 *__restrict__ rows, const int64_t *__restrict__ leaf
 	*reinterpret_cast<uint4 *>(planes + (int64_t)g * chunk_groups + 2 * b) = out;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid)
-{
-	const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
-	const int bytes = valid ? 16 : 0; // 0: the 16 bytes are zero-filled
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit()
 {
 	asm volatile("cp.async.commit_group;" ::: "memory");
@@ -118,18 +117,23 @@ k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_gro
 	const int64_t g_end = min(g_begin + groups_per_split, chunk_groups);
 	const int64_t n_stages = (g_end - g_begin + kMmGroups - 1) / kMmGroups;
 
-	// stage s: 2 sides x 64 rows x 96 bytes = 768 pieces of 16 bytes (two groups), 3 per thread
+	// stage s: 2 sides x 64 rows x 18 groups of 8 bytes (lo, hi).  Two threads per row, nine
+	// consecutive groups each: one global pointer and one shared-memory address per thread, the
+	// pieces at immediate offsets (the 32-byte sectors a piece leaves behind in L1 serve the next ones).
+	const int c_side = threadIdx.x >> 7, c_row = (threadIdx.x >> 1) & 63, c_half = threadIdx.x & 1;
+	const int c_genome = (c_side ? tj : ti) * kMmTile + c_row;
+	const uint2 *const c_src = planes + (int64_t)min(c_genome, n - 1) * chunk_groups + g_begin + 9 * c_half;
+	const uint32_t c_dst = (uint32_t)__cvta_generic_to_shared(&sm[0][c_side][c_row][2 * (9 * c_half + mm_skew(c_row))]);
+	constexpr uint32_t kStageBytes = 2 * kMmTile * kMmRowWords * 4;
 	auto issue = [&](int64_t s, int buf) {
-		const int64_t g0 = g_begin + s * kMmGroups;
+		const int64_t left = (g_end - g_begin) - s * kMmGroups - 9 * c_half; // groups of this thread's run that exist
+		const int n_valid = c_genome < n ? (int)min((int64_t)9, max((int64_t)0, left)) : 0;
+		const uint2 *src = c_src + s * kMmGroups;
+		const uint32_t dst = c_dst + (uint32_t)buf * kStageBytes;
 #pragma unroll
-		for (int q = 0; q < 3; q++) {
-			const int e = threadIdx.x + 256 * q;
-			const int side = e / 384, row = (e % 384) / 6, piece = e % 6;
-			const int genome = (side ? tj : ti) * kMmTile + row;
-			const int64_t grp = g0 + 2 * piece;
-			const bool valid = genome < n && grp < g_end; // (chunk_groups is even: a piece never straddles the end)
-			const uint2 *src = planes + (valid ? (int64_t)genome * chunk_groups + grp : 0);
-			cp_async16(&sm[buf][side][row][4 * piece], src, valid);
+		for (int q = 0; q < 9; q++) {
+			const int bytes = q < n_valid ? 8 : 0; // 0: zero-filled, nothing is read
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u * q), "l"(n_valid ? src + q : c_src), "r"(bytes) : "memory");
 		}
 		cp_async_commit();
 	};
@@ -145,15 +149,17 @@ k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_gro
 		}
 		__syncthreads();
 		const uint32_t two = one + one;
-#pragma unroll 1
+		// this thread's rows a = ty + 16 i and b = tx + 16 j: the skew of a row depends on bit 3 only, the same for every i / j
+		const uint32_t *const arow = &sm[buf][0][ty][2 * mm_skew(ty)], *const brow = &sm[buf][1][tx][2 * mm_skew(tx)];
+#pragma unroll 2
 		for (int k = 0; k < kMmGroups; k += 3) {
 			uint2 a[4][3], b[4][3]; // three groups each: (lo, hi)
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
 				for (int g = 0; g < 3; g++) {
-					a[i][g] = *reinterpret_cast<const uint2 *>(&sm[buf][0][ty + 16 * i][2 * (k + g)]);
-					b[i][g] = *reinterpret_cast<const uint2 *>(&sm[buf][1][tx + 16 * i][2 * (k + g)]);
+					a[i][g] = *reinterpret_cast<const uint2 *>(arow + 16 * i * kMmRowWords + 2 * (k + g));
+					b[i][g] = *reinterpret_cast<const uint2 *>(brow + 16 * i * kMmRowWords + 2 * (k + g));
 				}
 #pragma unroll
 			for (int i = 0; i < 4; i++)
@@ -225,7 +231,7 @@ int mismatch_tiles(Engine &e, int64_t *sites_out)
 	// column chunks: the bit planes of a chunk take n * chunk_groups * 8 bytes (default: at most 2 GB)
 	int64_t budget = (int64_t)2048 << 20;
 	if (const char *v = std::getenv("PGS_K2_PLANES_MB")) budget = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
-	static_assert(kMmGroups % 6 == 0, "a stage is whole 64-site blocks and whole adder steps");
+	static_assert(kMmGroups % 6 == 0 && 2 * kMmTile * kMmGroups == 9 * 256, "a stage is whole 64-site blocks and whole adder steps; nine pieces per thread");
 	int64_t chunk_blocks = std::max<int64_t>(kMmGroups / 2, budget / ((int64_t)n * 16));
 	chunk_blocks = std::min(chunk_blocks, blocks_total);
 	chunk_blocks = (chunk_blocks + kMmGroups / 2 - 1) / (kMmGroups / 2) * (kMmGroups / 2); // whole stages
