@@ -252,6 +252,9 @@ int pgs_copy_packed(pgs_engine *h, int32_t node, int64_t gene_index, void *dst);
 int pgs_copy_dense(pgs_engine *h, int32_t node, void *dst);
 /* Row index of (node, gene) or -1. */
 int64_t pgs_row_index(pgs_engine *h, int32_t node, int64_t gene_index);
+/* The host-side expander of PGS_OUT_HOST_EXPAND on its own (no engine, no device): `sites` bases of a
+ * packed row -> ASCII.  Returns the name of the code path in use ("avx2", "ssse3", "scalar"). */
+const char *pgs_expand_bases(const void *packed_row, int64_t sites, char *dst);
 /* Decision table of the branch above node: H[k] = floor(2^64 P(K >= k)), k = 0..64. */
 int pgs_get_edge_table(pgs_engine *h, int32_t node, uint64_t H[65], int32_t *kmax);
 

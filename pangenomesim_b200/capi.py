@@ -110,6 +110,8 @@ def load_library():
     lib.pgs_row_index.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
     lib.pgs_row_index.restype = C.c_int64
     lib.pgs_get_edge_table.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, P(C.c_int32)]
+    lib.pgs_expand_bases.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]
+    lib.pgs_expand_bases.restype = C.c_char_p
     _LIB = lib
     return lib
 
@@ -319,6 +321,14 @@ class Engine:
         rep = OutputReport()
         self._check(self._lib.pgs_write_outputs(self._h, C.byref(spec), C.byref(rep)))
         return rep.as_dict()
+
+
+def expand_bases(packed_words, sites: int):
+    """host-side expander of PGS_OUT_HOST_EXPAND: (ASCII bytes, code path name)"""
+    w = np.ascontiguousarray(packed_words, dtype=np.uint32)
+    buf = C.create_string_buffer(max(int(sites), 1))
+    kind = load_library().pgs_expand_bases(_ptr(w), sites, buf)
+    return buf.raw[:sites], kind.decode()
 
 
 def comm_unique_id() -> bytes:

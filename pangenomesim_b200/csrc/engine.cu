@@ -2,6 +2,7 @@
 // tables, launches.  There is no CPU path: every compute entry point ends in a CUDA kernel of
 // kernels.cu / format.cu and fails with PGS_ERR_NO_DEVICE / PGS_ERR_CUDA otherwise.
 #include "engine.h"
+#include "expand.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -635,6 +636,12 @@ int pgs_copy_dense(pgs_engine *h, int32_t node, void *dst)
 						(size_t)e.dense_gid.size() * (size_t)e.blocks * 16, cudaMemcpyDeviceToHost);
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_copy_dense");
 	return PGS_OK;
+}
+
+const char *pgs_expand_bases(const void *packed_row, int64_t sites, char *dst)
+{
+	if (packed_row && dst && sites > 0) pgs::expand_bases(packed_row, sites, dst);
+	return pgs::expand_kind();
 }
 
 int pgs_get_edge_table(pgs_engine *h, int32_t node, uint64_t H[65], int32_t *kmax)

@@ -27,3 +27,26 @@ def allreduce_mismatch(partial, group=None):
     import torch.distributed as dist
     dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     return partial
+
+
+def mismatch_tile_words(n_genomes: int) -> int:
+    """uint32 words of the packed upper-triangular 64 x 64 tiles K2 keeps on the device (include/pgs.h)"""
+    t = (n_genomes + 63) // 64
+    return t * (t + 1) // 2 * 4096
+
+
+def tiles_to_square(tiles, n_genomes: int):
+    """Packed upper-triangular tiles (numpy uint32, e.g. after an all-reduce of the engines' buffers) ->
+    the symmetric n x n matrix with a zero diagonal that pgs_mismatch returns."""
+    import numpy as np
+    t = (n_genomes + 63) // 64
+    tiles = np.asarray(tiles, dtype=np.uint32).reshape(t * (t + 1) // 2, 64, 64)
+    full = np.zeros((t * 64, t * 64), dtype=np.uint32)
+    k = 0
+    for ti in range(t):
+        for tj in range(ti, t):
+            block = tiles[k] if ti != tj else np.triu(tiles[k], 1)
+            full[64 * ti:64 * ti + 64, 64 * tj:64 * tj + 64] = block
+            k += 1
+    full = full[:n_genomes, :n_genomes]
+    return full + full.T

@@ -63,3 +63,22 @@ def test_product_does_not_reference_the_oracle():
             assert "oracle_" not in text and "liboracle" not in text and "ref_model" not in text, path
     so = ROOT / "pangenomesim_b200" / "lib" / "libpgs.so"
     assert b"liboracle" not in so.read_bytes()
+
+
+@pytest.mark.parametrize("sites", [1, 3, 4, 63, 64, 65, 127, 128, 129, 1000, 1500, 2000, 4099])
+def test_host_expander_matches_the_oracle(sites):
+    """the base expander of PGS_OUT_HOST_EXPAND (SIMD where the CPU has it) against the oracle's
+    unpack_ascii and a numpy restatement, every tail length"""
+    import numpy as np
+    from oracle import oracle_py
+    from pangenomesim_b200.capi import expand_bases
+    rng = np.random.default_rng(sites)
+    words = rng.integers(0, 2**32, size=(sites + 15) // 16 + 3, dtype=np.uint64).astype(np.uint32)
+    got, kind = expand_bases(words, sites)
+    assert kind in ("avx2", "ssse3", "scalar")
+    codes = (words[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3
+    want = bytes(b"ACGT"[c] for c in codes.reshape(-1)[:sites])
+    assert got == want
+    padded = np.zeros(4 * ((sites + 63) // 64), np.uint32)
+    padded[:len(words)] = words[:len(padded)]
+    assert got == oracle_py.unpack_ascii(padded, sites)

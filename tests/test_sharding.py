@@ -82,3 +82,25 @@ def test_two_rank_mismatch_allreduce_equals_single_rank():
             for j in range(n):
                 want[i, j] += oracle_py.mismatch(rows[i], rows[j])
     assert np.array_equal(got, want) and tmax == 2.0
+
+
+def test_packed_tiles_round_trip():
+    """the packed upper-triangular layout of K2's counts (include/pgs.h) and its unpacking"""
+    import numpy as np
+    from pangenomesim_b200.sharding import mismatch_tile_words, tiles_to_square
+    for n in (1, 2, 63, 64, 65, 130, 200):
+        rng = np.random.default_rng(n)
+        up = np.triu(rng.integers(0, 1000, size=(n, n)).astype(np.uint32), 1)
+        want = up + up.T
+        t = (n + 63) // 64
+        tiles = np.zeros((t * (t + 1) // 2, 64, 64), np.uint32)
+        k = 0
+        for ti in range(t):
+            for tj in range(ti, t):
+                blk = up[64 * ti:64 * ti + 64, 64 * tj:64 * tj + 64]
+                tiles[k, :blk.shape[0], :blk.shape[1]] = blk
+                k += 1
+        assert tiles.size == mismatch_tile_words(n)
+        assert np.array_equal(tiles_to_square(tiles.reshape(-1), n), want)
+        # partial results of two engines add up tile by tile
+        assert np.array_equal(tiles_to_square(tiles * 2, n), tiles_to_square(tiles, n) * 2)

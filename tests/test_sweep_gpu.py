@@ -497,3 +497,44 @@ def test_mismatch_tiles_chunks_and_edges(oracle, monkeypatch, n, L, G, planes_mb
                 assert np.array_equal(tiles[k], blockw), (ti, tj)
                 k += 1
         del load_library
+
+
+def test_two_engines_with_different_plans_share_a_device(oracle):
+    """the walk kernels' dynamic shared-memory limit is a per-function, per-device attribute: engines
+    with different stack depths (different trees and gene counts) on ONE device, planned and swept in
+    turn and at the same time from two threads, must not lower it under each other's feet"""
+    import threading
+    cases = []
+    for n, G, L in ((900, 40, 1000), (30, 7, 256), (2500, 16, 512)):
+        parent, rate, leaf = treegen.coalescent(n, seed=n, mut_rate=0.03)
+        root = len(parent) - 1
+        genes = treegen.gene_table(parent, leaf, n_core=G, n_acc=10, seed=n)
+        with build(77, L, parent, rate, leaf, genes) as keep:
+            want = np.stack([keep.copy_dense(v, G) for v in (0, n // 2, n - 1, root)])
+        cases.append((n, G, L, parent, rate, leaf, genes, root, want))
+    engines = [build(77, c[2], c[3], c[4], c[5], c[6], flags=0) for c in cases]
+    levels = {e.stats()["levels"] for e in engines}
+    assert len(levels) == 3
+    errors = []
+
+    def hammer(k):
+        try:
+            e, (n, G, L, parent, rate, leaf, genes, root, want) = engines[k], cases[k]
+            for rep in range(6):
+                if rep % 2:  # re-plan: sets the attribute again while the other engines launch
+                    e.set_tree(parent, rate, leaf)
+                    e.set_genes(*genes)
+                e.sweep()
+                e.sync()
+                got = np.stack([e.copy_dense(v, G) for v in (0, n // 2, n - 1, root)])
+                assert np.array_equal(got, want), (k, rep)
+        except Exception as ex:  # noqa: BLE001
+            errors.append((k, ex))
+    threads = [threading.Thread(target=hammer, args=(k,)) for k in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in engines:
+        e.close()
+    assert not errors, errors
