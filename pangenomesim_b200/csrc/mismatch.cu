@@ -91,7 +91,8 @@ __host__ __device__ inline int64_t tri_row_start(int64_t tiles, int64_t ti)
 // only sum and carry are counted: per three masks 8 ALU instructions (16 pipe cycles per warp) and
 // 2 POPC (16 XU cycles) -- the two pipes are level; a deeper adder tree would only load ALU more.
 // `one` is 1: the adds are written as multiply-adds so that they issue on the FMA pipe (IMAD).
-__global__ void __launch_bounds__(256, 2)
+template <int MINB, int UNROLL>
+__global__ void __launch_bounds__(256, MINB)
 k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_groups, int64_t groups_per_split,
 				  uint32_t *__restrict__ tiles_out, uint32_t one)
 {
@@ -151,7 +152,7 @@ k2_mismatch_tiles(const uint2 *__restrict__ planes, int32_t n, int64_t chunk_gro
 		const uint32_t two = one + one;
 		// this thread's rows a = ty + 16 i and b = tx + 16 j: the skew of a row depends on bit 3 only, the same for every i / j
 		const uint32_t *const arow = &sm[buf][0][ty][2 * mm_skew(ty)], *const brow = &sm[buf][1][tx][2 * mm_skew(tx)];
-#pragma unroll 2
+#pragma unroll UNROLL
 		for (int k = 0; k < kMmGroups; k += 3) {
 			uint2 a[4][3], b[4][3]; // three groups each: (lo, hi)
 #pragma unroll
@@ -256,7 +257,13 @@ int mismatch_tiles(Engine &e, int64_t *sites_out)
 		const int64_t groups_per_split = (stages + splits - 1) / splits * kMmGroups;
 		splits = (2 * nb + groups_per_split - 1) / groups_per_split;
 		dim3 grid((unsigned)tri, (unsigned)splits);
-		k2_mismatch_tiles<<<grid, 256, 0, e.stream>>>(e.d_planes.as<uint2>(), n, chunk_groups, groups_per_split, e.d_tiles.as<uint32_t>(), 1u);
+		static const int variant = std::getenv("PGS_K2_VARIANT") ? std::atoi(std::getenv("PGS_K2_VARIANT")) : 0; // development knob
+		if (variant == 1)
+			k2_mismatch_tiles<3, 1><<<grid, 256, 0, e.stream>>>(e.d_planes.as<uint2>(), n, chunk_groups, groups_per_split, e.d_tiles.as<uint32_t>(), 1u);
+		else if (variant == 2)
+			k2_mismatch_tiles<2, 1><<<grid, 256, 0, e.stream>>>(e.d_planes.as<uint2>(), n, chunk_groups, groups_per_split, e.d_tiles.as<uint32_t>(), 1u);
+		else
+			k2_mismatch_tiles<2, 2><<<grid, 256, 0, e.stream>>>(e.d_planes.as<uint2>(), n, chunk_groups, groups_per_split, e.d_tiles.as<uint32_t>(), 1u);
 	}
 	ce = cudaGetLastError();
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch launch");

@@ -540,124 +540,161 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 	// accessory genes: 0.37 ms with 48, 0.41 with 96, 0.62 with 192, 1.26 uncut.
 	int32_t unit_steps = 48;
 	if (const char *v = std::getenv("PGS_SPARSE_UNIT_STEPS")) unit_steps = std::max(1, std::atoi(v)); // tuning knob
-	std::vector<int64_t> stamp(N, -1);
-	std::vector<int32_t> rank_at(N, 0), sub(N, 0), acc(N, 0);
-	std::vector<char> cut(N, 0);
-	std::vector<int32_t> order, parked, unit_roots;
-	int64_t stored = 0, loaded = 0; // rows the sparse walk writes to / reads from memory
 	auto internal = [&](int32_t v) { return e.child_off[v + 1] > e.child_off[v]; };
-	auto row_of = [&](int32_t v) { return (uint32_t)(e.row_base[v] + dense_rows(e, p, v) + rank_at[v]); };
-	for (int64_t g = 0; g < e.n_genes; g++) {
-		const int64_t nb = p.gn_off[g], ne = p.gn_off[g + 1];
-		if (nb == ne) continue;
-		order.assign(p.gn_node.begin() + nb, p.gn_node.begin() + ne);
-		for (int64_t k = nb; k < ne; k++) {
-			const int32_t v = p.gn_node[k];
-			stamp[v] = g;
-			rank_at[v] = p.gn_rank[k];
-			sub[v] = 1;
-			acc[v] = internal(v) ? 1 : 0; // steps (internal nodes) of the piece of the subtree that is not cut off yet
-			cut[v] = 0;
-		}
-		// children before parents: subtree sizes, and a cut wherever a piece has grown to a unit
-		std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
-		const int32_t org = e.origin[g];
-		unit_roots.assign(1, org);
-		for (int32_t v : order) {
-			if (v == org) continue;
-			sub[e.parent[v]] += sub[v];
-			if (acc[v] >= unit_steps) {
-				cut[v] = 1;
-				unit_roots.push_back(v);
-			} else {
-				acc[e.parent[v]] += acc[v];
+
+	// Genes are independent: contiguous ranges of the gene table (balanced by rows) are planned side by
+	// side on a few host threads, each into its own lists; the lists are then joined in gene order, so
+	// the result does not depend on the number of threads.
+	struct Part {
+		std::vector<SparseUnit> units;
+		std::vector<SparseStep> steps;
+		std::vector<SparsePathEdge> paths;
+		int64_t stored = 0, loaded = 0; // rows the sparse walk writes to / reads from memory
+	};
+	auto plan_range = [&](int64_t g_lo, int64_t g_hi, Part &out) {
+		std::vector<int64_t> stamp(N, -1);
+		std::vector<int32_t> rank_at(N, 0), sub(N, 0), acc(N, 0);
+		std::vector<char> cut(N, 0);
+		std::vector<int32_t> order, parked, unit_roots;
+		auto row_of = [&](int32_t v) { return (uint32_t)(e.row_base[v] + dense_rows(e, p, v) + rank_at[v]); };
+		for (int64_t g = g_lo; g < g_hi; g++) {
+			const int64_t nb = p.gn_off[g], ne = p.gn_off[g + 1];
+			if (nb == ne) continue;
+			order.assign(p.gn_node.begin() + nb, p.gn_node.begin() + ne);
+			for (int64_t k = nb; k < ne; k++) {
+				const int32_t v = p.gn_node[k];
+				stamp[v] = g;
+				rank_at[v] = p.gn_rank[k];
+				sub[v] = 1;
+				acc[v] = internal(v) ? 1 : 0; // steps (internal nodes) of the piece of the subtree that is not cut off yet
+				cut[v] = 0;
 			}
-		}
-		if (p.sp_steps.size() + (size_t)(ne - nb) >= 0xFFFFFFFFull || p.sp_paths.size() >= 0xF0000000ull)
-			return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse walk steps; shard the genes");
-		for (int32_t ur : unit_roots) {
-			pgs::SparseUnit su{};
-			su.gid = (uint32_t)e.gene_id[g];
-			su.origin_row = ur == org ? row_of(org) : pgs::kNoRow;
-			su.step_begin = (uint32_t)p.sp_steps.size();
-			su.path_begin = (uint32_t)p.sp_paths.size();
-			if (ur == org) stored++;
-			{ // branches origin -> unit root, top down
-				const size_t first = p.sp_paths.size();
-				for (int32_t v = ur; v != org; v = e.parent[v]) {
-					const int32_t par = e.parent[v], leader = e.child[e.child_off[par]];
-					pgs::SparsePathEdge pe{};
-					pe.leader = (uint32_t)leader;
-					pe.edge = (uint32_t)v;
-					pe.side_h16 = (uint32_t)(e.h1_host[v] >> 48) | (v == leader ? 0u : 0x80000000u);
-					p.sp_paths.push_back(pe);
-				}
-				std::reverse(p.sp_paths.begin() + first, p.sp_paths.end());
-				su.path_len = (uint32_t)(p.sp_paths.size() - first);
-			}
-			parked.clear();
-			int32_t v = ur;
-			uint32_t load = 0, load_level = 0, load_row = 0; // how the next step gets its input (0: carried in registers)
-			bool have = internal(ur);
-			while (have) {
-				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
-				// a child that roots another unit is none of this unit's business
-				const bool ha = stamp[a] == g && !cut[a], hb = stamp[b] == g && !cut[b];
-				const bool da = ha && internal(a), db = hb && internal(b);
-				pgs::SparseStep st{};
-				st.dst_a = (ha && !da) ? row_of(a) : pgs::kNoRow; // a genome's row
-				st.dst_b = (hb && !db) ? row_of(b) : pgs::kNoRow;
-				st.edge_a = (uint32_t)a;
-				st.edge_b = (uint32_t)b;
-				st.h16 = (uint32_t)(e.h1_host[a] >> 48) | ((uint32_t)(e.h1_host[b] >> 48) << 16);
-				st.flags = (ha ? pgs::kSpHasA : 0u) | (hb ? pgs::kSpHasB : 0u) | load;
-				st.in_row = load_row;
-				st.levels = load_level << 8;
-				if (load == pgs::kSpLoadRow) loaded++;
-				int32_t carry = -1;
-				if (da && db) {
-					const bool a_first = sub[a] <= sub[b];
-					carry = a_first ? a : b;
-					const int32_t later = a_first ? b : a;
-					const int depth = (int)parked.size();
-					st.flags |= a_first ? pgs::kSpCarryA : pgs::kSpCarryB;
-					if (depth < smem_cap) {
-						st.flags |= a_first ? pgs::kSpParkB : pgs::kSpParkA;
-						st.levels |= (uint32_t)depth;
-					} else { // deeper than the shared-memory stack: parked in its own row
-						(a_first ? st.dst_b : st.dst_a) = row_of(later);
-					}
-					parked.push_back(later);
-				} else if (da) {
-					carry = a;
-					st.flags |= pgs::kSpCarryA;
-				} else if (db) {
-					carry = b;
-					st.flags |= pgs::kSpCarryB;
-				}
-				stored += (st.dst_a != pgs::kNoRow) + (st.dst_b != pgs::kNoRow);
-				if (ha || hb) p.sp_steps.push_back(st); // (both children cut off: nothing to do here)
-				if (carry >= 0) {
-					v = carry;
-					load = 0;
-				} else if (!parked.empty()) {
-					v = parked.back();
-					parked.pop_back();
-					const int depth = (int)parked.size();
-					if (depth < smem_cap) {
-						load = pgs::kSpLoadSmem;
-						load_level = (uint32_t)depth;
-					} else {
-						load = pgs::kSpLoadRow;
-						load_row = row_of(v);
-					}
+			// children before parents: subtree sizes, and a cut wherever a piece has grown to a unit
+			std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
+			const int32_t org = e.origin[g];
+			unit_roots.assign(1, org);
+			for (int32_t v : order) {
+				if (v == org) continue;
+				sub[e.parent[v]] += sub[v];
+				if (acc[v] >= unit_steps) {
+					cut[v] = 1;
+					unit_roots.push_back(v);
 				} else {
-					have = false;
+					acc[e.parent[v]] += acc[v];
 				}
 			}
-			su.n_steps = (uint32_t)(p.sp_steps.size() - su.step_begin);
-			p.sp_units.push_back(su);
+			for (int32_t ur : unit_roots) {
+				pgs::SparseUnit su{};
+				su.gid = (uint32_t)e.gene_id[g];
+				su.origin_row = ur == org ? row_of(org) : pgs::kNoRow;
+				su.step_begin = (uint32_t)out.steps.size();
+				su.path_begin = (uint32_t)out.paths.size();
+				if (ur == org) out.stored++;
+				{ // branches origin -> unit root, top down
+					const size_t first = out.paths.size();
+					for (int32_t v = ur; v != org; v = e.parent[v]) {
+						const int32_t par = e.parent[v], leader = e.child[e.child_off[par]];
+						pgs::SparsePathEdge pe{};
+						pe.leader = (uint32_t)leader;
+						pe.edge = (uint32_t)v;
+						pe.side_h16 = (uint32_t)(e.h1_host[v] >> 48) | (v == leader ? 0u : 0x80000000u);
+						out.paths.push_back(pe);
+					}
+					std::reverse(out.paths.begin() + first, out.paths.end());
+					su.path_len = (uint32_t)(out.paths.size() - first);
+				}
+				parked.clear();
+				int32_t v = ur;
+				uint32_t load = 0, load_level = 0, load_row = 0; // how the next step gets its input (0: carried in registers)
+				bool have = internal(ur);
+				while (have) {
+					const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
+					// a child that roots another unit is none of this unit's business
+					const bool ha = stamp[a] == g && !cut[a], hb = stamp[b] == g && !cut[b];
+					const bool da = ha && internal(a), db = hb && internal(b);
+					pgs::SparseStep st{};
+					st.dst_a = (ha && !da) ? row_of(a) : pgs::kNoRow; // a genome's row
+					st.dst_b = (hb && !db) ? row_of(b) : pgs::kNoRow;
+					st.edge_a = (uint32_t)a;
+					st.edge_b = (uint32_t)b;
+					st.h16 = (uint32_t)(e.h1_host[a] >> 48) | ((uint32_t)(e.h1_host[b] >> 48) << 16);
+					st.flags = (ha ? pgs::kSpHasA : 0u) | (hb ? pgs::kSpHasB : 0u) | load;
+					st.in_row = load_row;
+					st.levels = load_level << 8;
+					if (load == pgs::kSpLoadRow) out.loaded++;
+					int32_t carry = -1;
+					if (da && db) {
+						const bool a_first = sub[a] <= sub[b];
+						carry = a_first ? a : b;
+						const int32_t later = a_first ? b : a;
+						const int depth = (int)parked.size();
+						st.flags |= a_first ? pgs::kSpCarryA : pgs::kSpCarryB;
+						if (depth < smem_cap) {
+							st.flags |= a_first ? pgs::kSpParkB : pgs::kSpParkA;
+							st.levels |= (uint32_t)depth;
+						} else { // deeper than the shared-memory stack: parked in its own row
+							(a_first ? st.dst_b : st.dst_a) = row_of(later);
+						}
+						parked.push_back(later);
+					} else if (da) {
+						carry = a;
+						st.flags |= pgs::kSpCarryA;
+					} else if (db) {
+						carry = b;
+						st.flags |= pgs::kSpCarryB;
+					}
+					out.stored += (st.dst_a != pgs::kNoRow) + (st.dst_b != pgs::kNoRow);
+					if (ha || hb) out.steps.push_back(st); // (both children cut off: nothing to do here)
+					if (carry >= 0) {
+						v = carry;
+						load = 0;
+					} else if (!parked.empty()) {
+						v = parked.back();
+						parked.pop_back();
+						const int depth = (int)parked.size();
+						if (depth < smem_cap) {
+							load = pgs::kSpLoadSmem;
+							load_level = (uint32_t)depth;
+						} else {
+							load = pgs::kSpLoadRow;
+							load_row = row_of(v);
+						}
+					} else {
+						have = false;
+					}
+				}
+				su.n_steps = (uint32_t)(out.steps.size() - su.step_begin);
+				out.units.push_back(su);
+			}
 		}
+	};
+	const int64_t total_rows = p.gn_off[e.n_genes];
+	if (total_rows + 8 >= (int64_t)0xF0000000ll) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse rows on one engine; shard the genes");
+	unsigned workers = total_rows >= 200000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	std::vector<Part> parts(workers);
+	std::vector<int64_t> cuts(workers + 1, e.n_genes);
+	cuts[0] = 0;
+	for (unsigned w = 1; w < workers; w++) // first gene whose rows start at or beyond the w-th share
+		cuts[w] = std::lower_bound(p.gn_off.begin(), p.gn_off.begin() + e.n_genes, total_rows * w / workers) - p.gn_off.begin();
+	{
+		std::vector<std::thread> pool;
+		for (unsigned w = 1; w < workers; w++) pool.emplace_back(plan_range, cuts[w], cuts[w + 1], std::ref(parts[w]));
+		plan_range(cuts[0], cuts[1], parts[0]);
+		for (auto &th : pool) th.join();
+	}
+	int64_t stored = 0, loaded = 0;
+	for (Part &part : parts) { // join in gene order; a part's indices move behind what is already there
+		const uint32_t step0 = (uint32_t)p.sp_steps.size(), path0 = (uint32_t)p.sp_paths.size();
+		for (SparseUnit &u : part.units) {
+			u.step_begin += step0;
+			u.path_begin += path0;
+		}
+		p.sp_units.insert(p.sp_units.end(), part.units.begin(), part.units.end());
+		p.sp_steps.insert(p.sp_steps.end(), part.steps.begin(), part.steps.end());
+		p.sp_paths.insert(p.sp_paths.end(), part.paths.begin(), part.paths.end());
+		stored += part.stored;
+		loaded += part.loaded;
+		part = Part();
 	}
 	for (int k = 0; k < 4; k++) p.sp_steps.push_back(pgs::SparseStep{}); // the kernel prefetches a few steps past a unit's end
 	// lanes of a warp walk different units: sort by length so that they finish together, longest first
