@@ -87,50 +87,124 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 		e.dense_slot[dense[s].second] = (int32_t)s;
 	}
 
-	// ---- sparse genes: expand carriers, mark the nodes on the paths carrier -> origin
+	// ---- sparse genes: expand carriers, mark the nodes on the paths carrier -> origin.  Genes are
+	// independent: contiguous ranges of the table are marked side by side on a few host threads (each
+	// with its own stamp array), then joined in gene order.
+	struct Part {
+		std::vector<int32_t> carriers, nodes; // concatenated over the part's sparse genes
+		std::vector<int64_t> n_carriers, n_nodes; // per gene of the range (0 for dense genes)
+		std::string error;
+	};
+	auto mark_range = [&](int64_t g_lo, int64_t g_hi, Part &out) {
+		std::vector<int64_t> stamp(N, -1);
+		out.n_carriers.assign(g_hi - g_lo, 0);
+		out.n_nodes.assign(g_hi - g_lo, 0);
+		for (int64_t g = g_lo; g < g_hi; g++) {
+			if (e.dense_slot[g] >= 0) continue;
+			const int64_t b = carrier_off[g], c = carrier_off[g + 1];
+			const int32_t org = origin_node[g];
+			const size_t first_carrier = out.carriers.size(), first_node = out.nodes.size();
+			if (c - b == 1 && carrier_genome[b] == PGS_ALL_GENOMES) {
+				// every genome below a non-root origin, in all_order
+				for (int32_t i = 0; i < n; i++) {
+					int32_t v = e.genome_leaf[e.all_order[i]];
+					while (v != -1 && v != org) v = e.parent[v];
+					if (v == org) out.carriers.push_back(e.all_order[i]);
+				}
+			} else {
+				for (int64_t k = b; k < c; k++) {
+					const int32_t cg = carrier_genome[k];
+					if (cg < 0 || cg >= n) {
+						out.error = "pgs_set_genes: carrier genome out of range";
+						return;
+					}
+					out.carriers.push_back(cg);
+				}
+			}
+			for (size_t k = first_carrier; k < out.carriers.size(); k++) {
+				int32_t v = e.genome_leaf[out.carriers[k]];
+				if (stamp[v] == g) {
+					out.error = "pgs_set_genes: genome listed twice for a gene";
+					return;
+				}
+				while (stamp[v] != g) {
+					stamp[v] = g;
+					out.nodes.push_back(v);
+					if (v == org) break;
+					v = e.parent[v];
+					if (v < 0) {
+						out.error = "pgs_set_genes: carrier is not below the gene's origin";
+						return;
+					}
+				}
+			}
+			out.n_carriers[g - g_lo] = (int64_t)(out.carriers.size() - first_carrier);
+			out.n_nodes[g - g_lo] = (int64_t)(out.nodes.size() - first_node);
+		}
+	};
+	const int64_t entries = n_genes > 0 ? carrier_off[n_genes] : 0;
+	unsigned workers = entries >= 100000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	std::vector<Part> parts(workers);
+	std::vector<int64_t> cuts(workers + 1, n_genes);
+	cuts[0] = 0;
+	for (unsigned w = 1; w < workers; w++) // balanced by carrier entries
+		cuts[w] = std::lower_bound(carrier_off, carrier_off + n_genes, entries * w / workers) - carrier_off;
+	{
+		std::vector<std::thread> pool;
+		for (unsigned w = 1; w < workers; w++) pool.emplace_back(mark_range, cuts[w], cuts[w + 1], std::ref(parts[w]));
+		mark_range(cuts[0], cuts[1], parts[0]);
+		for (auto &th : pool) th.join();
+	}
+	for (const Part &part : parts)
+		if (!part.error.empty()) return e.fail(PGS_ERR_ARG, part.error);
+	// join in gene order: carrier lists, per-gene node lists, and the per-node lists of sparse genes
+	// (ascending gene index, because the genes are visited in that order)
 	e.carrier_off.assign(n_genes + 1, 0);
 	e.carrier_genome.clear();
-	std::vector<std::vector<int64_t>> at_node(N);
-	std::vector<int64_t> stamp(N, -1);
 	e.genome_gene_count.assign(n, D);
 	p.gn_off.assign(n_genes + 1, 0);
-	for (int64_t g = 0; g < n_genes; g++) {
-		e.carrier_off[g] = (int64_t)e.carrier_genome.size();
-		p.gn_off[g + 1] = p.gn_off[g];
-		if (e.dense_slot[g] >= 0) continue;
-		const int64_t b = carrier_off[g], c = carrier_off[g + 1];
-		const int32_t org = origin_node[g];
-		if (c - b == 1 && carrier_genome[b] == PGS_ALL_GENOMES) {
-			// every genome below a non-root origin, in all_order
-			for (int32_t i = 0; i < n; i++) {
-				int32_t v = e.genome_leaf[e.all_order[i]];
-				while (v != -1 && v != org) v = e.parent[v];
-				if (v == org) e.carrier_genome.push_back(e.all_order[i]);
-			}
-		} else {
-			for (int64_t k = b; k < c; k++) {
-				const int32_t cg = carrier_genome[k];
-				if (cg < 0 || cg >= n) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier genome out of range");
-				e.carrier_genome.push_back(cg);
+	e.sp_off.assign(N + 1, 0);
+	{
+		size_t total_carriers = 0, total_nodes = 0;
+		for (const Part &part : parts) {
+			total_carriers += part.carriers.size();
+			total_nodes += part.nodes.size();
+			for (int32_t v : part.nodes) e.sp_off[v + 1]++;
+		}
+		e.carrier_genome.reserve(total_carriers);
+		p.gn_node.reserve(total_nodes);
+		for (int32_t v = 0; v < N; v++) e.sp_off[v + 1] += e.sp_off[v];
+		e.sp_gene.resize(e.sp_off[N]);
+		p.gn_rank.resize(total_nodes);
+	}
+	{
+		std::vector<int64_t> fill(e.sp_off.begin(), e.sp_off.end() - 1);
+		for (unsigned w = 0; w < workers; w++) {
+			const Part &part = parts[w];
+			size_t ci = 0, ni = 0;
+			for (int64_t g = cuts[w]; g < cuts[w + 1]; g++) {
+				e.carrier_off[g] = (int64_t)e.carrier_genome.size();
+				p.gn_off[g] = (int64_t)p.gn_node.size();
+				const int64_t nc = part.n_carriers[g - cuts[w]], nn = part.n_nodes[g - cuts[w]];
+				for (int64_t k = 0; k < nc; k++) {
+					const int32_t cg = part.carriers[ci + k];
+					e.carrier_genome.push_back(cg);
+					e.genome_gene_count[cg]++;
+				}
+				for (int64_t k = 0; k < nn; k++) {
+					const int32_t v = part.nodes[ni + k];
+					p.gn_rank[p.gn_node.size()] = (int32_t)(fill[v] - e.sp_off[v]);
+					p.gn_node.push_back(v);
+					e.sp_gene[fill[v]++] = g;
+				}
+				ci += (size_t)nc;
+				ni += (size_t)nn;
 			}
 		}
-		for (int64_t k = e.carrier_off[g]; k < (int64_t)e.carrier_genome.size(); k++) {
-			int32_t v = e.genome_leaf[e.carrier_genome[k]];
-			if (stamp[v] == g) return e.fail(PGS_ERR_ARG, "pgs_set_genes: genome listed twice for a gene");
-			e.genome_gene_count[e.carrier_genome[k]]++;
-			while (stamp[v] != g) {
-				stamp[v] = g;
-				p.gn_node.push_back(v);
-				p.gn_rank.push_back((int32_t)at_node[v].size());
-				at_node[v].push_back(g);
-				if (v == org) break;
-				v = e.parent[v];
-				if (v < 0) return e.fail(PGS_ERR_ARG, "pgs_set_genes: carrier is not below the gene's origin");
-			}
-		}
-		p.gn_off[g + 1] = (int64_t)p.gn_node.size();
 	}
 	e.carrier_off[n_genes] = (int64_t)e.carrier_genome.size();
+	p.gn_off[n_genes] = (int64_t)p.gn_node.size();
+	parts.clear();
 	{ // gene ids must be unique across the whole table
 		std::vector<int64_t> ids(e.gene_id);
 		std::sort(ids.begin(), ids.end());
@@ -138,12 +212,6 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 			return e.fail(PGS_ERR_ARG, "pgs_set_genes: duplicate gene_id");
 	}
 
-	e.sp_off.assign(N + 1, 0);
-	for (int32_t v = 0; v < N; v++) e.sp_off[v + 1] = e.sp_off[v] + (int64_t)at_node[v].size();
-	e.sp_gene.resize(e.sp_off[N]);
-	for (int32_t v = 0; v < N; v++) std::copy(at_node[v].begin(), at_node[v].end(), e.sp_gene.begin() + e.sp_off[v]);
-	at_node.clear();
-	at_node.shrink_to_fit();
 	return PGS_OK;
 }
 

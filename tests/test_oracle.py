@@ -139,3 +139,31 @@ def test_low_rate_substitution_counts_are_binomial(oracle, rate):
         leaf = oracle.row(seed, parent, rates, node, 2, 7, S)
         diff = oracle.mismatch(root, leaf)
         assert abs(diff - S * p) < 4.0 * math.sqrt(S * p * (1 - p)), (seed, node, diff, S * p)
+
+
+def test_substitutions_are_sequence_independent_xor_masks():
+    """the property the fused sweeps are built on: a branch acts on a block as an XOR
+    with a mask that depends on (seed, edge, gene, block) only.  The same gene id placed at the root
+    and at an internal node u starts from the same origin row, so below u the two histories differ by
+    exactly the XOR of the masks on the path root -> u: one constant for every node below u."""
+    import numpy as np
+    import treegen
+    from oracle import oracle_py
+    seed, L, gid = 99, 1000, 12345
+    parent, rate, leaf = treegen.coalescent(40, seed=4, mut_rate=0.4)  # long branches: most blocks change somewhere
+    root = len(parent) - 1
+    from_root = oracle_py.gene_all_nodes(seed, parent, rate, root, gid, L)
+    ch = treegen.children_of(parent)
+    checked = 0
+    for u in range(40, root):  # internal nodes
+        from_u = oracle_py.gene_all_nodes(seed, parent, rate, u, gid, L)
+        assert np.array_equal(from_u[u], from_root[root])  # the origin row is keyed by the gene only
+        path_mask = from_root[u] ^ from_root[root]
+        assert path_mask.any()
+        stack = [u]
+        while stack:
+            v = stack.pop()
+            assert np.array_equal(from_root[v] ^ from_u[v], path_mask), (u, v)
+            checked += 1
+            stack.extend(ch[v])
+    assert checked > 200
