@@ -316,15 +316,19 @@ def k2_leg(torch, dist, eng, stats, rank, world, peaks):
     T = (n + 63) // 64
     tile_pairs = T * (T + 1) / 2.0 * 4096
     sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-    alu_peak = 148 * 64 * sm_mhz * 1e6 / 3.0 * 32  # site pairs per second at 3 ALU instructions per 32 site pairs
+    # The kernel's instruction mix per THREE 32-site masks of a genome pair: 8 ALU-pipe instructions (3 XOR + 3 LOP3
+    # for the masks, 2 LOP3 for the 3:2 carry-save adder; the pipe takes 16 lanes per clock per SM sub-partition: 16
+    # cycles per warp) and 2 POPC on the XU pipe (4 lanes per clock per sub-partition: 16 cycles per warp) -- the two
+    # pipes are level, 96 site pairs per lane per 16 cycles.  (POPC on XU at a quarter of the ALU rate: profiles/r02_k2_full.md.)
+    pipe_peak = 148 * 4 * 32 * 96 / 16.0 * sm_mhz * 1e6
     site_pairs_rank = pairs * (sites_all / world)
     out.update({"k2_ms": k2_ms, "site_pairs_total": pairs * sites_all,
                 "site_pairs_per_s": pairs * sites_all / (k2_ms * 1e-3),
-                "roofline": {"bound": "alu", "achieved": site_pairs_rank / (k2_ms * 1e-3), "peak": alu_peak, "unit": "site-pairs/s per GPU",
-                             "frac": site_pairs_rank / (k2_ms * 1e-3) / alu_peak,
-                             "frac_counting_whole_tiles": tile_pairs * (sites_all / world) / (k2_ms * 1e-3) / alu_peak,
-                             "definition": f"148 SMs x 64 ALU lanes per clock x {sm_mhz:.0f} MHz (max clock) / 3 ALU instructions "
-                                           "(XOR, LOP3, POPC) per 32 site pairs"},
+                "roofline": {"bound": "alu+xu", "achieved": site_pairs_rank / (k2_ms * 1e-3), "peak": pipe_peak, "unit": "site-pairs/s per GPU",
+                             "frac": site_pairs_rank / (k2_ms * 1e-3) / pipe_peak,
+                             "frac_counting_whole_tiles": tile_pairs * (sites_all / world) / (k2_ms * 1e-3) / pipe_peak,
+                             "definition": f"148 SMs x 4 sub-partitions x 32 lanes x 96 site pairs / 16 cycles x {sm_mhz:.0f} MHz (max clock): "
+                                           "per three masks 8 ALU instructions (2 cycles each per warp) and 2 POPC on the XU pipe (8 cycles each)"},
                 "what": f"k2_split_planes + k2_mismatch_tiles over {n} genomes x this rank's dense genes, max over ranks; "
                         "counts kept as packed upper-triangular tiles on the device"})
     return out
