@@ -119,6 +119,18 @@ __device__ __forceinline__ uint32_t pair_hits(uint32_t v, uint32_t hc)
 static __device__ __forceinline__ uint4 substitute_sites(uint4 x, uint4 w, int K, uint32_t edge, uint32_t gid,
 														  uint32_t blk, int valid, const PhiloxKeys &keys)
 {
+	if (K == 1) { // nearly every block that changes at all changes in one site: no loop, no 64-bit shifts
+		const uint32_t pos = __umulhi(w.z, 64u);
+		const uint32_t delta = 1u + __umulhi(w.z * 64u, 3u);
+		if ((int)pos < valid) { // (padding sites never change)
+			const uint32_t m = delta << (2u * (pos & 15u)), wi = pos >> 4;
+			x.x ^= wi == 0u ? m : 0u;
+			x.y ^= wi == 1u ? m : 0u;
+			x.z ^= wi == 2u ? m : 0u;
+			x.w ^= wi == 3u ? m : 0u;
+		}
+		return x;
+	}
 	uint32_t stream = 1;
 	uint64_t taken = 0, mlo = 0, mhi = 0;
 	int have = 2; // unread words of the current call
