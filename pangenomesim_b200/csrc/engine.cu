@@ -48,6 +48,7 @@ int Engine::cuda_fail(cudaError_t e, const char *what)
 
 int Engine::alloc(DevBuf &b, size_t bytes, const char *what)
 {
+	if (plan_only) return fail(PGS_ERR_NO_DEVICE, std::string("plan-only engine (PGS_PLAN_ONLY): no device memory for ") + what);
 	b.release();
 	if (bytes == 0) bytes = 16;
 	cudaError_t e = cudaMalloc(&b.p, bytes);
@@ -170,7 +171,7 @@ using pgs::Engine;
 #define ENGINE_OR_RETURN(h)                \
 	if (!(h)) return PGS_ERR_ARG;          \
 	Engine &e = (h)->e;                    \
-	{                                      \
+	if (!e.plan_only) {                    \
 		cudaError_t ce_ = cudaSetDevice(e.device); \
 		if (ce_ != cudaSuccess) return e.cuda_fail(ce_, "cudaSetDevice"); \
 	}
@@ -208,6 +209,20 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 		pgs::g_create_error = "pgs_create: gene_length out of range";
 		return PGS_ERR_ARG;
 	}
+	// Development knob: an engine without a device that can only PLAN (pgs_set_tree / pgs_set_genes up to
+	// the first device allocation, where it fails with PGS_ERR_NO_DEVICE) -- for timing and testing the
+	// host-side planner on machines without a GPU.  It computes nothing: there is no CPU path.
+	if (const char *v = std::getenv("PGS_PLAN_ONLY"))
+		if (std::atoi(v)) {
+			pgs_engine *h = new (std::nothrow) pgs_engine();
+			if (!h) return PGS_ERR_NOMEM;
+			h->e.cfg = *cfg;
+			h->e.plan_only = true;
+			h->e.blocks = (cfg->gene_length + 63) / 64;
+			h->e.last_valid = (int32_t)(cfg->gene_length - (h->e.blocks - 1) * 64);
+			*out = h;
+			return PGS_OK;
+		}
 	int count = 0;
 	cudaError_t ce = cudaGetDeviceCount(&count);
 	if (ce != cudaSuccess || count == 0) {
@@ -258,8 +273,10 @@ int pgs_create(const pgs_config *cfg, pgs_engine **out)
 void pgs_destroy(pgs_engine *h)
 {
 	if (!h) return;
-	cudaSetDevice(h->e.device);
-	cudaStreamSynchronize(h->e.stream);
+	if (!h->e.plan_only) {
+		cudaSetDevice(h->e.device);
+		cudaStreamSynchronize(h->e.stream);
+	}
 	delete h;
 }
 

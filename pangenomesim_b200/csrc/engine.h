@@ -24,6 +24,7 @@ struct DevBuf {
 struct Engine {
 	pgs_config cfg{};
 	int device = 0;
+	bool plan_only = false; // PGS_PLAN_ONLY: no device, planning only (development knob)
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // 0-2 sweep, 3-4 mismatch, 5 format, 6 between the dense and the sparse genes
 	std::string err;

@@ -34,8 +34,9 @@ struct SweepPlan {
 	std::vector<int64_t> gn_off;
 	std::vector<int32_t> gn_node, gn_rank;
 	std::vector<SparseUnit> sp_units;
-	std::vector<SparseStep> sp_steps;
-	std::vector<SparsePathEdge> sp_paths;
+	// steps and paths stay in the pieces the planner's threads produced (joined on the device: no host copy)
+	std::vector<std::vector<SparseStep>> sp_steps;
+	std::vector<std::vector<SparsePathEdge>> sp_paths;
 };
 
 int64_t dense_rows(const Engine &e, const SweepPlan &p, int32_t v)
@@ -144,6 +145,7 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 	};
 	const int64_t entries = n_genes > 0 ? carrier_off[n_genes] : 0;
 	unsigned workers = entries >= 100000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	if (const char *v = std::getenv("PGS_PLAN_THREADS")) workers = (unsigned)std::max(1, std::atoi(v)); // tuning knob
 	std::vector<Part> parts(workers);
 	std::vector<int64_t> cuts(workers + 1, n_genes);
 	cuts[0] = 0;
@@ -625,6 +627,8 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 		std::vector<char> cut(N, 0);
 		std::vector<int32_t> order, parked, unit_roots;
 		auto row_of = [&](int32_t v) { return (uint32_t)(e.row_base[v] + dense_rows(e, p, v) + rank_at[v]); };
+		// one allocation up front (a step per internal row at most: about half of the range's rows)
+		out.steps.reserve((size_t)(p.gn_off[g_hi] - p.gn_off[g_lo]) / 2 + 64);
 		for (int64_t g = g_lo; g < g_hi; g++) {
 			const int64_t nb = p.gn_off[g], ne = p.gn_off[g + 1];
 			if (nb == ne) continue;
@@ -739,35 +743,48 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 	const int64_t total_rows = p.gn_off[e.n_genes];
 	if (total_rows + 8 >= (int64_t)0xF0000000ll) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse rows on one engine; shard the genes");
 	unsigned workers = total_rows >= 200000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	if (const char *v = std::getenv("PGS_PLAN_THREADS")) workers = (unsigned)std::max(1, std::atoi(v)); // tuning knob
 	std::vector<Part> parts(workers);
 	std::vector<int64_t> cuts(workers + 1, e.n_genes);
 	cuts[0] = 0;
 	for (unsigned w = 1; w < workers; w++) // first gene whose rows start at or beyond the w-th share
 		cuts[w] = std::lower_bound(p.gn_off.begin(), p.gn_off.begin() + e.n_genes, total_rows * w / workers) - p.gn_off.begin();
+	const bool timing = std::getenv("PGS_PLAN_TIMING") != nullptr;
+	auto tp0 = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!timing) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "plan:   sparse %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tp0).count());
+		tp0 = t1;
+	};
 	{
 		std::vector<std::thread> pool;
 		for (unsigned w = 1; w < workers; w++) pool.emplace_back(plan_range, cuts[w], cuts[w + 1], std::ref(parts[w]));
 		plan_range(cuts[0], cuts[1], parts[0]);
 		for (auto &th : pool) th.join();
 	}
+	lap("ranges");
 	int64_t stored = 0, loaded = 0;
+	uint32_t step0 = 0, path0 = 0;
 	for (Part &part : parts) { // join in gene order; a part's indices move behind what is already there
-		const uint32_t step0 = (uint32_t)p.sp_steps.size(), path0 = (uint32_t)p.sp_paths.size();
 		for (SparseUnit &u : part.units) {
 			u.step_begin += step0;
 			u.path_begin += path0;
 		}
+		step0 += (uint32_t)part.steps.size();
+		path0 += (uint32_t)part.paths.size();
 		p.sp_units.insert(p.sp_units.end(), part.units.begin(), part.units.end());
-		p.sp_steps.insert(p.sp_steps.end(), part.steps.begin(), part.steps.end());
-		p.sp_paths.insert(p.sp_paths.end(), part.paths.begin(), part.paths.end());
+		p.sp_steps.push_back(std::move(part.steps));
+		p.sp_paths.push_back(std::move(part.paths));
 		stored += part.stored;
 		loaded += part.loaded;
-		part = Part();
 	}
-	for (int k = 0; k < 4; k++) p.sp_steps.push_back(pgs::SparseStep{}); // the kernel prefetches a few steps past a unit's end
+	lap("join");
+	p.sp_steps.emplace_back(4, pgs::SparseStep{}); // the kernel prefetches a few steps past a unit's end
 	// lanes of a warp walk different units: sort by length so that they finish together, longest first
 	std::stable_sort(p.sp_units.begin(), p.sp_units.end(),
 					 [](const pgs::SparseUnit &a, const pgs::SparseUnit &b) { return a.n_steps + a.path_len > b.n_steps + b.path_len; });
+	lap("sort");
 	e.n_sp_units = (int64_t)p.sp_units.size();
 	// rows K1 really moves: these instead of every sparse row written and every sparse parent row read
 	e.rows_stored += stored - e.sparse_rows_written;
@@ -789,8 +806,25 @@ int upload_plan(Engine &e, SweepPlan &p)
 	if ((rc = e.upload(e.d_walk_steps, p.walk_steps.data(), sizeof(WalkStep) * p.walk_steps.size(), "walk steps"))) return rc;
 	if ((rc = e.upload(e.d_walk_off, p.walk_off.data(), sizeof(int64_t) * p.walk_off.size(), "walk units"))) return rc;
 	if ((rc = e.upload(e.d_sp_units, p.sp_units.data(), sizeof(SparseUnit) * p.sp_units.size(), "sparse walk units"))) return rc;
-	if ((rc = e.upload(e.d_sp_steps, p.sp_steps.data(), sizeof(SparseStep) * p.sp_steps.size(), "sparse walk steps"))) return rc;
-	if ((rc = e.upload(e.d_sp_paths, p.sp_paths.data(), sizeof(SparsePathEdge) * p.sp_paths.size(), "sparse walk paths"))) return rc;
+	{ // pieces -> one device array each
+		auto upload_pieces = [&](DevBuf &b, const auto &pieces, const char *what) -> int {
+			size_t total = 0;
+			for (const auto &v : pieces) total += v.size() * sizeof(v[0]);
+			int r = e.alloc(b, total, what);
+			if (r) return r;
+			size_t at = 0;
+			for (const auto &v : pieces) {
+				if (v.empty()) continue;
+				const cudaError_t ce = cudaMemcpyAsync(static_cast<char *>(b.p) + at, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, e.stream);
+				if (ce != cudaSuccess) return e.cuda_fail(ce, what);
+				at += v.size() * sizeof(v[0]);
+			}
+			const cudaError_t ce = cudaStreamSynchronize(e.stream);
+			return ce == cudaSuccess ? PGS_OK : e.cuda_fail(ce, what);
+		};
+		if ((rc = upload_pieces(e.d_sp_steps, p.sp_steps, "sparse walk steps"))) return rc;
+		if ((rc = upload_pieces(e.d_sp_paths, p.sp_paths, "sparse walk paths"))) return rc;
+	}
 	if (e.sparse_walk && pgs::prepare_walk_sparse() != cudaSuccess)
 		return e.fail(PGS_ERR_CUDA, "pgs_set_genes: the sparse walk kernel's shared-memory stack does not fit this device");
 	if ((rc = e.upload(e.d_top_tasks, p.top_tasks.data(), sizeof(TopMaskTask) * p.top_tasks.size(), "top mask tasks"))) return rc;
