@@ -82,3 +82,28 @@ def test_host_expander_matches_the_oracle(sites):
     padded = np.zeros(4 * ((sites + 63) // 64), np.uint32)
     padded[:len(words)] = words[:len(padded)]
     assert got == oracle_py.unpack_ascii(padded, sites)
+
+
+def test_plan_only_knob_plans_and_computes_nothing(monkeypatch):
+    """PGS_PLAN_ONLY (development knob): an engine without a device runs the host-side planner and
+    fails at the first device allocation; nothing can be swept, counted or written with it"""
+    import numpy as np
+    import treegen
+    from pangenomesim_b200 import Engine, PgsError
+    monkeypatch.setenv("PGS_PLAN_ONLY", "1")
+    parent, rate, leaf = treegen.coalescent(50, seed=3, mut_rate=0.1)
+    genes = treegen.gene_table(parent, leaf, n_core=5, n_acc=20, seed=2)
+    with Engine(1, 300) as e:
+        e.set_tree(parent, rate, leaf)
+        with pytest.raises(PgsError) as ex:
+            e.set_genes(*genes)
+        assert ex.value.code == -6 and "plan-only" in ex.value.message
+        with pytest.raises(PgsError) as ex:  # a carrier that is not below its gene's origin is still caught by the planner
+            e.set_genes([7], [0], [0, 1], [1])
+        assert ex.value.code == -1
+        for call in (e.sweep, e.mismatch, lambda: e.write_outputs(None, 8 | 32, [], [])):
+            with pytest.raises(PgsError) as ex:
+                call()
+            assert ex.value.code == -2
+        assert e.stats()["n_nodes"] == len(parent) and e.stats()["rows_total"] == 0
+    del np
