@@ -11,9 +11,9 @@ LIBDIR   := pangenomesim_b200/lib
 BINDIR   := pangenomesim_b200/bin
 OBJDIR   := build/obj
 
-LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/plan.cu $(CSRC)/kernels.cu $(CSRC)/mismatch.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp $(CSRC)/expand.cpp
+LIB_SRCS := $(CSRC)/engine.cu $(CSRC)/plan.cu $(CSRC)/kernels.cu $(CSRC)/mismatch.cu $(CSRC)/mismatch_tc.cu $(CSRC)/format.cu $(CSRC)/edge_table.cpp $(CSRC)/expand.cpp
 LIB_HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/pgs.h
-LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/plan.o $(OBJDIR)/kernels.o $(OBJDIR)/mismatch.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o $(OBJDIR)/expand.o
+LIB_OBJS := $(OBJDIR)/engine.o $(OBJDIR)/plan.o $(OBJDIR)/kernels.o $(OBJDIR)/mismatch.o $(OBJDIR)/mismatch_tc.o $(OBJDIR)/format.o $(OBJDIR)/edge_table.o $(OBJDIR)/expand.o
 
 all: lib cli oracle
 

@@ -61,6 +61,11 @@ typedef struct pgs_config {
  * need: the rows of the genomes (leaves) and of the origins; pgs_copy_packed / pgs_copy_dense on
  * any other node then fail with PGS_ERR_STATE. */
 #define PGS_FLAG_KEEP_INTERNAL 2u
+/* Which kernel counts the pairwise mismatches (pgs_mismatch*): the popcount-XOR kernel, or the
+ * same counts as a +-1 contraction on the tensor cores (tcgen05, FP8 operands, FP32 accumulation --
+ * exact, the counts are identical integers).  Neither flag: the library's default. */
+#define PGS_FLAG_K2_POPC 4u
+#define PGS_FLAG_K2_TENSOR 8u
 
 /* sentinel carrier entry: "every genome below the origin node carries the gene" */
 #define PGS_ALL_GENOMES (-1)

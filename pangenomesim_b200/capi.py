@@ -18,6 +18,8 @@ _LIB = None
 PGS_ALL_GENOMES = -1
 PGS_FLAG_NO_GRAPH = 1
 PGS_FLAG_KEEP_INTERNAL = 2
+PGS_FLAG_K2_POPC = 4
+PGS_FLAG_K2_TENSOR = 8
 OUT_REF, OUT_CORE, OUT_ACCESSORY, OUT_GENOMES, OUT_MAF, OUT_ALL, OUT_DISCARD, OUT_PACKED, OUT_HOST_EXPAND = 1, 2, 4, 8, 16, 31, 32, 64, 128
 
 
