@@ -118,7 +118,7 @@ int plan_genes(Engine &e, int64_t n_genes, const int64_t *gene_id, const int32_t
 int64_t mismatch_tile_words(int32_t n);
 int mismatch_tiles(Engine &e, int64_t *sites_out);
 int mismatch_impl(const Engine &e);
-int mismatch_tiles_tensor(Engine &e, bool int8); // mismatch_tc.cu: tcgen05 path into e.d_tiles (allocated and cleared by mismatch_tiles)
+int mismatch_tiles_tensor(Engine &e, int impl); // mismatch_tc.cu: tcgen05 path into e.d_tiles (allocated and cleared by mismatch_tiles)
 int mismatch_square_device(Engine &e, uint32_t *out_device);
 int mismatch_tiles_to_host(Engine &e, uint32_t *out_host);
 int comm_unique_id(void *id128);

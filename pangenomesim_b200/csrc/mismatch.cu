@@ -214,15 +214,18 @@ int64_t mismatch_tile_words(int32_t n)
 	return tiles * (tiles + 1) / 2 * (kMmTile * kMmTile);
 }
 
-// Which K2: 0 = popcount kernel (this file), 1 = tensor cores with E4M3 operands, 2 = tensor cores
-// with INT8 operands (mismatch_tc.cu).  The counts are the same integers either way.
-// PGS_K2_IMPL=popc|tensor|tensor-i8 overrides the engine's flags.
+// Which K2: 0 = popcount kernel (this file); tensor cores (mismatch_tc.cu): 1 = CTA pairs with E4M3
+// operands, 2 = CTA pairs with INT8 operands, 3 / 4 = the single-CTA kernel (E4M3 / INT8).  The
+// counts are the same integers either way.
+// PGS_K2_IMPL=popc|tensor|tensor-i8|tensor-1cta|tensor-1cta-i8 overrides the engine's flags.
 int mismatch_impl(const Engine &e)
 {
 	if (const char *v = std::getenv("PGS_K2_IMPL")) {
 		if (!std::strcmp(v, "popc")) return 0;
 		if (!std::strcmp(v, "tensor")) return 1;
 		if (!std::strcmp(v, "tensor-i8")) return 2;
+		if (!std::strcmp(v, "tensor-1cta")) return 3;
+		if (!std::strcmp(v, "tensor-1cta-i8")) return 4;
 	}
 	if (e.cfg.flags & PGS_FLAG_K2_POPC) return 0;
 	if (e.cfg.flags & PGS_FLAG_K2_TENSOR) return 1;
@@ -243,7 +246,7 @@ int mismatch_tiles(Engine &e, int64_t *sites_out)
 	if (sites_out) *sites_out = D * e.cfg.gene_length;
 	const int64_t blocks_total = D * e.blocks; // 64-site blocks per genome
 	if (n < 2 || blocks_total == 0) return PGS_OK;
-	if (const int impl = mismatch_impl(e)) return mismatch_tiles_tensor(e, impl == 2);
+	if (const int impl = mismatch_impl(e)) return mismatch_tiles_tensor(e, impl);
 
 	// column chunks: the bit planes of a chunk take n * chunk_groups * 8 bytes (default: at most 2 GB)
 	int64_t budget = (int64_t)2048 << 20;

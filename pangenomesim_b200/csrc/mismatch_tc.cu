@@ -302,6 +302,188 @@ k2_tc_tiles(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 	}
 }
 
+// ---- the CTA-pair kernel -----------------------------------------------------------------------
+//
+// Two CTAs of one TPC (a cluster of two) work on one 256 x 512 tile with tcgen05.mma.cta_group::2:
+// CTA r holds rows [128 r, 128 r + 128) of the A side and, for each 256-column half h, rows
+// [256 h + 128 r, + 128) of the B side -- three 128 x 128-byte boxes per K slice, 48 KB per stage,
+// 48 bytes of operands per clock per SM at full tensor rate instead of the 96 of k2_tc_tiles.
+// Each CTA's accumulator is its 128 rows x 512 columns: all of its TMEM.  The leader (rank 0)
+// issues the MMAs (M = 256, N = 256, K = 32, twice per K step); both CTAs stream their boxes with
+// TMA, all of them signalling the LEADER's full barrier; tcgen05.commit multicasts the "stage is
+// free" / "accumulator is complete" arrivals to both CTAs.
+
+constexpr int kPairM = 256, kPairN = 512;
+constexpr uint32_t kPairBox = 128 * kTcKBytes;     // one 128-row box
+constexpr uint32_t kPairStage = 3 * kPairBox;      // A, B half 0, B half 1
+constexpr int kPairStages = 4;
+constexpr uint32_t kPairSmemBytes = kPairStages * kPairStage + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in CTA 0 of the pair (cute: Sm100MmaPeerBitMask)
+
+struct PairUnit {
+	int32_t tm, tn;           // rows [256 tm, + 256) x columns [512 tn, + 512)
+	int32_t t_begin, t_end;   // K range in triples (three slices = two 64-site blocks)
+	int32_t first_half;       // 1: the first 256 columns lie entirely below the diagonal -- skipped
+	int32_t atomic;           // 1: other units add to the same output tiles (K split) -- atomicAdd
+};
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int32_t c0, int32_t c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+				 "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+				 : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar)
+{
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+				 : "memory");
+}
+template <bool INT8> __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	if (INT8)
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+					 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+					 : "memory");
+	else
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+					 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+					 : "memory");
+}
+template <bool INT8> __host__ __device__ constexpr uint32_t tc_instr_desc_pair()
+{
+	return (INT8 ? (2u << 4) | (1u << 7) | (1u << 10) : (1u << 4)) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <bool INT8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__ units, int32_t n, int32_t real_blocks, uint32_t *__restrict__ tiles_out)
+{
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bars = base + kPairStages * kPairStage;
+	const uint32_t full0 = bars, empty0 = bars + 8 * kPairStages, tmem_full = bars + 16 * kPairStages, tmem_slot = tmem_full + 8;
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t rank;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+	const PairUnit u = units[blockIdx.x >> 1];
+	const int32_t n_slices = 3 * (u.t_end - u.t_begin);
+	const int n_halves = 2 - u.first_half;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < kPairStages; s++) {
+			mbar_init(full0 + 8 * s, 1);  // the leader's arrive.expect_tx; the bytes of both CTAs complete it
+			mbar_init(empty0 + 8 * s, 1); // one multicast commit per use
+		}
+		mbar_init(tmem_full, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) { // the same warp of both CTAs: all 512 columns of both SMs
+		asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+	}
+	tc_fence_before();
+	cluster_sync_all(); // the peer's barriers exist before anything signals them
+	tc_fence_after();
+	uint32_t tmem_acc;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot) : "memory");
+
+	if (warp == 0) {
+		if (lane == 0) {
+			const int32_t row_a = u.tm * kPairM + 128 * (int32_t)rank;
+			const int32_t row_b = u.tn * kPairN + 128 * (int32_t)rank;
+			const uint32_t bytes_both = 2u * kPairBox * (uint32_t)(1 + n_halves);
+			for (int32_t k = 0; k < n_slices; k++) {
+				const int s = k % kPairStages;
+				const uint32_t ph = (uint32_t)(k / kPairStages) & 1u;
+				mbar_wait(empty0 + 8 * s, ph ^ 1u);
+				if (rank == 0) mbar_expect_tx(full0 + 8 * s, bytes_both);
+				const uint32_t leader_full = (full0 + 8 * s) & kPeerBitMask;
+				const uint32_t st = base + s * kPairStage;
+				const int32_t kx = (3 * u.t_begin + k) * kTcKBytes;
+				tma_load_2d_pair(st, &map, leader_full, kx, row_a);
+				if (!u.first_half) tma_load_2d_pair(st + kPairBox, &map, leader_full, kx, row_b);
+				tma_load_2d_pair(st + 2 * kPairBox, &map, leader_full, kx, row_b + 256);
+			}
+		}
+	} else if (warp == 1) {
+		if (lane == 0 && rank == 0) {
+			constexpr uint32_t idesc = tc_instr_desc_pair<INT8>();
+			for (int32_t k = 0; k < n_slices; k++) {
+				const int s = k % kPairStages;
+				const uint32_t ph = (uint32_t)(k / kPairStages) & 1u;
+				mbar_wait(full0 + 8 * s, ph);
+				tc_fence_after();
+				const uint32_t st = base + s * kPairStage;
+				const uint64_t adesc = tc_smem_desc(st);
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					if (h < u.first_half) continue;
+					const uint64_t bdesc = tc_smem_desc(st + (1 + h) * kPairBox);
+#pragma unroll
+					for (int j = 0; j < kTcKBytes / 32; j++)
+						tc_mma_pair<INT8>(tmem_acc + 256u * h, adesc + 2 * j, bdesc + 2 * j, idesc, (uint32_t)(k | j));
+				}
+				tc_commit_pair(empty0 + 8 * s);
+			}
+			tc_commit_pair(tmem_full);
+		}
+	} else {
+		const int quarter = warp & 3;
+		const int row = 32 * quarter + lane;
+		const int32_t gi = u.tm * kPairM + 128 * (int32_t)rank + row;
+		const int32_t blocks_here = max(0, min(2 * u.t_end, real_blocks) - 2 * u.t_begin);
+		const int32_t k_real = blocks_here * kTcBlockBytes;
+		const int64_t tiles64 = (n + kMmTileTc - 1) / kMmTileTc;
+		const int64_t ti = gi / kMmTileTc;
+		if (n_slices > 0) {
+			mbar_wait(tmem_full, 0);
+			tc_fence_after();
+#pragma unroll 1
+			for (int c = 8 * u.first_half; c < kPairN / 32; c++) {
+				uint32_t r[32];
+				__syncwarp();
+				tc_ld32(tmem_acc + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(32 * c), r);
+				const int32_t gj0 = u.tn * kPairN + 32 * c;
+				const int64_t tj = gj0 / kMmTileTc;
+				if (gi < n && ti <= tj && gj0 < n) {
+					uint32_t *const dst = tiles_out + (tri_row_start_tc(tiles64, ti) + (tj - ti)) * (int64_t)(kMmTileTc * kMmTileTc) +
+										  (gi % kMmTileTc) * kMmTileTc + (gj0 % kMmTileTc);
+#pragma unroll
+					for (int j = 0; j < 32; j++) {
+						const int32_t dot = INT8 ? (int32_t)r[j] : __float2int_rn(__uint_as_float(r[j]));
+						const uint32_t mm = (uint32_t)(k_real - dot) >> 2;
+						r[j] = (gi < gj0 + j && gj0 + j < n) ? mm : 0u;
+					}
+					if (u.atomic) {
+#pragma unroll
+						for (int j = 0; j < 32; j++)
+							if (r[j]) atomicAdd(dst + j, r[j]);
+					} else { // this unit owns its output tiles during this launch
+						uint4 *const d4 = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+						for (int q = 0; q < 8; q++) {
+							uint4 v = d4[q];
+							v.x += r[4 * q], v.y += r[4 * q + 1], v.z += r[4 * q + 2], v.w += r[4 * q + 3];
+							d4[q] = v;
+						}
+					}
+				}
+			}
+		}
+		tc_fence_before();
+	}
+	cluster_sync_all(); // neither CTA may leave (or free TMEM) while the pair's MMAs read its shared memory
+	if (warp == 1) {
+		tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512) : "memory");
+	}
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -405,15 +587,104 @@ template <bool INT8> int run_tensor(Engine &e, int64_t budget)
 	return PGS_OK;
 }
 
+// Pair tiles of the upper triangle in launch order (bands of 4 tile rows, column by column), cut
+// into units: whole tiles while they fill complete waves of `slots` CTA pairs, the remaining tiles
+// split along K into equal pieces so that the last wave ends together (those pieces add atomically).
+std::vector<PairUnit> pair_units(int32_t n, int32_t triples, int slots)
+{
+	const int tm_count = (n + kPairM - 1) / kPairM, tn_count = (n + kPairN - 1) / kPairN;
+	std::vector<PairUnit> tiles;
+	constexpr int kBand = 4;
+	for (int band = 0; band < tm_count; band += kBand)
+		for (int tn = 0; tn < tn_count; tn++)
+			for (int tm = band; tm < std::min(band + kBand, tm_count); tm++)
+				if ((int64_t)tm * kPairM < (int64_t)tn * kPairN + kPairN - 1)
+					tiles.push_back(PairUnit{tm, tn, 0, triples, (int64_t)tn * kPairN + 255 < (int64_t)tm * kPairM ? 1 : 0, 0});
+	const size_t whole = tiles.size() / (size_t)slots * (size_t)slots;
+	const size_t rest = tiles.size() - whole;
+	const int pieces = rest ? (int)std::min<int64_t>(slots / (int64_t)rest, triples) : 1;
+	if (pieces <= 1) return tiles;
+	std::vector<PairUnit> units(tiles.begin(), tiles.begin() + (std::ptrdiff_t)whole);
+	const int32_t per = (triples + pieces - 1) / pieces;
+	for (size_t i = whole; i < tiles.size(); i++)
+		for (int32_t t = 0; t < triples; t += per) {
+			PairUnit u = tiles[i];
+			u.t_begin = t;
+			u.t_end = std::min(t + per, triples);
+			u.atomic = 1;
+			units.push_back(u);
+		}
+	return units;
+}
+
+template <bool INT8> int run_tensor_pair(Engine &e, int64_t budget)
+{
+	const int32_t n = e.n_genomes;
+	const int64_t D = (int64_t)e.dense_gid.size();
+	const int64_t blocks_total = D * e.blocks;
+	const int64_t n_pad = ((int64_t)n + kPairN - 1) / kPairN * kPairN;
+	int64_t chunk_blocks = std::max<int64_t>(2, budget / (n_pad * kTcBlockBytes));
+	chunk_blocks = std::min<int64_t>(chunk_blocks, 80000); // FP32 accumulation stays exact: 3 * 64 * 80000 < 2^24
+	chunk_blocks = std::min(chunk_blocks, blocks_total + (blocks_total & 1));
+	chunk_blocks &= ~(int64_t)1;
+	const int64_t pitch = chunk_blocks * kTcBlockBytes;
+	const size_t x_bytes = (size_t)n_pad * (size_t)pitch;
+	int rc;
+	if (e.d_planes.bytes < x_bytes && (rc = e.alloc(e.d_planes, x_bytes, "mismatch operand matrix"))) return rc;
+	cudaError_t ce = cudaMemsetAsync(e.d_planes.p, 0, x_bytes, e.stream);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "mismatch operand matrix");
+	CUtensorMap map;
+	if ((rc = make_map(e, &map, e.d_planes.p, n_pad, pitch, 128))) return rc;
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e.device);
+	const int slots = std::max(1, sms / 2);
+
+	// unit lists of a full chunk and of the (shorter) last chunk, uploaded once
+	const int64_t last_nb = blocks_total % chunk_blocks;
+	const std::vector<PairUnit> units_full = pair_units(n, (int32_t)(chunk_blocks / 2), slots);
+	const std::vector<PairUnit> units_last = last_nb ? pair_units(n, (int32_t)((last_nb + 1) / 2), slots) : std::vector<PairUnit>();
+	std::vector<PairUnit> all(units_full);
+	all.insert(all.end(), units_last.begin(), units_last.end());
+	if ((rc = e.upload_keep(e.d_mismatch, all.data(), all.size() * sizeof(PairUnit), "mismatch unit list"))) return rc;
+
+	ce = cudaFuncSetAttribute(k2_tc_pair<INT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "k2_tc_pair shared memory");
+
+	for (int64_t b0 = 0; b0 < blocks_total; b0 += chunk_blocks) {
+		const int64_t nb = std::min(chunk_blocks, blocks_total - b0);
+		const bool last = nb < chunk_blocks;
+		if (b0 > 0 && last) { // the tail of every row must read as zero
+			ce = cudaMemsetAsync(e.d_planes.p, 0, x_bytes, e.stream);
+			if (ce != cudaSuccess) return e.cuda_fail(ce, "mismatch operand matrix");
+		}
+		const int64_t items = (int64_t)n * nb * 4;
+		k2_expand_pm1<INT8><<<(unsigned)((items + 255) / 256), 256, 0, e.stream>>>(reinterpret_cast<const uint32_t *>(e.tables.rows),
+																					 e.d_leaf_base_words.as<int64_t>(), n, b0, nb, pitch,
+																					 e.d_planes.as<uint8_t>());
+		const PairUnit *const list = e.d_mismatch.as<PairUnit>() + (last ? units_full.size() : 0);
+		const size_t count = last ? units_last.size() : units_full.size();
+		k2_tc_pair<INT8><<<(unsigned)(2 * count), kTcThreads, kPairSmemBytes, e.stream>>>(map, list, n, (int32_t)nb, e.d_tiles.as<uint32_t>());
+	}
+	ce = cudaGetLastError();
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch (tensor) launch");
+	return PGS_OK;
+}
+
 } // namespace
 
 // Same contract as mismatch_tiles (mismatch.cu): partial counts of this engine's dense genes into
 // e.d_tiles, asynchronous on the engine's stream.  e.d_tiles is allocated and cleared by the caller.
-int mismatch_tiles_tensor(Engine &e, bool int8)
+// impl: 1 = CTA pairs, E4M3; 2 = CTA pairs, INT8; 3 / 4 = the single-CTA kernel, E4M3 / INT8.
+int mismatch_tiles_tensor(Engine &e, int impl)
 {
 	int64_t budget = (int64_t)2048 << 20;
 	if (const char *v = std::getenv("PGS_K2_PLANES_MB")) budget = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
-	return int8 ? run_tensor<true>(e, budget) : run_tensor<false>(e, budget);
+	switch (impl) {
+	case 1: return run_tensor_pair<false>(e, budget);
+	case 2: return run_tensor_pair<true>(e, budget);
+	case 3: return run_tensor<false>(e, budget);
+	default: return run_tensor<true>(e, budget);
+	}
 }
 
 } // namespace pgs
