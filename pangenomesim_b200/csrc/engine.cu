@@ -31,6 +31,9 @@ Engine::~Engine()
 		if (p) cudaFreeHost(p);
 	for (auto &x : ev)
 		if (x) cudaEventDestroy(x);
+	for (auto &x : mm_ev)
+		if (x) cudaEventDestroy(x);
+	if (aux_stream) cudaStreamDestroy(aux_stream);
 	if (own_stream) cudaStreamDestroy(own_stream);
 }
 

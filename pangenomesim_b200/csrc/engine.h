@@ -79,6 +79,8 @@ struct Engine {
 	DevBuf d_dense_tasks, d_sparse_tasks, d_root_tasks, d_leaf_base_words, d_mismatch, d_tab8, d_walk_steps, d_walk_off, d_unit_path_off, d_unit_path, d_unit_store, d_top_tasks, d_sp_units, d_sp_steps, d_sp_paths, d_planes, d_tiles;
 	char *h_mm_stage[2] = {nullptr, nullptr}; // pinned staging of pgs_mismatch's result
 	size_t mm_stage_bytes = 0;
+	cudaStream_t aux_stream = nullptr; // K2 on the tensor cores: the operand expansion runs beside the tile kernel
+	cudaEvent_t mm_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	void *comm = nullptr;       // ncclComm_t of pgs_comm_init (one engine per process), else nullptr
 	int comm_world = 1, comm_rank = 0;
 	// K3's tables and per-chunk index buffers: kept between pgs_write_outputs calls (they change with

@@ -215,9 +215,10 @@ int64_t mismatch_tile_words(int32_t n)
 }
 
 // Which K2: 0 = popcount kernel (this file); tensor cores (mismatch_tc.cu): 1 = CTA pairs with E4M3
-// operands, 2 = CTA pairs with INT8 operands, 3 / 4 = the single-CTA kernel (E4M3 / INT8).  The
+// operands, 2 = CTA pairs with INT8 operands, 3 / 4 = the single-CTA kernel (E4M3 / INT8), 5 = CTA pairs with
+// E2M1 operands and unit block scales.  The
 // counts are the same integers either way.
-// PGS_K2_IMPL=popc|tensor|tensor-i8|tensor-1cta|tensor-1cta-i8 overrides the engine's flags.
+// PGS_K2_IMPL=popc|tensor|tensor-i8|tensor-fp4|tensor-1cta|tensor-1cta-i8 overrides the engine's flags.
 int mismatch_impl(const Engine &e)
 {
 	if (const char *v = std::getenv("PGS_K2_IMPL")) {
@@ -226,6 +227,7 @@ int mismatch_impl(const Engine &e)
 		if (!std::strcmp(v, "tensor-i8")) return 2;
 		if (!std::strcmp(v, "tensor-1cta")) return 3;
 		if (!std::strcmp(v, "tensor-1cta-i8")) return 4;
+		if (!std::strcmp(v, "tensor-fp4")) return 5;
 	}
 	if (e.cfg.flags & PGS_FLAG_K2_POPC) return 0;
 	if (e.cfg.flags & PGS_FLAG_K2_TENSOR) return 1;

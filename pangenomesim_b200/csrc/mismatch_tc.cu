@@ -151,6 +151,17 @@ template <bool INT8> __host__ __device__ constexpr uint32_t tc_instr_desc()
 
 // ---- expansion ---------------------------------------------------------------------------------
 
+// even bits of x -> low 16 bits
+__device__ __forceinline__ uint32_t even_bits16(uint32_t x)
+{
+	x &= 0x55555555u;
+	x = (x | (x >> 1)) & 0x33333333u;
+	x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+	x = (x | (x >> 4)) & 0x00FF00FFu;
+	x = (x | (x >> 8)) & 0x0000FFFFu;
+	return x;
+}
+
 // bits 0, 2, 4, 6 of b -> the low bit of bytes 0..3 (the partial products that collide land on bits 7, 13, 19: masked)
 __device__ __forceinline__ uint32_t spread4(uint32_t b)
 {
@@ -165,16 +176,24 @@ template <bool INT8> __device__ __forceinline__ uint32_t pm1_bytes(uint32_t bits
 // One thread = one 16-site word of one genome: 4 bytes in, 48 bytes out (16 lo, 16 hi, 16 lo^hi).
 // X[g * pitch + (block - first_block) * 192 + word * 48 ...].  Padding sites (code 0 in every row)
 // are expanded like any other site: they always match and the epilogue counts them in S.
+// Blocks [n_blocks, out_blocks) -- the odd block that completes the last K triple -- are written as
+// zeros (they add nothing to a dot product).  Rows of padding genomes are never written and may
+// hold anything: an output element depends on its own two rows only, and those outputs are dropped.
 template <bool INT8>
 __global__ void __launch_bounds__(256)
 k2_expand_pm1(const uint32_t *__restrict__ rows, const int64_t *__restrict__ leaf_base_words, int32_t n, int64_t first_block, int64_t n_blocks,
-			  int64_t pitch, uint8_t *__restrict__ X)
+			  int64_t out_blocks, int64_t pitch, uint8_t *__restrict__ X)
 {
-	const int64_t words = n_blocks * 4;
+	const int64_t words = out_blocks * 4;
 	const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
 	if (idx >= (int64_t)n * words) return;
 	const int32_t g = (int32_t)(idx / words);
 	const int64_t w = idx - (int64_t)g * words;
+	if (w >= n_blocks * 4) {
+		uint4 *const z = reinterpret_cast<uint4 *>(X + (int64_t)g * pitch + w * 48);
+		z[0] = z[1] = z[2] = make_uint4(0, 0, 0, 0);
+		return;
+	}
 	const uint32_t v = __ldg(rows + leaf_base_words[g] + first_block * 4 + w);
 	uint4 lo, hi, xo;
 	uint32_t *const lp = &lo.x, *const hp = &hi.x, *const xp = &xo.x;
@@ -305,26 +324,51 @@ k2_tc_tiles(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // ---- the CTA-pair kernel -----------------------------------------------------------------------
 //
 // Two CTAs of one TPC (a cluster of two) work on one 256 x 512 tile with tcgen05.mma.cta_group::2:
-// CTA r holds rows [128 r, 128 r + 128) of the A side and, for each 256-column half h, rows
-// [256 h + 128 r, + 128) of the B side -- three 128 x 128-byte boxes per K slice, 48 KB per stage,
-// 48 bytes of operands per clock per SM at full tensor rate instead of the 96 of k2_tc_tiles.
-// Each CTA's accumulator is its 128 rows x 512 columns: all of its TMEM.  The leader (rank 0)
-// issues the MMAs (M = 256, N = 256, K = 32, twice per K step); both CTAs stream their boxes with
-// TMA, all of them signalling the LEADER's full barrier; tcgen05.commit multicasts the "stage is
-// free" / "accumulator is complete" arrivals to both CTAs.
+// CTA r holds rows [128 r, 128 r + 128) of the A side and, for each column half h (N_h <= 256
+// columns, a multiple of 16), rows [N_h / 2 * r, + N_h / 2) of the B side -- three 128 x 128-byte
+// boxes per K slice, 48 KB per stage, 48 bytes of operands per clock per SM at full tensor rate
+// instead of the 96 of k2_tc_tiles.  Each CTA's accumulator is its 128 rows x 512 columns: all of
+// its TMEM.  The leader (rank 0) issues the MMAs (M = 256, N = N_h, twice per K step); both CTAs
+// stream their boxes with TMA, all of them signalling the LEADER's full barrier; tcgen05.commit
+// multicasts the "stage is free" / "accumulator is complete" arrivals to both CTAs.
+//
+// MODE: operands E4M3 (kind::f8f6f4), INT8 (kind::i8), or E2M1 -- +-1 are exact in FP4 as well --
+// with kind::mxf4 block scaling, every scale 2^0: twice the K per instruction (64), half the
+// operand bytes per site.  The scale factors live in TMEM; all of them are the UE8M0 byte 127, so
+// the epilogue warps fill 32 columns with 0x7F7F7F7F once and every scale-factor read of any MMA
+// finds 1.0 there, whatever its layout.  Those 32 columns come out of the second column half
+// (N_1 <= 224: a 256 x 480 tile).
 
-constexpr int kPairM = 256, kPairN = 512;
+enum : int { kModeE4M3 = 0, kModeInt8 = 1, kModeFp4 = 2 };
+
+constexpr int kPairM = 256;
 constexpr uint32_t kPairBox = 128 * kTcKBytes;     // one 128-row box
 constexpr uint32_t kPairStage = 3 * kPairBox;      // A, B half 0, B half 1
 constexpr int kPairStages = 4;
 constexpr uint32_t kPairSmemBytes = kPairStages * kPairStage + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in CTA 0 of the pair (cute: Sm100MmaPeerBitMask)
+constexpr uint32_t kSfColumn = 480;                // FP4: TMEM columns [480, 512) hold the scale factors
+
+__host__ __device__ constexpr int pair_tile_n(int mode)
+{
+	return mode == kModeFp4 ? 480 : 512;
+}
+__host__ __device__ constexpr int pair_block_bytes(int mode) // expanded bytes per 64-site block
+{
+	return mode == kModeFp4 ? 96 : 192;
+}
+__host__ __device__ constexpr int pair_blocks_per_triple(int mode) // 64-site blocks in three 128-byte K slices
+{
+	return 384 / pair_block_bytes(mode);
+}
 
 struct PairUnit {
-	int32_t tm, tn;           // rows [256 tm, + 256) x columns [512 tn, + 512)
-	int32_t t_begin, t_end;   // K range in triples (three slices = two 64-site blocks)
-	int32_t first_half;       // 1: the first 256 columns lie entirely below the diagonal -- skipped
-	int32_t atomic;           // 1: other units add to the same output tiles (K split) -- atomicAdd
+	int32_t tm, tn;         // rows [256 tm, + 256) x columns [TILE_N tn, + TILE_N)
+	int32_t t_begin, t_end; // K range in triples (three 128-byte slices)
+	int32_t n0, n1;         // columns of the two halves that are computed (multiples of 16; 0: the half is skipped --
+	                        // entirely below the diagonal or beyond the last genome)
+	int32_t atomic;         // 1: other units add to the same output tiles (K split) -- atomicAdd
+	int32_t pad;
 };
 
 __device__ __forceinline__ void cluster_sync_all()
@@ -342,23 +386,40 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar)
 	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
 				 : "memory");
 }
-template <bool INT8> __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+template <int MODE>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t tmem_sf)
 {
-	if (INT8)
+	if (MODE == kModeInt8)
 		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
 					 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
 					 : "memory");
-	else
+	else if (MODE == kModeE4M3)
 		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
 					 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
 					 : "memory");
+	else
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%5], "
+					 "p;\n\t}" ::"r"(tmem_d),
+					 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sf)
+					 : "memory");
 }
-template <bool INT8> __host__ __device__ constexpr uint32_t tc_instr_desc_pair()
+// M = 256; N is added at run time ((N >> 3) << 17).  Block-scaled form (cute::UMMA::InstrDescriptorBlockScaled):
+// A / B format 1 = E2M1 (bits 7-9, 10-12), scale format UE8M0 (bit 23), scale-factor ids 0, K = 64 (bit 31 = 0).
+template <int MODE> __host__ __device__ constexpr uint32_t tc_instr_desc_pair()
 {
-	return (INT8 ? (2u << 4) | (1u << 7) | (1u << 10) : (1u << 4)) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+	return (MODE == kModeInt8 ? (2u << 4) | (1u << 7) | (1u << 10) : MODE == kModeE4M3 ? (1u << 4) : (1u << 7) | (1u << 10) | (1u << 23)) |
+		   ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void tc_st32_const(uint32_t taddr, uint32_t v)
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+				 "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+				 "r"(v)
+				 : "memory");
+	asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <bool INT8>
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__ units, int32_t n, int32_t real_blocks, uint32_t *__restrict__ tiles_out)
 {
@@ -372,7 +433,8 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
 	const PairUnit u = units[blockIdx.x >> 1];
 	const int32_t n_slices = 3 * (u.t_end - u.t_begin);
-	const int n_halves = 2 - u.first_half;
+	const int32_t col0[2] = {u.tn * pair_tile_n(MODE), u.tn * pair_tile_n(MODE) + 256}; // first genome of each column half
+	const int32_t nh[2] = {u.n0, u.n1};
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < kPairStages; s++) {
@@ -387,16 +449,20 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 	}
 	tc_fence_before();
-	cluster_sync_all(); // the peer's barriers exist before anything signals them
+	__syncthreads();
 	tc_fence_after();
 	uint32_t tmem_acc;
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot) : "memory");
+	if (MODE == kModeFp4 && warp >= 2) // every scale factor = 2^0
+		tc_st32_const(tmem_acc + ((uint32_t)(32 * (warp & 3)) << 16) + kSfColumn, 0x7F7F7F7Fu);
+	tc_fence_before();
+	cluster_sync_all(); // the peer's barriers (and scale factors) exist before anything uses them
+	tc_fence_after();
 
 	if (warp == 0) {
 		if (lane == 0) {
 			const int32_t row_a = u.tm * kPairM + 128 * (int32_t)rank;
-			const int32_t row_b = u.tn * kPairN + 128 * (int32_t)rank;
-			const uint32_t bytes_both = 2u * kPairBox * (uint32_t)(1 + n_halves);
+			const uint32_t bytes_both = 2u * kPairBox * (uint32_t)(1 + (nh[0] > 0) + (nh[1] > 0));
 			for (int32_t k = 0; k < n_slices; k++) {
 				const int s = k % kPairStages;
 				const uint32_t ph = (uint32_t)(k / kPairStages) & 1u;
@@ -406,13 +472,14 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 				const uint32_t st = base + s * kPairStage;
 				const int32_t kx = (3 * u.t_begin + k) * kTcKBytes;
 				tma_load_2d_pair(st, &map, leader_full, kx, row_a);
-				if (!u.first_half) tma_load_2d_pair(st + kPairBox, &map, leader_full, kx, row_b);
-				tma_load_2d_pair(st + 2 * kPairBox, &map, leader_full, kx, row_b + 256);
+#pragma unroll
+				for (int h = 0; h < 2; h++) // rows past the last genome are zero-filled by the TMA unit
+					if (nh[h]) tma_load_2d_pair(st + (1 + h) * kPairBox, &map, leader_full, kx, col0[h] + (nh[h] >> 1) * (int32_t)rank);
 			}
 		}
 	} else if (warp == 1) {
 		if (lane == 0 && rank == 0) {
-			constexpr uint32_t idesc = tc_instr_desc_pair<INT8>();
+			constexpr uint32_t idesc = tc_instr_desc_pair<MODE>();
 			for (int32_t k = 0; k < n_slices; k++) {
 				const int s = k % kPairStages;
 				const uint32_t ph = (uint32_t)(k / kPairStages) & 1u;
@@ -422,11 +489,12 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 				const uint64_t adesc = tc_smem_desc(st);
 #pragma unroll
 				for (int h = 0; h < 2; h++) {
-					if (h < u.first_half) continue;
+					if (!nh[h]) continue;
 					const uint64_t bdesc = tc_smem_desc(st + (1 + h) * kPairBox);
+					const uint32_t idesc_h = idesc | ((uint32_t)(nh[h] >> 3) << 17);
 #pragma unroll
-					for (int j = 0; j < kTcKBytes / 32; j++)
-						tc_mma_pair<INT8>(tmem_acc + 256u * h, adesc + 2 * j, bdesc + 2 * j, idesc, (uint32_t)(k | j));
+					for (int j = 0; j < kTcKBytes / 32; j++) // 32 bytes of K per instruction (32 E4M3 / INT8 or 64 E2M1 entries)
+						tc_mma_pair<MODE>(tmem_acc + 256u * h, adesc + 2 * j, bdesc + 2 * j, idesc_h, (uint32_t)(k | j), tmem_acc + kSfColumn);
 				}
 				tc_commit_pair(empty0 + 8 * s);
 			}
@@ -436,40 +504,45 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 		const int quarter = warp & 3;
 		const int row = 32 * quarter + lane;
 		const int32_t gi = u.tm * kPairM + 128 * (int32_t)rank + row;
-		const int32_t blocks_here = max(0, min(2 * u.t_end, real_blocks) - 2 * u.t_begin);
-		const int32_t k_real = blocks_here * kTcBlockBytes;
+		constexpr int kBpt = pair_blocks_per_triple(MODE);
+		const int32_t blocks_here = max(0, min(kBpt * u.t_end, real_blocks) - kBpt * u.t_begin);
+		const int32_t k_real = blocks_here * 192; // K entries that are real sites: 3 per site
 		const int64_t tiles64 = (n + kMmTileTc - 1) / kMmTileTc;
 		const int64_t ti = gi / kMmTileTc;
 		if (n_slices > 0) {
 			mbar_wait(tmem_full, 0);
 			tc_fence_after();
 #pragma unroll 1
-			for (int c = 8 * u.first_half; c < kPairN / 32; c++) {
-				uint32_t r[32];
-				__syncwarp();
-				tc_ld32(tmem_acc + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(32 * c), r);
-				const int32_t gj0 = u.tn * kPairN + 32 * c;
-				const int64_t tj = gj0 / kMmTileTc;
-				if (gi < n && ti <= tj && gj0 < n) {
-					uint32_t *const dst = tiles_out + (tri_row_start_tc(tiles64, ti) + (tj - ti)) * (int64_t)(kMmTileTc * kMmTileTc) +
-										  (gi % kMmTileTc) * kMmTileTc + (gj0 % kMmTileTc);
+			for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+				for (int c = 0; 32 * c < nh[h]; c++) {
+					uint32_t r[32];
+					__syncwarp();
+					tc_ld32(tmem_acc + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(256 * h + 32 * c), r);
+					const int32_t gj0 = col0[h] + 32 * c;
+					const int32_t gj_end = min(n, col0[h] + nh[h]); // columns past N_h hold whatever an earlier CTA left in TMEM
+					const int64_t tj = gj0 / kMmTileTc;
+					if (gi < n && ti <= tj && gj0 < gj_end) {
+						uint32_t *const dst = tiles_out + (tri_row_start_tc(tiles64, ti) + (tj - ti)) * (int64_t)(kMmTileTc * kMmTileTc) +
+											  (gi % kMmTileTc) * kMmTileTc + (gj0 % kMmTileTc);
 #pragma unroll
-					for (int j = 0; j < 32; j++) {
-						const int32_t dot = INT8 ? (int32_t)r[j] : __float2int_rn(__uint_as_float(r[j]));
-						const uint32_t mm = (uint32_t)(k_real - dot) >> 2;
-						r[j] = (gi < gj0 + j && gj0 + j < n) ? mm : 0u;
-					}
-					if (u.atomic) {
+						for (int j = 0; j < 32; j++) {
+							const int32_t dot = MODE == kModeInt8 ? (int32_t)r[j] : __float2int_rn(__uint_as_float(r[j]));
+							const uint32_t mm = (uint32_t)(k_real - dot) >> 2;
+							r[j] = (gi < gj0 + j && gj0 + j < gj_end) ? mm : 0u;
+						}
+						if (u.atomic) {
 #pragma unroll
-						for (int j = 0; j < 32; j++)
-							if (r[j]) atomicAdd(dst + j, r[j]);
-					} else { // this unit owns its output tiles during this launch
-						uint4 *const d4 = reinterpret_cast<uint4 *>(dst);
+							for (int j = 0; j < 32; j++)
+								if (r[j]) atomicAdd(dst + j, r[j]);
+						} else { // this unit owns its output tiles during this launch
+							uint4 *const d4 = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
-						for (int q = 0; q < 8; q++) {
-							uint4 v = d4[q];
-							v.x += r[4 * q], v.y += r[4 * q + 1], v.z += r[4 * q + 2], v.w += r[4 * q + 3];
-							d4[q] = v;
+							for (int q = 0; q < 8; q++) {
+								uint4 v = d4[q];
+								v.x += r[4 * q], v.y += r[4 * q + 1], v.z += r[4 * q + 2], v.w += r[4 * q + 3];
+								d4[q] = v;
+							}
 						}
 					}
 				}
@@ -482,6 +555,43 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 		tc_fence_after();
 		asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512) : "memory");
 	}
+}
+
+// FP4 operands: one thread = two 16-site words (half a block) of one genome: 8 bytes in, 48 bytes
+// out -- 16 bytes of lo entries (32 nibbles), 16 of hi, 16 of lo ^ hi; nibble = E2M1 +1 (0x2) or -1
+// (0xA).  The order of the entries inside a row is the same for every genome, which is all a dot
+// product needs.  Blocks [n_blocks, out_blocks) are written as zeros.
+__device__ __forceinline__ uint32_t spread8_to_nibble_msb(uint32_t b) // bit k of the low byte -> bit 4 k + 3
+{
+	uint32_t x = b & 0xFFu;
+	x = (x | (x << 12)) & 0x000F000Fu;
+	x = (x | (x << 6)) & 0x03030303u;
+	x = (x | (x << 3)) & 0x11111111u;
+	return x << 3;
+}
+__global__ void __launch_bounds__(256)
+k2_expand_fp4(const uint2 *__restrict__ rows, const int64_t *__restrict__ leaf_base_words, int32_t n, int64_t first_block, int64_t n_blocks,
+			  int64_t out_blocks, int64_t pitch, uint8_t *__restrict__ X)
+{
+	const int64_t halves = out_blocks * 2;
+	const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+	if (idx >= (int64_t)n * halves) return;
+	const int32_t g = (int32_t)(idx / halves);
+	const int64_t w = idx - (int64_t)g * halves;
+	uint4 *const out = reinterpret_cast<uint4 *>(X + (int64_t)g * pitch + w * 48);
+	if (w >= n_blocks * 2) {
+		out[0] = out[1] = out[2] = make_uint4(0, 0, 0, 0);
+		return;
+	}
+	const uint2 v = __ldg(rows + (leaf_base_words[g] >> 1) + first_block * 2 + w);
+	const uint32_t l0 = even_bits16(v.x), h0 = even_bits16(v.x >> 1), l1 = even_bits16(v.y), h1 = even_bits16(v.y >> 1);
+	uint4 lo, hi;
+	lo.x = spread8_to_nibble_msb(l0), lo.y = spread8_to_nibble_msb(l0 >> 8), lo.z = spread8_to_nibble_msb(l1), lo.w = spread8_to_nibble_msb(l1 >> 8);
+	hi.x = spread8_to_nibble_msb(h0), hi.y = spread8_to_nibble_msb(h0 >> 8), hi.z = spread8_to_nibble_msb(h1), hi.w = spread8_to_nibble_msb(h1 >> 8);
+	constexpr uint32_t one = 0x22222222u;
+	out[0] = make_uint4(lo.x | one, lo.y | one, lo.z | one, lo.w | one);
+	out[1] = make_uint4(hi.x | one, hi.y | one, hi.z | one, hi.w | one);
+	out[2] = make_uint4((lo.x ^ hi.x) | one, (lo.y ^ hi.y) | one, (lo.z ^ hi.z) | one, (lo.w ^ hi.w) | one);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -546,11 +656,8 @@ template <bool INT8> int run_tensor(Engine &e, int64_t budget)
 	const int64_t pitch = chunk_blocks * kTcBlockBytes;
 	const size_t x_bytes = (size_t)n_pad * (size_t)pitch;
 	int rc;
-	const bool fresh = e.d_planes.bytes < x_bytes;
-	if (fresh && (rc = e.alloc(e.d_planes, x_bytes, "mismatch operand matrix"))) return rc;
-	// rows of the padding genomes and (last chunk) the tail of every row must read as zero
-	cudaError_t ce = cudaMemsetAsync(e.d_planes.p, 0, x_bytes, e.stream);
-	if (ce != cudaSuccess) return e.cuda_fail(ce, "mismatch operand matrix");
+	if (e.d_planes.bytes < x_bytes && (rc = e.alloc(e.d_planes, x_bytes, "mismatch operand matrix"))) return rc;
+	cudaError_t ce;
 
 	CUtensorMap map_a, map_b;
 	if ((rc = make_map(e, &map_a, e.d_planes.p, n_pad, pitch, kTcM))) return rc;
@@ -565,13 +672,9 @@ template <bool INT8> int run_tensor(Engine &e, int64_t budget)
 
 	for (int64_t b0 = 0; b0 < blocks_total; b0 += chunk_blocks) {
 		const int64_t nb = std::min(chunk_blocks, blocks_total - b0);
-		if (b0 > 0 && nb < chunk_blocks) {
-			ce = cudaMemsetAsync(e.d_planes.p, 0, x_bytes, e.stream);
-			if (ce != cudaSuccess) return e.cuda_fail(ce, "mismatch operand matrix");
-		}
-		const int64_t items = (int64_t)n * nb * 4;
+		const int64_t items = (int64_t)n * (nb + (nb & 1)) * 4;
 		k2_expand_pm1<INT8><<<(unsigned)((items + 255) / 256), 256, 0, e.stream>>>(reinterpret_cast<const uint32_t *>(e.tables.rows),
-																					 e.d_leaf_base_words.as<int64_t>(), n, b0, nb, pitch,
+																					 e.d_leaf_base_words.as<int64_t>(), n, b0, nb, nb + (nb & 1), pitch,
 																					 e.d_planes.as<uint8_t>());
 		const int64_t triples = (nb + 1) / 2;
 		// split K so that few tiles still fill the 148 SMs
@@ -590,19 +693,36 @@ template <bool INT8> int run_tensor(Engine &e, int64_t budget)
 // Pair tiles of the upper triangle in launch order (bands of 4 tile rows, column by column), cut
 // into units: whole tiles while they fill complete waves of `slots` CTA pairs, the remaining tiles
 // split along K into equal pieces so that the last wave ends together (those pieces add atomically).
-std::vector<PairUnit> pair_units(int32_t n, int32_t triples, int slots)
+std::vector<PairUnit> pair_units(int32_t n, int32_t triples, int slots, int tile_n, int n1_max)
 {
-	const int tm_count = (n + kPairM - 1) / kPairM, tn_count = (n + kPairN - 1) / kPairN;
+	const int tm_count = (n + kPairM - 1) / kPairM, tn_count = (n + tile_n - 1) / tile_n;
 	std::vector<PairUnit> tiles;
 	constexpr int kBand = 4;
+	auto cols = [&](int64_t first, int cap) { // computed columns of a half starting at genome `first`: up to the last genome, in 16s
+		return (int32_t)std::max<int64_t>(0, std::min<int64_t>(cap, (n - first + 15) / 16 * 16));
+	};
 	for (int band = 0; band < tm_count; band += kBand)
 		for (int tn = 0; tn < tn_count; tn++)
-			for (int tm = band; tm < std::min(band + kBand, tm_count); tm++)
-				if ((int64_t)tm * kPairM < (int64_t)tn * kPairN + kPairN - 1)
-					tiles.push_back(PairUnit{tm, tn, 0, triples, (int64_t)tn * kPairN + 255 < (int64_t)tm * kPairM ? 1 : 0, 0});
+			for (int tm = band; tm < std::min(band + kBand, tm_count); tm++) {
+				const int64_t row_first = (int64_t)tm * kPairM, c0 = (int64_t)tn * tile_n, c1 = c0 + 256;
+				PairUnit u{tm, tn, 0, triples, cols(c0, 256), cols(c1, n1_max), 0, 0};
+				if (c0 + u.n0 - 1 <= row_first) u.n0 = 0; // no pair i < j in this half
+				if (c1 + u.n1 - 1 <= row_first) u.n1 = 0;
+				if (u.n0 || u.n1) tiles.push_back(u);
+			}
 	const size_t whole = tiles.size() / (size_t)slots * (size_t)slots;
 	const size_t rest = tiles.size() - whole;
-	const int pieces = rest ? (int)std::min<int64_t>(slots / (int64_t)rest, triples) : 1;
+	// pieces per remaining tile: the last rounds take ceil(rest * p / slots) / p of a tile's time; every piece
+	// pays its own epilogue (about 2 % of a whole tile)
+	int pieces = 1;
+	double best = 1e30;
+	for (int p = 1; rest && p <= std::max<int64_t>(12, std::min<int64_t>(slots / (int64_t)rest, 32)) && p <= triples; p++) {
+		const double cost = (double)((rest * p + slots - 1) / slots) / p + 0.02 * p;
+		if (cost < best - 1e-9) {
+			best = cost;
+			pieces = p;
+		}
+	}
 	if (pieces <= 1) return tiles;
 	std::vector<PairUnit> units(tiles.begin(), tiles.begin() + (std::ptrdiff_t)whole);
 	const int32_t per = (triples + pieces - 1) / pieces;
@@ -617,55 +737,84 @@ std::vector<PairUnit> pair_units(int32_t n, int32_t triples, int slots)
 	return units;
 }
 
-template <bool INT8> int run_tensor_pair(Engine &e, int64_t budget)
+// The expansion of chunk c + 1 runs on a second stream beside the tile kernel of chunk c (two operand
+// buffers): it is memory-bound work that fits into the SMs next to the one resident tile CTA.
+int aux_stream(Engine &e)
 {
+	if (e.aux_stream) return PGS_OK;
+	int lo = 0, hi = 0;
+	cudaDeviceGetStreamPriorityRange(&lo, &hi);
+	cudaError_t ce = cudaStreamCreateWithPriority(&e.aux_stream, cudaStreamNonBlocking, hi);
+	for (int i = 0; i < 5 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&e.mm_ev[i], cudaEventDisableTiming);
+	return ce == cudaSuccess ? PGS_OK : e.cuda_fail(ce, "mismatch helper stream");
+}
+
+template <int MODE> int run_tensor_pair(Engine &e, int64_t budget)
+{
+	constexpr int kBpt = pair_blocks_per_triple(MODE), kBlockBytes = pair_block_bytes(MODE), kTileN = pair_tile_n(MODE);
 	const int32_t n = e.n_genomes;
 	const int64_t D = (int64_t)e.dense_gid.size();
 	const int64_t blocks_total = D * e.blocks;
-	const int64_t n_pad = ((int64_t)n + kPairN - 1) / kPairN * kPairN;
-	int64_t chunk_blocks = std::max<int64_t>(2, budget / (n_pad * kTcBlockBytes));
+	// column chunks of whole K triples, two operand buffers inside the budget
+	int64_t chunk_blocks = std::max<int64_t>(kBpt, budget / 2 / ((int64_t)n * kBlockBytes));
 	chunk_blocks = std::min<int64_t>(chunk_blocks, 80000); // FP32 accumulation stays exact: 3 * 64 * 80000 < 2^24
-	chunk_blocks = std::min(chunk_blocks, blocks_total + (blocks_total & 1));
-	chunk_blocks &= ~(int64_t)1;
-	const int64_t pitch = chunk_blocks * kTcBlockBytes;
-	const size_t x_bytes = (size_t)n_pad * (size_t)pitch;
+	chunk_blocks = std::min(chunk_blocks, (blocks_total + kBpt - 1) / kBpt * kBpt);
+	chunk_blocks = chunk_blocks / kBpt * kBpt;
+	const int64_t pitch = chunk_blocks * kBlockBytes;
+	const size_t x_bytes = ((size_t)n * (size_t)pitch + 1023) / 1024 * 1024;
+	const int64_t n_chunks = (blocks_total + chunk_blocks - 1) / chunk_blocks;
+	const int n_bufs = n_chunks > 1 ? 2 : 1;
 	int rc;
-	if (e.d_planes.bytes < x_bytes && (rc = e.alloc(e.d_planes, x_bytes, "mismatch operand matrix"))) return rc;
-	cudaError_t ce = cudaMemsetAsync(e.d_planes.p, 0, x_bytes, e.stream);
-	if (ce != cudaSuccess) return e.cuda_fail(ce, "mismatch operand matrix");
-	CUtensorMap map;
-	if ((rc = make_map(e, &map, e.d_planes.p, n_pad, pitch, 128))) return rc;
+	if (e.d_planes.bytes < n_bufs * x_bytes && (rc = e.alloc(e.d_planes, n_bufs * x_bytes, "mismatch operand matrix"))) return rc;
+	if ((rc = aux_stream(e))) return rc;
+	CUtensorMap map[2];
+	for (int b = 0; b < n_bufs; b++)
+		if ((rc = make_map(e, &map[b], e.d_planes.as<uint8_t>() + b * x_bytes, n, pitch, 128))) return rc;
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e.device);
 	const int slots = std::max(1, sms / 2);
 
 	// unit lists of a full chunk and of the (shorter) last chunk, uploaded once
 	const int64_t last_nb = blocks_total % chunk_blocks;
-	const std::vector<PairUnit> units_full = pair_units(n, (int32_t)(chunk_blocks / 2), slots);
-	const std::vector<PairUnit> units_last = last_nb ? pair_units(n, (int32_t)((last_nb + 1) / 2), slots) : std::vector<PairUnit>();
+	const std::vector<PairUnit> units_full = pair_units(n, (int32_t)(chunk_blocks / kBpt), slots, kTileN, kTileN - 256);
+	const std::vector<PairUnit> units_last =
+		last_nb ? pair_units(n, (int32_t)((last_nb + kBpt - 1) / kBpt), slots, kTileN, kTileN - 256) : std::vector<PairUnit>();
 	std::vector<PairUnit> all(units_full);
 	all.insert(all.end(), units_last.begin(), units_last.end());
 	if ((rc = e.upload_keep(e.d_mismatch, all.data(), all.size() * sizeof(PairUnit), "mismatch unit list"))) return rc;
 
-	ce = cudaFuncSetAttribute(k2_tc_pair<INT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
+	cudaError_t ce = cudaFuncSetAttribute(k2_tc_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "k2_tc_pair shared memory");
 
-	for (int64_t b0 = 0; b0 < blocks_total; b0 += chunk_blocks) {
+	// mm_ev[0]: the rows exist (main stream); [1], [2]: buffer b is expanded; [3], [4]: buffer b has been consumed
+	ce = cudaEventRecord(e.mm_ev[0], e.stream);
+	if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e.aux_stream, e.mm_ev[0], 0);
+	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch (tensor) streams");
+	for (int64_t c = 0; c < n_chunks; c++) {
+		const int b = (int)(c & 1) % n_bufs;
+		const int64_t b0 = c * chunk_blocks;
 		const int64_t nb = std::min(chunk_blocks, blocks_total - b0);
+		const int64_t out_blocks = (nb + kBpt - 1) / kBpt * kBpt;
 		const bool last = nb < chunk_blocks;
-		if (b0 > 0 && last) { // the tail of every row must read as zero
-			ce = cudaMemsetAsync(e.d_planes.p, 0, x_bytes, e.stream);
-			if (ce != cudaSuccess) return e.cuda_fail(ce, "mismatch operand matrix");
+		uint8_t *const X = e.d_planes.as<uint8_t>() + b * x_bytes;
+		if (c >= 2 && (ce = cudaStreamWaitEvent(e.aux_stream, e.mm_ev[3 + b], 0)) != cudaSuccess) break;
+		if (MODE == kModeFp4) {
+			const int64_t items = (int64_t)n * out_blocks * 2;
+			k2_expand_fp4<<<(unsigned)((items + 255) / 256), 256, 0, e.aux_stream>>>(reinterpret_cast<const uint2 *>(e.tables.rows),
+																					  e.d_leaf_base_words.as<int64_t>(), n, b0, nb, out_blocks, pitch, X);
+		} else {
+			const int64_t items = (int64_t)n * out_blocks * 4;
+			k2_expand_pm1<MODE == kModeInt8><<<(unsigned)((items + 255) / 256), 256, 0, e.aux_stream>>>(
+				reinterpret_cast<const uint32_t *>(e.tables.rows), e.d_leaf_base_words.as<int64_t>(), n, b0, nb, out_blocks, pitch, X);
 		}
-		const int64_t items = (int64_t)n * nb * 4;
-		k2_expand_pm1<INT8><<<(unsigned)((items + 255) / 256), 256, 0, e.stream>>>(reinterpret_cast<const uint32_t *>(e.tables.rows),
-																					 e.d_leaf_base_words.as<int64_t>(), n, b0, nb, pitch,
-																					 e.d_planes.as<uint8_t>());
+		if ((ce = cudaEventRecord(e.mm_ev[1 + b], e.aux_stream)) != cudaSuccess) break;
+		if ((ce = cudaStreamWaitEvent(e.stream, e.mm_ev[1 + b], 0)) != cudaSuccess) break;
 		const PairUnit *const list = e.d_mismatch.as<PairUnit>() + (last ? units_full.size() : 0);
 		const size_t count = last ? units_last.size() : units_full.size();
-		k2_tc_pair<INT8><<<(unsigned)(2 * count), kTcThreads, kPairSmemBytes, e.stream>>>(map, list, n, (int32_t)nb, e.d_tiles.as<uint32_t>());
+		k2_tc_pair<MODE><<<(unsigned)(2 * count), kTcThreads, kPairSmemBytes, e.stream>>>(map[b], list, n, (int32_t)nb, e.d_tiles.as<uint32_t>());
+		if ((ce = cudaEventRecord(e.mm_ev[3 + b], e.stream)) != cudaSuccess) break;
 	}
-	ce = cudaGetLastError();
+	if (ce == cudaSuccess) ce = cudaGetLastError();
 	if (ce != cudaSuccess) return e.cuda_fail(ce, "pgs_mismatch (tensor) launch");
 	return PGS_OK;
 }
@@ -674,16 +823,18 @@ template <bool INT8> int run_tensor_pair(Engine &e, int64_t budget)
 
 // Same contract as mismatch_tiles (mismatch.cu): partial counts of this engine's dense genes into
 // e.d_tiles, asynchronous on the engine's stream.  e.d_tiles is allocated and cleared by the caller.
-// impl: 1 = CTA pairs, E4M3; 2 = CTA pairs, INT8; 3 / 4 = the single-CTA kernel, E4M3 / INT8.
+// impl: 1 = CTA pairs, E4M3; 2 = CTA pairs, INT8; 3 / 4 = the single-CTA kernel, E4M3 / INT8;
+// 5 = CTA pairs, E2M1 with unit block scales.
 int mismatch_tiles_tensor(Engine &e, int impl)
 {
-	int64_t budget = (int64_t)2048 << 20;
+	int64_t budget = (int64_t)4096 << 20;
 	if (const char *v = std::getenv("PGS_K2_PLANES_MB")) budget = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
 	switch (impl) {
-	case 1: return run_tensor_pair<false>(e, budget);
-	case 2: return run_tensor_pair<true>(e, budget);
-	case 3: return run_tensor<false>(e, budget);
-	default: return run_tensor<true>(e, budget);
+	case 1: return run_tensor_pair<kModeE4M3>(e, budget);
+	case 2: return run_tensor_pair<kModeInt8>(e, budget);
+	case 3: return run_tensor<false>(e, budget / 2);
+	case 4: return run_tensor<true>(e, budget / 2);
+	default: return run_tensor_pair<kModeFp4>(e, budget);
 	}
 }
 

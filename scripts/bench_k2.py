@@ -13,7 +13,7 @@ from pangenomesim_b200.capi import host_coalescent  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
-impls = sys.argv[4].split(",") if len(sys.argv) > 4 else ["popc", "tensor", "tensor-i8", "tensor-1cta"]
+impls = sys.argv[4].split(",") if len(sys.argv) > 4 else ["popc", "tensor", "tensor-i8", "tensor-fp4", "tensor-1cta"]
 parent, rate, leaf = host_coalescent(n, 1, 0.05)
 e = Engine(1, L)
 e.set_tree(parent, rate, leaf)

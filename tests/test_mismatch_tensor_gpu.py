@@ -37,10 +37,10 @@ def numpy_counts(oracle, e, n, L, G):
 # both sides; an odd number of 64-site blocks (zero tail); a single block; several column chunks
 # with a short last one
 CASES = [(100, 1000, 7, None), (300, 130, 33, None), (129, 64, 1, None), (2, 100, 5, None), (333, 448, 21, "1"), (700, 1000, 3, "2"),
-         (257, 1500, 2, None), (1100, 200, 5, None)]
+         (257, 1500, 2, None), (1100, 200, 5, None), (500, 64, 7, None), (1000, 192, 9, "1")]
 
 
-@pytest.mark.parametrize("impl", ["tensor", "tensor-i8", "tensor-1cta", "tensor-1cta-i8"])
+@pytest.mark.parametrize("impl", ["tensor", "tensor-i8", "tensor-fp4", "tensor-1cta", "tensor-1cta-i8"])
 @pytest.mark.parametrize("n,L,G,budget_mb", CASES)
 def test_tensor_counts_equal_numpy_and_popc(oracle, monkeypatch, impl, n, L, G, budget_mb):
     if budget_mb:
