@@ -280,15 +280,16 @@ def mismatch_allreduce_leg(torch, dist, Engine, rank, world, local):
             "bytes": int(part.numel() * 4), "pair01_observed": obs, "pair01_jc_expected": float(p)}
 
 
-def k2_leg(torch, dist, eng, stats, rank, world, peaks):
+def k2_leg(torch, dist, eng, stats, rank, world, peaks, popc_runs=1):
     """K2 (pairwise mismatch, north_star part 3) on this rank's genes at the config's FULL size, and
     -- N > 1 -- the path's only collective at its real size: the NCCL all-reduce of the packed
-    upper-triangular counts (pgs_mismatch_allreduce).  ALU-bound: per genome pair and 32 sites the
-    kernel issues XOR + LOP3 + POPC on the ALU pipe (the add rides the FMA pipe as an IMAD):
-    3 ALU instructions per 32 site pairs; the pipe takes 64 lanes per clock per SM."""
+    upper-triangular counts (pgs_mismatch_allreduce).  Measured with the library's default kernel
+    (the +-1 contraction on the tensor cores, FP4 operands) and, beside it, with the FP8 variant and
+    with the popcount-XOR kernel north_star names -- all three produce the same integers."""
     from pangenomesim_b200.capi import comm_unique_id
     n, L = stats["n_genomes"], eng.gene_length
     out = {}
+    os.environ.pop("PGS_K2_IMPL", None)
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -312,25 +313,47 @@ def k2_leg(torch, dist, eng, stats, rank, world, peaks):
         eng.mismatch_tiles_device()
         k2_ms, sites_all = eng.stats()["mismatch_ms"], float(stats["n_dense_genes"]) * L
     pairs = n * (n - 1) / 2.0
-    # tiles of the upper triangle are computed whole (64 x 64, diagonal tiles in full): the kernel's own work
-    T = (n + 63) // 64
-    tile_pairs = T * (T + 1) / 2.0 * 4096
-    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-    # The kernel's instruction mix per THREE 32-site masks of a genome pair: 8 ALU-pipe instructions (3 XOR + 3 LOP3
-    # for the masks, 2 LOP3 for the 3:2 carry-save adder; the pipe takes 16 lanes per clock per SM sub-partition: 16
-    # cycles per warp) and 2 POPC on the XU pipe (4 lanes per clock per sub-partition: 16 cycles per warp) -- the two
-    # pipes are level, 96 site pairs per lane per 16 cycles.  (POPC on XU at a quarter of the ALU rate: profiles/r02_k2_full.md.)
-    pipe_peak = 148 * 4 * 32 * 96 / 16.0 * sm_mhz * 1e6
     site_pairs_rank = pairs * (sites_all / world)
-    out.update({"k2_ms": k2_ms, "site_pairs_total": pairs * sites_all,
-                "site_pairs_per_s": pairs * sites_all / (k2_ms * 1e-3),
-                "roofline": {"bound": "alu+xu", "achieved": site_pairs_rank / (k2_ms * 1e-3), "peak": pipe_peak, "unit": "site-pairs/s per GPU",
-                             "frac": site_pairs_rank / (k2_ms * 1e-3) / pipe_peak,
-                             "frac_counting_whole_tiles": tile_pairs * (sites_all / world) / (k2_ms * 1e-3) / pipe_peak,
-                             "definition": f"148 SMs x 4 sub-partitions x 32 lanes x 96 site pairs / 16 cycles x {sm_mhz:.0f} MHz (max clock): "
-                                           "per three masks 8 ALU instructions (2 cycles each per warp) and 2 POPC on the XU pipe (8 cycles each)"},
-                "what": f"k2_split_planes + k2_mismatch_tiles over {n} genomes x this rank's dense genes, max over ranks; "
-                        "counts kept as packed upper-triangular tiles on the device"})
+    # Tensor-core bound: three +-1 entries per site (the tetrahedron encoding, mismatch_tc.cu) = 3 multiply-adds = 6 flop
+    # per site pair.  Peak: B200's dense FP4 rate; no FP4 GEMM was measured on this pool, so the figure is the nominal
+    # 9 PFLOP/s of B200_PROFILING.md (the measured cuBLAS bf16 burst of MEASURED_PEAKS.json x 4 is printed beside it).
+    fp4_peak = 9.0e15
+    bf16 = float(peaks.get("bf16_tflops", 0.0)) * 1e12
+    flops = 6.0 * site_pairs_rank / (k2_ms * 1e-3)
+    out.update({"k2_ms": k2_ms, "kernel": "k2_expand_fp4 + k2_tc_pair<FP4> (tcgen05.mma.cta_group::2.kind::mxf4, unit block scales)",
+                "site_pairs_total": pairs * sites_all, "site_pairs_per_s": pairs * sites_all / (k2_ms * 1e-3),
+                "roofline": {"bound": "tensor", "achieved": flops / 1e12, "peak": fp4_peak / 1e12, "unit": "TFLOP/s per GPU (FP4, dense)",
+                             "frac": flops / fp4_peak, "peak_is": "nominal (B200_PROFILING.md)",
+                             "frac_of_4x_measured_bf16_burst": (flops / (4 * bf16)) if bf16 else None,
+                             "definition": "6 flop per site pair (3 multiply-adds: a base is the +-1 vector ((-1)^lo, (-1)^hi, (-1)^(lo^hi)); "
+                                           "mismatches = (3 S - dot) / 4) x n (n - 1) / 2 pairs x this rank's sites / CUDA-event time of the "
+                                           "whole pgs_mismatch_tiles_device call (operand expansion included)"},
+                "what": f"{n} genomes x this rank's dense genes, max over ranks; counts kept as packed upper-triangular tiles on the device"})
+    # the other kernels on the same rows (rank-local, no collective)
+    variants = {}
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    for impl, runs in (("tensor", 2), ("popc", popc_runs)):
+        if runs <= 0:
+            continue
+        os.environ["PGS_K2_IMPL"] = impl
+        for _ in range(runs):
+            eng.mismatch_tiles_device()
+        ms = eng.stats()["mismatch_ms"]
+        v = {"k2_ms": ms, "site_pairs_per_s_this_rank": site_pairs_rank / (ms * 1e-3)}
+        if impl == "popc":
+            # per THREE 32-site masks of a genome pair: 8 ALU-pipe instructions (2 cycles each per warp) and 2 POPC on the
+            # XU pipe (8 cycles each): the pipes are level, 96 site pairs per lane per 16 cycles (profiles/r02_k2_full.md)
+            pipe_peak = 148 * 4 * 32 * 96 / 16.0 * sm_mhz * 1e6
+            v.update({"kernel": "k2_split_planes + k2_mismatch_tiles (XOR / LOP3 / carry-save adder / POPC)",
+                      "roofline": {"bound": "alu+xu", "achieved": v["site_pairs_per_s_this_rank"], "peak": pipe_peak, "unit": "site-pairs/s per GPU",
+                                   "frac": v["site_pairs_per_s_this_rank"] / pipe_peak}})
+        else:
+            v.update({"kernel": "k2_expand_pm1 + k2_tc_pair<E4M3> (kind::f8f6f4)",
+                      "roofline": {"bound": "tensor", "achieved": 6.0 * v["site_pairs_per_s_this_rank"] / 1e12, "peak": 4500.0,
+                                   "unit": "TFLOP/s per GPU (FP8, dense, nominal)", "frac": 6.0 * v["site_pairs_per_s_this_rank"] / 4.5e15}})
+        variants[impl] = v
+    os.environ.pop("PGS_K2_IMPL", None)
+    out["variants"] = variants
     return out
 
 

@@ -62,8 +62,9 @@ typedef struct pgs_config {
  * any other node then fail with PGS_ERR_STATE. */
 #define PGS_FLAG_KEEP_INTERNAL 2u
 /* Which kernel counts the pairwise mismatches (pgs_mismatch*): the popcount-XOR kernel, or the
- * same counts as a +-1 contraction on the tensor cores (tcgen05, FP8 operands, FP32 accumulation --
- * exact, the counts are identical integers).  Neither flag: the library's default. */
+ * same counts as a +-1 contraction on the tensor cores (tcgen05, FP4 operands with unit block
+ * scales, FP32 accumulation -- exact: the counts are identical integers, checked against each
+ * other by tests/test_mismatch_tensor_gpu.py).  Neither flag: the tensor-core kernel. */
 #define PGS_FLAG_K2_POPC 4u
 #define PGS_FLAG_K2_TENSOR 8u
 

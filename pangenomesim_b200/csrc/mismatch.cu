@@ -230,8 +230,7 @@ int mismatch_impl(const Engine &e)
 		if (!std::strcmp(v, "tensor-fp4")) return 5;
 	}
 	if (e.cfg.flags & PGS_FLAG_K2_POPC) return 0;
-	if (e.cfg.flags & PGS_FLAG_K2_TENSOR) return 1;
-	return 0;
+	return 5; // PGS_FLAG_K2_TENSOR or neither flag: the fastest of the exact kernels
 }
 
 // Partial mismatch counts of this engine's dense genes into e.d_tiles (packed upper-triangular

@@ -348,6 +348,7 @@ constexpr int kPairStages = 4;
 constexpr uint32_t kPairSmemBytes = kPairStages * kPairStage + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in CTA 0 of the pair (cute: Sm100MmaPeerBitMask)
 constexpr uint32_t kSfColumn = 480;                // FP4: TMEM columns [480, 512) hold the scale factors
+constexpr int kPairPrefetchLead = 48;              // K slices before the end at which the epilogue warps start prefetching
 
 __host__ __device__ constexpr int pair_tile_n(int mode)
 {
@@ -427,6 +428,7 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 	const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t bars = base + kPairStages * kPairStage;
 	const uint32_t full0 = bars, empty0 = bars + 8 * kPairStages, tmem_full = bars + 16 * kPairStages, tmem_slot = tmem_full + 8;
+	const uint32_t near_end = tmem_full + 16; // "the last K slices are under way" (multicast commit, like tmem_full)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint32_t rank;
@@ -442,6 +444,7 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 			mbar_init(empty0 + 8 * s, 1); // one multicast commit per use
 		}
 		mbar_init(tmem_full, 1);
+		mbar_init(near_end, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) { // the same warp of both CTAs: all 512 columns of both SMs
@@ -497,7 +500,9 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 						tc_mma_pair<MODE>(tmem_acc + 256u * h, adesc + 2 * j, bdesc + 2 * j, idesc_h, (uint32_t)(k | j), tmem_acc + kSfColumn);
 				}
 				tc_commit_pair(empty0 + 8 * s);
+				if (k == n_slices - kPairPrefetchLead) tc_commit_pair(near_end); // the epilogue warps may start fetching their output lines
 			}
+			if (n_slices < kPairPrefetchLead) tc_commit_pair(near_end);
 			tc_commit_pair(tmem_full);
 		}
 	} else {
@@ -510,6 +515,18 @@ k2_tc_pair(const __grid_constant__ CUtensorMap map, const PairUnit *__restrict__
 		const int64_t tiles64 = (n + kMmTileTc - 1) / kMmTileTc;
 		const int64_t ti = gi / kMmTileTc;
 		if (n_slices > 0) {
+			// the counts are added to what earlier column chunks left in memory: pull those lines into L2 while the
+			// last K slices are still being multiplied
+			mbar_wait(near_end, 0);
+			if (!u.atomic && gi < n)
+				for (int h = 0; h < 2; h++)
+					for (int c = 0; 32 * c < nh[h]; c++) {
+						const int32_t gj0 = col0[h] + 32 * c;
+						const int64_t tj = gj0 / kMmTileTc;
+						if (ti <= tj && gj0 < n)
+							asm volatile("prefetch.global.L2 [%0];" ::"l"(tiles_out + (tri_row_start_tc(tiles64, ti) + (tj - ti)) * (int64_t)(kMmTileTc * kMmTileTc) +
+																		  (gi % kMmTileTc) * kMmTileTc + (gj0 % kMmTileTc)));
+					}
 			mbar_wait(tmem_full, 0);
 			tc_fence_after();
 #pragma unroll 1
@@ -765,7 +782,10 @@ template <int MODE> int run_tensor_pair(Engine &e, int64_t budget)
 	const int64_t n_chunks = (blocks_total + chunk_blocks - 1) / chunk_blocks;
 	const int n_bufs = n_chunks > 1 ? 2 : 1;
 	int rc;
-	if (e.d_planes.bytes < n_bufs * x_bytes && (rc = e.alloc(e.d_planes, n_bufs * x_bytes, "mismatch operand matrix"))) return rc;
+	if (e.d_planes.bytes < n_bufs * x_bytes && (rc = e.alloc(e.d_planes, n_bufs * x_bytes, "mismatch operand matrix"))) {
+		if (rc == PGS_ERR_NOMEM && budget > ((int64_t)256 << 20)) return run_tensor_pair<MODE>(e, budget / 2); // shorter chunks
+		return rc;
+	}
 	if ((rc = aux_stream(e))) return rc;
 	CUtensorMap map[2];
 	for (int b = 0; b < n_bufs; b++)
@@ -827,7 +847,9 @@ template <int MODE> int run_tensor_pair(Engine &e, int64_t budget)
 // 5 = CTA pairs, E2M1 with unit block scales.
 int mismatch_tiles_tensor(Engine &e, int impl)
 {
-	int64_t budget = (int64_t)4096 << 20;
+	// Two operand buffers.  A tile's epilogue (read-modify-write of its counts) is paid once per column chunk, so a
+	// chunk should hold some 2000 blocks: 4 GB up to n = 10 000, more for more genomes (config 5: 16 GB of the 180).
+	int64_t budget = std::min<int64_t>((int64_t)16384 << 20, std::max<int64_t>((int64_t)4096 << 20, (int64_t)e.n_genomes * 96 * 2 * 2048));
 	if (const char *v = std::getenv("PGS_K2_PLANES_MB")) budget = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
 	switch (impl) {
 	case 1: return run_tensor_pair<kModeE4M3>(e, budget);
