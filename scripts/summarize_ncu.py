@@ -47,8 +47,8 @@ def main():
             w.writerow([r[idx[k]] for k in keys])
     with open(out + ".md", "w") as f:
         f.write(f"# ncu summary of `{rep}` ({len(data)} launches, --set full --clock-control none)\n\n")
-        f.write("| " + " | ".join(["#", "kernel", "grid", "time", "DRAM rd", "DRAM wr", "DRAM GB/s", "DRAM %", "SM %", "regs", "warps act %", "issue %"]) + " |\n")
-        f.write("|" + "---|" * 12 + "\n")
+        f.write("| " + " | ".join(["#", "kernel", "grid", "time", "DRAM rd", "DRAM wr", "DRAM GB/s", "DRAM %", "SM %", "regs", "warps act %", "issue %", "tensor pipe %", "SM GHz"]) + " |\n")
+        f.write("|" + "---|" * 14 + "\n")
         for i, r in enumerate(data):
             g = lambda k: r[idx[k]] if k in idx else ""
             u = lambda k: units[idx[k]] if k in idx else ""
@@ -63,7 +63,8 @@ def main():
             f.write(f"| {i} | {name} | {g('Grid Size')} | {t:.1f} {tu} | {rd/1e6:.1f} MB | {wr/1e6:.1f} MB | {(rd+wr)/tsec/1e9:.0f} | "
                     f"{g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} | {g('sm__throughput.avg.pct_of_peak_sustained_elapsed')} | "
                     f"{g('launch__registers_per_thread')} | {g('sm__warps_active.avg.pct_of_peak_sustained_active')} | "
-                    f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} |\n")
+                    f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} | "
+                    f"{g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')} | {g('sm__cycles_elapsed.avg.per_second')} |\n")
     print("wrote", out + ".csv", out + ".md")
 
 
