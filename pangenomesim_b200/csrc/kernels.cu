@@ -4,7 +4,9 @@
 // are whole multiples of what the 148 SMs hold.
 #include "kernels.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 namespace pgs {
 
@@ -377,6 +379,25 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 		cur[j].lo = make_uint4(0u, 0u, 0u, 0u);
 		cur[j].hi = cur[j].lo;
 	}
+	// Launched as a programmatic dependent of k1_top_masks (launch_walk_variant): this CTA may have become
+	// resident while the last CTAs of that grid were still drawing masks.  Everything above reads only
+	// tables uploaded by pgs_set_genes; the rows below are valid once the whole preceding grid has
+	// completed and flushed, which is what this waits for (a no-op without the launch attribute).
+	if (u.trace && threadIdx.x == 0) {
+		unsigned long long now;
+		uint32_t sm;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+		u.trace[4 * blockIdx.x] = now;
+		u.trace[4 * blockIdx.x + 3] = sm;
+	}
+	const int32_t path_end = __ldg(u.unit_path_off + unit + 1), path_begin = __ldg(u.unit_path_off + unit);
+	const int64_t store = __ldg(u.unit_store + unit);
+	const int64_t begin = __ldg(u.unit_off + unit), end = __ldg(u.unit_off + unit + 1);
+	// (the operands tie the table loads above to this side of the wait: ptxas otherwise moves the wait to the kernel's top)
+	asm volatile("griddepcontrol.wait; // %0 %1 %2 %3 %4 %5 %6" ::"r"(gid[0]), "r"(gid[PAIRS - 1]), "r"(path_end), "r"(path_begin),
+				 "l"(store), "l"(begin), "l"(end)
+				 : "memory");
 	{
 		// The unit's root value: the origin row XORed with the masks of the branches on the path from
 		// the tree's root (k1_top_masks wrote both; every load is independent of the others).
@@ -384,8 +405,8 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 #pragma unroll
 		for (int j = 0; j < PAIRS; j++)
 			if (active[j]) cur[j] = ld_stream256(reinterpret_cast<const U32x8 *>(base + u.root_off) + p[j]);
-		const int32_t pe = __ldg(u.unit_path_off + unit + 1);
-		int32_t k = __ldg(u.unit_path_off + unit);
+		const int32_t pe = path_end;
+		int32_t k = path_begin;
 		for (; k + 2 <= pe; k += 2) { // two masks in flight per pair
 			const int64_t off0 = __ldg(u.unit_path + k), off1 = __ldg(u.unit_path + k + 1);
 #pragma unroll
@@ -402,14 +423,17 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 			for (int j = 0; j < PAIRS; j++)
 				if (active[j]) cur[j] = cur[j] ^ ld_stream256(reinterpret_cast<const U32x8 *>(base + off) + p[j]);
 		}
-		const int64_t store = __ldg(u.unit_store + unit);
 		if (store >= 0) { // the unit's root is a genome directly below a top node
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++)
 				if (active[j]) st_leaf256(reinterpret_cast<U32x8 *>(reinterpret_cast<uint4 *>(t.rows) + store) + p[j], cur[j]);
 		}
 	}
-	const int64_t begin = __ldg(u.unit_off + unit), end = __ldg(u.unit_off + unit + 1);
+	if (u.trace && threadIdx.x == 0) { // (the operand makes the clock wait for the root value)
+		unsigned long long now;
+		asm volatile("mov.u64 %0, %%globaltimer; // %1" : "=l"(now) : "r"(cur[0].lo.x ^ cur[PAIRS - 1].hi.w));
+		u.trace[4 * blockIdx.x + 1] = now;
+	}
 	for (int64_t i0 = begin; i0 < end; i0 += kWalkChunk) {
 		const int cnt = (int)min((int64_t)kWalkChunk, end - i0);
 		WalkStep *const s_steps = s_steps_all[warp];
@@ -511,6 +535,11 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 			}
 		}
 	}
+	if (u.trace) { // (warp 0's clock after the CTA's last warp would need a barrier; the per-warp maximum does it)
+		unsigned long long now;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+		if (lane == 0) atomicMax(u.trace + 4 * blockIdx.x + 2, now);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,6 +557,9 @@ k1_top_masks(const __grid_constant__ DeviceTables t, const TopMaskTask *__restri
 {
 	const uint32_t task = blockIdx.x / slabs_per_task, slab = blockIdx.x - task * slabs_per_task;
 	const uint32_t p = slab * kThreads + threadIdx.x;
+	// the walk behind this launch may be placed once every CTA of this grid has got this far (it still
+	// waits for the grid's completion before it reads a mask: griddepcontrol.wait in k1_walk_dense)
+	asm volatile("griddepcontrol.launch_dependents;");
 	if (p >= pairs_per_node) return;
 	const TopMaskTask &tk = tasks[task];
 	const uint32_t idx = 2u * p;
@@ -620,7 +652,39 @@ static void launch_walk_variant(const DeviceTables &t, const WalkUnits &u, int32
 	const uint32_t per_cta = kThreads * PAIRS;
 	const unsigned grid = (unsigned)((uint64_t)((pairs + per_cta - 1) / per_cta) * (uint32_t)u.n_units);
 	const size_t dyn = (size_t)smem_levels * PAIRS * 2 * sizeof(uint4) * kThreads; // allowed by prepare_walk_dense
-	k1_walk_dense<MINB, PAIRS, QUAD, HINTS><<<grid, kThreads, dyn, s>>>(t, u, pairs);
+	// Programmatic dependent launch behind k1_top_masks (the launch before this one in the stream, also
+	// when captured into the sweep's graph): CTAs are placed while that grid drains and run their
+	// table-only set-up; the kernel's griddepcontrol.wait orders every read of a row after the masks.
+	static const bool pdl = [] { const char *v = std::getenv("PGS_NO_PDL"); return !(v && std::atoi(v)); }(); // (A/B knob)
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(kThreads);
+	cfg.dynamicSmemBytes = dyn;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl ? 1 : 0;
+	if (const char *path = std::getenv("PGS_WALK_TRACE")) { // development: per-CTA clocks of this launch into a file (plain launches only)
+		WalkUnits ut = u;
+		const size_t bytes = (size_t)grid * 4 * sizeof(unsigned long long);
+		if (cudaMalloc(&ut.trace, bytes) != cudaSuccess) return;
+		cudaMemsetAsync(ut.trace, 0, bytes, s);
+		cudaLaunchKernelEx(&cfg, k1_walk_dense<MINB, PAIRS, QUAD, HINTS>, t, ut, pairs);
+		std::vector<unsigned long long> host((size_t)grid * 4);
+		cudaStreamSynchronize(s);
+		cudaMemcpy(host.data(), ut.trace, bytes, cudaMemcpyDeviceToHost);
+		cudaFree(ut.trace);
+		if (FILE *f = std::fopen(path, "w")) {
+			const unsigned n_slabs = grid / (unsigned)u.n_units;
+			for (unsigned c = 0; c < grid; c++)
+				std::fprintf(f, "%u %u %llu %llu %llu %llu\n", c / n_slabs, c % n_slabs, host[4 * c], host[4 * c + 1], host[4 * c + 2], host[4 * c + 3]);
+			std::fclose(f);
+		}
+		return;
+	}
+	cudaLaunchKernelEx(&cfg, k1_walk_dense<MINB, PAIRS, QUAD, HINTS>, t, u, pairs);
 }
 
 template <int MINB, int PAIRS, bool QUAD, bool HINTS>

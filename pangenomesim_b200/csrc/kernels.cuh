@@ -164,6 +164,7 @@ struct WalkUnits {
 	const int64_t *unit_store;
 	int64_t root_off;
 	int32_t n_units;
+	unsigned long long *trace; // development (PGS_WALK_TRACE): per CTA {start, walk begins, end [ns], SM}; nullptr = off
 };
 void launch_walk_dense(const DeviceTables &t, const WalkUnits &u, int32_t smem_levels, int variant, cudaStream_t s);
 

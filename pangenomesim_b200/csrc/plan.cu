@@ -433,9 +433,22 @@ int plan_walk(Engine &e, SweepPlan &p)
 			const size_t lo = std::min<size_t>(40, std::max<size_t>(8, (size_t)N / 128));
 			target_units = std::min<size_t>(120, std::max<size_t>(lo, (1800 + slabs - 1) / slabs));
 		}
-		if (const char *u = std::getenv("PGS_WALK_UNITS")) target_units = (size_t)std::max(1, std::atoi(u)); // tuning knob
+		// Many units are wanted when there are few column slabs.  Beyond ~60 the last third of them is cut
+		// without top nodes (carve_units below: pieces reached across entry steps in registers): no mask
+		// rows, no longer mask paths.  An eighth of config 4: 0.2747 ms against 0.2768 with 120 top-cut
+		// units, 0.2755 / 0.2793 with 60 / 40 of 120 (profiles/r02_shard_of.txt).
+		size_t carve_units = 0;
+		if (target_units > 60) {
+			carve_units = target_units;
+			target_units = std::max<size_t>(60, target_units * 2 / 3);
+		}
+		if (const char *u = std::getenv("PGS_WALK_UNITS")) { // tuning knob
+			target_units = (size_t)std::max(1, std::atoi(u));
+			carve_units = 0;
+		}
+		if (const char *v = std::getenv("PGS_WALK_CARVE")) carve_units = (size_t)std::max(0, std::atoi(v)); // tuning knob
 		std::vector<int32_t> roots{e.root};
-		std::vector<char> top(N, 0);
+		std::vector<char> top(N, 0), piece_root(N, 0);
 		size_t n_top = 0;
 		while (roots.size() < target_units && n_top < 4 * target_units) { // (a caterpillar never widens)
 			size_t best = 0;
@@ -485,6 +498,12 @@ int plan_walk(Engine &e, SweepPlan &p)
 			tk.h2b = e.kmax_host[b] >= 2 ? e.tab_host[e.tab_off_host[b] + 1] : 0;
 			p.top_tasks.push_back(tk);
 		}
+		// CTAs start in task order and a task costs what its branches' substitutions cost: the long
+		// branches next to the root (the highest node indices) go first, not into the tail of the launch
+		if (!std::getenv("PGS_TOP_UNSORTED")) // (A/B knob)
+			std::stable_sort(p.top_tasks.begin() + 1, p.top_tasks.end(), [&](const pgs::TopMaskTask &x, const pgs::TopMaskTask &y) {
+				return e.rate[x.edge_a] + e.rate[x.edge_b] > e.rate[y.edge_a] + e.rate[y.edge_b];
+			});
 		auto make_step = [&](int32_t v, uint32_t flags) {
 			const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1]; // a < b: a leads the pair
 			pgs::WalkStep s{};
@@ -511,15 +530,26 @@ int plan_walk(Engine &e, SweepPlan &p)
 		e.rows_loaded = e.sparse_rows_read;
 		// Depth-first step list of the subtree below `start`, smaller child first.  The unit's root
 		// value is in registers when the first step begins (unit prologue of k1_walk_dense).
-		auto emit_walk = [&](int32_t start) {
+		// A PIECE of a unit: the subtree below `start` without the subtrees of the pieces cut out of it
+		// (piece_root[] marks their roots).  Its walk begins at the unit's root -- that is the value the
+		// prologue delivers -- and follows `entry`, the nodes from the unit's root down to start's parent,
+		// in registers: one step each that keeps only the child on the path (nothing stored or parked; the
+		// piece that owns the node stores its other child).  Cheap, because the branches inside a unit are
+		// short; no mask rows and no longer mask paths as another top node would cost.
+		auto emit_walk = [&](int32_t start, const std::vector<int32_t> &entry) {
 			const int64_t stack_base = pool_slots; // this walk's deep parked rows: slots stack_base + depth - smem_cap
 			int64_t deepest = 0;
 			std::vector<int32_t> parked;
+			for (size_t i = 0; i < entry.size(); i++) {
+				const int32_t v = entry[i], next = i + 1 < entry.size() ? entry[i + 1] : start;
+				walk_steps.push_back(make_step(v, next == e.child[e.child_off[v]] ? pgs::kWalkCarryA : pgs::kWalkCarryB));
+			}
 			int32_t v = start;
 			bool in_reg = true, have = internal(start);
 			while (have) {
 				const int32_t a = e.child[e.child_off[v]], b = e.child[e.child_off[v] + 1];
-				const bool ia = internal(a), ib = internal(b);
+				const bool ca = piece_root[a] != 0, cb = piece_root[b] != 0; // cut out: another piece's business
+				const bool ia = internal(a) && !ca, ib = internal(b) && !cb;
 				uint32_t f = 0;
 				if (!in_reg && smem_level[v] >= 0) {
 					f |= pgs::kWalkLoadSmem;
@@ -527,8 +557,8 @@ int plan_walk(Engine &e, SweepPlan &p)
 					f |= pgs::kWalkLoad;
 					e.rows_loaded += D;
 				}
-				if (!ia) f |= pgs::kWalkStoreA; // a genome's row
-				if (!ib) f |= pgs::kWalkStoreB;
+				if (!ia && !ca) f |= pgs::kWalkStoreA; // a genome's row
+				if (!ib && !cb) f |= pgs::kWalkStoreB;
 				int32_t carry = -1;
 				if (ia && ib) {
 					const bool a_first = size[a] <= size[b];
@@ -570,9 +600,96 @@ int plan_walk(Engine &e, SweepPlan &p)
 			}
 			pool_slots += deepest;
 		};
+		// Pieces.  A unit may be cut further without another top node: the nodes marked piece_root[] start
+		// walks of their own (emit_walk's entry steps).  Two rules:
+		//  * carve_units = T2 (above; PGS_WALK_CARVE): the top-down split continues until there are T2
+		//    subtrees; the nodes split in this stage stay with the piece above them;
+		//  * PGS_WALK_PIECE=P (off by default): bottom up, a node whose part of the unit has grown to P steps
+		//    becomes a piece root (pieces of P .. 2P steps).  Measured on an eighth of config 4 this evens
+		//    out the end of the launch (the SMs finish within 7 us instead of 22) but costs more than that in
+		//    prologues (origin row + path masks, ~4.5 us per CTA) and entry steps: 0.289-0.313 ms against 0.276.
+		// Neither cuts deeper below the unit's root than kMaxEntry steps.
+		struct Piece {
+			int32_t unit_root, start;
+			int64_t steps; // its own steps, entry included
+			std::vector<int32_t> entry;
+		};
+		std::vector<Piece> pieces;
+		{
+			int64_t piece_steps = (int64_t)1 << 40;
+			if (const char *v = std::getenv("PGS_WALK_PIECE")) piece_steps = std::max(1, std::atoi(v)); // tuning knob
+			constexpr int kMaxEntry = 24;
+			std::vector<int64_t> acc(N, 0);
+			std::vector<int32_t> depth(N, 0), nodes;
+			{ // depth below the unit's root, for every internal node of every unit
+				for (int32_t r : roots) {
+					if (!internal(r)) continue;
+					nodes.assign(1, r);
+					depth[r] = 0;
+					for (size_t i = 0; i < nodes.size(); i++)
+						for (int32_t c = e.child_off[nodes[i]]; c < e.child_off[nodes[i] + 1]; c++)
+							if (internal(e.child[c])) {
+								depth[e.child[c]] = depth[nodes[i]] + 1;
+								nodes.push_back(e.child[c]);
+							}
+				}
+			}
+			if (carve_units > 0) {
+				std::vector<int32_t> cand;
+				for (int32_t r : roots)
+					if (internal(r)) cand.push_back(r);
+				size_t splits = 0;
+				while (cand.size() < carve_units && splits < 4 * carve_units) {
+					size_t best = cand.size();
+					for (size_t i = 0; i < cand.size(); i++)
+						if (depth[cand[i]] < kMaxEntry && (best == cand.size() || size[cand[i]] > size[cand[best]])) best = i;
+					if (best == cand.size() || size[cand[best]] < 32) break;
+					const int32_t v = cand[best];
+					piece_root[v] = 0; // stays with the piece above it (a unit's root: with the unit's remainder)
+					splits++;
+					cand.erase(cand.begin() + best);
+					for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
+						if (internal(e.child[c])) {
+							piece_root[e.child[c]] = 1;
+							cand.push_back(e.child[c]);
+						}
+				}
+			}
+			for (int32_t r : roots) {
+				if (!internal(r)) {
+					pieces.push_back(Piece{r, r, 0, {}});
+					continue;
+				}
+				// the unit's internal nodes, parents before children
+				nodes.assign(1, r);
+				for (size_t i = 0; i < nodes.size(); i++)
+					for (int32_t c = e.child_off[nodes[i]]; c < e.child_off[nodes[i] + 1]; c++)
+						if (internal(e.child[c])) nodes.push_back(e.child[c]);
+				for (size_t i = nodes.size(); i-- > 0;) {
+					const int32_t v = nodes[i];
+					acc[v] = 1;
+					for (int32_t c = e.child_off[v]; c < e.child_off[v + 1]; c++)
+						if (internal(e.child[c]) && !piece_root[e.child[c]]) acc[v] += acc[e.child[c]];
+					if (v != r && acc[v] >= piece_steps && depth[v] <= kMaxEntry) piece_root[v] = 1;
+					if (v != r && piece_root[v]) {
+						Piece pc{r, v, acc[v] + depth[v], {}};
+						for (int32_t w = e.parent[v];; w = e.parent[w]) {
+							pc.entry.push_back(w);
+							if (w == r) break;
+						}
+						std::reverse(pc.entry.begin(), pc.entry.end());
+						pieces.push_back(std::move(pc));
+					}
+				}
+				pieces.push_back(Piece{r, r, acc[r], {}});
+			}
+			// longest piece first (CTAs are numbered piece-major: the shortest pieces fill the tail of the launch)
+			std::stable_sort(pieces.begin(), pieces.end(), [](const Piece &x, const Piece &y) { return x.steps > y.steps; });
+		}
 		walk_off.push_back(0);
 		p.unit_path_off.push_back(0);
-		for (int32_t r : roots) {
+		for (const Piece &pc : pieces) {
+			const int32_t r = pc.unit_root;
 			// the masks on the path root -> r, and where the value goes if r is a genome
 			for (int32_t v = r; v != e.root; v = e.parent[v]) p.unit_path.push_back(mask_off[v]);
 			p.unit_path_off.push_back((int32_t)p.unit_path.size());
@@ -580,11 +697,11 @@ int plan_walk(Engine &e, SweepPlan &p)
 			const bool genome = !internal(r);
 			p.unit_store.push_back(genome ? loc[r] : -1);
 			if (genome) e.rows_stored += D;
-			emit_walk(r);
+			emit_walk(pc.start, pc.entry);
 			walk_off.push_back((int64_t)walk_steps.size());
 		}
-		e.walk_pass_units.push_back((int32_t)roots.size());
-		e.n_walk_units = (int32_t)roots.size();
+		e.walk_pass_units.push_back((int32_t)pieces.size());
+		e.n_walk_units = (int32_t)pieces.size();
 		e.walk = true;
 	}
 	rows += pool_slots * D;

@@ -396,6 +396,35 @@ def test_fused_walk_kernel_variants_and_stack_placement(oracle, monkeypatch, var
                 assert np.array_equal(got, want), (L, rep)
 
 
+@pytest.mark.parametrize("units,piece,carve", [(1, 1, 0), (3, 2, 0), (8, 5, 0), (40, 16, 0), (2, 1 << 30, 0), (1, 1 << 30, 12), (4, 1 << 30, 40), (6, 20, 30)])
+@pytest.mark.parametrize("shape", ["coalescent", "caterpillar", "balanced"])
+def test_fused_walk_units_cut_into_pieces(oracle, monkeypatch, units, piece, carve, shape):
+    """units of the dense walk cut into pieces (a piece reaches its root from the unit's root across entry
+    steps in registers; the pieces cut out of it are skipped): every cut gives the level-synchronous rows"""
+    monkeypatch.setenv("PGS_WALK_UNITS", str(units))
+    monkeypatch.setenv("PGS_WALK_PIECE", str(piece))
+    monkeypatch.setenv("PGS_WALK_CARVE", str(carve))
+    if shape == "coalescent":
+        parent, rate, leaf = treegen.coalescent(500, seed=8, mut_rate=0.05)
+    else:
+        parent, rate, leaf = _caterpillar(300, 0.004) if shape == "caterpillar" else _balanced(8, 0.02)
+    n, L, seed, G = int((leaf >= 0).sum()), 1000, 91, 9
+    root = len(parent) - 1
+    genes = core_table(G, root)
+    with build(seed, L, parent, rate, leaf, genes) as keep:
+        want = np.stack([keep.copy_dense(v, G) for v in list(range(n)) + [root]])
+    with build(seed, L, parent, rate, leaf, genes, flags=0) as walk:
+        assert walk.stats()["sweep_mode"] == 1
+        for rep in range(2):
+            if rep:
+                walk.sweep()
+                walk.sync()
+            got = np.stack([walk.copy_dense(v, G) for v in list(range(n)) + [root]])
+            assert np.array_equal(got, want), rep
+    for v in (0, n // 3, n - 1):
+        assert np.array_equal(want[v][3], oracle.row(seed, parent, rate, v, root, 3, L))
+
+
 def _check_sparse_walk(oracle, e, seed, parent, rate, leaf, genes, L):
     gene_id, origin, off, car = genes
     genome_leaf = {int(g): v for v, g in enumerate(leaf) if g >= 0}
