@@ -42,6 +42,16 @@ UNIT = "leaf-nt/s"
 CFG = {"num_genomes": 10000, "core_size": 5000, "gene_length": 1000, "mut_rate": 0.01, "seed": 1}
 
 
+_REAL_STDOUT = None
+
+
+def emit(text):
+    """the bench line, to the process's original stdout (main() points fd 1 at stderr: library chatter)"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def _jsonable(x):
     """numpy scalars / arrays that slipped into the result line"""
     if isinstance(x, np.generic):
@@ -69,6 +79,15 @@ def workload_name(n_gpus, weak=False, config=4):
         shard = (f" x{n_gpus} (weak: one such gene set per GPU)" if weak else f" (its genes sharded {n_gpus}-way, one shard per GPU)")
     return (f"config{config}: num-genomes={c['num_genomes']} core-size={c['core_size']}{shard} gene-length={c['gene_length']}"
             f" mut-rate={c['mut_rate']}{extra} seed={c['seed']}")
+
+
+def bench_config(n_gpus, config=4):
+    """`config` of the JSON line -- the same dictionary from both arms (--impl b200 / reference); what one
+    rank holds is in the GPU arm's `shard` key, the reference arm's sample in its `cpu_baseline`"""
+    c = CFG if config == 4 else CONFIGS[config]
+    store_gb = c["num_genomes"] * c["core_size"] * ((c["gene_length"] + 63) // 64) * 16 / 1e9
+    return {"workload": workload_name(n_gpus, config=config),
+            "l2": f"inputs_larger_than_l2: every step rewrites the whole row store ({store_gb:.1f} GB of genome rows over {n_gpus} GPU(s), L2 = 126 MB)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -221,14 +240,14 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(1), "sample": sample},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": bench_config(args.gpus, 4),  # the same dictionary as the GPU arm's (the sample is described in cpu_baseline)
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference" if have_ref else "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0
 
 
@@ -500,6 +519,13 @@ def main():
     ap.add_argument("--shard-of", type=int, default=0, help="development: on ONE GPU, sweep only rank 0's shard of a SHARD_OF-way split "
                                                                 "of config 4 (what each GPU of a strong-scaling run does)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on
+    # the first communicator, whoever creates it): file descriptor 1 is pointed at stderr for the whole
+    # run and the line goes to a private copy of the original stdout (emit()).
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.small:
         CFG.update(num_genomes=100, core_size=1000)
     if args.impl == "reference":
@@ -750,20 +776,20 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(world, config=args.config),
-                       "l2": f"inputs_larger_than_l2 ({st['device_bytes'] / 1e9:.1f} GB of rows per GPU, rewritten every step)"
-                             if st["device_bytes"] > 400e6 else
-                             f"{st['device_bytes'] / 1e6:.0f} MB of rows per GPU, rewritten every step (not larger than L2)",
-                       "rng": "Philox4x32-10 keyed (seed, edge, gene, 64-site block); 16-bit decision fields, one call per sibling pair and 4 blocks",
-                       "genes_total": w["n_genes_total"], "genes_this_rank": st["n_genes"], "dense_genes_this_rank": st["n_dense_genes"],
-                       "rows_per_gpu": st["rows_total"], "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"],
-                       "sweep": "fused walks (k1_top_masks + k1_walk_dense, k1_walk_sparse)" if st["sweep_mode"] == 1 else "level-synchronous"},
+            "config": bench_config(world, args.config),
+            "shard": {"l2": f"inputs_larger_than_l2 ({st['device_bytes'] / 1e9:.1f} GB of rows per GPU, rewritten every step)"
+                            if st["device_bytes"] > 400e6 else
+                            f"{st['device_bytes'] / 1e6:.0f} MB of rows per GPU, rewritten every step (not larger than L2)",
+                      "rng": "Philox4x32-10 keyed (seed, edge, gene, 64-site block); 16-bit decision fields, one call per sibling pair and 4 blocks",
+                      "genes_total": w["n_genes_total"], "genes_this_rank": st["n_genes"], "dense_genes_this_rank": st["n_dense_genes"],
+                      "rows_per_gpu": st["rows_total"], "levels": st["levels"], "hbm_bytes_per_gpu": st["device_bytes"],
+                      "sweep": "fused walks (k1_top_masks + k1_walk_dense, k1_walk_sparse)" if st["sweep_mode"] == 1 else "level-synchronous"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps * world, "clocks": clocks,
             "e2e_device_formatter": e2e_device, "e2e_host_expand": e2e_host,
             "mismatch": k2, "mismatch_allreduce_check": mm_leg, "weak_scaling": weak, "cli_multi_device": cli, "e2e_files": files, "e2e_packed": e2e_packed,
         }
-        print(json.dumps(line, default=_jsonable), flush=True)
+        emit(json.dumps(line, default=_jsonable))
     if world > 1:
         dist.destroy_process_group()
     return 0
