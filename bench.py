@@ -688,7 +688,7 @@ def main():
             wall = max_over_ranks(time.perf_counter() - t0)
             host = bool(what & OUT_HOST_EXPAND)
             # bytes that cross PCIe per step: the text itself, or the packed rows of every record / MAF line
-            d2h = int(rep["records"]) * row_bytes_packed if host else int(rep["bytes"])
+            d2h = int(rep["d2h_bytes"])
             return {"value": leaf_nt_all * args.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": d2h, "text_bytes_per_step": int(rep["bytes"]), "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * wall / args.e2e_steps, "k3_device_ms_per_step": rep["device_ms"],
@@ -699,8 +699,9 @@ def main():
         e2e_device = e2e_run(OUT_GENOMES | OUT_MAF | OUT_DISCARD,
                              "formatted by K3 on the GPU, the text copied into pinned host memory and dropped")
         e2e_host = e2e_run(OUT_GENOMES | OUT_MAF | OUT_DISCARD | OUT_HOST_EXPAND,
-                           f"PGS_OUT_HOST_EXPAND: packed rows copied into pinned host memory, every genomeNNN.fasta and every run of "
-                           f"256 MAF lines written in full (headers + bases, AVX2) into a worker thread's buffer by {threads} host threads, then dropped")
+                           f"PGS_OUT_HOST_EXPAND: packed rows copied into pinned host memory (genome order for the FASTA files, MAF line order), "
+                           f"every genomeNNN.fasta and every run of 256 MAF lines written in full (headers + bases, SIMD) through L2-sized "
+                           f"buffers by {threads} host threads, then dropped")
         e2e = dict(e2e_host if e2e_host["value"] >= e2e_device["value"] else e2e_device)
         e2e["mode"] = "host_expand" if e2e is not None and e2e_host["value"] >= e2e_device["value"] else "device_formatter"
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PGS_ABI_VERSION 2
+#define PGS_ABI_VERSION 3
 
 typedef struct pgs_engine pgs_engine;
 
@@ -232,6 +232,8 @@ typedef struct pgs_output_report {
 	int64_t files, bytes, records;
 	double device_ms; /* K3 kernel time */
 	double wall_ms;   /* whole call */
+	int64_t d2h_bytes; /* bytes copied device -> host by the call: the text (K3), or the packed rows behind it
+	                    * (PGS_OUT_HOST_EXPAND: once per record and once per MAF line).  ABI 3 */
 } pgs_output_report;
 
 int pgs_write_outputs(pgs_engine *h, const pgs_output_spec *spec, pgs_output_report *report);

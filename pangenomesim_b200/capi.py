@@ -61,7 +61,7 @@ class OutputSpec(C.Structure):
 
 class OutputReport(C.Structure):
     _fields_ = [("files", C.c_int64), ("bytes", C.c_int64), ("records", C.c_int64),
-                ("device_ms", C.c_double), ("wall_ms", C.c_double)]
+                ("device_ms", C.c_double), ("wall_ms", C.c_double), ("d2h_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

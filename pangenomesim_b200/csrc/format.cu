@@ -972,6 +972,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 
 	Writer w(e, spec);
 	double device_ms = 0.0;
+	int64_t d2h_bytes = 0; // what the call copies from the device (text, or packed rows)
 	int64_t records = 0;
 
 	// A chunk = kernels writing into d_stage[slot] + the list of file pieces it holds.  The chunk
@@ -1019,9 +1020,9 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		ck(cudaStreamWaitEvent(copy_stream, formatted[s], 0));
 		if (direct) {
 			for (const Segment &sg : *direct)
-				ck(cudaMemcpyAsync(h_stage[s].p + sg.dst_off, sg.src, (size_t)sg.bytes, cudaMemcpyDeviceToHost, copy_stream));
+				ck(cudaMemcpyAsync(h_stage[s].p + sg.dst_off, sg.src, (size_t)sg.bytes, cudaMemcpyDeviceToHost, copy_stream)), d2h_bytes += sg.bytes;
 		} else {
-			ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream));
+			ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)bytes, cudaMemcpyDeviceToHost, copy_stream)), d2h_bytes += bytes;
 		}
 		ck(cudaEventRecord(copied[s], copy_stream));
 		if (!pipe_ok()) return false;
@@ -1098,6 +1099,9 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		if (!Writer::write_range(fd, data, len, offset, msg)) w.fail(path + ": " + msg);
 		::close(fd);
 	};
+	// records expanded into a worker's buffer at a time: ~256 KB of text (PGS_HX_RUN_RECORDS: tuning / test knob)
+	int64_t kHxRunRecords = std::max<int64_t>(1, ((int64_t)256 << 10) / (e.cfg.gene_length + 24));
+	if (const char *v = std::getenv("PGS_HX_RUN_RECORDS")) kHxRunRecords = std::max(1, std::atoi(v));
 	// a worker thread's own buffer, kept between tasks (no zero-filling, no reallocation per file)
 	auto thread_buffer = [](size_t bytes) -> char * {
 		thread_local std::unique_ptr<char[]> buf;
@@ -1154,9 +1158,45 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	// them is delivered first
 	if (host_expand && (!drain(0) || !drain(1))) return fail_out(PGS_ERR_IO, w.error);
 
+	// ---- both texts from ONE copy of the rows (PGS_HX_ONE_COPY=1; off by default).  genomeNNN.fasta wants the rows
+	// genome by genome, alignment.maf gene by gene; they are shipped twice (25.6 GB for config 4).  With the knob, when
+	// both are asked for and the text goes to memory (sink / PGS_OUT_DISCARD), the rows cross PCIe once, in MAF line
+	// order (k3_gather_maf_rows), and every chunk of genes yields its MAF blocks AND, for every genome, the piece of
+	// genomeNNN.fasta that holds the chunk's genes (records follow the gene table in the file, so the piece is one
+	// contiguous range).  Measured on the 16-core GPU box (config 4): 0.676 s per step against 0.538 with two copies --
+	// the call is bound by the host's cores once PCIe carries a quarter of the text, and a genome's rows of a chunk lie
+	// 2.5 MB apart (one 4 KB page per gene and group of genomes; 25 % slower per core in scripts/expand_bench.cpp's
+	// strided variant).  It pays where PCIe is slower or the host has more cores per GPU.
+	const bool fused = host_expand && (spec->what & PGS_OUT_GENOMES) && (spec->what & PGS_OUT_MAF) && !shard &&
+					   ((spec->what & PGS_OUT_DISCARD) || spec->sink) && std::getenv("PGS_HX_ONE_COPY") && std::atoi(std::getenv("PGS_HX_ONE_COPY"));
+	std::vector<int32_t> order_pos;  // genome -> its position in all_order (= its line in a dense gene's MAF block, less one)
+	std::vector<int32_t> sp_line;    // per sparse row of a LEAF: the genome's index in the gene's carrier list
+	std::vector<int64_t> dense_by_gene((size_t)ht.n_dense); // dense slots in the order of the gene table (= of the files)
+	if (host_expand && (spec->what & PGS_OUT_GENOMES)) {
+		for (int64_t sl = 0; sl < ht.n_dense; sl++) dense_by_gene[(size_t)sl] = sl;
+		std::sort(dense_by_gene.begin(), dense_by_gene.end(), [&](int64_t a, int64_t b) { return ht.dense_gene[a] < ht.dense_gene[b]; });
+	}
+	if (fused) {
+		order_pos.assign(n, 0);
+		for (int32_t i = 0; i < n; i++) order_pos[e.all_order[i]] = i;
+		sp_line.assign(e.sp_gene.size(), 0);
+		const int64_t per_task = 4096;
+		for (int64_t g0 = 0; g0 < G; g0 += per_task)
+			xpool->submit([&, g0] {
+				for (int64_t g = g0; g < std::min(G, g0 + per_task); g++) {
+					if (e.dense_slot[g] >= 0) continue;
+					for (int64_t k = e.carrier_off[g]; k < e.carrier_off[g + 1]; k++) {
+						const int32_t leaf = e.genome_leaf[e.carrier_genome[k]];
+						sp_line[(size_t)(e.sp_off[leaf] + sparse_rank(ht, leaf, g))] = (int32_t)(k - e.carrier_off[g]);
+					}
+				}
+			});
+		xpool->wait_all();
+	}
+
 	// ---- genomeNNN.fasta, host-expanded: a genome's rows lie together in the store (its leaf's
 	// region), so a chunk is a handful of plain copies; one task per genome writes the whole file
-	if ((spec->what & PGS_OUT_GENOMES) && host_expand) {
+	if ((spec->what & PGS_OUT_GENOMES) && host_expand && !fused) {
 		struct Chunk {
 			int32_t i = 0, j = 0;
 			int slot = 0;
@@ -1172,7 +1212,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			const char *run_src = nullptr;
 			int64_t run_dst = 0, run_len = 0;
 			auto flush = [&]() {
-				if (run_len) ck(cudaMemcpyAsync(h_stage[s].p + run_dst, run_src, (size_t)run_len, cudaMemcpyDeviceToHost, copy_stream));
+				if (run_len) ck(cudaMemcpyAsync(h_stage[s].p + run_dst, run_src, (size_t)run_len, cudaMemcpyDeviceToHost, copy_stream)), d2h_bytes += run_len;
 				run_len = 0;
 			};
 			while (j < n) {
@@ -1210,19 +1250,47 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				const char *region = h_stage[cur.slot].p + cur.region_off[g - cur.i];
 				xpool->submit([&, g, region] {
 					const int64_t bytes = genome_bytes[g], nrows = genome_rows[g], L = ht.L;
-					char *buf = thread_buffer((size_t)bytes);
-					char text[64];
-					for (int64_t sl = 0; sl < nrows; sl++) {
-						const RecordInfo ri = fasta_record(ht, g, sl, text);
-						char *d = buf + ri.off;
-						std::memcpy(d, text, (size_t)ri.plen);
-						expand_bases(region + sl * row_bytes, L, d + ri.plen);
-						d[ri.plen + L] = '\n';
-					}
 					char name[64];
 					const int nl = format_genome_name(g, name, sizeof name);
+					const std::string file = std::string(name, (size_t)nl) + ".fasta";
 					const int64_t at = shard ? shard->genome_offset[g] : 0;
-					hx_deliver(std::string(name, (size_t)nl) + ".fasta", at, buf, bytes, at == 0);
+					// The file is written in runs of kHxRunRecords records through a buffer that stays in the
+					// core's L2: storing a whole 5 MB file first streams it through the L3 / DRAM at about half
+					// the rate (scripts/expand_bench.cpp: 11.5 against 22.7 GB/s of text per core on the GPU box).
+					// Records follow the gene table in the file, rows lie dense genes first (by gene id), then
+					// the leaf's sparse genes: the two lists, each ascending in the table index, are merged so
+					// that a run of records is one contiguous range of the file.
+					const int32_t leaf = ht.genome_leaf[g];
+					const int64_t *sp = ht.sp_gene + ht.sp_off[leaf];
+					const int64_t n_sp = ht.sp_off[leaf + 1] - ht.sp_off[leaf];
+					int64_t di = 0, si = 0; // next dense slot in table order, next sparse row
+					auto next_slot = [&]() -> int64_t {
+						if (si >= n_sp || (di < ht.n_dense && ht.dense_gene[dense_by_gene[di]] < sp[si])) return dense_by_gene[di++];
+						return ht.n_dense + si++;
+					};
+					char text[64];
+					int64_t done = 0, run_begin = 0;
+					do {
+						const int64_t now = std::min(nrows - done, kHxRunRecords);
+						int64_t run_len = 0;
+						char *buf = nullptr;
+						for (int64_t k = 0; k < now; k++) {
+							const int64_t sl = next_slot();
+							const RecordInfo ri = fasta_record(ht, g, sl, text);
+							if (k == 0) { // (records of a run have the same length up to the digits of the gene id: a bound)
+								run_begin = ri.off;
+								buf = thread_buffer((size_t)(now * (ri.plen + 16 + L + 1)));
+							}
+							char *d = buf + (ri.off - run_begin);
+							std::memcpy(d, text, (size_t)ri.plen);
+							expand_bases(region + sl * row_bytes, L, d + ri.plen);
+							d[ri.plen + L] = '\n';
+							run_len = ri.off - run_begin + ri.plen + L + 1;
+						}
+						hx_deliver(file, at + run_begin, buf, run_len, at == 0 && done == 0);
+						done += now;
+					} while (done < nrows);
+					(void)bytes;
 				});
 			}
 			for (int32_t g = cur.i; g < cur.j; g++) records += genome_rows[g];
@@ -1270,6 +1338,18 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		}
 	}
 
+	// (fused: genomes without a gene still get their empty file; the FASTA records are counted here)
+	if (fused) {
+		for (int32_t g = 0; g < n; g++) {
+			records += genome_rows[g];
+			if (genome_rows[g] == 0) {
+				char name[64];
+				const int nl = format_genome_name(g, name, sizeof name);
+				hx_deliver(std::string(name, (size_t)nl) + ".fasta", 0, nullptr, 0, true);
+			}
+		}
+	}
+
 	// ---- alignment.maf, host-expanded: a kernel gathers the rows of a chunk's lines in line order,
 	// the host writes the headers and expands the bases -- into the mapped file, into a buffer handed
 	// to the sink, or (PGS_OUT_DISCARD) block by block into the workers' own buffers
@@ -1302,6 +1382,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		}
 		if (const char *v = std::getenv("PGS_WRITE_MMAP")) can_map = can_map && std::atoi(v) != 0; // tuning knob
 		int64_t packed_cap = std::min<int64_t>(stage, (int64_t)64 << 20); // 64 MB of rows = ~260 MB of text per chunk
+		if (fused) packed_cap = stage; // (the pieces of the FASTA files grow with the chunk: ~100 records each at 256 MB)
 		for (int64_t g = 0; g < G; g++) packed_cap = std::max(packed_cap, maf_lines[g] * row_bytes);
 		if (packed_cap > stage) {
 			if (fd >= 0) ::close(fd);
@@ -1347,7 +1428,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			}
 			ck(cudaEventRecord(formatted[s], e.stream));
 			ck(cudaStreamWaitEvent(copy_stream, formatted[s], 0));
-			if (items > 0) ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)(items * row_bytes), cudaMemcpyDeviceToHost, copy_stream));
+			if (items > 0) ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)(items * row_bytes), cudaMemcpyDeviceToHost, copy_stream)), d2h_bytes += items * row_bytes;
 			ck(cudaEventRecord(copied[s], copy_stream));
 			return cp;
 		};
@@ -1457,6 +1538,84 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				}
 			}
 			records += cur->lines_prefix.back();
+			if (fused) {
+				// genomes in groups of eight neighbours of all_order: their rows of a dense gene are eight
+				// neighbouring lines of the chunk (2 KB), and eight pieces of ~100 records fit the L2
+				// (fewer where a genome's piece is large -- many genes per chunk: about 1 MB of text per task)
+				constexpr int kGroup = 8;
+				const int64_t piece_guess = (cur->lines_prefix.back() / std::max<int32_t>(n, 1) + 1) * (ht.L + 32);
+				const int group = (int)std::max<int64_t>(1, std::min<int64_t>(kGroup, ((int64_t)1 << 20) / piece_guess));
+				for (int32_t p0 = 0; p0 < n; p0 += group)
+					xpool->submit([&, cp, p0, group] {
+						const int64_t L = ht.L;
+						const int cnt = (int)std::min<int64_t>(group, n - p0);
+						struct Cursor {
+							int32_t genome, leaf;
+							const int64_t *sp; // the leaf's sparse genes (ascending table index)
+							int64_t n_sp, si;
+							char *buf;
+							int64_t begin, len; // the piece: offset of its first record in the file, bytes so far
+						} cs[kGroup];
+						// a record: '>' name(<= 16) '.' id(<= 10) '\n' bases '\n'; a genome's piece: its genes of the chunk
+						const int64_t dense_here = ht.dense_before[cp->g2] - ht.dense_before[cp->g];
+						int64_t need = 0, caps[kGroup];
+						for (int i = 0; i < cnt; i++) {
+							Cursor &c = cs[i];
+							c.genome = e.all_order[p0 + i];
+							c.leaf = ht.genome_leaf[c.genome];
+							c.sp = ht.sp_gene + ht.sp_off[c.leaf];
+							c.n_sp = ht.sp_off[c.leaf + 1] - ht.sp_off[c.leaf];
+							c.si = std::lower_bound(c.sp, c.sp + c.n_sp, cp->g) - c.sp;
+							const int64_t sparse_here = (std::lower_bound(c.sp, c.sp + c.n_sp, cp->g2) - c.sp) - c.si;
+							caps[i] = (dense_here + sparse_here) * (L + 32);
+							need += caps[i];
+							c.begin = -1;
+							c.len = 0;
+						}
+						char *all = thread_buffer((size_t)need);
+						for (int i = 0; i < cnt; i++) {
+							cs[i].buf = all;
+							all += caps[i];
+						}
+						const char *rows_in = h_stage[cp->slot].p;
+						char text[64];
+						for (int64_t k = cp->g; k < cp->g2; k++) {
+							const int64_t first_line = cp->lines_prefix[k - cp->g];
+							const bool dense = ht.dense_slot[k] >= 0;
+							if (k + 2 < cp->g2 && ht.dense_slot[k + 2] >= 0) { // the group's rows two genes ahead
+								const char *nx = rows_in + (cp->lines_prefix[k + 2 - cp->g] + 1 + p0) * row_bytes;
+								for (int64_t b = 0; b < cnt * row_bytes; b += 64) __builtin_prefetch(nx + b, 0, 3);
+							}
+							for (int i = 0; i < cnt; i++) {
+								Cursor &c = cs[i];
+								int64_t slot, line;
+								if (dense) {
+									slot = ht.dense_slot[k];
+									line = 1 + p0 + i;
+								} else {
+									if (c.si >= c.n_sp || c.sp[c.si] != k) continue;
+									slot = ht.n_dense + c.si;
+									line = 1 + sp_line[(size_t)(ht.sp_off[c.leaf] + c.si)];
+									c.si++;
+								}
+								const RecordInfo ri = fasta_record(ht, c.genome, slot, text);
+								if (c.begin < 0) c.begin = ri.off;
+								char *d = c.buf + (ri.off - c.begin);
+								std::memcpy(d, text, (size_t)ri.plen);
+								expand_bases(rows_in + (first_line + line) * row_bytes, L, d + ri.plen);
+								d[ri.plen + L] = '\n';
+								c.len = ri.off - c.begin + ri.plen + L + 1;
+							}
+						}
+						for (int i = 0; i < cnt; i++) {
+							const Cursor &c = cs[i];
+							if (c.begin < 0) continue;
+							char name[64];
+							const int nl = format_genome_name(c.genome, name, sizeof name);
+							hx_deliver(std::string(name, (size_t)nl) + ".fasta", c.begin, c.buf, c.len, c.begin == 0);
+						}
+					});
+			}
 			if (!more) {
 				xpool->wait_all();
 				finish_chunk(*cur);
@@ -1602,6 +1761,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	if (report) {
 		*report = w.rep;
 		report->records = records;
+		report->d2h_bytes = d2h_bytes;
 		report->device_ms = device_ms;
 		report->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 	}

@@ -643,7 +643,7 @@ int plan_walk(Engine &e, SweepPlan &p)
 					size_t best = cand.size();
 					for (size_t i = 0; i < cand.size(); i++)
 						if (depth[cand[i]] < kMaxEntry && (best == cand.size() || size[cand[i]] > size[cand[best]])) best = i;
-					if (best == cand.size() || size[cand[best]] < 32) break;
+					if (best == cand.size() || size[cand[best]] < 64) break; // (as the top cut: a small tree is cut no further than before)
 					const int32_t v = cand[best];
 					piece_root[v] = 0; // stays with the piece above it (a unit's root: with the unit's remainder)
 					splits++;

@@ -1,10 +1,25 @@
-timeout 900 python -m pytest tests/test_sweep_gpu.py -m gpu -x -q -k pieces 2>&1 | tail -3
-sed -i 's/for rep in 1 2 3/for rep in 1 2/' scripts/ab_shard.sh
-SHARDS=8 bash scripts/ab_shard.sh "base X=1" \
-  "u20c120 PGS_WALK_UNITS=20 PGS_WALK_CARVE=120" "u30c120 PGS_WALK_UNITS=30 PGS_WALK_CARVE=120" "u40c120 PGS_WALK_UNITS=40 PGS_WALK_CARVE=120" \
-  "u60c120 PGS_WALK_UNITS=60 PGS_WALK_CARVE=120" "u80c120 PGS_WALK_UNITS=80 PGS_WALK_CARVE=120" \
-  "u30c100 PGS_WALK_UNITS=30 PGS_WALK_CARVE=100" "u60c100 PGS_WALK_UNITS=60 PGS_WALK_CARVE=100" \
-  "u30c140 PGS_WALK_UNITS=30 PGS_WALK_CARVE=140" "u60c140 PGS_WALK_UNITS=60 PGS_WALK_CARVE=140" "u80c160 PGS_WALK_UNITS=80 PGS_WALK_CARVE=160" "u120c160 PGS_WALK_CARVE=160"
-export PGS_NO_GRAPH=1
-PGS_WALK_UNITS=40 PGS_WALK_CARVE=120 PGS_WALK_TRACE=gpurun_out/trace8_carve.txt python bench.py --shard-of 8 --steps 2 --warmup 3 --no-e2e --no-cpu --no-mismatch > /dev/null 2>gpurun_out/tr.err
-python scripts/walk_trace.py gpurun_out/trace8_carve.txt
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_format_gpu.py -m gpu -q -x > gpurun_out/pytest_fmt.log 2>&1; echo rc=$?; tail -5 gpurun_out/pytest_fmt.log
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_full.log 2>&1; echo rc=$?; tail -3 gpurun_out/pytest_full.log
+timeout 900 python bench.py --steps 20 --warmup 5 --no-mismatch --no-files > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -c 300 gpurun_out/bench_c4.err
+python - <<'PY'
+import json
+l=json.load(open('gpurun_out/bench_c4.json'))
+for k in ('e2e_host_expand','e2e_device_formatter','e2e_packed'):
+    d=l[k]; print(k, d['ms_per_step'], d.get('text_gb_per_s'), d.get('d2h_gb_per_s'), d.get('d2h_bytes_per_step'))
+PY
+PGS_HX_TWO_PASS=1 timeout 300 python bench.py --steps 5 --warmup 3 --no-mismatch --no-files --no-cpu > gpurun_out/t.json 2>/dev/null; python -c "
+import json
+l=json.load(open('gpurun_out/t.json')); d=l['e2e_host_expand']; print('two-pass', d['ms_per_step'], d['text_gb_per_s'], d['d2h_bytes_per_step'])"
+for mb in 128 512; do PGS_STAGE_MB=$mb timeout 300 python bench.py --steps 5 --warmup 3 --no-mismatch --no-files --no-cpu > gpurun_out/t.json 2>/dev/null; python -c "
+import json
+l=json.load(open('gpurun_out/t.json')); d=l['e2e_host_expand']; print('stage', $mb, d['ms_per_step'], d['text_gb_per_s'])"; done
+timeout 400 python bench.py --config 3 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -c 300 gpurun_out/bench_c3.err
+timeout 600 python bench.py --config 5 --steps 10 --warmup 3 --no-cpu --e2e-steps 1 --no-mismatch > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; tail -c 300 gpurun_out/bench_c5.err
+python - <<'PY'
+import json
+for c in (3,5):
+    l=json.load(open(f'gpurun_out/bench_c{c}.json'))
+    for k in ('e2e_host_expand','e2e_device_formatter'):
+        d=l[k]; print(c, k, d['ms_per_step'], d.get('text_gb_per_s'), d.get('d2h_gb_per_s'), d.get('plan_ms_per_step'))
+PY

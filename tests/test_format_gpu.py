@@ -81,6 +81,7 @@ def run_case(oracle, tmp_path, n, L, n_core, n_acc, seed, all_order=None, use_si
     if what & OUT_HOST_EXPAND:  # and the same totals when the text is produced and dropped
         rep2 = e.write_outputs(None, what | OUT_DISCARD, ref_core, ref_acc)
         assert rep2["files"] == rep["files"] and rep2["bytes"] == rep["bytes"] and rep2["records"] == rep["records"]
+        assert 0 < rep2["d2h_bytes"] < rep2["bytes"]  # packed rows (and the text of the three small reference files)
     e.close()
 
 
@@ -246,10 +247,16 @@ def test_host_expand_sink_and_order(oracle, tmp_path):
     run_case(oracle, tmp_path, n=13, L=130, n_core=3, n_acc=25, seed=8, all_order=order, use_sink=True, what=OUT_ALL | OUT_HOST_EXPAND)
 
 
+@pytest.mark.parametrize("run_records", [None, "7", "1", "one-copy"])
 @pytest.mark.parametrize("use_sink", [False, True])
-def test_host_expand_many_chunks(oracle, tmp_path, monkeypatch, use_sink):
+def test_host_expand_many_chunks(oracle, tmp_path, monkeypatch, use_sink, run_records):
     """1 MB staging: the genomes and the MAF lines take several chunks each (double buffering,
     mapped windows of the MAF file at unaligned offsets)"""
+    # ("one-copy": both texts from one copy of the rows, chunk of genes by chunk of genes; sink and PGS_OUT_DISCARD only)
+    if run_records == "one-copy":
+        monkeypatch.setenv("PGS_HX_ONE_COPY", "1")
+    elif run_records:  # genomeNNN.fasta delivered in several pieces (runs of records through an L2-sized buffer)
+        monkeypatch.setenv("PGS_HX_RUN_RECORDS", run_records)
     monkeypatch.setenv("PGS_STAGE_MB", "1")
     monkeypatch.setenv("PGS_EXPAND_THREADS", "5")
     run_case(oracle, tmp_path, n=150, L=1000, n_core=30, n_acc=40, seed=12, use_sink=use_sink, what=OUT_ALL | OUT_HOST_EXPAND)
