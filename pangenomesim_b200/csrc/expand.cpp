@@ -6,7 +6,6 @@
 // the host's cores write the text where it has to end up.  Output bytes are identical.
 #include "expand.h"
 
-#include <cstdlib>
 #include <cstring>
 
 #if defined(__x86_64__)
@@ -88,31 +87,6 @@ __attribute__((target("avx2"))) void expand_avx2(const unsigned char *src, int64
 	}
 	if (s < sites) expand_ssse3(src + s / 4, sites - s, dst + s);
 }
-
-// AVX-512 VBMI: 16 packed bytes (64 sites) -> 64 ASCII bytes in four byte-wise instructions.  VPERMB puts the
-// packed bytes 2j, 2j+1 into quadword j; VPMULTISHIFTQB makes byte i of a quadword the eight bits from bit 2i on
-// (its low two bits are the code of site 8j + i); AND 3; VPSHUFB picks the letter.  Half the shuffle work of
-// the AVX2 path per byte of text.
-__attribute__((target("avx512f,avx512bw,avx512vbmi"))) void expand_avx512(const unsigned char *src, int64_t sites, char *dst)
-{
-	alignas(64) unsigned char idx[64], ctrl[64];
-	for (int j = 0; j < 8; j++)
-		for (int b = 0; b < 8; b++) {
-			idx[8 * j + b] = (unsigned char)(2 * j + (b & 1));
-			ctrl[8 * j + b] = (unsigned char)(2 * b);
-		}
-	const __m512i vidx = _mm512_load_si512(idx), vctrl = _mm512_load_si512(ctrl);
-	const __m512i three = _mm512_set1_epi8(3);
-	const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'G', 'T', 'A', 'C', 'G', 'T', 'A', 'C', 'G', 'T', 'A', 'C', 'G', 'T'));
-	int64_t s = 0;
-	for (; s + 64 <= sites; s += 64) {
-		const __m512i x = _mm512_castsi128_si512(_mm_loadu_si128(reinterpret_cast<const __m128i *>(src + s / 4)));
-		const __m512i q = _mm512_permutexvar_epi8(vidx, x);
-		const __m512i code = _mm512_and_si512(_mm512_multishift_epi64_epi8(vctrl, q), three);
-		_mm512_storeu_si512(dst + s, _mm512_shuffle_epi8(lut, code));
-	}
-	if (s < sites) expand_avx2(src + s / 4, sites - s, dst + s);
-}
 #endif
 
 typedef void (*expand_fn)(const unsigned char *, int64_t, char *);
@@ -121,10 +95,6 @@ expand_fn pick()
 {
 #if defined(__x86_64__)
 	__builtin_cpu_init();
-	if (__builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw")) {
-		const char *v = std::getenv("PGS_EXPAND_ISA"); // tuning knob: "avx2" keeps the 256-bit path
-		if (!v || std::strcmp(v, "avx2") != 0) return expand_avx512;
-	}
 	if (__builtin_cpu_supports("avx2")) return expand_avx2;
 	if (__builtin_cpu_supports("ssse3")) return expand_ssse3;
 #endif
@@ -142,7 +112,6 @@ void expand_bases(const void *packed_row, int64_t sites, char *dst)
 const char *expand_kind()
 {
 #if defined(__x86_64__)
-	if (g_expand == expand_avx512) return "avx512vbmi";
 	if (g_expand == expand_avx2) return "avx2";
 	if (g_expand == expand_ssse3) return "ssse3";
 #endif

@@ -75,7 +75,7 @@ def test_host_expander_matches_the_oracle(sites):
     rng = np.random.default_rng(sites)
     words = rng.integers(0, 2**32, size=(sites + 15) // 16 + 3, dtype=np.uint64).astype(np.uint32)
     got, kind = expand_bases(words, sites)
-    assert kind in ("avx512vbmi", "avx2", "ssse3", "scalar")
+    assert kind in ("avx2", "ssse3", "scalar")
     codes = (words[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3
     want = bytes(b"ACGT"[c] for c in codes.reshape(-1)[:sites])
     assert got == want
@@ -108,22 +108,3 @@ def test_plan_only_knob_plans_and_computes_nothing(monkeypatch):
         assert e.stats()["n_nodes"] == len(parent) and e.stats()["rows_total"] == 0
     del np
 
-
-def test_host_expander_256_bit_path_in_a_fresh_process():
-    """where the CPU has AVX-512 VBMI the 512-bit expander is picked when the library is loaded;
-    PGS_EXPAND_ISA=avx2 keeps the 256-bit one: both against numpy"""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import numpy as np\n"
-        "from pangenomesim_b200.capi import expand_bases\n"
-        "for sites in (1, 63, 64, 65, 127, 128, 129, 1000, 4099):\n"
-        "    w = np.random.default_rng(sites).integers(0, 2**32, size=(sites + 15) // 16 + 3, dtype=np.uint64).astype(np.uint32)\n"
-        "    got, kind = expand_bases(w, sites)\n"
-        "    assert kind in ('avx2', 'ssse3', 'scalar'), kind\n"
-        "    codes = (w[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3\n"
-        "    assert got == bytes(b'ACGT'[c] for c in codes.reshape(-1)[:sites])\n"
-    )
-    env = dict(os.environ, PGS_EXPAND_ISA="avx2")
-    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT, env=env)
