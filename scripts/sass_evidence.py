@@ -16,13 +16,15 @@ KERNELS = [  # (object, substring of the demangled name, what to show)
     ("kernels.o", "k1_walk_dense<3, 2, true, true>", "dense walk, quads, 3 CTAs/SM (config 4 default)"),
     ("kernels.o", "k1_top_masks", "origin rows + masks of the top branches"),
     ("kernels.o", "k1_walk_sparse", "sparse (accessory) walk"),
-    ("mismatch.o", "k2_mismatch_tiles", "pairwise mismatch tiles"),
+    ("mismatch_tc.o", "k2_tc_pair<", "pairwise mismatch on the tensor cores, CTA pair (default: FP4)"),
+    ("mismatch_tc.o", "k2_expand_fp4", "operand expansion for the FP4 tensor kernel"),
+    ("mismatch.o", "k2_mismatch_tiles", "pairwise mismatch tiles (popcount kernel)"),
     ("mismatch.o", "k2_split_planes", "bit-plane split"),
     ("format.o", "k3_maf", "MAF formatter"),
     ("format.o", "k3_genome_fasta", "genome FASTA formatter"),
     ("format.o", "k3_gather_maf_rows", "row gather for host-expanded MAF"),
 ]
-INTERESTING = re.compile(r"\b(LDG|STG|LDS|STS|LDGSTS|LDGDEPBAR|POPC|ATOM|ATOMG|RED|REDG|BAR|UTMA\w*|UBLKCP|UTC\w*|HMMA|IMMA|LDL|STL|CCTL|PREFETCH)\b")
+INTERESTING = re.compile(r"\b(LDG|STG|LDS|STS|LDGSTS|LDGDEPBAR|POPC|ATOM|ATOMG|RED|REDG|BAR|UTMA\w*|UBLKCP|UTC\w*|HMMA|IMMA|LDL|STL|CCTL|PREFETCH|LDTM|STTM|ACQBULK|PREEXIT|SYNCS|UCGABAR\w*)\b")
 
 
 def demangle(name):
