@@ -108,3 +108,23 @@ def test_plan_only_knob_plans_and_computes_nothing(monkeypatch):
         assert e.stats()["n_nodes"] == len(parent) and e.stats()["rows_total"] == 0
     del np
 
+
+
+@pytest.mark.parametrize("env", [{}, {"PGS_WALK_PIECE": "41"}, {"PGS_WALK_UNITS": "40", "PGS_WALK_CARVE": "160"},
+                                 {"PGS_WALK_UNITS": "1", "PGS_WALK_PIECE": "1"}, {"PGS_WALK_CARVE": "100000"}])
+def test_planner_cuts_a_big_tree_on_the_cpu(monkeypatch, env):
+    """the dense walk's planner on config 4's tree size and an eighth of its genes (units, carved units,
+    bottom-up pieces, every knob at its extreme) runs through on a machine without a device: plan-only
+    engines fail at the first device allocation, i.e. after the whole plan has been built"""
+    import treegen
+    from pangenomesim_b200 import Engine, PgsError
+    monkeypatch.setenv("PGS_PLAN_ONLY", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 10000
+    parent, rate, leaf = treegen.coalescent(n, seed=1, mut_rate=0.01)
+    with Engine(1, 1000) as e:
+        e.set_tree(parent, rate, leaf)
+        with pytest.raises(PgsError) as ex:
+            e.set_core_genes(625, 2 * n - 2)
+        assert ex.value.code == -6 and "plan-only" in ex.value.message
