@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo rc=$?; tail -c 300 gpurun_out/bench_c4.err
-timeout 400 python bench.py --config 3 --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo rc=$?; tail -c 300 gpurun_out/bench_c3.err
-timeout 900 python bench.py --config 5 --steps 10 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo rc=$?; tail -c 300 gpurun_out/bench_c5.err
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo rc=$?
-python -c "
-import __graft_entry__ as g
-g.smoke(); print('smoke ok')"
+timeout 900 python -m pytest tests/test_sweep_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -3
+sed -i 's/for rep in 1 2 3/for rep in 1 2/' scripts/ab_shard.sh
+SHARDS="8 4 2 1" bash scripts/ab_shard.sh "one PGS_TOP_TASKS_PER_CTA=1" "folded X=1" "two PGS_TOP_TASKS_PER_CTA=2" "four PGS_TOP_TASKS_PER_CTA=4"
+export PGS_NO_GRAPH=1
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-mismatch --shard-of 8"
+ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 4 --csv --log-file gpurun_out/r02_launches_shard8.csv $CMD > gpurun_out/ncu_l8.log 2>&1
+grep -v "^==" gpurun_out/r02_launches_shard8.csv | awk -F'","' '{print $5, $9, $NF}' | tail -4
