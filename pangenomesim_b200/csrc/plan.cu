@@ -144,7 +144,7 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 		}
 	};
 	const int64_t entries = n_genes > 0 ? carrier_off[n_genes] : 0;
-	unsigned workers = entries >= 100000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	unsigned workers = entries >= 100000 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
 	if (const char *v = std::getenv("PGS_PLAN_THREADS")) workers = (unsigned)std::max(1, std::atoi(v)); // tuning knob
 	std::vector<Part> parts(workers);
 	std::vector<int64_t> cuts(workers + 1, n_genes);
@@ -160,49 +160,75 @@ int plan_gene_table(Engine &e, SweepPlan &p, int64_t n_genes, const int64_t *gen
 	for (const Part &part : parts)
 		if (!part.error.empty()) return e.fail(PGS_ERR_ARG, part.error);
 	// join in gene order: carrier lists, per-gene node lists, and the per-node lists of sparse genes
-	// (ascending gene index, because the genes are visited in that order)
+	// (ascending gene index inside a node).  The parts hold disjoint, ascending gene ranges, so every part
+	// owns a known slice of each list -- of each node's list too, from the per-part node counts -- and the
+	// parts are copied side by side on the threads that marked them.
 	e.carrier_off.assign(n_genes + 1, 0);
-	e.carrier_genome.clear();
 	e.genome_gene_count.assign(n, D);
 	p.gn_off.assign(n_genes + 1, 0);
 	e.sp_off.assign(N + 1, 0);
-	{
-		size_t total_carriers = 0, total_nodes = 0;
-		for (const Part &part : parts) {
-			total_carriers += part.carriers.size();
-			total_nodes += part.nodes.size();
-			for (int32_t v : part.nodes) e.sp_off[v + 1]++;
-		}
-		e.carrier_genome.reserve(total_carriers);
-		p.gn_node.reserve(total_nodes);
-		for (int32_t v = 0; v < N; v++) e.sp_off[v + 1] += e.sp_off[v];
-		e.sp_gene.resize(e.sp_off[N]);
-		p.gn_rank.resize(total_nodes);
+	std::vector<size_t> carrier_base(workers + 1, 0), node_base(workers + 1, 0);
+	std::vector<std::vector<int64_t>> fill(workers); // per part: where its next entry of a node's list goes
+	for (unsigned w = 0; w < workers; w++) {
+		carrier_base[w + 1] = carrier_base[w] + parts[w].carriers.size();
+		node_base[w + 1] = node_base[w] + parts[w].nodes.size();
 	}
 	{
-		std::vector<int64_t> fill(e.sp_off.begin(), e.sp_off.end() - 1);
+		std::vector<std::thread> pool;
+		auto count = [&](unsigned w) {
+			fill[w].assign(N, 0);
+			for (int32_t v : parts[w].nodes) fill[w][v]++;
+		};
+		for (unsigned w = 1; w < workers; w++) pool.emplace_back(count, w);
+		count(0);
+		for (auto &th : pool) th.join();
+	}
+	for (int32_t v = 0; v < N; v++) {
+		int64_t at = e.sp_off[v];
 		for (unsigned w = 0; w < workers; w++) {
+			const int64_t c = fill[w][v];
+			fill[w][v] = at;
+			at += c;
+		}
+		e.sp_off[v + 1] = at;
+	}
+	e.carrier_genome.resize(carrier_base[workers]);
+	p.gn_node.resize(node_base[workers]);
+	p.gn_rank.resize(node_base[workers]);
+	e.sp_gene.resize(e.sp_off[N]);
+	{
+		std::vector<std::vector<int64_t>> per_genome(workers);
+		auto place = [&](unsigned w) {
 			const Part &part = parts[w];
+			std::vector<int64_t> &count = per_genome[w], &next = fill[w];
+			count.assign(n, 0);
 			size_t ci = 0, ni = 0;
 			for (int64_t g = cuts[w]; g < cuts[w + 1]; g++) {
-				e.carrier_off[g] = (int64_t)e.carrier_genome.size();
-				p.gn_off[g] = (int64_t)p.gn_node.size();
+				e.carrier_off[g] = (int64_t)(carrier_base[w] + ci);
+				p.gn_off[g] = (int64_t)(node_base[w] + ni);
 				const int64_t nc = part.n_carriers[g - cuts[w]], nn = part.n_nodes[g - cuts[w]];
 				for (int64_t k = 0; k < nc; k++) {
 					const int32_t cg = part.carriers[ci + k];
-					e.carrier_genome.push_back(cg);
-					e.genome_gene_count[cg]++;
+					e.carrier_genome[carrier_base[w] + ci + k] = cg;
+					count[cg]++;
 				}
 				for (int64_t k = 0; k < nn; k++) {
 					const int32_t v = part.nodes[ni + k];
-					p.gn_rank[p.gn_node.size()] = (int32_t)(fill[v] - e.sp_off[v]);
-					p.gn_node.push_back(v);
-					e.sp_gene[fill[v]++] = g;
+					const int64_t at = next[v]++;
+					p.gn_rank[node_base[w] + ni + k] = (int32_t)(at - e.sp_off[v]);
+					p.gn_node[node_base[w] + ni + k] = v;
+					e.sp_gene[at] = g;
 				}
 				ci += (size_t)nc;
 				ni += (size_t)nn;
 			}
-		}
+		};
+		std::vector<std::thread> pool;
+		for (unsigned w = 1; w < workers; w++) pool.emplace_back(place, w);
+		place(0);
+		for (auto &th : pool) th.join();
+		for (unsigned w = 0; w < workers; w++)
+			for (int32_t i = 0; i < n; i++) e.genome_gene_count[i] += per_genome[w][i];
 	}
 	e.carrier_off[n_genes] = (int64_t)e.carrier_genome.size();
 	p.gn_off[n_genes] = (int64_t)p.gn_node.size();
@@ -363,7 +389,7 @@ void plan_edge_tables(Engine &e)
 		for (int32_t v = lo; v < hi; v++)
 			e.kmax_host[v] = (v == e.root) ? 0 : pgs::build_edge_table(e.rate[v], all.data() + (size_t)v * 65);
 	};
-	unsigned workers = N >= 4096 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	unsigned workers = N >= 4096 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
 	std::vector<std::thread> pool;
 	for (unsigned w = 1; w < workers; w++)
 		pool.emplace_back(build, (int32_t)((int64_t)N * w / workers), (int32_t)((int64_t)N * (w + 1) / workers));
@@ -742,14 +768,13 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 		std::vector<int64_t> stamp(N, -1);
 		std::vector<int32_t> rank_at(N, 0), sub(N, 0), acc(N, 0);
 		std::vector<char> cut(N, 0);
-		std::vector<int32_t> order, parked, unit_roots;
+		std::vector<int32_t> order, parked, unit_roots, level_count;
 		auto row_of = [&](int32_t v) { return (uint32_t)(e.row_base[v] + dense_rows(e, p, v) + rank_at[v]); };
 		// one allocation up front (a step per internal row at most: about half of the range's rows)
 		out.steps.reserve((size_t)(p.gn_off[g_hi] - p.gn_off[g_lo]) / 2 + 64);
 		for (int64_t g = g_lo; g < g_hi; g++) {
 			const int64_t nb = p.gn_off[g], ne = p.gn_off[g + 1];
 			if (nb == ne) continue;
-			order.assign(p.gn_node.begin() + nb, p.gn_node.begin() + ne);
 			for (int64_t k = nb; k < ne; k++) {
 				const int32_t v = p.gn_node[k];
 				stamp[v] = g;
@@ -758,8 +783,15 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 				acc[v] = internal(v) ? 1 : 0; // steps (internal nodes) of the piece of the subtree that is not cut off yet
 				cut[v] = 0;
 			}
-			// children before parents: subtree sizes, and a cut wherever a piece has grown to a unit
-			std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return e.level[a] > e.level[b]; });
+			// children before parents: subtree sizes, and a cut wherever a piece has grown to a unit.
+			// Deepest level first by a counting sort (a few dozen levels; std::sort was half of this loop's time).
+			{
+				level_count.assign((size_t)e.max_level + 2, 0);
+				for (int64_t k = nb; k < ne; k++) level_count[e.max_level - e.level[p.gn_node[k]] + 1]++;
+				for (size_t l = 1; l < level_count.size(); l++) level_count[l] += level_count[l - 1];
+				order.resize((size_t)(ne - nb));
+				for (int64_t k = nb; k < ne; k++) order[level_count[e.max_level - e.level[p.gn_node[k]]]++] = p.gn_node[k];
+			}
 			const int32_t org = e.origin[g];
 			unit_roots.assign(1, org);
 			for (int32_t v : order) {
@@ -859,7 +891,7 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 	};
 	const int64_t total_rows = p.gn_off[e.n_genes];
 	if (total_rows + 8 >= (int64_t)0xF0000000ll) return e.fail(PGS_ERR_ARG, "pgs_set_genes: more than 2^32 sparse rows on one engine; shard the genes");
-	unsigned workers = total_rows >= 200000 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+	unsigned workers = total_rows >= 200000 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
 	if (const char *v = std::getenv("PGS_PLAN_THREADS")) workers = (unsigned)std::max(1, std::atoi(v)); // tuning knob
 	std::vector<Part> parts(workers);
 	std::vector<int64_t> cuts(workers + 1, e.n_genes);
@@ -897,6 +929,25 @@ int plan_sparse_walk(Engine &e, SweepPlan &p)
 		loaded += part.loaded;
 	}
 	lap("join");
+	if (timing) { // order-independent checksum of the units and their step lists (compare two planner builds without a device)
+		auto fnv = [](const void *q, size_t bytes) {
+			uint64_t h = 1469598103934665603ull;
+			const unsigned char *b = static_cast<const unsigned char *>(q);
+			for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull;
+			return h;
+		};
+		uint64_t sum = 0;
+		size_t piece = 0, base = 0;
+		for (const SparseUnit &u : p.sp_units) { // units are still in gene order: a unit's steps lie in one piece
+			while (u.step_begin >= base + p.sp_steps[piece].size() && piece + 1 < p.sp_steps.size()) base += p.sp_steps[piece++].size();
+			const uint32_t key[4] = {u.gid, u.n_steps, u.path_len, u.origin_row};
+			uint64_t h = fnv(key, sizeof key);
+			if (u.n_steps) h ^= fnv(p.sp_steps[piece].data() + (u.step_begin - base), sizeof(SparseStep) * u.n_steps);
+			sum += h * 0x9E3779B97F4A7C15ull;
+		}
+		std::fprintf(stderr, "plan:   sparse units %zu checksum %016llx\n", p.sp_units.size(), (unsigned long long)sum);
+		tp0 = std::chrono::steady_clock::now();
+	}
 	p.sp_steps.emplace_back(4, pgs::SparseStep{}); // the kernel prefetches a few steps past a unit's end
 	// lanes of a warp walk different units: sort by length so that they finish together, longest first
 	std::stable_sort(p.sp_units.begin(), p.sp_units.end(),
@@ -1011,6 +1062,23 @@ int plan_genes(Engine &e, int64_t n_genes, const int64_t *gene_id, const int32_t
 	};
 	if ((rc = plan_gene_table(e, p, n_genes, gene_id, origin_node, carrier_off, carrier_genome, all_order))) return rc;
 	lap("gene table");
+	if (timing) { // FNV-1a over the joined tables: two builds of the planner can be compared without a device
+		uint64_t h = 1469598103934665603ull;
+		auto mix = [&](const void *q, size_t bytes) {
+			const unsigned char *b = static_cast<const unsigned char *>(q);
+			for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull;
+		};
+		mix(e.carrier_off.data(), e.carrier_off.size() * sizeof(int64_t));
+		mix(e.carrier_genome.data(), e.carrier_genome.size() * sizeof(int32_t));
+		mix(e.genome_gene_count.data(), e.genome_gene_count.size() * sizeof(e.genome_gene_count[0]));
+		mix(e.sp_off.data(), e.sp_off.size() * sizeof(int64_t));
+		mix(e.sp_gene.data(), e.sp_gene.size() * sizeof(int64_t));
+		mix(p.gn_off.data(), p.gn_off.size() * sizeof(int64_t));
+		mix(p.gn_node.data(), p.gn_node.size() * sizeof(int32_t));
+		mix(p.gn_rank.data(), p.gn_rank.size() * sizeof(int32_t));
+		std::fprintf(stderr, "plan: gene table checksum %016llx\n", (unsigned long long)h);
+		t0 = std::chrono::steady_clock::now();
+	}
 	if ((rc = plan_layout(e, p))) return rc;
 	lap("layout");
 	plan_level_tasks(e, p);

@@ -1,6 +1,10 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_sweep_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -3
-SHARDS="8 4 1" bash scripts/ab_shard.sh "registers PGS_NO_ASYNC_PROLOGUE=1" "staged X=1"
-export PGS_NO_GRAPH=1
-PGS_WALK_TRACE=gpurun_out/trace8_async.txt python bench.py --shard-of 8 --steps 2 --warmup 3 --no-e2e --no-cpu --no-mismatch > /dev/null 2>gpurun_out/tr.err
-python scripts/walk_trace.py gpurun_out/trace8_async.txt | head -6
+S=$(date +%s)
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+echo "tests: $(( $(date +%s) - S )) s"; S=$(date +%s)
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+echo "smoke: $(( $(date +%s) - S )) s"; S=$(date +%s)
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -c 300 gpurun_out/bench_default.err
+echo "bench: $(( $(date +%s) - S )) s"; S=$(date +%s)
+timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+echo "ref: $(( $(date +%s) - S )) s"
