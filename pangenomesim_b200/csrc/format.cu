@@ -794,6 +794,14 @@ int copy_origin_ascii(Engine &e, int64_t gene_index, char *dst)
 int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *report)
 {
 	const auto wall0 = std::chrono::steady_clock::now();
+	const bool timing = std::getenv("PGS_OUT_TIMING") != nullptr; // development knob: phase times on stderr
+	auto lap_t0 = wall0;
+	auto lap = [&](const char *what) {
+		if (!timing) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "out: %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - lap_t0).count());
+		lap_t0 = t1;
+	};
 	if (!spec->sink && !spec->out_dir && !(spec->what & PGS_OUT_DISCARD))
 		return e.fail(PGS_ERR_ARG, "pgs_write_outputs: neither out_dir nor sink");
 	const int64_t G = e.n_genes, D = (int64_t)e.dense_gid.size(), L = e.cfg.gene_length;
@@ -804,6 +812,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	OutputPlan plan;
 	int rc = build_output_plan(e, spec, plan);
 	if (rc) return rc;
+	lap("output plan");
 	auto &dense_before = plan.dense_before;
 	auto &dense_digits_before = plan.dense_digits_before;
 	auto &sp_digits = plan.sp_digits;
@@ -883,6 +892,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	mt.ref_size = ref_size;
 	mt.n_genomes = n;
 
+	lap("table upload");
 	// ---- staging: two device buffers + two pinned buffers
 	int64_t stage = (int64_t)256 << 20; // 64 MB chunks: K3 123 ms per config-4 output, 256 MB: 60 ms (launch-bound below)
 	if (const char *v = std::getenv("PGS_STAGE_MB")) stage = std::max<int64_t>(1, std::atol(v)) << 20; // tuning knob
@@ -1126,6 +1136,20 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		ck(cudaStreamWaitEvent(copy_stream, formatted[0], 0));
 	}
 
+	lap("staging, pool");
+	// (timing knob) where the host-expanded phases wait: for the copy engine (PCIe-bound) or for the pool (host-bound)
+	double wait_copy_ms = 0, wait_pool_ms = 0;
+	auto timed = [&](double &acc, auto &&fn) {
+		if (!timing) return fn();
+		const auto t0 = std::chrono::steady_clock::now();
+		auto r = fn();
+		acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		return r;
+	};
+	auto lap_waits = [&](const char *what) {
+		if (timing) std::fprintf(stderr, "out:   %s waited %.2f ms for copies, %.2f ms for the pool\n", what, wait_copy_ms, wait_pool_ms);
+		wait_copy_ms = wait_pool_ms = 0;
+	};
 	// ---- ref.fasta, core.fasta, accessory.fasta
 	struct RefFile {
 		uint32_t flag;
@@ -1203,6 +1227,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		xpool->wait_all();
 	}
 
+	lap("reference files");
 	// ---- genomeNNN.fasta, host-expanded: a genome's rows lie together in the store (its leaf's
 	// region), so a chunk is a handful of plain copies; one task per genome writes the whole file
 	if ((spec->what & PGS_OUT_GENOMES) && host_expand && !fused) {
@@ -1250,10 +1275,10 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			Chunk next;
 			next.i = n;
 			if (cur.j < n) {
-				xpool->wait_all(); // the tasks that read the other pinned buffer are done
+				timed(wait_pool_ms, [&] { xpool->wait_all(); return 0; }); // the tasks that read the other pinned buffer are done
 				next = issue(cur.j, cur.slot ^ 1);
 			}
-			ck(cudaEventSynchronize(copied[cur.slot]));
+			ck(timed(wait_copy_ms, [&] { return cudaEventSynchronize(copied[cur.slot]); }));
 			if (!pipe_ok()) return fail_out(PGS_ERR_CUDA, w.error);
 			for (int32_t g = cur.i; g < cur.j; g++) {
 				const char *region = h_stage[cur.slot].p + cur.region_off[g - cur.i];
@@ -1305,7 +1330,8 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			for (int32_t g = cur.i; g < cur.j; g++) records += genome_rows[g];
 			cur = std::move(next);
 		}
-		xpool->wait_all();
+		timed(wait_pool_ms, [&] { xpool->wait_all(); return 0; });
+		lap_waits("genome files");
 		slot = 0;
 		{
 			std::lock_guard<std::mutex> l(w.err_mutex);
@@ -1359,6 +1385,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		}
 	}
 
+	lap("genome files");
 	// ---- alignment.maf, host-expanded: a kernel gathers the rows of a chunk's lines in line order,
 	// the host writes the headers and expands the bases -- into the mapped file, into a buffer handed
 	// to the sink, or (PGS_OUT_DISCARD) block by block into the workers' own buffers
@@ -1390,21 +1417,86 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			can_map = ::fstat(fd, &sb) == 0 && (int64_t)sb.st_size >= file_begin + maf_total;
 		}
 		if (const char *v = std::getenv("PGS_WRITE_MMAP")) can_map = can_map && std::atoi(v) != 0; // tuning knob
+		int64_t kMafTaskLines = 1024;
+		if (const char *v = std::getenv("PGS_HX_TASK_LINES")) kMafTaskLines = std::max(1, std::atoi(v)); // tuning knob
 		int64_t packed_cap = std::min<int64_t>(stage, (int64_t)64 << 20); // 64 MB of rows = ~260 MB of text per chunk
 		if (fused) packed_cap = stage; // (the pieces of the FASTA files grow with the chunk: ~100 records each at 256 MB)
-		for (int64_t g = 0; g < G; g++) packed_cap = std::max(packed_cap, maf_lines[g] * row_bytes);
+		int64_t largest = 0;
+		for (int64_t g = 0; g < G; g++) largest = std::max(largest, maf_lines[g] * row_bytes);
+		packed_cap = std::max(packed_cap, largest);
 		if (packed_cap > stage) {
 			if (fd >= 0) ::close(fd);
 			return fail_out(PGS_ERR_NOMEM, "pgs_write_outputs: a gene's rows do not fit the staging buffer");
 		}
+		// A ring of slots.  With two slots and a barrier between chunks the copy engine and the pool took turns: the
+		// next copy was issued only once the tasks of the chunk before had finished (config 4: 1.5 ms per 64 MB chunk
+		// against 1.2 ms of copy).  Each staging buffer is cut into up to four slots (rows, then the chunk's
+		// lines_prefix table on the device side); a slot is busy from the issue of its copy until the chunk's last task
+		// is done, chunks retire in order.  Text handed to a sink is built in one buffer per slot: two slots there.
+		const int64_t aux_room = (int64_t)64 << 10; // lines_prefix of at most 8191 genes
+		auto stride_of = [&](int per_buffer) { return (stage / per_buffer) & ~(int64_t)255; }; // (16-byte stores, 8-byte table)
+		int spb = 1;
+		if (!fused && !to_sink)
+			for (spb = 4; spb > 1; spb--) {
+				const int64_t cap = stride_of(spb) - aux_room;
+				if (cap >= largest && cap >= ((int64_t)8 << 20)) break;
+			}
+		if (const char *v = std::getenv("PGS_HX_RING")) // tuning / test knob: slots per staging buffer
+			if (!fused && !to_sink) spb = std::max(1, std::min(4, std::atoi(v)));
+		if (spb > 1) {
+			const int64_t cap = stride_of(spb) - aux_room;
+			if (cap < largest || cap < row_bytes) spb = 1; else packed_cap = std::min(packed_cap, cap);
+		}
+		const int R = 2 * spb;
+		const int64_t slot_stride = spb > 1 ? stride_of(spb) : 0;
+		const int64_t max_chunk_genes = spb > 1 ? aux_room / 8 - 1 : 65536;
 		struct Chunk {
 			int64_t g = 0, g2 = 0, bytes = 0, file_pos = 0;
 			int slot = 0;
 			bool first = false;
 			std::vector<int64_t> lines_prefix, block_off;
+			char *h_rows = nullptr; // the slot's rows in pinned memory
 			char *window = nullptr; // where the chunk's text goes (mapped file / sink buffer), nullptr: workers' own buffers
 			void *map = nullptr;
 			size_t map_len = 0;
+			std::atomic<int64_t> pending{0}; // tasks of the chunk that have not finished
+		};
+		struct RingEvents { // one pair per slot, destroyed on every way out
+			std::vector<cudaEvent_t> formatted, copied;
+			~RingEvents()
+			{
+				for (auto x : formatted) if (x) cudaEventDestroy(x);
+				for (auto x : copied) if (x) cudaEventDestroy(x);
+			}
+		} ring;
+		ring.formatted.assign(R, nullptr);
+		ring.copied.assign(R, nullptr);
+		for (int i = 0; i < R; i++) {
+			ck(cudaEventCreateWithFlags(&ring.formatted[i], cudaEventDisableTiming));
+			ck(cudaEventCreateWithFlags(&ring.copied[i], cudaEventDisableTiming));
+		}
+		if (!pipe_ok()) {
+			if (fd >= 0) ::close(fd);
+			return fail_out(PGS_ERR_CUDA, w.error);
+		}
+		std::mutex ring_m;
+		std::condition_variable ring_cv;
+		auto task_done = [&](Chunk *c) {
+			if (c->pending.fetch_sub(1) == 1) {
+				std::lock_guard<std::mutex> l(ring_m);
+				ring_cv.notify_all();
+			}
+		};
+		auto submit_for = [&](Chunk *c, std::function<void()> fn) {
+			c->pending.fetch_add(1);
+			xpool->submit([&task_done, c, fn = std::move(fn)] {
+				fn();
+				task_done(c);
+			});
+		};
+		auto wait_chunk = [&](Chunk &c) {
+			std::unique_lock<std::mutex> l(ring_m);
+			ring_cv.wait(l, [&] { return c.pending.load() == 0; });
 		};
 		std::vector<char> sink_buf[2];
 		auto issue = [&](int64_t g, int s, bool first, int64_t file_pos) {
@@ -1417,7 +1509,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			c.bytes = first ? hlen : 0;
 			c.lines_prefix.push_back(0);
 			int64_t g2 = g, packed = 0;
-			while (g2 < G && packed + maf_lines[g2] * row_bytes <= packed_cap && (g2 - g) < 65536) {
+			while (g2 < G && packed + maf_lines[g2] * row_bytes <= packed_cap && (g2 - g) < max_chunk_genes) {
 				c.block_off.push_back(c.bytes);
 				c.bytes += maf_bytes[g2];
 				packed += maf_lines[g2] * row_bytes;
@@ -1426,19 +1518,24 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 			}
 			c.g2 = g2;
 			const int64_t items = c.lines_prefix.back();
-			begin_chunk(s);
+			// the slot: a whole staging buffer (its table in d_aux_a), or a quarter of one with the table behind the rows
+			const int buf = s / spb;
+			const int64_t at = (int64_t)(s % spb) * slot_stride;
+			char *const d_rows = d_stage[buf].as<char>() + at;
+			c.h_rows = h_stage[buf].p + at;
+			int64_t *const d_prefix = spb > 1 ? reinterpret_cast<int64_t *>(d_rows + (slot_stride - aux_room)) : d_aux_a[s].as<int64_t>();
 			if (items > 0) {
-				if (h2d(d_aux_a[s], c.lines_prefix)) ck(cudaErrorUnknown);
+				ck(cudaMemcpyAsync(d_prefix, c.lines_prefix.data(), sizeof(int64_t) * c.lines_prefix.size(), cudaMemcpyHostToDevice, e.stream));
 				ck(cudaEventRecord(k0, e.stream));
 				k3_gather_maf_rows<<<(unsigned)((items + kFmtWarps - 1) / kFmtWarps), kFmtWarps * 32, 0, e.stream>>>(
-					t, mt, d_stage[s].as<uint4>(), g, (int32_t)(g2 - g), d_aux_a[s].as<int64_t>());
+					t, mt, reinterpret_cast<uint4 *>(d_rows), g, (int32_t)(g2 - g), d_prefix);
 				ck(cudaGetLastError());
 				ck(cudaEventRecord(k1, e.stream));
 			}
-			ck(cudaEventRecord(formatted[s], e.stream));
-			ck(cudaStreamWaitEvent(copy_stream, formatted[s], 0));
-			if (items > 0) ck(cudaMemcpyAsync(h_stage[s].p, d_stage[s].p, (size_t)(items * row_bytes), cudaMemcpyDeviceToHost, copy_stream)), d2h_bytes += items * row_bytes;
-			ck(cudaEventRecord(copied[s], copy_stream));
+			ck(cudaEventRecord(ring.formatted[s], e.stream));
+			ck(cudaStreamWaitEvent(copy_stream, ring.formatted[s], 0));
+			if (items > 0) ck(cudaMemcpyAsync(c.h_rows, d_rows, (size_t)(items * row_bytes), cudaMemcpyDeviceToHost, copy_stream)), d2h_bytes += items * row_bytes;
+			ck(cudaEventRecord(ring.copied[s], copy_stream));
 			return cp;
 		};
 		auto finish_chunk = [&](Chunk &c) { // all of the chunk's tasks are done
@@ -1450,20 +1547,36 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				hx_bytes += c.bytes;
 			}
 		};
-		std::unique_ptr<Chunk> cur = issue(0, slot, true, file_begin), prev;
+		// the staging buffers are free: the reference files were drained, the genome files' tasks have finished
+		ck(cudaStreamWaitEvent(e.stream, copied[0], 0));
+		ck(cudaStreamWaitEvent(e.stream, copied[1], 0));
+		std::deque<std::unique_ptr<Chunk>> copying, expanding; // copy issued / tasks submitted, both in chunk order
+		auto retire_front = [&]() {
+			timed(wait_pool_ms, [&] { wait_chunk(*expanding.front()); return 0; });
+			finish_chunk(*expanding.front());
+			expanding.pop_front();
+		};
+		int64_t g_next = 0, pos_next = file_begin;
+		int slot_next = 0;
+		bool first_chunk = true, gathered = false;
 		for (;;) {
-			std::unique_ptr<Chunk> next;
-			const bool more = cur->g2 < G;
-			if (more || prev) xpool->wait_all(); // the tasks that read the other pinned buffer are done
-			if (prev) finish_chunk(*prev);
-			prev.reset();
-			if (more) next = issue(cur->g2, cur->slot ^ 1, false, cur->file_pos + cur->bytes);
-			ck(cudaEventSynchronize(copied[cur->slot]));
-			if (cur->lines_prefix.back() > 0 && !more && cudaEventSynchronize(k1) == cudaSuccess) {
-				float ms = 0; // (the gather kernels are a few microseconds each: the last one stands for the call's K3 time)
-				if (cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) device_ms += ms;
+			while ((first_chunk || g_next < G) && (int)(copying.size() + expanding.size()) < R) {
+				std::unique_ptr<Chunk> c = issue(g_next, slot_next, first_chunk, pos_next);
+				slot_next = (slot_next + 1) % R;
+				g_next = c->g2;
+				pos_next += c->bytes;
+				first_chunk = false;
+				gathered = gathered || c->lines_prefix.back() > 0;
+				copying.push_back(std::move(c));
 			}
+			if (copying.empty()) break;
+			std::unique_ptr<Chunk> cur = std::move(copying.front());
+			copying.pop_front();
+			ck(timed(wait_copy_ms, [&] { return cudaEventSynchronize(ring.copied[cur->slot]); }));
 			if (!pipe_ok()) {
+				xpool->wait_all(); // (tasks of earlier chunks point into them)
+				for (auto &c : expanding)
+					if (c->map) ::munmap(c->map, c->map_len);
 				if (fd >= 0) ::close(fd);
 				return fail_out(PGS_ERR_CUDA, w.error);
 			}
@@ -1476,8 +1589,10 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				if (cur->map == MAP_FAILED) {
 					const std::string msg = path + ": mmap: " + std::strerror(errno);
 					cur->map = nullptr;
-					::close(fd);
 					xpool->wait_all();
+					for (auto &c : expanding)
+						if (c->map) ::munmap(c->map, c->map_len);
+					::close(fd);
 					return fail_out(PGS_ERR_IO, msg);
 				}
 				cur->window = static_cast<char *>(cur->map) + (cur->file_pos - map_start);
@@ -1494,15 +1609,20 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				}
 				if (!to_sink) hx_bytes += hlen;
 			}
-			// tasks: runs of at most 256 lines of one gene's block
-			const Chunk *cp = cur.get();
+			// tasks: up to kMafTaskLines lines of one gene's block, written in runs of at most 256 lines (a run is what
+			// passes through a worker's L2-sized buffer).  One task per run made the submitting thread the bottleneck
+			// of the phase: 1000 submissions per 64 MB chunk, 0.8 ms of the chunk's 1.5 (the copy takes 1.2).
+			Chunk *const cp = cur.get();
+			cp->pending.fetch_add(1); // held until every task has been submitted
 			for (int64_t k = 0; k < cur->g2 - cur->g; k++) {
 				const int64_t lines = cur->lines_prefix[k + 1] - cur->lines_prefix[k];
-				for (int64_t j0 = 0; j0 < lines; j0 += 256) {
-					const int64_t j1 = std::min(lines, j0 + 256);
-					xpool->submit([&, cp, k, lines, j0, j1] {
+				for (int64_t t0 = 0; t0 < lines; t0 += kMafTaskLines) {
+					const int64_t t1 = std::min(lines, t0 + kMafTaskLines);
+					submit_for(cp, [&, cp, k, lines, t0, t1] {
+						for (int64_t j0 = t0; j0 < t1; j0 += 256) {
+						const int64_t j1 = std::min(t1, j0 + 256);
 						const int64_t g = cp->g + k, L = ht.L;
-						const char *rows_in = h_stage[cp->slot].p + (cp->lines_prefix[k] + j0) * row_bytes;
+						const char *rows_in = cp->h_rows + (cp->lines_prefix[k] + j0) * row_bytes;
 						char text[96];
 						// line offsets grow with j: the run [j0, j1) is one contiguous range of the block
 						const int64_t run_begin = maf_line(ht, hm, g, j0, lines, text).off;
@@ -1543,6 +1663,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 							if (!Writer::write_range(fd, base, run_end - run_begin, cp->file_pos + cp->block_off[k] + run_begin, msg))
 								w.fail(path + ": " + msg);
 						}
+						}
 					});
 				}
 			}
@@ -1555,7 +1676,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				const int64_t piece_guess = (cur->lines_prefix.back() / std::max<int32_t>(n, 1) + 1) * (ht.L + 32);
 				const int group = (int)std::max<int64_t>(1, std::min<int64_t>(kGroup, ((int64_t)1 << 20) / piece_guess));
 				for (int32_t p0 = 0; p0 < n; p0 += group)
-					xpool->submit([&, cp, p0, group] {
+					submit_for(cp, [&, cp, p0, group] {
 						const int64_t L = ht.L;
 						const int cnt = (int)std::min<int64_t>(group, n - p0);
 						struct Cursor {
@@ -1586,7 +1707,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 							cs[i].buf = all;
 							all += caps[i];
 						}
-						const char *rows_in = h_stage[cp->slot].p;
+						const char *rows_in = cp->h_rows;
 						char text[64];
 						for (int64_t k = cp->g; k < cp->g2; k++) {
 							const int64_t first_line = cp->lines_prefix[k - cp->g];
@@ -1625,13 +1746,18 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 						}
 					});
 			}
-			if (!more) {
-				xpool->wait_all();
-				finish_chunk(*cur);
-				break;
-			}
-			prev = std::move(cur);
-			cur = std::move(next);
+			task_done(cp);
+			expanding.push_back(std::move(cur));
+			// chunks that are done leave; with every slot taken the oldest one has to
+			while (!expanding.empty() &&
+				   ((int)(copying.size() + expanding.size()) >= R || expanding.front()->pending.load() == 0))
+				retire_front();
+		}
+		while (!expanding.empty()) retire_front();
+		lap_waits("alignment.maf");
+		if (gathered && cudaEventSynchronize(k1) == cudaSuccess) {
+			float ms = 0; // (the gather kernels are a few microseconds each: the last one stands for the call's K3 time)
+			if (cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) device_ms += ms;
 		}
 		if (fd >= 0) ::close(fd);
 		slot = 0;
@@ -1689,6 +1815,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		}
 	}
 
+	lap("alignment.maf");
 	// ---- genomes.pgs2 (optional): the genomes' packed 2-bit rows exactly as they
 	// lie in the store, behind an index -- an eighth of the text's bytes over PCIe and to disk.
 	// No kernel: the rows are copied straight from the store.  Layout: include/pgs.h.
@@ -1769,6 +1896,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 	w.rep.bytes += hx_bytes.load();
 	if (report) {
 		*report = w.rep;
+		lap("packed, drain");
 		report->records = records;
 		report->d2h_bytes = d2h_bytes;
 		report->device_ms = device_ms;

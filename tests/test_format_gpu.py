@@ -247,6 +247,19 @@ def test_host_expand_sink_and_order(oracle, tmp_path):
     run_case(oracle, tmp_path, n=13, L=130, n_core=3, n_acc=25, seed=8, all_order=order, use_sink=True, what=OUT_ALL | OUT_HOST_EXPAND)
 
 
+@pytest.mark.parametrize("ring,task_lines,mmap", [("1", "1024", "1"), ("2", "40", "1"), ("4", "40", "1"), ("4", "300", "0"), ("3", "1", "1")])
+def test_host_expand_maf_ring(oracle, tmp_path, monkeypatch, ring, task_lines, mmap):
+    """alignment.maf through the ring of staging slots (PGS_HX_RING slots per buffer, 1 MB staging: dozens of
+    chunks in flight, retired in order), tasks of several 256-line runs / several tasks per block, mapped
+    windows and pwrite: same bytes as the reference layout"""
+    monkeypatch.setenv("PGS_STAGE_MB", "1")
+    monkeypatch.setenv("PGS_HX_RING", ring)
+    monkeypatch.setenv("PGS_HX_TASK_LINES", task_lines)
+    monkeypatch.setenv("PGS_WRITE_MMAP", mmap)
+    monkeypatch.setenv("PGS_EXPAND_THREADS", "7")
+    run_case(oracle, tmp_path, n=600, L=1000, n_core=25, n_acc=40, seed=14, what=OUT_ALL | OUT_HOST_EXPAND)
+
+
 @pytest.mark.parametrize("run_records", [None, "7", "1", "one-copy"])
 @pytest.mark.parametrize("use_sink", [False, True])
 def test_host_expand_many_chunks(oracle, tmp_path, monkeypatch, use_sink, run_records):
