@@ -328,8 +328,11 @@ class Engine:
 def expand_bases(packed_words, sites: int):
     """host-side expander of PGS_OUT_HOST_EXPAND: (ASCII bytes, code path name)"""
     w = np.ascontiguousarray(packed_words, dtype=np.uint32)
-    buf = C.create_string_buffer(max(int(sites), 1))
+    guard = b"\xaa" * 64  # nothing may be written behind the last site
+    buf = C.create_string_buffer(b"\x00" * int(sites) + guard)
     kind = load_library().pgs_expand_bases(_ptr(w), sites, buf)
+    if buf.raw[sites:sites + 64] != guard:
+        raise PgsError(-1, "pgs_expand_bases wrote behind the last site")
     return buf.raw[:sites], kind.decode()
 
 

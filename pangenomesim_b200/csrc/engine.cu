@@ -66,8 +66,12 @@ int Engine::alloc(DevBuf &b, size_t bytes, const char *what)
 
 int Engine::upload(DevBuf &b, const void *src, size_t bytes, const char *what)
 {
-	int rc = alloc(b, bytes, what);
-	if (rc) return rc;
+	// a buffer that fits without being more than twice too large is used again: cudaFree / cudaMalloc synchronise
+	// the device, and a re-plan (every pgs_set_genes) replaces some twenty tables of unchanged size
+	if (!b.p || b.bytes < bytes || b.bytes > 2 * bytes + ((size_t)1 << 20) || plan_only) {
+		const int rc = alloc(b, bytes, what);
+		if (rc) return rc;
+	}
 	if (bytes) {
 		cudaError_t e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);

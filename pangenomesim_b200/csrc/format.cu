@@ -101,6 +101,42 @@ __host__ __device__ inline char *put_genome_name(char *p, int64_t genome)
 	return put_uint(p, (uint64_t)genome + 1, 3);
 }
 
+// Host-side decimal conversion for the PGS_OUT_HOST_EXPAND headers (one per kilobyte of text on sixteen cores:
+// the division loops above were as expensive as expanding the record's bases): digit count by comparison,
+// two digits per division through a table.  Same characters as put_uint.
+static const char kDigitPairs[201] = "00010203040506070809101112131415161718192021222324252627282930313233343536373839"
+									 "40414243444546474849505152535455565758596061626364656667686970717273747576777879"
+									 "8081828384858687888990919293949596979899";
+static inline int host_dec_digits(uint64_t x)
+{
+	int d = 1;
+	while (x >= 10000) {
+		x /= 10000;
+		d += 4;
+	}
+	return d + (x >= 1000 ? 3 : x >= 100 ? 2 : x >= 10 ? 1 : 0);
+}
+static inline char *host_put_uint(char *p, uint64_t x, int min_digits)
+{
+	int d = host_dec_digits(x);
+	if (d < min_digits) d = min_digits;
+	char *q = p + d;
+	while (x >= 100) {
+		const uint64_t r = x % 100;
+		x /= 100;
+		q -= 2;
+		std::memcpy(q, kDigitPairs + 2 * r, 2);
+	}
+	if (x >= 10) {
+		q -= 2;
+		std::memcpy(q, kDigitPairs + 2 * x, 2);
+	} else {
+		*--q = (char)('0' + (int)x);
+	}
+	while (q > p) *--q = '0';
+	return p + d;
+}
+
 // four sites (8 bits) -> four ASCII bytes: spread the 2-bit codes to nibbles, then let PRMT pick
 // the bytes of "ACGT"
 __device__ __forceinline__ uint32_t ascii4(uint32_t bits8)
@@ -1298,28 +1334,42 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 					const int64_t *sp = ht.sp_gene + ht.sp_off[leaf];
 					const int64_t n_sp = ht.sp_off[leaf + 1] - ht.sp_off[leaf];
 					int64_t di = 0, si = 0; // next dense slot in table order, next sparse row
-					auto next_slot = [&]() -> int64_t {
-						if (si >= n_sp || (di < ht.n_dense && ht.dense_gene[dense_by_gene[di]] < sp[si])) return dense_by_gene[di++];
-						return ht.n_dense + si++;
-					};
+					// The record's place in the file as fasta_record computes it, without its search: while the two
+					// lists are merged, si IS the number of the leaf's sparse genes before the record's gene.
 					char text[64];
+					text[0] = '>';
+					char *const after_name = put_genome_name(text + 1, g);
+					*after_name = '.';
+					const int64_t per_record = genome_name_len(g) + L + 4;
+					const int64_t *const leaf_digits = ht.sp_digits + ht.sp_off[leaf] + leaf;
 					int64_t done = 0, run_begin = 0;
 					do {
 						const int64_t now = std::min(nrows - done, kHxRunRecords);
 						int64_t run_len = 0;
 						char *buf = nullptr;
 						for (int64_t k = 0; k < now; k++) {
-							const int64_t sl = next_slot();
-							const RecordInfo ri = fasta_record(ht, g, sl, text);
-							if (k == 0) { // (records of a run have the same length up to the digits of the gene id: a bound)
-								run_begin = ri.off;
-								buf = thread_buffer((size_t)(now * (ri.plen + 16 + L + 1)));
+							int64_t sl, gene;
+							const int64_t srank = si;
+							if (si >= n_sp || (di < ht.n_dense && ht.dense_gene[dense_by_gene[di]] < sp[si])) {
+								sl = dense_by_gene[di++];
+								gene = ht.dense_gene[sl];
+							} else {
+								sl = ht.n_dense + si;
+								gene = sp[si++];
 							}
-							char *d = buf + (ri.off - run_begin);
-							std::memcpy(d, text, (size_t)ri.plen);
-							expand_bases(region + sl * row_bytes, L, d + ri.plen);
-							d[ri.plen + L] = '\n';
-							run_len = ri.off - run_begin + ri.plen + L + 1;
+							char *const text_end = host_put_uint(after_name + 1, (uint64_t)ht.gene_id[gene], 1);
+							*text_end = '\n';
+							const int plen = (int)(text_end + 1 - text);
+							const int64_t off = (ht.dense_before[gene] + srank) * per_record + ht.dense_digits_before[gene] + leaf_digits[srank];
+							if (k == 0) { // (records of a run have the same length up to the digits of the gene id: a bound)
+								run_begin = off;
+								buf = thread_buffer((size_t)(now * (plen + 16 + L + 1)));
+							}
+							char *d = buf + (off - run_begin);
+							std::memcpy(d, text, (size_t)plen);
+							expand_bases(region + sl * row_bytes, L, d + plen);
+							d[plen + L] = '\n';
+							run_len = off - run_begin + plen + L + 1;
 						}
 						hx_deliver(file, at + run_begin, buf, run_len, at == 0 && done == 0);
 						done += now;
@@ -1649,13 +1699,48 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 							base = thread_buffer((size_t)(run_end - run_begin));
 							base_off = run_begin;
 						}
+						// what the block's carrier lines share (maf_line's layout): "s genomeNNN" + ".<id> 0 <L> + " + size + ' '
+						char mid[48];
+						int mid_len;
+						{
+							char *q = mid;
+							*q++ = '.';
+							q = host_put_uint(q, (uint64_t)ht.gene_id[g], 1);
+							q = put_str(q, " 0 ");
+							q = host_put_uint(q, (uint64_t)L, 1);
+							q = put_str(q, " + ");
+							mid_len = (int)(q - mid);
+						}
+						const bool dense = ht.dense_slot[g] >= 0;
+						const int idd = host_dec_digits((uint64_t)ht.gene_id[g]), ld = host_dec_digits((uint64_t)L);
+						const int64_t ref_len = 2 + 9 + 1 + idd + 3 + ld + 3 + host_dec_digits((uint64_t)hm.ref_size) + 1 + L + 1;
+						const int64_t per_line = idd + ld + L + 11;
+						const int32_t *const genomes = dense ? hm.all_order : hm.carrier_genome + hm.carrier_off[g];
+						const int64_t *const prefix = dense ? hm.all_prefix : hm.carrier_prefix + hm.carrier_off[g] + g;
+						std::memcpy(text, "s genome", 8);
 						for (int64_t j = j0; j < j1; j++) {
-							const RecordInfo ri = maf_line(ht, hm, g, j, lines, text);
-							char *d = base + (ri.off - base_off);
-							std::memcpy(d, text, (size_t)ri.plen);
-							expand_bases(rows_in + (j - j0) * row_bytes, L, d + ri.plen);
-							d[ri.plen + L] = '\n';
-							if (ri.tail == 2) d[ri.plen + L + 1] = '\n';
+							int64_t off;
+							int plen;
+							if (j == 0) { // the reference line (with the block's "a\n")
+								const RecordInfo ri = maf_line(ht, hm, g, 0, lines, text);
+								off = ri.off;
+								plen = ri.plen;
+							} else {
+								const int64_t c = j - 1;
+								const int32_t genome = genomes[c];
+								char *q = host_put_uint(text + 8, (uint64_t)genome + 1, 3);
+								std::memcpy(q, mid, (size_t)mid_len);
+								q = host_put_uint(q + mid_len, (uint64_t)(ht.genome_count[genome] * L), 1);
+								*q++ = ' ';
+								plen = (int)(q - text);
+								off = 2 + ref_len + c * per_line + prefix[c];
+							}
+							char *d = base + (off - base_off);
+							std::memcpy(d, text, (size_t)plen);
+							if (j == 0) std::memcpy(text, "s genome", 8); // (maf_line wrote "a\ns genomeref..." there)
+							expand_bases(rows_in + (j - j0) * row_bytes, L, d + plen);
+							d[plen + L] = '\n';
+							if (j == lines - 1) d[plen + L + 1] = '\n'; // the blank line behind a block (std::endl at pangenomesim.cxx:289)
 						}
 						if (!to_sink) hx_bytes += run_end - run_begin;
 						if (spill) {

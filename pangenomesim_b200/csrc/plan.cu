@@ -978,8 +978,10 @@ int upload_plan(Engine &e, SweepPlan &p)
 		auto upload_pieces = [&](DevBuf &b, const auto &pieces, const char *what) -> int {
 			size_t total = 0;
 			for (const auto &v : pieces) total += v.size() * sizeof(v[0]);
-			int r = e.alloc(b, total, what);
-			if (r) return r;
+			if (!b.p || b.bytes < total || b.bytes > 2 * total + ((size_t)1 << 20)) { // (kept across re-plans, as Engine::upload does)
+				const int r = e.alloc(b, total, what);
+				if (r) return r;
+			}
 			size_t at = 0;
 			for (const auto &v : pieces) {
 				if (v.empty()) continue;

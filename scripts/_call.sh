@@ -1,10 +1,15 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_format_gpu.py tests/test_host_cli.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -5
-export PGS_OUT_TIMING=1
-echo "== config 4"
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-mismatch --no-files --e2e-steps 2 2>gpurun_out/c4.err >gpurun_out/c4.json; grep -E "^out" gpurun_out/c4.err | grep -v " 0.0[0-9] ms\| 0.1[0-9] ms" | tail -14
-python -c "
-import json; l=json.load(open('gpurun_out/c4.json')); print('e2e host', l['e2e_host_expand']['ms_per_step'], 'dev', l['e2e_device_formatter']['ms_per_step'], 'packed', l['e2e_packed']['ms_per_step'])"
-for r in 1 2; do echo "== ring $r"; PGS_HX_RING=$r timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-mismatch --no-files --e2e-steps 2 2>&1 >/dev/null | grep -E "^out.*maf" | tail -2; done
-echo "== task lines 256 / 4096"
-for r in 256 4096; do PGS_HX_TASK_LINES=$r timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-mismatch --no-files --e2e-steps 2 2>&1 >/dev/null | grep -E "^out.*maf" | tail -2; done
+S=$(date +%s)
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+echo "tests: $(( $(date +%s) - S )) s"; S=$(date +%s)
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?"
+timeout 400 python bench.py --config 3 --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "c3 rc=$?"
+timeout 600 python bench.py --config 5 --steps 10 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "c5 rc=$?"
+echo "bench: $(( $(date +%s) - S )) s"
+python - <<'PY'
+import json
+for c in (4,3,5):
+    l=json.load(open(f'gpurun_out/bench_c{c}.json'))
+    h=l['e2e_host_expand']; d=l['e2e_device_formatter']
+    print(c, 'sweep ms', round(l['ms_per_step'],4), 'frac', round(l['roofline']['frac'],3), 'e2e host', round(h['ms_per_step'],1), 'plan', round(h['plan_ms_per_step'],1), 'dev', round(d['ms_per_step'],1), 'plan', round(d['plan_ms_per_step'],1), 'packed', round(l['e2e_packed']['ms_per_step'],1), l['clocks']['reasons'])
+PY

@@ -65,7 +65,7 @@ def test_product_does_not_reference_the_oracle():
     assert b"liboracle" not in so.read_bytes()
 
 
-@pytest.mark.parametrize("sites", [1, 3, 4, 63, 64, 65, 127, 128, 129, 1000, 1500, 2000, 4099])
+@pytest.mark.parametrize("sites", [1, 3, 4, 60, 63, 64, 65, 68, 100, 124, 127, 128, 129, 132, 188, 192, 196, 252, 1000, 1001, 1500, 2000, 4096, 4099, 4100])
 def test_host_expander_matches_the_oracle(sites):
     """the base expander of PGS_OUT_HOST_EXPAND (SIMD where the CPU has it) against the oracle's
     unpack_ascii and a numpy restatement, every tail length"""
