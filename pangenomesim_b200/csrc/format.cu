@@ -1471,6 +1471,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		if (const char *v = std::getenv("PGS_HX_TASK_LINES")) kMafTaskLines = std::max(1, std::atoi(v)); // tuning knob
 		int64_t packed_cap = std::min<int64_t>(stage, (int64_t)64 << 20); // 64 MB of rows = ~260 MB of text per chunk
 		if (fused) packed_cap = stage; // (the pieces of the FASTA files grow with the chunk: ~100 records each at 256 MB)
+		if (const char *v = std::getenv("PGS_HX_CHUNK_MB")) packed_cap = std::min<int64_t>(stage, std::max<int64_t>(1, std::atol(v)) << 20); // tuning knob
 		int64_t largest = 0;
 		for (int64_t g = 0; g < G; g++) largest = std::max(largest, maf_lines[g] * row_bytes);
 		packed_cap = std::max(packed_cap, largest);
@@ -1492,7 +1493,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 				if (cap >= largest && cap >= ((int64_t)8 << 20)) break;
 			}
 		if (const char *v = std::getenv("PGS_HX_RING")) // tuning / test knob: slots per staging buffer
-			if (!fused && !to_sink) spb = std::max(1, std::min(4, std::atoi(v)));
+			if (!to_sink) spb = std::max(1, std::min(4, std::atoi(v)));
 		if (spb > 1) {
 			const int64_t cap = stride_of(spb) - aux_room;
 			if (cap < largest || cap < row_bytes) spb = 1; else packed_cap = std::min(packed_cap, cap);
@@ -1770,6 +1771,10 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 							int64_t n_sp, si;
 							char *buf;
 							int64_t begin, len; // the piece: offset of its first record in the file, bytes so far
+							char name[24];      // ">genomeNNN"
+							int name_len;
+							int64_t per_record;          // bytes of a record less the digits of its gene id
+							const int64_t *leaf_digits;  // digits of the leaf's sparse gene ids before its r-th
 						} cs[kGroup];
 						// a record: '>' name(<= 16) '.' id(<= 10) '\n' bases '\n'; a genome's piece: its genes of the chunk
 						const int64_t dense_here = ht.dense_before[cp->g2] - ht.dense_before[cp->g];
@@ -1786,6 +1791,10 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 							need += caps[i];
 							c.begin = -1;
 							c.len = 0;
+							c.name[0] = '>';
+							c.name_len = (int)(put_genome_name(c.name + 1, c.genome) - c.name);
+							c.per_record = genome_name_len(c.genome) + L + 4;
+							c.leaf_digits = ht.sp_digits + ht.sp_off[c.leaf] + c.leaf;
 						}
 						char *all = thread_buffer((size_t)need);
 						for (int i = 0; i < cnt; i++) {
@@ -1794,6 +1803,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 						}
 						const char *rows_in = cp->h_rows;
 						char text[64];
+						text[0] = '.';
 						for (int64_t k = cp->g; k < cp->g2; k++) {
 							const int64_t first_line = cp->lines_prefix[k - cp->g];
 							const bool dense = ht.dense_slot[k] >= 0;
@@ -1801,25 +1811,30 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 								const char *nx = rows_in + (cp->lines_prefix[k + 2 - cp->g] + 1 + p0) * row_bytes;
 								for (int64_t b = 0; b < cnt * row_bytes; b += 64) __builtin_prefetch(nx + b, 0, 3);
 							}
+							// ".<gene id>\n" is the same for the whole group
+							char *const id_end = host_put_uint(text + 1, (uint64_t)ht.gene_id[k], 1);
+							*id_end = '\n';
+							const int id_len = (int)(id_end + 1 - text);
 							for (int i = 0; i < cnt; i++) {
 								Cursor &c = cs[i];
-								int64_t slot, line;
+								int64_t line;
+								const int64_t srank = c.si; // the leaf's sparse genes before gene k (fasta_record's search, for free)
 								if (dense) {
-									slot = ht.dense_slot[k];
 									line = 1 + p0 + i;
 								} else {
 									if (c.si >= c.n_sp || c.sp[c.si] != k) continue;
-									slot = ht.n_dense + c.si;
 									line = 1 + sp_line[(size_t)(ht.sp_off[c.leaf] + c.si)];
 									c.si++;
 								}
-								const RecordInfo ri = fasta_record(ht, c.genome, slot, text);
-								if (c.begin < 0) c.begin = ri.off;
-								char *d = c.buf + (ri.off - c.begin);
-								std::memcpy(d, text, (size_t)ri.plen);
-								expand_bases(rows_in + (first_line + line) * row_bytes, L, d + ri.plen);
-								d[ri.plen + L] = '\n';
-								c.len = ri.off - c.begin + ri.plen + L + 1;
+								const int64_t off = (ht.dense_before[k] + srank) * c.per_record + ht.dense_digits_before[k] + c.leaf_digits[srank];
+								if (c.begin < 0) c.begin = off;
+								char *d = c.buf + (off - c.begin);
+								std::memcpy(d, c.name, (size_t)c.name_len); // ">genomeNNN"
+								std::memcpy(d + c.name_len, text, (size_t)id_len);
+								const int plen = c.name_len + id_len;
+								expand_bases(rows_in + (first_line + line) * row_bytes, L, d + plen);
+								d[plen + L] = '\n';
+								c.len = off - c.begin + plen + L + 1;
 							}
 						}
 						for (int i = 0; i < cnt; i++) {

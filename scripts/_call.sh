@@ -1,15 +1,12 @@
 mkdir -p gpurun_out
-S=$(date +%s)
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-echo "tests: $(( $(date +%s) - S )) s"; S=$(date +%s)
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?"
-timeout 400 python bench.py --config 3 --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "c3 rc=$?"
-timeout 600 python bench.py --config 5 --steps 10 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "c5 rc=$?"
-echo "bench: $(( $(date +%s) - S )) s"
-python - <<'PY'
-import json
-for c in (4,3,5):
-    l=json.load(open(f'gpurun_out/bench_c{c}.json'))
-    h=l['e2e_host_expand']; d=l['e2e_device_formatter']
-    print(c, 'sweep ms', round(l['ms_per_step'],4), 'frac', round(l['roofline']['frac'],3), 'e2e host', round(h['ms_per_step'],1), 'plan', round(h['plan_ms_per_step'],1), 'dev', round(d['ms_per_step'],1), 'plan', round(d['plan_ms_per_step'],1), 'packed', round(l['e2e_packed']['ms_per_step'],1), l['clocks']['reasons'])
-PY
+timeout 900 python -m pytest tests/test_format_gpu.py -m gpu -x -q 2>&1 | tail -3
+export PGS_OUT_TIMING=1
+run() { echo "== $*"; env "$@" timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-mismatch --no-files --e2e-steps 2 2>gpurun_out/x.err >gpurun_out/x.json; grep -E "^out" gpurun_out/x.err | grep -E "genome files|alignment.maf" | grep -v " 0.00 ms" | sed -n 3,6p
+python -c "
+import json; l=json.load(open('gpurun_out/x.json')); print('e2e host', round(l['e2e_host_expand']['ms_per_step'],1), 'packed', round(l['e2e_packed']['ms_per_step'],1))"; }
+run PGS_X=1
+run PGS_HX_ONE_COPY=1
+run PGS_HX_ONE_COPY=1 PGS_HX_RING=2
+run PGS_HX_ONE_COPY=1 PGS_HX_RING=4
+run PGS_HX_ONE_COPY=1 PGS_STAGE_MB=512 PGS_HX_RING=2
+run PGS_HX_ONE_COPY=1 PGS_STAGE_MB=1024 PGS_HX_RING=4
