@@ -514,6 +514,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the bounded write-to-files leg (N=1 only)")
     ap.add_argument("--no-mismatch", action="store_true", help="skip the K2 legs")
+    ap.add_argument("--no-cli", action="store_true", help="skip the multi-device CLI leg (N > 1)")
     ap.add_argument("--files-genes", type=int, default=1000, help="genes of the write-to-files leg (20 MB of text each)")
     ap.add_argument("--small", action="store_true", help="debug: config 2 sized workload")
     ap.add_argument("--shard-of", type=int, default=0, help="development: on ONE GPU, sweep only rank 0's shard of a SHARD_OF-way split "
@@ -764,7 +765,7 @@ def main():
     # of its GPU and waits on the CPU (a gloo barrier: no kernel spins beside the CLI's own work)
     cli = None
     eng.close()
-    if world > 1 and not args.no_e2e:
+    if world > 1 and not args.no_e2e and not args.no_cli:
         torch.cuda.synchronize()
         cpu_group = dist.new_group(backend="gloo")
         dist.barrier(group=cpu_group)

@@ -988,6 +988,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		if (k1) cudaEventDestroy(k1);
 		if (copy_stream) cudaStreamDestroy(copy_stream);
 	};
+	const unsigned copy_wait_flag = std::getenv("PGS_SPIN_SYNC") ? 0u : (unsigned)cudaEventBlockingSync; // tuning knob: spin as before
 	cudaError_t ce = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
 	for (int i = 0; i < 2 && ce == cudaSuccess; i++) {
 		if (e.stage_bytes < stage) {
@@ -1000,7 +1001,8 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		}
 		h_stage[i].p = e.h_stage[i];
 		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&formatted[i], cudaEventDisableTiming);
-		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+		// (blocking: the thread that waits for a copy sleeps instead of spinning on a core the expander's pool wants)
+		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming | copy_wait_flag);
 		if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming);
 	}
 	if (ce == cudaSuccess) ce = cudaEventCreate(&k0);
@@ -1524,7 +1526,7 @@ int write_outputs(Engine &e, const pgs_output_spec *spec, pgs_output_report *rep
 		ring.copied.assign(R, nullptr);
 		for (int i = 0; i < R; i++) {
 			ck(cudaEventCreateWithFlags(&ring.formatted[i], cudaEventDisableTiming));
-			ck(cudaEventCreateWithFlags(&ring.copied[i], cudaEventDisableTiming));
+			ck(cudaEventCreateWithFlags(&ring.copied[i], cudaEventDisableTiming | copy_wait_flag));
 		}
 		if (!pipe_ok()) {
 			if (fd >= 0) ::close(fd);
