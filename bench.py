@@ -437,7 +437,9 @@ def files_leg(eng, parent, rate, leaf, genes, root, n, L):
         car_off = np.arange(genes + 1, dtype=np.int64)
         car = np.full(genes, PGS_ALL_GENOMES, np.int32)
         out = {}
-        for mode, extra in (("host_expand", OUT_HOST_EXPAND), ("device_formatter", 0)):
+        # (the first pass over a fresh box's page cache pays the first touch of 20 GB of guest memory -- 2.6 s against
+        # 1.8-2.0 s for the same call afterwards: one untimed warm-up pass, as every other leg has)
+        for mode, extra in (("warm-up", OUT_HOST_EXPAND), ("host_expand", OUT_HOST_EXPAND), ("device_formatter", 0)):
             sub = os.path.join(d, mode)
             os.mkdir(sub)
             t0 = time.perf_counter()
@@ -449,11 +451,12 @@ def files_leg(eng, parent, rate, leaf, genes, root, n, L):
             out[mode] = {"value": float(n) * genes * L / wall, "unit": UNIT, "seconds": wall, "bytes": int(rep["bytes"]),
                          "files": int(rep["files"]), "gb_per_s": rep["bytes"] / wall / 1e9}
             shutil.rmtree(sub, ignore_errors=True)
+        out.pop("warm-up", None)
         best = max(out, key=lambda k: out[k]["value"])
         res = dict(out[best])
         res.update(mode=best, modes=out, dir=base,
                    what=f"{n} genomes x the first {genes} genes of config 4: host tables -> sweep -> "
-                        f"{res['files']} files on {base} (page cache), then removed; host_expand = packed rows over PCIe, text written by the "
+                        f"{res['files']} files on {base} (page cache), then removed, after one untimed warm-up pass; host_expand = packed rows over PCIe, text written by the "
                         f"host's cores (whole genomeNNN.fasta files, the MAF through a mapping); device_formatter = K3's text over PCIe")
         return res
     except Exception as ex:  # a full or read-only scratch directory must not cost the bench line

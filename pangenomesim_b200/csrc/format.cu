@@ -754,9 +754,10 @@ static int build_output_plan(Engine &e, const pgs_output_spec *spec, OutputPlan 
 	}
 	// genes per genome over the whole alignment (all shards): the MAF "source size" field
 	p.genome_count = shard ? std::vector<int64_t>(shard->genome_gene_total, shard->genome_gene_total + n) : e.genome_gene_count;
-	auto carrier_term = [&](int32_t genome) {
-		return (int64_t)genome_name_len(genome) + dec_digits((uint64_t)(p.genome_count[genome] * L));
-	};
+	// (one term per genome, looked up per carrier entry: config 3 has two million of those)
+	std::vector<int32_t> term(n);
+	for (int32_t i = 0; i < n; i++) term[i] = genome_name_len(i) + dec_digits((uint64_t)(p.genome_count[i] * L));
+	auto carrier_term = [&](int32_t genome) { return (int64_t)term[genome]; };
 	p.all_prefix.assign(n + 1, 0);
 	for (int32_t i = 0; i < n; i++) p.all_prefix[i + 1] = p.all_prefix[i] + carrier_term(e.all_order[i]);
 	p.carrier_prefix.assign(e.carrier_genome.size() + G + 1, 0);
