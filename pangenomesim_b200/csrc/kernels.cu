@@ -94,6 +94,20 @@ __device__ __forceinline__ U32x8 ld_stream256(const U32x8 *p)
 				 : "l"(p));
 	return r;
 }
+// The same through the coherent path, for rows that the grid BEFORE this one wrote while this grid may already
+// have been resident (programmatic dependent launch): ptxas treats ld.global.nc as a load of read-only data and
+// schedules it ABOVE griddepcontrol.wait (SASS: LDG...CONSTANT before ACQBULK) -- the walk then read its origin
+// row before k1_top_masks had written it whenever that grid was slow to start (several processes on one GPU).
+__device__ __forceinline__ U32x8 ld_written256(const U32x8 *p)
+{
+	U32x8 r;
+	asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				 : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y),
+				   "=r"(r.hi.z), "=r"(r.hi.w)
+				 : "l"(p)
+				 : "memory");
+	return r;
+}
 __device__ __forceinline__ void st_stream256(U32x8 *p, const U32x8 &v)
 {
 	asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.lo.x),
@@ -404,7 +418,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 		const uint4 *const base = reinterpret_cast<const uint4 *>(t.rows);
 #pragma unroll
 		for (int j = 0; j < PAIRS; j++)
-			if (active[j]) cur[j] = ld_stream256(reinterpret_cast<const U32x8 *>(base + u.root_off) + p[j]);
+			if (active[j]) cur[j] = ld_written256(reinterpret_cast<const U32x8 *>(base + u.root_off) + p[j]);
 		const int32_t pe = path_end;
 		int32_t k = path_begin;
 		for (; k + 2 <= pe; k += 2) { // two masks in flight per pair
@@ -412,8 +426,8 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++) {
 				if (!active[j]) continue;
-				const U32x8 m0 = ld_stream256(reinterpret_cast<const U32x8 *>(base + off0) + p[j]);
-				const U32x8 m1 = ld_stream256(reinterpret_cast<const U32x8 *>(base + off1) + p[j]);
+				const U32x8 m0 = ld_written256(reinterpret_cast<const U32x8 *>(base + off0) + p[j]);
+				const U32x8 m1 = ld_written256(reinterpret_cast<const U32x8 *>(base + off1) + p[j]);
 				cur[j] = cur[j] ^ m0 ^ m1;
 			}
 		}
@@ -421,7 +435,7 @@ k1_walk_dense(const __grid_constant__ DeviceTables t, const __grid_constant__ Wa
 			const int64_t off = __ldg(u.unit_path + k);
 #pragma unroll
 			for (int j = 0; j < PAIRS; j++)
-				if (active[j]) cur[j] = cur[j] ^ ld_stream256(reinterpret_cast<const U32x8 *>(base + off) + p[j]);
+				if (active[j]) cur[j] = cur[j] ^ ld_written256(reinterpret_cast<const U32x8 *>(base + off) + p[j]);
 		}
 		if (store >= 0) { // the unit's root is a genome directly below a top node
 #pragma unroll

@@ -1,9 +1,6 @@
-mkdir -p gpurun_out
-run() { env "$@" timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-mismatch --e2e-steps 1 2>gpurun_out/x.err >gpurun_out/x.json
-python -c "
-import json; l=json.load(open('gpurun_out/x.json')); m=l['e2e_files']['modes']; print('$*', {k:round(v['seconds'],3) for k,v in m.items()}, 'e2e host', round(l['e2e_host_expand']['ms_per_step'],1))"; }
-run PGS_HX_RING=1
-run PGS_X=1
-run PGS_X=2
-run PGS_HX_TASK_LINES=256
-run PGS_X=3
+for j in 1 2 3 4; do python scripts/flake.py pangenomesim_b200/bin/pangenomesim-b200 30 fixed$j > gpurun_out/flake_fixed$j.log 2>&1 & done; wait
+grep -h "bad runs" gpurun_out/flake_fixed*.log
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for s in 1 8; do timeout 200 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu --no-mismatch --shard-of $s > gpurun_out/shard$s.json 2>/dev/null; python -c "
+import json
+l=json.load(open('gpurun_out/shard$s.json')); print('shard-of', $s, round(l['ms_per_step'],4))"; done

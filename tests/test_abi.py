@@ -128,3 +128,35 @@ def test_planner_cuts_a_big_tree_on_the_cpu(monkeypatch, env):
         with pytest.raises(PgsError) as ex:
             e.set_core_genes(625, 2 * n - 2)
         assert ex.value.code == -6 and "plan-only" in ex.value.message
+
+
+def test_walk_reads_no_row_above_the_dependent_launch_wait():
+    """k1_walk_dense is launched as a programmatic dependent of k1_top_masks: nothing that grid writes (origin
+    rows, path masks -- the 256-bit row loads) may be read above griddepcontrol.wait.  ptxas moves ld.global.nc
+    loads above the wait (SASS: LDG...CONSTANT before ACQBULK), which let a unit start from a stale origin row
+    when k1_top_masks was slow to start (seen as rare wrong core genes with several processes on one GPU):
+    the prologue's row loads are coherent loads and must stay below ACQBULK in every variant."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists():
+        pytest.skip("cuobjdump not available")
+    so = ROOT / "pangenomesim_b200" / "lib" / "libpgs.so"
+    sass = subprocess.run([exe, "-sass", str(so)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    name, waited = None, False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip() if "k1_walk_dense" in line else None
+            waited = False
+            if name:
+                seen += 1
+            continue
+        if not name:
+            continue
+        if "ACQBULK" in line:
+            waited = True
+        elif "LDG" in line and ".256" in line:
+            assert waited, f"{name}: a row is loaded above griddepcontrol.wait: {line.strip()}"
+            assert "CONSTANT" not in line or waited
+    assert seen >= 4  # the four instantiations of the walk
