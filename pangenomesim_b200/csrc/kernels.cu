@@ -583,6 +583,10 @@ k1_top_masks(const __grid_constant__ DeviceTables t, const TopMaskTask *__restri
 	const int valid_hi = (blk + 2 == t.blocks) ? t.last_valid : 64;
 	const uint32_t edge_a = tk.edge_a, edge_b = tk.edge_b;
 	if (edge_a == kRootEdge) { // the dense genes' origin rows: what gene::gene(len, -1, id) draws (gene.cxx:13-25)
+		if (tk.h1a) { // (test knob PGS_TEST_ORIGIN_DELAY: write them late)
+			const long long t0 = clock64();
+			while (clock64() - t0 < (long long)tk.h1a) {}
+		}
 		U32x8 r;
 		r.lo = root_block(gid, blk, 64, t.keys);
 		r.hi = root_block(gid, blk + 1u, valid_hi, t.keys);

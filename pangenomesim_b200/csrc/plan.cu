@@ -508,6 +508,9 @@ int plan_walk(Engine &e, SweepPlan &p)
 			pgs::TopMaskTask tk{};
 			tk.ma_off = loc[e.root];
 			tk.edge_a = pgs::kRootEdge;
+			// test knob: the origin rows are written this many clock cycles late, so that a walk that read one above
+			// its griddepcontrol.wait gets a stale row every time (tests/test_sweep_gpu.py)
+			if (const char *v = std::getenv("PGS_TEST_ORIGIN_DELAY")) tk.h1a = (uint64_t)std::max(0L, std::atol(v));
 			p.top_tasks.push_back(tk);
 		}
 		for (int32_t v = 0; v < N; v++) {

@@ -567,3 +567,51 @@ def test_two_engines_with_different_plans_share_a_device(oracle):
     for e in engines:
         e.close()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("delay", [None, "400000"])
+def test_walk_never_starts_from_a_stale_origin_row(oracle, monkeypatch, delay):
+    """k1_walk_dense is a programmatic dependent of k1_top_masks, which writes the origin rows: an engine that
+    alternates between two gene tables (same layout, other gene ids -> other origin rows at the same
+    addresses) while other engines keep the GPU busy must never carry the OTHER table's origin row into its
+    genomes (ptxas once scheduled the origin row's ld.global.nc above griddepcontrol.wait).  With
+    PGS_TEST_ORIGIN_DELAY the origin rows are written 0.2 ms late: a load above the wait is stale every time."""
+    import threading
+    if delay:
+        monkeypatch.setenv("PGS_TEST_ORIGIN_DELAY", delay)
+    n, G, L = 300, 24, 128
+    parent, rate, leaf = treegen.coalescent(n, seed=5, mut_rate=0.02)
+    root = len(parent) - 1
+    tables, wants = [], []
+    for first_id in (0, 1000):
+        genes = list(treegen.gene_table(parent, leaf, n_core=G, n_acc=0, seed=3))
+        genes[0] = np.asarray(genes[0], dtype=np.int64) + first_id
+        with build(91, L, parent, rate, leaf, genes) as e:  # level-synchronous engine: no dependent launch in it
+            wants.append(np.stack([e.copy_dense(v, G) for v in (0, n // 3, n - 1, root)]))
+        tables.append(genes)
+    assert not np.array_equal(wants[0], wants[1])
+    stop = threading.Event()
+
+    def noise(k):  # other engines sweeping in a loop: the top-mask grid of the engine under test starts late
+        p2, r2, l2 = treegen.coalescent(2000, seed=k, mut_rate=0.02)
+        g2 = treegen.gene_table(p2, l2, n_core=64, n_acc=0, seed=k)
+        with build(k, 1000, p2, r2, l2, g2, flags=0) as e2:
+            while not stop.is_set():
+                e2.sweep()
+                e2.sync()
+    threads = [threading.Thread(target=noise, args=(k,)) for k in (1, 2, 3)]
+    for t in threads:
+        t.start()
+    try:
+        with build(91, L, parent, rate, leaf, tables[0], flags=0) as e:
+            for rep in range(40):
+                which = rep % 2
+                e.set_genes(*tables[which])
+                e.sweep()
+                e.sync()
+                got = np.stack([e.copy_dense(v, G) for v in (0, n // 3, n - 1, root)])
+                assert np.array_equal(got, wants[which]), rep
+    finally:
+        stop.set()
+        for t in threads:
+            t.join()
