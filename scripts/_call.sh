@@ -1,8 +1,6 @@
+# what the driver runs at round end, in one GPU call: GPU tests, smoke, both bench arms
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=power.limit,power.draw,clocks.sm,temperature.gpu --format=csv,noheader
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?"
-python - <<'PY'
-import json
-l=json.load(open('gpurun_out/bench_c4.json'))
-print('value %.4g ms %.4f frac %.3f e2e %.4g (%.1f ms) k2 %.1f' % (l['value'], l['ms_per_step'], l['roofline']['frac'], l['e2e']['value'], l['e2e']['ms_per_step'], l['mismatch']['k2_ms']), l['clocks'])
-PY
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
